@@ -1,0 +1,8 @@
+"""dvt_circuits_b200 - B200-native batch verifier for the DKG checks of metacraft-labs/dvt-circuits
+`crates/dkg` (Feldman share verification, key aggregation, BLS partial-signature checks).
+
+This package is a thin ctypes binding over the C ABI in include/dkgv.h (libdkgv.so, hand-written
+CUDA for sm_100a).  There is NO CPU fallback: importing works without a GPU (so symbol/ABI tests can
+run), but creating a `Verifier` raises when the library or a CUDA device is missing.
+"""
+from .binding import (DkgvError, Verifier, Status, lib_path, load_library, DECLARED_SYMBOLS)  # noqa: F401

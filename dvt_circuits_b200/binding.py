@@ -1,0 +1,183 @@
+"""ctypes binding of include/dkgv.h.  numpy arrays for host buffers, raw device pointers (e.g.
+torch.Tensor.data_ptr()) for the *_dev entry points."""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class DkgvError(RuntimeError):
+    pass
+
+
+class Status(enum.IntEnum):
+    """dkgv_status of include/dkgv.h (one code per reference exit)."""
+    OK = 0
+    SLASHABLE_SECRET_RANGE = 1
+    SLASHABLE_COMMIT_HASH = 2
+    SLASHABLE_DST_NOT_FOUND = 3
+    SLASHABLE_SHARE_MISMATCH = 4
+    SLASHABLE_BAD_PK = 5
+    SLASHABLE_BAD_SIG = 6
+    SLASHABLE_SIG_INVALID = 7
+    SLASHABLE_KEY_MISMATCH = 8
+    UNSLASHABLE_COMMIT_SIG = 16
+    UNSLASHABLE_COMMIT_HASH = 17
+    UNSLASHABLE_GEN_HASH = 18
+    UNSLASHABLE_PERP_NOT_FOUND = 19
+    UNSLASHABLE_SIG_INVALID = 20
+    ERR_LEN = 32
+    ERR_MSG_MISMATCH = 33
+    ERR_AGG_MISMATCH_VV = 34
+    ERR_AGG_MISMATCH_PK = 35
+    ERR_ZERO_ID = 36
+    ERR_DUP_ID = 37
+    PANIC_BAD_G1 = 48
+    PANIC_BAD_G2 = 49
+    PANIC_BAD_SCALAR = 50
+    PANIC_INDEX = 51
+    PANIC_PRECHECK = 52
+    PANIC_BAD_IDENTITY = 53
+
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_u32p = ctypes.POINTER(ctypes.c_uint32)
+_vp = ctypes.c_void_p
+_u32 = ctypes.c_uint32
+
+# symbol -> (restype, argtypes); must list every function include/dkgv.h declares
+DECLARED_SYMBOLS = {
+    "dkgv_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "dkgv_ctx_destroy": (None, [_vp]),
+    "dkgv_last_error": (ctypes.c_char_p, [_vp]),
+    "dkgv_launch_count": (ctypes.c_uint64, [_vp]),
+    "dkgv_sync": (ctypes.c_int, [_vp]),
+    "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_feldman_eval": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_g1_fixed_base_mul": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
+    "dkgv_g1_decompress_check": (ctypes.c_int, [_vp, _u32, _vp, _vp]),
+    "dkgv_fr_poly_eval": (ctypes.c_int, [_vp, _u32, _u32, _vp, _u32, _vp, _vp]),
+}
+
+
+def lib_path():
+    return os.path.join(_HERE, "libdkgv.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libdkgv.so and set prototypes.  Raises DkgvError when the CUDA extension is missing -
+    there is deliberately no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise DkgvError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in DECLARED_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _host(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp) if a is not None and a.size else None
+
+
+class Verifier:
+    """One dkgv_ctx bound to one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = _vp()
+        rc = self._lib.dkgv_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise DkgvError(f"dkgv_ctx_create failed ({rc}): {self._lib.dkgv_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dkgv_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DkgvError(f"dkgv call failed ({rc}): {self._lib.dkgv_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(self._lib.dkgv_launch_count(self._h))
+
+    def sync(self):
+        self._ck(self._lib.dkgv_sync(self._h))
+
+    # ---- share verification ------------------------------------------------------------------
+    def share_matrix_verify(self, vv, ids, shares):
+        """vv [n_d, t, 48] u8, ids [n_r] u32, shares [n_d, n_r, 32] u8 -> status [n_d, n_r] u8"""
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        n_d, t = vv.shape[0], vv.shape[1]
+        ids = _host(ids, np.uint32)
+        n_r = ids.shape[0]
+        shares = _host(shares, np.uint8, (n_d, n_r, 32))
+        status = np.empty((n_d, n_r), dtype=np.uint8)
+        self._ck(self._lib.dkgv_share_matrix_verify(self._h, n_d, n_r, t, _p(vv), _p(ids), _p(shares), _p(status)))
+        return status
+
+    def share_matrix_verify_dev(self, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, stream=None):
+        """device pointers (ints); asynchronous"""
+        self._ck(self._lib.dkgv_share_matrix_verify_dev(self._h, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, stream))
+
+    def feldman_eval(self, vv, ids):
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        n_d, t = vv.shape[0], vv.shape[1]
+        ids = _host(ids, np.uint32)
+        out = np.empty((n_d, ids.shape[0], 48), dtype=np.uint8)
+        row = np.empty((n_d,), dtype=np.uint8)
+        self._ck(self._lib.dkgv_feldman_eval(self._h, n_d, ids.shape[0], t, _p(vv), _p(ids), _p(out), _p(row)))
+        return out, row
+
+    def g1_fixed_base_mul(self, scalars):
+        scalars = _host(scalars, np.uint8)
+        m = scalars.shape[0]
+        out = np.empty((m, 48), dtype=np.uint8)
+        st = np.empty((m,), dtype=np.uint8)
+        self._ck(self._lib.dkgv_g1_fixed_base_mul(self._h, m, _p(scalars), _p(out), _p(st)))
+        return out, st
+
+    def g1_decompress_check(self, pts):
+        pts = _host(pts, np.uint8)
+        m = pts.shape[0]
+        st = np.empty((m,), dtype=np.uint8)
+        self._ck(self._lib.dkgv_g1_decompress_check(self._h, m, _p(pts), _p(st)))
+        return st
+
+    def fr_poly_eval(self, coeffs, ids):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8)
+        n_d, t = coeffs.shape[0], coeffs.shape[1]
+        ids = _host(ids, np.uint32)
+        out = np.empty((n_d, ids.shape[0], 32), dtype=np.uint8)
+        self._ck(self._lib.dkgv_fr_poly_eval(self._h, n_d, t, _p(coeffs), ids.shape[0], _p(ids), _p(out)))
+        return out

@@ -1,0 +1,395 @@
+// CUDA kernels (sm_100a) and the C ABI of include/dkgv.h.
+// Hot path: Feldman share verification for a (dealer x recipient) matrix -
+//   crates/dkg/src/verification.rs:129-146 + crates/dkg/src/dkg_math.rs:160-174.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "feldman.cuh"
+
+using namespace dkgv;
+
+// ============================================================================ kernels
+// Fixed-base table: entry (w, b) = (b * 2^(8w)) * G in affine Montgomery form.
+__global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= GTAB_WINDOWS * 256) return;
+  uint32_t w = tid >> 8, b = tid & 255;
+  G1Aff a = gtab_entry(w, b);
+  uint32_t* e = gtab + (size_t)tid * 24;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    e[i] = a.x.l[i];
+    e[12 + i] = a.y.l[i];
+  }
+}
+
+// Decode + subgroup-check the verification vectors into the limb-planar layout of feldman.cuh.
+//   vv [n_d][t][48]  ->  limbs/inf;  dealer_bad[d] |= 1 when any coefficient fails to decode
+//   (the reference panics on `.expect("Invalid pubkey")`, verification.rs:132-137).
+__global__ void __launch_bounds__(128)
+k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
+                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)n_pad * t) return;
+  uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
+  G1Aff a;
+  a.x = zero<FpParams>();
+  a.y = zero<FpParams>();
+  a.inf = 1;
+  if (d < n_d) {
+    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, true);
+    if (st != G1_DEC_OK) dealer_bad[d] = 1;
+    if (point_status) point_status[(size_t)d * t + k] = (uint8_t)st;
+  }
+  vv_store(limbs, inf, n_pad, k, d, a);
+}
+
+// The hot kernel.  Thread = one share (dealer d, recipient column j); the 32 lanes of a warp hold
+// 32 consecutive dealers and ONE recipient id, so the double-and-add over the id bits is
+// warp-uniform (no divergence) and every coefficient load is a fully coalesced 128 B line per limb.
+constexpr int SV_WARPS = 4;
+__global__ void __launch_bounds__(SV_WARPS * 32)
+k_share_verify(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
+               const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status,
+               uint32_t n_d, uint32_t n_r, uint32_t t) {
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t d = blockIdx.x * 32 + lane;
+  uint32_t j = blockIdx.y * SV_WARPS + warp;
+  if (j >= n_r) return;
+  bool active = d < n_d;
+  uint32_t dd = active ? d : n_d - 1;
+  uint32_t id = ids[j];
+
+  uint8_t st = share_check(vv, t, dd, id, shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
+  if (active) status[(size_t)d * n_r + j] = st;
+}
+
+// evaluate_polynomial for every (dealer, id) with compressed output
+__global__ void __launch_bounds__(SV_WARPS * 32)
+k_feldman_eval(VVView vv, const uint32_t* __restrict__ ids, uint8_t* __restrict__ out, uint32_t n_d, uint32_t n_r, uint32_t t) {
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t d = blockIdx.x * 32 + lane;
+  uint32_t j = blockIdx.y * SV_WARPS + warp;
+  if (j >= n_r) return;
+  bool active = d < n_d;
+  uint32_t dd = active ? d : n_d - 1;
+  G1Proj ev = feldman_eval(vv, t, dd, ids[j]);
+  G1Aff a = g1_to_affine(ev);
+  uint8_t enc[48];
+  g1_compress(a, enc);
+  if (active) {
+    uint8_t* o = out + ((size_t)d * n_r + j) * 48;
+#pragma unroll
+    for (int i = 0; i < 48; i++) o[i] = enc[i];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_fixed_base_mul(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ out,
+                 uint8_t* __restrict__ status, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  uint32_t s[8];
+  bool ok = fr_raw_from_be32(s, scalars + (size_t)i * 32);
+  G1Aff a = g1_to_affine(fixed_base_mul(gtab, s));
+  uint8_t enc[48];
+  g1_compress(a, enc);
+#pragma unroll
+  for (int k = 0; k < 48; k++) out[(size_t)i * 48 + k] = ok ? enc[k] : 0;
+  status[i] = ok ? DKGV_OK : DKGV_SLASHABLE_SECRET_RANGE;
+}
+
+__global__ void __launch_bounds__(128)
+k_g1_decompress_check(const uint8_t* __restrict__ in, uint8_t* __restrict__ st, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G1Aff a;
+  st[i] = (uint8_t)g1_decompress(in + (size_t)i * 48, &a, true);
+}
+
+// Dealer-side helper used to build synthetic ceremonies (not part of verification):
+// out[d][j] = sum_k coeffs[d][k] * ids[j]^k mod r, 32-byte big-endian in and out.
+__global__ void __launch_bounds__(128)
+k_fr_poly_eval(const uint8_t* __restrict__ coeffs, const uint32_t* __restrict__ ids, uint8_t* __restrict__ out, uint32_t n_d,
+               uint32_t n_r, uint32_t t) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t d = blockIdx.y;
+  if (j >= n_r || d >= n_d) return;
+  Fr x = zero<FrParams>();
+  x.l[0] = ids[j];
+  x = to_mont(x);
+  Fr acc = zero<FrParams>();
+#pragma unroll 1
+  for (int k = (int)t - 1; k >= 0; k--) {
+    Fr c;
+    fr_raw_from_be32(c.l, coeffs + ((size_t)d * t + k) * 32);
+    acc = add(mul(acc, x), to_mont(c));
+  }
+  acc = from_mont(acc);
+  uint8_t* o = out + ((size_t)d * n_r + j) * 32;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = o + 28 - 4 * i;
+    q[0] = (uint8_t)(acc.l[i] >> 24);
+    q[1] = (uint8_t)(acc.l[i] >> 16);
+    q[2] = (uint8_t)(acc.l[i] >> 8);
+    q[3] = (uint8_t)acc.l[i];
+  }
+}
+
+// ============================================================================ host side
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace
+
+struct dkgv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t* gtab = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+  DevBuf vv_limbs, vv_inf, dealer_bad;           // session scratch (decoded verification vectors)
+  DevBuf in_a, in_b, in_c, out_a, out_b;         // staging for the host-pointer entry points
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+static int fail(dkgv_ctx* ctx, const char* msg) {
+  ctx->err = msg;
+  return -1;
+}
+
+extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return -2;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return -1;
+  }
+  dkgv_ctx* ctx = new (std::nothrow) dkgv_ctx();
+  if (!ctx) return -3;
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    dkgv_ctx_destroy(ctx);
+    return -2;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
+  if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
+  k_build_gtab<<<GTAB_WINDOWS * 256 / 128, 128, 0, ctx->stream>>>(ctx->gtab);
+  ctx->launches++;
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("k_build_gtab", e);
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b})
+    b->release();
+  if (ctx->gtab) cudaFree(ctx->gtab);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* dkgv_last_error(const dkgv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" uint64_t dkgv_launch_count(const dkgv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int dkgv_sync(dkgv_ctx* ctx) {
+  if (!ctx) return -1;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// decode vv into the ctx session buffers (asynchronous on s)
+static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, uint8_t* d_point_status, cudaStream_t s,
+                          VVView* view, uint32_t* n_pad_out) {
+  uint32_t n_pad = (n_d + 31) & ~31u;
+  uint32_t tt = t ? t : 1;
+  CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
+  CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
+  CK(ctx->dealer_bad.reserve(n_pad));
+  CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
+  if (t) {
+    size_t total = (size_t)n_pad * t;
+    k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                  (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
+                                                                  d_point_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  view->limbs = (const uint32_t*)ctx->vv_limbs.p;
+  view->inf = (const uint8_t*)ctx->vv_inf.p;
+  view->n_pad = n_pad;
+  *n_pad_out = n_pad;
+  return 0;
+}
+
+extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
+                                            const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, void* stream) {
+  if (!ctx) return -1;
+  if (n_d == 0 || n_r == 0) return 0;
+  if (!d_ids || !d_shares || !d_status || (t && !d_vv)) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  VVView view;
+  uint32_t n_pad;
+  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad);
+  if (rc) return rc;
+  dim3 grid(n_pad / 32, (n_r + SV_WARPS - 1) / SV_WARPS);
+  k_share_verify<<<grid, SV_WARPS * 32, 0, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status,
+                                              n_d, n_r, t);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* vv,
+                                        const uint32_t* ids, const uint8_t* shares, uint8_t* status) {
+  if (!ctx) return -1;
+  if (n_d == 0 || n_r == 0) return 0;
+  if (!ids || !shares || !status || (t && !vv)) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t vvb = (size_t)n_d * t * 48, idb = (size_t)n_r * 4, shb = (size_t)n_d * n_r * 32, stb = (size_t)n_d * n_r;
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->in_b.reserve(idb));
+  CK(ctx->in_c.reserve(shb));
+  CK(ctx->out_a.reserve(stb));
+  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_c.p, shares, shb, cudaMemcpyHostToDevice, s));
+  int rc = dkgv_share_matrix_verify_dev(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p,
+                                        (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_feldman_eval(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_ids, uint32_t t, const uint8_t* vv, const uint32_t* ids,
+                                 uint8_t* out, uint8_t* row_status) {
+  if (!ctx) return -1;
+  if (n_d == 0 || n_ids == 0) return 0;
+  if (!ids || !out || !row_status || (t && !vv)) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t vvb = (size_t)n_d * t * 48, idb = (size_t)n_ids * 4, ob = (size_t)n_d * n_ids * 48;
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->in_b.reserve(idb));
+  CK(ctx->out_a.reserve(ob));
+  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
+  VVView view;
+  uint32_t n_pad;
+  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, nullptr, s, &view, &n_pad);
+  if (rc) return rc;
+  dim3 grid(n_pad / 32, (n_ids + SV_WARPS - 1) / SV_WARPS);
+  k_feldman_eval<<<grid, SV_WARPS * 32, 0, s>>>(view, (const uint32_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, n_d, n_ids, t);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, ob, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(row_status, ctx->dealer_bad.p, n_d, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (uint32_t i = 0; i < n_d; i++) row_status[i] = row_status[i] ? DKGV_PANIC_BAD_G1 : DKGV_OK;
+  return 0;
+}
+
+extern "C" int dkgv_g1_fixed_base_mul(dkgv_ctx* ctx, uint32_t m, const uint8_t* scalars, uint8_t* out, uint8_t* status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!scalars || !out || !status) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve((size_t)m * 32));
+  CK(ctx->out_a.reserve((size_t)m * 48));
+  CK(ctx->out_b.reserve(m));
+  CK(cudaMemcpyAsync(ctx->in_a.p, scalars, (size_t)m * 32, cudaMemcpyHostToDevice, s));
+  k_fixed_base_mul<<<(m + 127) / 128, 128, 0, s>>>((const uint8_t*)ctx->in_a.p, ctx->gtab, (uint8_t*)ctx->out_a.p,
+                                                  (uint8_t*)ctx->out_b.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)m * 48, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status, ctx->out_b.p, m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_g1_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!in || !decode_status) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve((size_t)m * 48));
+  CK(ctx->out_b.reserve(m));
+  CK(cudaMemcpyAsync(ctx->in_a.p, in, (size_t)m * 48, cudaMemcpyHostToDevice, s));
+  k_g1_decompress_check<<<(m + 127) / 128, 128, 0, s>>>((const uint8_t*)ctx->in_a.p, (uint8_t*)ctx->out_b.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(decode_status, ctx->out_b.p, m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_fr_poly_eval(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* coeffs, uint32_t n_r, const uint32_t* ids,
+                                 uint8_t* out) {
+  if (!ctx) return -1;
+  if (n_d == 0 || n_r == 0) return 0;
+  if (!ids || !out || (t && !coeffs)) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t cb = (size_t)n_d * t * 32, ob = (size_t)n_d * n_r * 32;
+  CK(ctx->in_a.reserve(cb ? cb : 1));
+  CK(ctx->in_b.reserve((size_t)n_r * 4));
+  CK(ctx->out_a.reserve(ob));
+  if (cb) CK(cudaMemcpyAsync(ctx->in_a.p, coeffs, cb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
+  dim3 grid((n_r + 127) / 128, n_d);
+  k_fr_poly_eval<<<grid, 128, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, n_d, n_r, t);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, ob, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}

@@ -1,0 +1,119 @@
+// Per-thread building blocks of the Feldman share check (host/device so the very same code is
+// exercised by the CPU-side emulation tests):
+//   evaluate_polynomial  crates/dkg/src/dkg_math.rs:160-174  (Horner in the exponent)
+//   G * s                crates/dkg/src/crypto/bls_keys.rs:133-137
+//   compare              crates/dkg/src/verification.rs:140-146
+//
+// HBM layout of a session's verification vectors ("coefficient-major, limb-planar"):
+//   limbs[(k*24 + w) * n_pad + d]   w-th 32-bit limb (x: 0..11, y: 12..23, Montgomery form) of
+//                                   coefficient k of dealer d;  n_pad = dealers rounded up to 32
+//   inf[k * n_pad + d]              1 when the coefficient is the identity
+// so that the 32 lanes of a warp (32 consecutive dealers, one recipient id) read 128 contiguous
+// bytes per limb.
+#pragma once
+#include "../../include/dkgv.h"
+#include "g1.cuh"
+
+namespace dkgv {
+
+struct VVView {
+  const uint32_t* limbs;
+  const uint8_t* inf;
+  uint32_t n_pad;
+};
+
+DKGV_HD G1Aff vv_load(const VVView& v, uint32_t k, uint32_t d) {
+  G1Aff a;
+  const uint32_t* base = v.limbs + (size_t)k * 24 * v.n_pad + d;
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    a.x.l[w] = base[(size_t)w * v.n_pad];
+    a.y.l[w] = base[(size_t)(w + 12) * v.n_pad];
+  }
+  a.inf = v.inf[(size_t)k * v.n_pad + d];
+  return a;
+}
+
+DKGV_HD void vv_store(uint32_t* limbs, uint8_t* inf, uint32_t n_pad, uint32_t k, uint32_t d, const G1Aff& a) {
+  uint32_t* base = limbs + (size_t)k * 24 * n_pad + d;
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    base[(size_t)w * n_pad] = a.x.l[w];
+    base[(size_t)(w + 12) * n_pad] = a.y.l[w];
+  }
+  inf[(size_t)k * n_pad + d] = (uint8_t)(a.inf != 0);
+}
+
+// [k]P for a small public scalar (recipient id): left-to-right binary, top bit free.
+// Control flow depends on k only - warp-uniform when all lanes share the id.
+DKGV_HD G1Proj g1_mul_small(const G1Proj& p, uint32_t k) {
+  if (k == 0) return g1_identity();
+  int top = 31;
+  while (!((k >> top) & 1)) top--;
+  G1Proj acc = p;
+#pragma unroll 1
+  for (int b = top - 1; b >= 0; b--) {
+    acc = g1_dbl(acc);
+    if ((k >> b) & 1) acc = g1_add(acc, p);
+  }
+  return acc;
+}
+
+// sum_k C_k * id^k by Horner from the top coefficient (dkg_math.rs:160-174)
+DKGV_HD G1Proj feldman_eval(const VVView& v, uint32_t t, uint32_t d, uint32_t id) {
+  if (t == 0) return g1_identity();
+  G1Proj acc = g1_from_affine(vv_load(v, t - 1, d));
+#pragma unroll 1
+  for (int k = (int)t - 2; k >= 0; k--) {
+    acc = g1_mul_small(acc, id);
+    acc = g1_add_mixed(acc, vv_load(v, (uint32_t)k, d));
+  }
+  return acc;
+}
+
+// Fixed-base table for the generator: gtab[(w*256 + b) * 24 + limb] = affine Montgomery
+// (b * 2^(8w)) * G, w = 0..31, b = 1..255 (entry b = 0 unused).
+constexpr int GTAB_WINDOWS = 32;
+constexpr size_t GTAB_WORDS = (size_t)GTAB_WINDOWS * 256 * 24;
+
+DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 limbs, < r*/) {
+  G1Proj acc = g1_identity();
+#pragma unroll 1
+  for (int w = 0; w < GTAB_WINDOWS; w++) {
+    uint32_t byte = (s_raw[w >> 2] >> (8 * (w & 3))) & 0xff;
+    const uint32_t* e = gtab + ((size_t)w * 256 + byte) * 24;
+    G1Aff q;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      q.x.l[i] = e[i];
+      q.y.l[i] = e[12 + i];
+    }
+    q.inf = (byte == 0);
+    acc = g1_add_mixed(acc, q);
+  }
+  return acc;
+}
+
+// table entry (w, b) = (b * 2^(8w)) * G, affine
+DKGV_HD G1Aff gtab_entry(uint32_t w, uint32_t b) {
+  G1Proj p = g1_from_affine(g1_generator());
+#pragma unroll 1
+  for (uint32_t i = 0; i < 8 * w; i++) p = g1_dbl(p);
+  return g1_to_affine(g1_mul_small(p, b));
+}
+
+// One share: status of (dealer d, recipient id) - the body of verify_seed_exchange_commitment
+// after the hash / lookup checks (crates/dkg/src/verification.rs:92-99,129-146).
+DKGV_HD uint8_t share_check(const VVView& vv, uint32_t t, uint32_t d, uint32_t id, const uint8_t* secret_be,
+                            const uint32_t* gtab, bool dealer_bad) {
+  G1Proj ev = feldman_eval(vv, t, d, id);
+  uint32_t s[8];
+  bool in_range = fr_raw_from_be32(s, secret_be);
+  G1Proj gs = fixed_base_mul(gtab, s);
+  uint8_t st = g1_eq(ev, gs) ? DKGV_OK : DKGV_SLASHABLE_SHARE_MISMATCH;
+  if (dealer_bad) st = DKGV_PANIC_BAD_G1;
+  if (!in_range) st = DKGV_SLASHABLE_SECRET_RANGE;
+  return st;
+}
+
+}  // namespace dkgv

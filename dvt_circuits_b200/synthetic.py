@@ -1,0 +1,56 @@
+"""Deterministic synthetic DKG ceremonies: dealer polynomials, Feldman verification
+vectors vv[i][k] = G * a_{i,k}, shares s_{i,j} = f_i(id_j) mod r, and seeded corruptions drawn from
+the reference's own mutation taxonomy (test_vectors/*: -bad- = one bit flipped, -wrong- = another
+valid value, out-of-range secret).  Set-up work (G*a, f_i(id)) runs on the GPU through the C ABI and
+is excluded from every timed region."""
+import numpy as np
+
+R_INT = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+DEFAULT_SEED = 0xD1C62026
+
+
+def make_coefficients(n_dealers, t, seed=DEFAULT_SEED, dealer_offset=0):
+    """[n_dealers, t, 32] big-endian scalars < 2^248 < r; dealer d's row depends only on (seed, d)."""
+    out = np.zeros((n_dealers, t, 32), dtype=np.uint8)
+    for d in range(n_dealers):
+        rng = np.random.Generator(np.random.PCG64([seed, dealer_offset + d]))
+        out[d, :, 1:] = rng.integers(0, 256, size=(t, 31), dtype=np.uint8)
+    return out
+
+
+def make_session(verifier, n_dealers, n_recipients, t, seed=DEFAULT_SEED, dealer_offset=0, ids=None):
+    """-> dict(vv [n_d,t,48], ids [n_r] u32, shares [n_d,n_r,32], coeffs)"""
+    coeffs = make_coefficients(n_dealers, t, seed, dealer_offset)
+    if ids is None:
+        ids = np.arange(1, n_recipients + 1, dtype=np.uint32)
+    vv, st = verifier.g1_fixed_base_mul(coeffs.reshape(-1, 32))
+    assert not st.any()
+    shares = verifier.fr_poly_eval(coeffs, ids)
+    return {"vv": vv.reshape(n_dealers, t, 48), "ids": np.asarray(ids, dtype=np.uint32), "shares": shares, "coeffs": coeffs}
+
+
+def corrupt_shares(shares, p_bad, seed=DEFAULT_SEED):
+    """Bernoulli(p_bad) per share; returns (mutated copy, expected status array).
+    kinds: 0 flip one bit (-> SHARE_MISMATCH), 1 replace by the share of the next dealer, same
+    recipient (-> SHARE_MISMATCH), 2 secret >= r (-> SECRET_RANGE)."""
+    n_d, n_r, _ = shares.shape
+    rng = np.random.Generator(np.random.PCG64([seed, 0xBAD]))
+    bad = rng.random((n_d, n_r)) < p_bad
+    kind = rng.integers(0, 3, size=(n_d, n_r))
+    bit = rng.integers(0, 248, size=(n_d, n_r))
+    out = shares.copy()
+    expected = np.zeros((n_d, n_r), dtype=np.uint8)
+    di, ji = np.nonzero(bad)
+    for d, j in zip(di.tolist(), ji.tolist()):
+        k = kind[d, j]
+        if k == 0 or n_d == 1 and k == 1:
+            b = int(bit[d, j])
+            out[d, j, 31 - b // 8] ^= 1 << (b % 8)
+            expected[d, j] = 4
+        elif k == 1:
+            out[d, j] = shares[(d + 1) % n_d, j]
+            expected[d, j] = 4 if (shares[(d + 1) % n_d, j] != shares[d, j]).any() else 0
+        else:
+            out[d, j] = 0xFF
+            expected[d, j] = 1
+    return out, expected

@@ -1,0 +1,107 @@
+/* dkgv.h - C ABI of the B200-native batch verifier for the DKG checks of metacraft-labs/dvt-circuits
+ * `crates/dkg`.  This is the drop-in boundary: a Rust `-sys` crate binds
+ * exactly these symbols; no CUDA or torch types appear in the signatures.
+ *
+ * Conventions
+ *  - All byte encodings are the reference's wire formats (crates/dkg/src/types.rs:396-407):
+ *    G1 = 48 B compressed big-endian, G2 = 96 B compressed (c1 || c0), scalars = 32 B big-endian,
+ *    hashes = 32 B.  Arrays are dense row-major.
+ *  - Every function returns 0 on success, <0 on argument / CUDA error (message via
+ *    dkgv_last_error).  Per-item outcomes are written to caller-allocated `status` arrays using
+ *    the dkgv_status codes below: one code per distinct exit of the reference
+ *    (Ok / SlashableError / UnslashableError / io::Error / panic!).
+ *  - Pointers named `h_*`/unprefixed are HOST pointers; functions ending in `_dev` take DEVICE
+ *    pointers (current device of the ctx) and a stream handle and do not synchronise.
+ *  - A ctx is single-owner (Send, not Sync), bound to one GPU.  Multi-GPU = one ctx per
+ *    process/GPU; shard rows (dealers / items) across ranks, gather the status bytes.
+ *  - There is no CPU fallback: without a CUDA device dkgv_ctx_create fails.
+ */
+#ifndef DKGV_H
+#define DKGV_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dkgv_ctx dkgv_ctx;
+
+/* per-item outcome codes; comments cite the reference exit each one stands for */
+enum dkgv_status {
+  DKGV_OK = 0,
+  DKGV_SLASHABLE_SECRET_RANGE = 1,   /* verification.rs:92-99   secret >= r                      */
+  DKGV_SLASHABLE_COMMIT_HASH = 2,    /* verification.rs:101-114 [auth] seed-exchange hash        */
+  DKGV_SLASHABLE_DST_NOT_FOUND = 3,  /* verification.rs:116-126 dst_base_hash not in base_hashes */
+  DKGV_SLASHABLE_SHARE_MISMATCH = 4, /* verification.rs:140-146 G*s != sum C_k id^k              */
+  DKGV_SLASHABLE_BAD_PK = 5,         /* verification.rs:440-446 partial_pubkey undecodable       */
+  DKGV_SLASHABLE_BAD_SIG = 6,        /* verification.rs:448-454 message_signature undecodable    */
+  DKGV_SLASHABLE_SIG_INVALID = 7,    /* verification.rs:456-461 pairing check false              */
+  DKGV_SLASHABLE_KEY_MISMATCH = 8,   /* verification.rs:413-418 expected key != partial key (Q1) */
+  DKGV_UNSLASHABLE_COMMIT_SIG = 16,  /* verification.rs:76-89, 488-493 identity signature        */
+  DKGV_UNSLASHABLE_COMMIT_HASH = 17, /* verification.rs:470-477                                  */
+  DKGV_UNSLASHABLE_GEN_HASH = 18,    /* verification.rs:250-257, 388-393                         */
+  DKGV_UNSLASHABLE_PERP_NOT_FOUND = 19, /* verification.rs:511-519                               */
+  DKGV_UNSLASHABLE_SIG_INVALID = 20, /* verification.rs:243-248                                  */
+  DKGV_ERR_LEN = 32,                 /* verification.rs:218-223, 270-275; dkg_math.rs:183-188    */
+  DKGV_ERR_MSG_MISMATCH = 33,        /* verification.rs:224-231                                  */
+  DKGV_ERR_AGG_MISMATCH_VV = 34,     /* verification.rs:301-309                                  */
+  DKGV_ERR_AGG_MISMATCH_PK = 35,     /* verification.rs:320-328                                  */
+  DKGV_ERR_ZERO_ID = 36,             /* dkg_math.rs:201-206                                      */
+  DKGV_ERR_DUP_ID = 37,              /* dkg_math.rs:212-217                                      */
+  DKGV_PANIC_BAD_G1 = 48,            /* .expect on G1 decode: verification.rs:136,241,288,314    */
+  DKGV_PANIC_BAD_G2 = 49,            /* .expect on G2 decode: verification.rs:238                */
+  DKGV_PANIC_BAD_SCALAR = 50,        /* dkg_math.rs:84                                           */
+  DKGV_PANIC_INDEX = 51,             /* dkg_math.rs:235-239 ragged verification vectors          */
+  DKGV_PANIC_PRECHECK = 52,          /* guest pre-checks, bad_share_exchange_prove/main.rs:24-43 */
+  DKGV_PANIC_BAD_IDENTITY = 53       /* verification.rs:369-372, 478-481                         */
+};
+
+/* G1 / G2 decode results (dkgv_g1_decompress_check) */
+enum dkgv_decode { DKGV_DEC_OK = 0, DKGV_DEC_BAD_FLAGS = 1, DKGV_DEC_X_RANGE = 2, DKGV_DEC_NOT_ON_CURVE = 3, DKGV_DEC_NOT_IN_SUBGROUP = 4 };
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Binds to CUDA device `device`, builds the fixed-base table for G1 generator multiplication.   */
+int dkgv_ctx_create(int device, dkgv_ctx** out);
+void dkgv_ctx_destroy(dkgv_ctx* ctx);
+const char* dkgv_last_error(const dkgv_ctx* ctx); /* ctx may be NULL: last create error */
+/* number of kernel launches issued through this ctx so far (bench accounting) */
+uint64_t dkgv_launch_count(const dkgv_ctx* ctx);
+int dkgv_sync(dkgv_ctx* ctx);
+
+/* ---- Feldman share verification (replaces the loop body of verify_seed_exchange_commitment,
+ *      crates/dkg/src/verification.rs:129-146, for a whole (dealer x recipient) matrix) ------- */
+/* vv      [n_dealers][t][48]   verification vectors (base_pubkeys of each dealer)
+ * ids     [n_recipients]       recipient id = 1 + index of dst_base_hash in sorted base_hashes
+ * shares  [n_dealers][n_recipients][32] big-endian secrets
+ * status  [n_dealers][n_recipients]  out: OK / SLASHABLE_SECRET_RANGE / PANIC_BAD_G1 / SLASHABLE_SHARE_MISMATCH
+ * t == 0 evaluates to the identity, t == 1 to C_0 (dkg_math.rs:161-166).                        */
+int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t,
+                             const uint8_t* vv, const uint32_t* ids, const uint8_t* shares, uint8_t* status);
+/* same with device-resident buffers, asynchronous on `stream` (a cudaStream_t, may be NULL) */
+int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t,
+                                 const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
+                                 uint8_t* d_status, void* stream);
+
+/* ---- evaluate_polynomial (crates/dkg/src/dkg_math.rs:160-174), batched ---------------------- */
+/* out[d][j] = compress( sum_k vv[d][k] * ids[j]^k ), 48 B each; status per dealer row
+ * (OK / PANIC_BAD_G1).                                                                          */
+int dkgv_feldman_eval(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_ids, uint32_t t, const uint8_t* vv,
+                      const uint32_t* ids, uint8_t* out, uint8_t* row_status);
+
+/* ---- G * s (BlsSecretKey::to_public_key, crates/dkg/src/crypto/bls_keys.rs:133-137) --------- */
+/* out[i] = compress(G * scalars[i]); status OK / SLASHABLE_SECRET_RANGE (scalar >= r)           */
+int dkgv_g1_fixed_base_mul(dkgv_ctx* ctx, uint32_t m, const uint8_t* scalars, uint8_t* out, uint8_t* status);
+
+/* ---- G1 decoding with subgroup check (to_g1_affine, crypto/bls_common.rs:108-112) ----------- */
+int dkgv_g1_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status);
+
+/* ---- dealer-side helper for building synthetic ceremonies (not a verification step) --------- */
+/* out[d][j] = sum_k coeffs[d][k] * ids[j]^k mod r ; coeffs [n_dealers][t][32] BE (< r), out BE   */
+int dkgv_fr_poly_eval(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* coeffs, uint32_t n_ids,
+                      const uint32_t* ids, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKGV_H */

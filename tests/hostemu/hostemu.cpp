@@ -1,0 +1,90 @@
+// TEST HARNESS ONLY - not part of the product.  Compiles the device headers
+// (dvt_circuits_b200/csrc/*.cuh) for the host with plain g++ so that `-m "not gpu"` tests can check
+// the exact per-thread logic of the CUDA kernels (formulas, codecs, Horner, window tables)
+// against the oracle on a machine without a GPU.  The only thing not covered here is the PTX
+// carry-chain Montgomery product, which the `-m gpu` tests pin on a real B200.
+// Nothing under dvt_circuits_b200/ links or loads this file.
+#include <cstring>
+#include <vector>
+
+#include "../../dvt_circuits_b200/csrc/feldman.cuh"
+
+using namespace dkgv;
+
+extern "C" {
+
+// canonical 48-byte big-endian a, b -> canonical a*b mod p, a+b, a-b
+void he_fp_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t* add48, uint8_t* sub48, uint8_t* inv48) {
+  Fp a, b;
+  fp_raw_from_be48(a.l, a48);
+  fp_raw_from_be48(b.l, b48);
+  a = to_mont(a);
+  b = to_mont(b);
+  fp_raw_to_be48(mul48, from_mont(mul(a, b)).l);
+  fp_raw_to_be48(add48, from_mont(add(a, b)).l);
+  fp_raw_to_be48(sub48, from_mont(sub(a, b)).l);
+  fp_raw_to_be48(inv48, from_mont(fp_inv(a)).l);
+}
+
+void he_fr_mul(const uint8_t* a32, const uint8_t* b32, uint8_t* out32) {
+  Fr a, b;
+  fr_raw_from_be32(a.l, a32);
+  fr_raw_from_be32(b.l, b32);
+  Fr r = from_mont(mul(to_mont(a), to_mont(b)));
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = out32 + 28 - 4 * i;
+    q[0] = r.l[i] >> 24; q[1] = r.l[i] >> 16; q[2] = r.l[i] >> 8; q[3] = r.l[i];
+  }
+}
+
+uint32_t he_g1_decompress(const uint8_t* in48, uint8_t* recompressed48) {
+  G1Aff a;
+  uint32_t st = g1_decompress(in48, &a, true);
+  if (st == G1_DEC_OK) g1_compress(a, recompressed48);
+  return st;
+}
+
+// out = compress(P + Q), compress(2P), compress([k]P) through the projective formulas
+uint32_t he_g1_ops(const uint8_t* p48, const uint8_t* q48, uint32_t k, uint8_t* add48, uint8_t* madd48, uint8_t* dbl48, uint8_t* mul48) {
+  G1Aff p, q;
+  if (g1_decompress(p48, &p, false) || g1_decompress(q48, &q, false)) return 1;
+  G1Proj pp = g1_from_affine(p), qq = g1_from_affine(q);
+  g1_compress(g1_to_affine(g1_add(pp, qq)), add48);
+  g1_compress(g1_to_affine(g1_add_mixed(pp, q)), madd48);
+  g1_compress(g1_to_affine(g1_dbl(pp)), dbl48);
+  g1_compress(g1_to_affine(g1_mul_small(pp, k)), mul48);
+  return g1_eq(g1_add(pp, qq), g1_add_mixed(pp, q)) ? 0 : 2;
+}
+
+// One emulated "thread" of k_share_verify / k_feldman_eval for dealer 0 of a 1-dealer session.
+// vv: [t][48]; returns status; eval48 = compress(evaluate_polynomial), pk48 = compress(G*s)
+uint32_t he_share_check(const uint8_t* vv, uint32_t t, uint32_t id, const uint8_t* secret32, uint8_t* eval48, uint8_t* pk48) {
+  const uint32_t n_pad = 32;
+  uint32_t tt = t ? t : 1;
+  std::vector<uint32_t> limbs((size_t)tt * 24 * n_pad, 0);
+  std::vector<uint8_t> inf((size_t)tt * n_pad, 1);
+  bool bad = false;
+  for (uint32_t k = 0; k < t; k++) {
+    G1Aff a;
+    if (g1_decompress(vv + (size_t)k * 48, &a, true) != G1_DEC_OK) bad = true;
+    vv_store(limbs.data(), inf.data(), n_pad, k, 0, a);
+  }
+  VVView view{limbs.data(), inf.data(), n_pad};
+  // the 32 table entries this scalar touches, computed by the same routine as k_build_gtab
+  std::vector<uint32_t> gtab(GTAB_WORDS, 0);
+  uint32_t s[8];
+  fr_raw_from_be32(s, secret32);
+  for (int w = 0; w < GTAB_WINDOWS; w++) {
+    uint32_t byte = (s[w >> 2] >> (8 * (w & 3))) & 0xff;
+    if (!byte) continue;
+    G1Aff e = gtab_entry(w, byte);
+    for (int i = 0; i < 12; i++) {
+      gtab[((size_t)w * 256 + byte) * 24 + i] = e.x.l[i];
+      gtab[((size_t)w * 256 + byte) * 24 + 12 + i] = e.y.l[i];
+    }
+  }
+  g1_compress(g1_to_affine(feldman_eval(view, t, 0, id)), eval48);
+  g1_compress(g1_to_affine(fixed_base_mul(gtab.data(), s)), pk48);
+  return share_check(view, t, 0, id, secret32, gtab.data(), bad);
+}
+}
