@@ -8,17 +8,16 @@
 #include <new>
 #include <string>
 
-#include "feldman.cuh"
+#include "vm.cuh"
 
 using namespace dkgv;
 
 // ============================================================================ kernels
-// Fixed-base table: entry (w, b) = (b * 2^(8w)) * G in affine Montgomery form.
+// Offset fixed-base table of the generator (layout in feldman.cuh).
 __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= GTAB_WINDOWS * 256) return;
-  uint32_t w = tid >> 8, b = tid & 255;
-  G1Aff a = gtab_entry(w, b);
+  if (tid >= GTAB_ENTRIES) return;
+  G1Aff a = gtab_entry(tid);
   uint32_t* e = gtab + (size_t)tid * 24;
 #pragma unroll
   for (int i = 0; i < 12; i++) {
@@ -51,20 +50,23 @@ k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32
 // The hot kernel.  Thread = one share (dealer d, recipient column j); the 32 lanes of a warp hold
 // 32 consecutive dealers and ONE recipient id, so the double-and-add over the id bits is
 // warp-uniform (no divergence) and every coefficient load is a fully coalesced 128 B line per limb.
-constexpr int SV_WARPS = 4;
-__global__ void __launch_bounds__(SV_WARPS * 32)
+// Field operands live in the shared-memory operand file of vm.cuh (13 slots x 48 B per thread).
+constexpr int SV_WARPS = 4;   // k_feldman_eval (inlined formulas, cold path)
+constexpr int SVM_NT = 64;    // threads per block of the hot kernel: 2 warps = 2 recipient ids
+constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 3 * SVM_NT * sizeof(U4);
+__global__ void __launch_bounds__(SVM_NT)
 k_share_verify(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
                const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status,
                uint32_t n_d, uint32_t n_r, uint32_t t) {
+  extern __shared__ U4 opfile[];
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t d = blockIdx.x * 32 + lane;
-  uint32_t j = blockIdx.y * SV_WARPS + warp;
+  uint32_t j = blockIdx.y * (SVM_NT / 32) + warp;
   if (j >= n_r) return;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
-  uint32_t id = ids[j];
-
-  uint8_t st = share_check(vv, t, dd, id, shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
+  OpFile f{opfile + threadIdx.x, SVM_NT};
+  uint8_t st = vm_share_check(f, vv, t, dd, ids[j], shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
   if (active) status[(size_t)d * n_r + j] = st;
 }
 
@@ -214,7 +216,11 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
   if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
-  k_build_gtab<<<GTAB_WINDOWS * 256 / 128, 128, 0, ctx->stream>>>(ctx->gtab);
+  if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVM_SMEM)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute smem", e);
+  if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute carveout", e);
+  k_build_gtab<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
   ctx->launches++;
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("k_build_gtab", e);
   *out = ctx;
@@ -276,8 +282,8 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   uint32_t n_pad;
   int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad);
   if (rc) return rc;
-  dim3 grid(n_pad / 32, (n_r + SV_WARPS - 1) / SV_WARPS);
-  k_share_verify<<<grid, SV_WARPS * 32, 0, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status,
+  dim3 grid(n_pad / 32, (n_r + SVM_NT / 32 - 1) / (SVM_NT / 32));
+  k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status,
                                               n_d, n_r, t);
   ctx->launches++;
   CK(cudaGetLastError());

@@ -71,35 +71,51 @@ DKGV_HD G1Proj feldman_eval(const VVView& v, uint32_t t, uint32_t d, uint32_t id
   return acc;
 }
 
-// Fixed-base table for the generator: gtab[(w*256 + b) * 24 + limb] = affine Montgomery
-// (b * 2^(8w)) * G, w = 0..31, b = 1..255 (entry b = 0 unused).
+// Offset fixed-base table for the generator (no zero digits, so the mixed addition never meets the
+// identity and needs no select):
+//   gtab[(w*256 + b) * 24 ..] = ((b + 1) * 2^(8w)) * G      b = 0..255, w = 0..31   (affine Montgomery)
+//   gtab[32*256*24 ..]        = -(sum_w 2^(8w)) * G         (correction point)
+// G*s = sum_w gtab[w][byte_w(s)] + correction.
 constexpr int GTAB_WINDOWS = 32;
-constexpr size_t GTAB_WORDS = (size_t)GTAB_WINDOWS * 256 * 24;
+constexpr uint32_t GTAB_ENTRIES = GTAB_WINDOWS * 256 + 1;
+constexpr size_t GTAB_WORDS = (size_t)GTAB_ENTRIES * 24;
 
-DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 limbs, < r*/) {
-  G1Proj acc = g1_identity();
+DKGV_HD G1Aff gtab_entry(uint32_t idx) {
+  if (idx < GTAB_WINDOWS * 256) {
+    uint32_t w = idx >> 8, b = idx & 255;
+    G1Proj p = g1_from_affine(g1_generator());
 #pragma unroll 1
-  for (int w = 0; w < GTAB_WINDOWS; w++) {
-    uint32_t byte = (s_raw[w >> 2] >> (8 * (w & 3))) & 0xff;
-    const uint32_t* e = gtab + ((size_t)w * 256 + byte) * 24;
-    G1Aff q;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      q.x.l[i] = e[i];
-      q.y.l[i] = e[12 + i];
-    }
-    q.inf = (byte == 0);
-    acc = g1_add_mixed(acc, q);
+    for (uint32_t i = 0; i < 8 * w; i++) p = g1_dbl(p);
+    return g1_to_affine(g1_mul_small(p, b + 1));
   }
-  return acc;
+  G1Proj g = g1_from_affine(g1_generator()), acc = g1_identity();
+#pragma unroll 1
+  for (uint32_t w = 0; w < GTAB_WINDOWS; w++) {
+    acc = g1_add(acc, g);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) g = g1_dbl(g);
+  }
+  return g1_to_affine(g1_neg(acc));
 }
 
-// table entry (w, b) = (b * 2^(8w)) * G, affine
-DKGV_HD G1Aff gtab_entry(uint32_t w, uint32_t b) {
-  G1Proj p = g1_from_affine(g1_generator());
+DKGV_HD uint32_t gtab_index(const uint32_t* s_raw, int w) {
+  return w < GTAB_WINDOWS ? (uint32_t)w * 256 + ((s_raw[w >> 2] >> (8 * (w & 3))) & 0xff) : (uint32_t)GTAB_WINDOWS * 256;
+}
+
+DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 limbs*/) {
+  G1Proj acc = g1_identity();
 #pragma unroll 1
-  for (uint32_t i = 0; i < 8 * w; i++) p = g1_dbl(p);
-  return g1_to_affine(g1_mul_small(p, b));
+  for (int w = 0; w <= GTAB_WINDOWS; w++) {
+    const uint32_t* e = gtab + (size_t)gtab_index(s_raw, w) * 24;
+    Fp x, y;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      x.l[i] = e[i];
+      y.l[i] = e[12 + i];
+    }
+    acc = g1_add_mixed_nz(acc, x, y);
+  }
+  return acc;
 }
 
 // One share: status of (dealer d, recipient id) - the body of verify_seed_exchange_commitment

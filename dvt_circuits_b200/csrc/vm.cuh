@@ -1,0 +1,256 @@
+// "Operand file" execution model for the hot kernels.
+//
+// Why: a G1 formula with every 381-bit Montgomery product inlined is ~4k SASS instructions; the
+// Horner loop body (double, add, mixed add) came to 331 KB of code and ncu showed the warps stalled
+// on instruction fetch 65 % of the time (profiles/r1_share_verify_v0_inlined.md).  Here every field
+// routine exists ONCE (noinline), operands live in a per-thread file in shared memory, and a point
+// formula is a short sequence of calls - the whole kernel is a few thousand instructions and stays
+// resident in the instruction cache.  Register use drops to ~70, so occupancy is bounded by the
+// operand file (13 slots x 48 B per thread) instead.
+//
+// Shared-memory layout: slot s of thread t is three 16-byte chunks at
+//     file[(s*3 + c) * NT + t]            (NT = threads per block)
+// so a warp's LDS.128/STS.128 touch 32 consecutive 16-byte words: conflict-free.
+//
+// The same code runs on the host (tests/hostemu) with the file in ordinary memory.
+#pragma once
+#include "feldman.cuh"
+
+#if defined(__CUDACC__)
+#define DKGV_NI __host__ __device__ __noinline__
+#else
+#define DKGV_NI static
+#endif
+
+namespace dkgv {
+
+struct alignas(16) U4 {
+  uint32_t x, y, z, w;
+};
+
+struct OpFile {
+  U4* base;         // this thread's chunk 0 of slot 0
+  uint32_t stride;  // U4 elements between consecutive chunks (= threads per block)
+};
+
+DKGV_HD Fp of_load(const OpFile& f, int s) {
+  Fp r;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    U4 v = f.base[(size_t)(s * 3 + c) * f.stride];
+    r.l[4 * c] = v.x;
+    r.l[4 * c + 1] = v.y;
+    r.l[4 * c + 2] = v.z;
+    r.l[4 * c + 3] = v.w;
+  }
+  return r;
+}
+DKGV_HD void of_store(const OpFile& f, int s, const Fp& a) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    U4 v;
+    v.x = a.l[4 * c];
+    v.y = a.l[4 * c + 1];
+    v.z = a.l[4 * c + 2];
+    v.w = a.l[4 * c + 3];
+    f.base[(size_t)(s * 3 + c) * f.stride] = v;
+  }
+}
+
+// ---- field routines on slots (one copy each) ---------------------------------------------
+DKGV_NI void vm_mul(OpFile f, int d, int a, int b) { of_store(f, d, mul(of_load(f, a), of_load(f, b))); }
+DKGV_NI void vm_add(OpFile f, int d, int a, int b) { of_store(f, d, add(of_load(f, a), of_load(f, b))); }
+DKGV_NI void vm_sub(OpFile f, int d, int a, int b) { of_store(f, d, sub(of_load(f, a), of_load(f, b))); }
+DKGV_NI void vm_mul12(OpFile f, int d, int a) { of_store(f, d, fp_mul12(of_load(f, a))); }
+// d = (a1 + a2) * (b1 + b2)
+DKGV_NI void vm_addmul(OpFile f, int d, int a1, int a2, int b1, int b2) {
+  of_store(f, d, mul(add(of_load(f, a1), of_load(f, a2)), add(of_load(f, b1), of_load(f, b2))));
+}
+DKGV_NI void vm_copy3(OpFile f, int d, int a) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) f.base[(size_t)(d * 3 + i) * f.stride] = f.base[(size_t)(a * 3 + i) * f.stride];
+}
+DKGV_NI bool vm_eq(OpFile f, int a, int b) { return eq(of_load(f, a), of_load(f, b)); }
+
+// ---- slot map --------------------------------------------------------------------------------
+enum : int { AX = 0, AY, AZ, BX, BY, BZ, T0, T1, T2, T3, T4, T5, T6, VM_SLOTS };
+
+DKGV_HD void vm_set_point(const OpFile& f, int s, const G1Proj& p) {
+  of_store(f, s, p.x);
+  of_store(f, s + 1, p.y);
+  of_store(f, s + 2, p.z);
+}
+DKGV_HD G1Proj vm_get_point(const OpFile& f, int s) {
+  G1Proj p;
+  p.x = of_load(f, s);
+  p.y = of_load(f, s + 1);
+  p.z = of_load(f, s + 2);
+  return p;
+}
+
+// A <- A + B, both projective (RCB Alg. 7, complete; B may be the identity (0:1:0))
+DKGV_NI void vm_g1_add(OpFile f) {
+  vm_mul(f, T0, AX, BX);
+  vm_mul(f, T1, AY, BY);
+  vm_mul(f, T2, AZ, BZ);
+  vm_addmul(f, T3, AX, AY, BX, BY);
+  vm_add(f, T4, T0, T1);
+  vm_sub(f, T3, T3, T4);
+  vm_addmul(f, T4, AY, AZ, BY, BZ);
+  vm_add(f, T5, T1, T2);
+  vm_sub(f, T4, T4, T5);
+  vm_addmul(f, T5, AX, AZ, BX, BZ);
+  vm_add(f, T6, T0, T2);
+  vm_sub(f, T5, T5, T6);  // "Y3" of the paper; A is dead from here on
+  vm_add(f, AX, T0, T0);
+  vm_add(f, T0, AX, T0);
+  vm_mul12(f, T2, T2);
+  vm_add(f, AZ, T1, T2);
+  vm_sub(f, T1, T1, T2);
+  vm_mul12(f, T5, T5);
+  vm_mul(f, AX, T4, T5);
+  vm_mul(f, T2, T3, T1);
+  vm_sub(f, AX, T2, AX);
+  vm_mul(f, T5, T5, T0);
+  vm_mul(f, T1, T1, AZ);
+  vm_add(f, AY, T1, T5);
+  vm_mul(f, T0, T0, T3);
+  vm_mul(f, AZ, AZ, T4);
+  vm_add(f, AZ, AZ, T0);
+}
+
+// A <- 2A (RCB Alg. 9)
+DKGV_NI void vm_g1_dbl(OpFile f) {
+  vm_mul(f, T0, AY, AY);
+  vm_add(f, T3, T0, T0);
+  vm_add(f, T3, T3, T3);
+  vm_add(f, T3, T3, T3);  // Z3' = 8 Y^2
+  vm_mul(f, T1, AY, AZ);
+  vm_mul(f, T2, AZ, AZ);
+  vm_mul12(f, T2, T2);
+  vm_mul(f, T4, T2, T3);  // X3'
+  vm_add(f, T5, T0, T2);  // Y3'
+  vm_mul(f, AZ, T1, T3);
+  vm_add(f, T1, T2, T2);
+  vm_add(f, T2, T1, T2);
+  vm_sub(f, T0, T0, T2);
+  vm_mul(f, T5, T0, T5);
+  vm_mul(f, T1, AX, AY);
+  vm_add(f, AY, T4, T5);
+  vm_mul(f, T4, T0, T1);
+  vm_add(f, AX, T4, T4);
+}
+
+// P <- P + Q with P projective at slots (p, p+1, p+2) and Q = (x, y) affine, never the identity,
+// at slots (T5, T6) (RCB Alg. 8).  P may alias nothing in T0..T6.
+DKGV_NI void vm_g1_madd(OpFile f, int p) {
+  const int X1 = p, Y1 = p + 1, Z1 = p + 2, QX = T5, QY = T6;
+  vm_mul(f, T0, X1, QX);
+  vm_mul(f, T1, Y1, QY);
+  vm_addmul(f, T3, QX, QY, X1, Y1);
+  vm_add(f, T4, T0, T1);
+  vm_sub(f, T3, T3, T4);
+  vm_mul(f, T4, QY, Z1);
+  vm_add(f, T4, T4, Y1);
+  vm_mul(f, T2, QX, Z1);
+  vm_add(f, T2, T2, X1);  // "Y3" pre; Q, X1, Y1 dead
+  vm_mul12(f, T5, Z1);    // t2
+  vm_add(f, X1, T0, T0);
+  vm_add(f, T0, X1, T0);
+  vm_add(f, Z1, T1, T5);
+  vm_sub(f, T1, T1, T5);
+  vm_mul12(f, T2, T2);
+  vm_mul(f, X1, T4, T2);
+  vm_mul(f, T5, T3, T1);
+  vm_sub(f, X1, T5, X1);
+  vm_mul(f, T2, T2, T0);
+  vm_mul(f, T1, T1, Z1);
+  vm_add(f, Y1, T1, T2);
+  vm_mul(f, T0, T0, T3);
+  vm_mul(f, Z1, Z1, T4);
+  vm_add(f, Z1, Z1, T0);
+}
+
+// A <- [k]A, small public scalar, warp-uniform control flow (left-to-right binary, top bit free)
+DKGV_HD void vm_g1_mul_small(const OpFile& f, uint32_t k) {
+  if (k == 0) {
+    vm_set_point(f, AX, g1_identity());
+    return;
+  }
+  if ((k & (k - 1)) != 0) vm_copy3(f, BX, AX);
+  int top = 31;
+  while (!((k >> top) & 1)) top--;
+#pragma unroll 1
+  for (int b = top - 1; b >= 0; b--) {
+    vm_g1_dbl(f);
+    if ((k >> b) & 1) vm_g1_add(f);
+  }
+}
+
+// coefficient k of dealer d -> projective point at slots (s, s+1, s+2); identity -> (0 : 1 : 0)
+DKGV_HD void vm_load_coeff(const OpFile& f, int s, const VVView& v, uint32_t k, uint32_t d) {
+  G1Aff a = vv_load(v, k, d);
+  vm_set_point(f, s, g1_from_affine(a));
+}
+
+// Horner in the exponent (dkg_math.rs:160-174): A <- sum_k C_k id^k
+DKGV_HD void vm_feldman_eval(const OpFile& f, const VVView& v, uint32_t t, uint32_t d, uint32_t id) {
+  if (t == 0) {
+    vm_set_point(f, AX, g1_identity());
+    return;
+  }
+  vm_load_coeff(f, AX, v, t - 1, d);
+#pragma unroll 1
+  for (int k = (int)t - 2; k >= 0; k--) {
+    vm_g1_mul_small(f, id);
+    vm_load_coeff(f, BX, v, (uint32_t)k, d);
+    vm_g1_add(f);
+  }
+}
+
+DKGV_HD void vm_load_affine_q(const OpFile& f, const uint32_t* e) {
+  Fp x, y;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.l[i] = e[i];
+    y.l[i] = e[12 + i];
+  }
+  of_store(f, T5, x);
+  of_store(f, T6, y);
+}
+
+// B <- G * s  (s raw little-endian limbs, any 256-bit value; the caller range-checks it)
+DKGV_HD void vm_fixed_base_mul(const OpFile& f, const uint32_t* gtab, const uint32_t* s_raw) {
+  vm_set_point(f, BX, g1_identity());
+#pragma unroll 1
+  for (int w = 0; w <= GTAB_WINDOWS; w++) {
+    vm_load_affine_q(f, gtab + (size_t)gtab_index(s_raw, w) * 24);
+    vm_g1_madd(f, BX);
+  }
+}
+
+// A == B as projective points (verification.rs:140 compares the compressed encodings)
+DKGV_HD bool vm_g1_eq_ab(const OpFile& f) {
+  bool ia = is_zero(of_load(f, AZ)), ib = is_zero(of_load(f, BZ));
+  vm_mul(f, T0, AX, BZ);
+  vm_mul(f, T1, BX, AZ);
+  vm_mul(f, T2, AY, BZ);
+  vm_mul(f, T3, BY, AZ);
+  bool e = vm_eq(f, T0, T1) && vm_eq(f, T2, T3);
+  return (ia || ib) ? (ia && ib) : e;
+}
+
+// one share (same contract as share_check in feldman.cuh)
+DKGV_HD uint8_t vm_share_check(const OpFile& f, const VVView& vv, uint32_t t, uint32_t d, uint32_t id, const uint8_t* secret_be,
+                               const uint32_t* gtab, bool dealer_bad) {
+  vm_feldman_eval(f, vv, t, d, id);
+  uint32_t s[8];
+  bool in_range = fr_raw_from_be32(s, secret_be);
+  vm_fixed_base_mul(f, gtab, s);
+  uint8_t st = vm_g1_eq_ab(f) ? DKGV_OK : DKGV_SLASHABLE_SHARE_MISMATCH;
+  if (dealer_bad) st = DKGV_PANIC_BAD_G1;
+  if (!in_range) st = DKGV_SLASHABLE_SECRET_RANGE;
+  return st;
+}
+
+}  // namespace dkgv

@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../dvt_circuits_b200/csrc/feldman.cuh"
+#include "../../dvt_circuits_b200/csrc/vm.cuh"
 
 using namespace dkgv;
 
@@ -70,21 +70,34 @@ uint32_t he_share_check(const uint8_t* vv, uint32_t t, uint32_t id, const uint8_
     vv_store(limbs.data(), inf.data(), n_pad, k, 0, a);
   }
   VVView view{limbs.data(), inf.data(), n_pad};
-  // the 32 table entries this scalar touches, computed by the same routine as k_build_gtab
+  // the 33 table entries this scalar touches, computed by the same routine as k_build_gtab
   std::vector<uint32_t> gtab(GTAB_WORDS, 0);
   uint32_t s[8];
   fr_raw_from_be32(s, secret32);
-  for (int w = 0; w < GTAB_WINDOWS; w++) {
-    uint32_t byte = (s[w >> 2] >> (8 * (w & 3))) & 0xff;
-    if (!byte) continue;
-    G1Aff e = gtab_entry(w, byte);
+  for (int w = 0; w <= GTAB_WINDOWS; w++) {
+    uint32_t idx = gtab_index(s, w);
+    G1Aff e = gtab_entry(idx);
     for (int i = 0; i < 12; i++) {
-      gtab[((size_t)w * 256 + byte) * 24 + i] = e.x.l[i];
-      gtab[((size_t)w * 256 + byte) * 24 + 12 + i] = e.y.l[i];
+      gtab[(size_t)idx * 24 + i] = e.x.l[i];
+      gtab[(size_t)idx * 24 + 12 + i] = e.y.l[i];
     }
   }
   g1_compress(g1_to_affine(feldman_eval(view, t, 0, id)), eval48);
   g1_compress(g1_to_affine(fixed_base_mul(gtab.data(), s)), pk48);
-  return share_check(view, t, 0, id, secret32, gtab.data(), bad);
+  uint32_t st = share_check(view, t, 0, id, secret32, gtab.data(), bad);
+  // the operand-file (vm.cuh) formulation used by the hot kernel must agree
+  const uint32_t NT = 4, me = 2;  // pretend to be thread 2 of a 4-thread block
+  std::vector<U4> file((size_t)VM_SLOTS * 3 * NT);
+  OpFile f{file.data() + me, NT};
+  uint32_t st_vm = vm_share_check(f, view, t, 0, id, secret32, gtab.data(), bad);
+  if (st_vm != st) return 0x100 | st_vm;
+  vm_feldman_eval(f, view, t, 0, id);
+  uint8_t ev2[48];
+  g1_compress(g1_to_affine(vm_get_point(f, AX)), ev2);
+  if (memcmp(ev2, eval48, 48)) return 0x200;
+  vm_fixed_base_mul(f, gtab.data(), s);
+  g1_compress(g1_to_affine(vm_get_point(f, BX)), ev2);
+  if (memcmp(ev2, pk48, 48)) return 0x300;
+  return st;
 }
 }

@@ -14,11 +14,14 @@ print("setup s", time.time() - t0, flush=True)
 dev = torch.device("cuda:0")
 d_vv = torch.from_numpy(s["vv"]).to(dev); d_ids = torch.from_numpy(s["ids"].view(np.int32)).to(dev)
 d_sh = torch.from_numpy(s["shares"]).to(dev); d_st = torch.empty((nd, n), dtype=torch.uint8, device=dev)
-stream = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream()
+torch.cuda.synchronize()
+stream = ts.cuda_stream
+assert stream != 0
 for rep in range(reps):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(ts)
     v.share_matrix_verify_dev(nd, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh.data_ptr(), d_st.data_ptr(), stream)
-    e1.record(); torch.cuda.synchronize()
+    e1.record(ts); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(json.dumps({"n": n, "t": t, "dealers": nd, "ms": ms, "shares_per_s": nd * n / ms * 1e3, "bad": int(d_st.count_nonzero())}), flush=True)
