@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py - verified shares/s on the synthetic DKG ceremony n=1024, t=683 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (decode + subgroup-check the verification vectors, Feldman
+evaluation in the exponent for every (dealer, recipient), G*s, compare) over the whole share matrix.
+With N ranks the ONE ceremony is sharded by dealer row blocks (strong scaling, as BASELINE.json names
+it); the only exchange is an NCCL all-gather of the per-share verdict bytes, inside the timed region.
+
+`value`     device-timed, inputs resident in HBM, max over ranks.
+`e2e`       same metric through the reference-facing C ABI with HOST (pinned) buffers:
+            H2D of vv + shares + ids and D2H of the verdicts inside the timed region.
+`roofline`  integer-pipe roofline of the dominant kernel (k_share_verify): canonical 32x32->64
+            multiply-accumulates per second (84 314 modmul/share x 300 MAC) against
+            the IMAD.WIDE peak measured live by bench/imad_peak on the same GPU.
+`cpu_baseline` the CPU oracle in reference-faithful mode (per-op affine round trips, constant-time
+            255-step scalar multiplication - the reference's operation sequence) on a bounded sample
+            of the same matrix, all host cores.  A restatement, not the Rust binary (no cargo here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_PART, THRESH = 1024, 683
+MODMUL_PER_SHARE = 84314      # SURVEY.md 8(d), canonical small-scalar Horner + fixed-base + compare
+MAC_PER_MODMUL = 300          # 2*12^2 + 12 wide multiply-accumulates per 12-limb Montgomery product
+PAPER_PEAK_MAC = 148 * 64 * 1.965e9
+METRIC = "verified shares/sec (n=1024,t=683)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_PART, help="participants (default: the BASELINE config)")
+    ap.add_argument("--t", type=int, default=THRESH)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_int_peak():
+    """IMAD.WIDE lane-ops/s measured live with bench/imad_peak; falls back to the paper figure."""
+    exe = os.path.join(ROOT, "bench", "imad_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120, check=True).stdout
+        j = json.loads(out)
+        return {"imad_wide": j["imad_wide"]["lane_ops_per_s"], "imad_wide_x": j["imad_wide_x"]["lane_ops_per_s"],
+                "fp_mul_per_s": j["fp_mul_32warps_per_sm"]["modmul_per_s"], "source": "measured live (bench/imad_peak)"}
+    except Exception as e:  # noqa: BLE001
+        return {"imad_wide": PAPER_PEAK_MAC, "imad_wide_x": None, "fp_mul_per_s": None,
+                "source": f"fallback paper peak 148 SM x 64 lanes x 1.965 GHz ({type(e).__name__})"}
+
+
+def cpu_baseline(n, t, cols, threads):
+    """oracle in reference-faithful mode on a bounded sample of the same matrix (threads x cols shares:
+    one dealer row per host thread, `cols` recipient ids spread over 1..n).  The sample rows reuse one
+    dealer's polynomial - the faithful cost per share depends on t only - and the verification vector is
+    decoded once per row, which under-counts the reference (it decodes all t points per share,
+    verification.rs:132-137): the baseline is favoured, not the GPU."""
+    import numpy as np
+    import oracle_lib as O
+    from dvt_circuits_b200 import synthetic
+    rows = max(1, threads)
+    coeffs = synthetic.make_coefficients(1, t)
+    ids = np.unique(np.linspace(1, n, cols).astype(np.uint32))
+    cols = len(ids)
+    vv1 = np.zeros((t, 48), dtype=np.uint8)
+    cs = [int.from_bytes(coeffs[0, k].tobytes(), "big") for k in range(t)]
+    for k in range(t):
+        st, pk = O.g1_fixed_base(coeffs[0, k].tobytes(), O.FAST)
+        vv1[k] = np.frombuffer(pk, dtype=np.uint8)
+    sh1 = np.zeros((cols, 32), dtype=np.uint8)
+    for j, i in enumerate(ids.tolist()):
+        acc = 0
+        for c in reversed(cs):
+            acc = (acc * i + c) % synthetic.R_INT
+        sh1[j] = np.frombuffer(acc.to_bytes(32, "big"), dtype=np.uint8)
+    vv = np.broadcast_to(vv1, (rows, t, 48)).copy()
+    shares = np.broadcast_to(sh1, (rows, cols, 32)).copy()
+    t0 = time.perf_counter()
+    st = O.share_matrix(vv, ids, shares, O.FAITHFUL, threads=threads)
+    dt = time.perf_counter() - t0
+    assert not st.any(), "CPU oracle rejected a valid synthetic share"
+    t1 = time.perf_counter()
+    st = O.share_matrix(vv, ids, shares, O.FAST, threads=threads)
+    dt_fast = time.perf_counter() - t1
+    return {"value": rows * cols / dt, "unit": "shares/s", "cores": threads, "kind": "port",
+            "sample": f"{rows}x{cols} shares of the n={n},t={t} matrix, oracle faithful mode (reference op sequence), {dt:.1f}s wall",
+            "fast_mode_value": rows * cols / dt_fast, "n_shares": rows * cols}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same metric.  The Rust crate cannot be built
+    in this image (no cargo/rustc, un-vendored git dependencies), so this times the C++ oracle in
+    reference-faithful mode on all host cores, one bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    cols = args.cpu_sample or 24
+    vals, cb = [], None
+    for i in range(args.warmup + args.steps):
+        if i < args.warmup and i > 0:
+            continue  # one warm-up pass is enough for a CPU loop; keeps the run within minutes
+        cb = cpu_baseline(args.n, args.t, cols, threads)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = statistics.mean(vals)
+    line = {"metric": METRIC, "value": v, "unit": "shares/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * cb["n_shares"] / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 limbs (381-bit Montgomery Fp)", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"synthetic DKG n={args.n}, t={args.t}: share-matrix verification, bounded sample of {cb['n_shares']} shares per step",
+                       "n": args.n, "t": args.t},
+            "cpu_baseline": {"value": v, "unit": "shares/s", "cores": threads, "kind": "port", "sample": cb["sample"]},
+            "e2e": {"value": v, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "C++ oracle restating the reference's operation sequence; the Rust reference itself cannot be built here"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dvt_circuits_b200 as dk
+    from dvt_circuits_b200 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n, t = args.n, args.t
+    if n % world:
+        raise SystemExit("participants must divide by the number of ranks")
+    rows = n // world
+
+    v = dk.Verifier(local)
+    sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
+    ts = torch.cuda.Stream(device=dev)
+    stream = ts.cuda_stream
+    with torch.cuda.stream(ts):
+        d_vv = torch.from_numpy(sess["vv"]).to(dev)
+        d_ids = torch.from_numpy(sess["ids"].view(np.int32)).to(dev)
+        d_sh = torch.from_numpy(sess["shares"]).to(dev)
+        d_st = torch.empty((rows, n), dtype=torch.uint8, device=dev)
+        d_all = torch.empty((n, n), dtype=torch.uint8, device=dev) if world > 1 else d_st
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # pinned host copies for the end-to-end leg
+    h_vv = torch.from_numpy(sess["vv"]).pin_memory()
+    h_ids = torch.from_numpy(sess["ids"].view(np.int32)).pin_memory()
+    h_sh = torch.from_numpy(sess["shares"]).pin_memory()
+    h_st = torch.empty((rows, n), dtype=torch.uint8).pin_memory()
+
+    def step_device():
+        v.share_matrix_verify_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh.data_ptr(), d_st.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_st)
+
+    def step_e2e():
+        rc = v._lib.dkgv_share_matrix_verify(v._h, rows, n, t, h_vv.data_ptr(), h_ids.data_ptr(), h_sh.data_ptr(), h_st.data_ptr())
+        v._ck(rc)
+        if world > 1:
+            d_st.copy_(h_st, non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak = measured_int_peak() if rank == 0 else None
+
+    with torch.cuda.stream(ts):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = v.launch_count
+        step_ms, hot_ms = [], []
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            step_device()
+            e1.record(ts)
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            hot_ms.append(v.last_hot_kernel_ms())
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = v.launch_count - launches0
+        clocks = sampler.stop() if rank == 0 else None
+
+        total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        ms_per_step = float(total_ms.item()) / args.steps
+        bad = int(d_all.count_nonzero().item())
+
+        # end-to-end through the host-pointer C ABI
+        step_e2e()
+        barrier()
+        e2e_t = []
+        for _ in range(args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            step_e2e()
+            torch.cuda.synchronize()
+            e2e_t.append(time.perf_counter() - t0)
+        e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+        e2e_s_per_step = float(e2e_total.item()) / args.steps
+        bad_e2e = int(h_st.count_nonzero().item())
+
+    if rank == 0:
+        shares = n * n
+        value = shares / (ms_per_step * 1e-3)
+        hot = statistics.mean(hot_ms)
+        units_per_launch = rows * n
+        achieved = units_per_launch * MODMUL_PER_SHARE * MAC_PER_MODMUL / (hot * 1e-3)
+        algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        line = {
+            "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (381-bit Montgomery Fp, 255-bit Fr)", "data": "synthetic",
+            "config": {"workload": f"synthetic DKG n={n}, t={t}: full {n}x{n} share-matrix verification, dealer row blocks over {world} GPU(s)",
+                       "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
+                       "parallelism": f"row-block x{world}, NCCL all-gather of verdict bytes" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",
+                    "h2d_bytes_per_step": int(h_vv.numel() + h_sh.numel() + h_ids.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(h_st.numel()) * world, "timing": "host wall clock around dkgv_share_matrix_verify, max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "int_pipe", "kernel": "k_share_verify", "achieved": achieved / 1e9, "peak": peak["imad_wide"] / 1e9,
+                         "unit": "G wide-MAC/s (32x32->64)", "frac": achieved / peak["imad_wide"], "peak_source": peak["source"],
+                         "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
+                         "frac_of_carry_chain_peak": (achieved / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                         "kernel_ms": hot, "kernel_share_of_step": hot / statistics.mean(step_ms),
+                         "units_per_launch": units_per_launch, "modmul_per_unit": MODMUL_PER_SHARE, "mac_per_modmul": MAC_PER_MODMUL,
+                         "traffic": None,
+                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (hot * 1e-3) / 1e9,
+                                 "note": "integer-bound path: HBM use is a rounding error"}},
+            "parity": {"bad_verdicts_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_baseline(n, t, args.cpu_sample or 24, threads)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    v.close()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,6 +55,7 @@ DECLARED_SYMBOLS = {
     "dkgv_last_error": (ctypes.c_char_p, [_vp]),
     "dkgv_launch_count": (ctypes.c_uint64, [_vp]),
     "dkgv_sync": (ctypes.c_int, [_vp]),
+    "dkgv_last_hot_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_feldman_eval": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
@@ -130,6 +131,11 @@ class Verifier:
     @property
     def launch_count(self):
         return int(self._lib.dkgv_launch_count(self._h))
+
+    def last_hot_kernel_ms(self):
+        ms = ctypes.c_float()
+        self._ck(self._lib.dkgv_last_hot_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def sync(self):
         self._ck(self._lib.dkgv_sync(self._h))

@@ -175,6 +175,8 @@ struct dkgv_ctx {
   std::string err;
   DevBuf vv_limbs, vv_inf, dealer_bad;           // session scratch (decoded verification vectors)
   DevBuf in_a, in_b, in_c, out_a, out_b;         // staging for the host-pointer entry points
+  cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;  // bracket the hot kernel (roofline timing)
+  bool hot_recorded = false;
 };
 
 #define CK(call)                                                                          \
@@ -214,6 +216,8 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev_hot0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_hot1)) != cudaSuccess)
+    return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
   if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVM_SMEM)) != cudaSuccess)
@@ -234,12 +238,22 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b})
     b->release();
   if (ctx->gtab) cudaFree(ctx->gtab);
+  if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
+  if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 extern "C" const char* dkgv_last_error(const dkgv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" uint64_t dkgv_launch_count(const dkgv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return -1;
+  if (!ctx->hot_recorded) return fail(ctx, "no hot kernel launched yet");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_hot1));
+  CK(cudaEventElapsedTime(ms, ctx->ev_hot0, ctx->ev_hot1));
+  return 0;
+}
 extern "C" int dkgv_sync(dkgv_ctx* ctx) {
   if (!ctx) return -1;
   CK(cudaSetDevice(ctx->device));
@@ -283,8 +297,11 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad);
   if (rc) return rc;
   dim3 grid(n_pad / 32, (n_r + SVM_NT / 32 - 1) / (SVM_NT / 32));
+  CK(cudaEventRecord(ctx->ev_hot0, s));
   k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status,
                                               n_d, n_r, t);
+  CK(cudaEventRecord(ctx->ev_hot1, s));
+  ctx->hot_recorded = true;
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -68,6 +68,9 @@ const char* dkgv_last_error(const dkgv_ctx* ctx); /* ctx may be NULL: last creat
 /* number of kernel launches issued through this ctx so far (bench accounting) */
 uint64_t dkgv_launch_count(const dkgv_ctx* ctx);
 int dkgv_sync(dkgv_ctx* ctx);
+/* device time (CUDA events on the launching stream) of the most recent hot-kernel launch
+ * (k_share_verify) issued through this ctx; blocks until that launch has finished */
+int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms);
 
 /* ---- Feldman share verification (replaces the loop body of verify_seed_exchange_commitment,
  *      crates/dkg/src/verification.rs:129-146, for a whole (dealer x recipient) matrix) ------- */
