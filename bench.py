@@ -33,8 +33,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_PART, THRESH = 1024, 683
-MODMUL_PER_SHARE = 84314      # SURVEY.md 8(d), canonical small-scalar Horner + fixed-base + compare
 MAC_PER_MODMUL = 300          # 2*12^2 + 12 wide multiply-accumulates per 12-limb Montgomery product
+
+
+def canonical_modmul_per_share(n, t):
+    """Horner, left-to-right binary [j]y (double 8, add 12, mixed add 11), + 356 for
+    G*s and the comparison; averaged over ids 1..n.  (n=1024, t=683) -> 84 314."""
+    tot = sum(8 * (j.bit_length() - 1) + 12 * (bin(j).count("1") - 1) + 11 for j in range(1, n + 1))
+    return (t - 1) * tot / n + 356
+
+
+def executed_modmul_per_share(n, t):
+    """what k_share_verify really executes: signed-digit chain (vm.cuh make_small_chain), full add (12)
+    for the coefficient, 33 mixed adds (11) + 4 for G*s and the comparison."""
+    def cost(pos, neg):
+        m = pos | neg
+        return 8 * (m.bit_length() - 1) + 12 * (bin(m).count("1") - 1)
+    tot = 0
+    for j in range(1, n + 1):
+        k3 = 3 * j
+        tot += min(cost(j, 0), cost((k3 & ~j) >> 1, (~k3 & j) >> 1)) + 12
+    return (t - 1) * tot / n + 33 * 11 + 4
 PAPER_PEAK_MAC = 148 * 64 * 1.965e9
 METRIC = "verified shares/sec (n=1024,t=683)"
 
@@ -286,7 +305,9 @@ def run_b200(args):
         value = shares / (ms_per_step * 1e-3)
         hot = statistics.mean(hot_ms)
         units_per_launch = rows * n
+        MODMUL_PER_SHARE = canonical_modmul_per_share(n, t)
         achieved = units_per_launch * MODMUL_PER_SHARE * MAC_PER_MODMUL / (hot * 1e-3)
+        executed = units_per_launch * executed_modmul_per_share(n, t) * MAC_PER_MODMUL / (hot * 1e-3)
         algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -304,6 +325,8 @@ def run_b200(args):
                          "unit": "G wide-MAC/s (32x32->64)", "frac": achieved / peak["imad_wide"], "peak_source": peak["source"],
                          "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
                          "frac_of_carry_chain_peak": (achieved / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                         "executed_gmac_per_s": executed / 1e9, "executed_frac_of_carry_chain_peak": (executed / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                         "executed_modmul_per_unit": executed_modmul_per_share(n, t),
                          "kernel_ms": hot, "kernel_share_of_step": hot / statistics.mean(step_ms),
                          "units_per_launch": units_per_launch, "modmul_per_unit": MODMUL_PER_SHARE, "mac_per_modmul": MAC_PER_MODMUL,
                          "traffic": None,

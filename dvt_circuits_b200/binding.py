@@ -66,7 +66,8 @@ DECLARED_SYMBOLS = {
 
 
 def lib_path():
-    return os.path.join(_HERE, "libdkgv.so")
+    # DKGV_LIB lets experiments point at an alternative build of the SAME CUDA library
+    return os.environ.get("DKGV_LIB") or os.path.join(_HERE, "libdkgv.so")
 
 
 _LIB = None

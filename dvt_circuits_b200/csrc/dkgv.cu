@@ -8,7 +8,7 @@
 #include <new>
 #include <string>
 
-#include "vm.cuh"
+#include "vm30.cuh"
 
 using namespace dkgv;
 
@@ -47,15 +47,61 @@ k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32
   vv_store(limbs, inf, n_pad, k, d, a);
 }
 
+// Same decode, written in the 13 x 30-bit layout of vm30.cuh for the hot kernel.
+__global__ void __launch_bounds__(128)
+k_decompress_vv30(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
+                  uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)n_pad * t) return;
+  uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
+  G1Aff a;
+  a.x = zero<FpParams>();
+  a.y = zero<FpParams>();
+  a.inf = 1;
+  if (d < n_d) {
+    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, true);
+    if (st != G1_DEC_OK) dealer_bad[d] = 1;
+  }
+  vv30_store(limbs, inf, n_pad, k, d, fp30_from_fp(a.x), fp30_from_fp(a.y), a.inf != 0);
+}
+
+__global__ void __launch_bounds__(128) k_build_gtab30(const uint32_t* __restrict__ gtab, uint32_t* __restrict__ gtab30) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= GTAB_ENTRIES) return;
+  Fp x, y;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.l[i] = gtab[(size_t)tid * 24 + i];
+    y.l[i] = gtab[(size_t)tid * 24 + 12 + i];
+  }
+  Fp30 x30 = fp30_from_fp(x), y30 = fp30_from_fp(y);
+#pragma unroll
+  for (int i = 0; i < 13; i++) {
+    gtab30[(size_t)tid * 26 + i] = x30.l[i];
+    gtab30[(size_t)tid * 26 + 13 + i] = y30.l[i];
+  }
+}
+
 // The hot kernel.  Thread = one share (dealer d, recipient column j); the 32 lanes of a warp hold
 // 32 consecutive dealers and ONE recipient id, so the double-and-add over the id bits is
 // warp-uniform (no divergence) and every coefficient load is a fully coalesced 128 B line per limb.
 // Field operands live in the shared-memory operand file of vm.cuh (13 slots x 48 B per thread).
+// -DDKGV_HOT_FP30 selects the experimental carry-free 13 x 30-bit backend (vm30.cuh) instead; it is
+// slower on B200 (profiles/r1_fp30_experiment.md) and kept for reference only.
 constexpr int SV_WARPS = 4;   // k_feldman_eval (inlined formulas, cold path)
-constexpr int SVM_NT = 64;    // threads per block of the hot kernel: 2 warps = 2 recipient ids
+#ifndef DKGV_SVM_NT
+#define DKGV_SVM_NT 32  // measured on B200: 32 -> 306k, 64 -> 286k, 128 -> 276k shares/s (n_r=1024,t=683,n_d=256)
+#endif
+constexpr int SVM_NT = DKGV_SVM_NT;  // threads per block of the hot kernel: one recipient id per warp
+#ifdef DKGV_HOT_FP30
+constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 4 * SVM_NT * sizeof(U4);
+typedef VV30View HotView;
+#else
 constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 3 * SVM_NT * sizeof(U4);
+typedef VVView HotView;
+#endif
 __global__ void __launch_bounds__(SVM_NT)
-k_share_verify(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
+k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
                const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status,
                uint32_t n_d, uint32_t n_r, uint32_t t) {
   extern __shared__ U4 opfile[];
@@ -65,8 +111,13 @@ k_share_verify(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t
   if (j >= n_r) return;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
+#ifdef DKGV_HOT_FP30
+  OpFile30 f{opfile + threadIdx.x, SVM_NT};
+  uint8_t st = v30_share_check(f, vv, t, dd, ids[j], shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
+#else
   OpFile f{opfile + threadIdx.x, SVM_NT};
   uint8_t st = vm_share_check(f, vv, t, dd, ids[j], shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
+#endif
   if (active) status[(size_t)d * n_r + j] = st;
 }
 
@@ -171,6 +222,7 @@ struct dkgv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint32_t* gtab = nullptr;
+  uint32_t* gtab30 = nullptr;
   uint64_t launches = 0;
   std::string err;
   DevBuf vv_limbs, vv_inf, dealer_bad;           // session scratch (decoded verification vectors)
@@ -226,6 +278,11 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
     return bail("cudaFuncSetAttribute carveout", e);
   k_build_gtab<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
   ctx->launches++;
+#ifdef DKGV_HOT_FP30
+  if ((e = cudaMalloc(&ctx->gtab30, GTAB30_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab30", e);
+  k_build_gtab30<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab, ctx->gtab30);
+  ctx->launches++;
+#endif
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("k_build_gtab", e);
   *out = ctx;
   return 0;
@@ -238,6 +295,7 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b})
     b->release();
   if (ctx->gtab) cudaFree(ctx->gtab);
+  if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -263,18 +321,22 @@ extern "C" int dkgv_sync(dkgv_ctx* ctx) {
 
 // decode vv into the ctx session buffers (asynchronous on s)
 static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, uint8_t* d_point_status, cudaStream_t s,
-                          VVView* view, uint32_t* n_pad_out) {
+                          VVView* view, uint32_t* n_pad_out, bool layout30 = false) {
   uint32_t n_pad = (n_d + 31) & ~31u;
   uint32_t tt = t ? t : 1;
-  CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
+  CK(ctx->vv_limbs.reserve((size_t)tt * (layout30 ? 26 : 24) * n_pad * 4));
   CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
   CK(ctx->dealer_bad.reserve(n_pad));
   CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
   if (t) {
     size_t total = (size_t)n_pad * t;
-    k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                  (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
-                                                                  d_point_status);
+    if (layout30)
+      k_decompress_vv30<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                      (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
+    else
+      k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                    (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
+                                                                    d_point_status);
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -294,11 +356,20 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   VVView view;
   uint32_t n_pad;
-  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad);
+#ifdef DKGV_HOT_FP30
+  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, true);
   if (rc) return rc;
+  HotView hv{view.limbs, view.inf, view.n_pad};
+  const uint32_t* hot_tab = ctx->gtab30;
+#else
+  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false);
+  if (rc) return rc;
+  HotView hv = view;
+  const uint32_t* hot_tab = ctx->gtab;
+#endif
   dim3 grid(n_pad / 32, (n_r + SVM_NT / 32 - 1) / (SVM_NT / 32));
   CK(cudaEventRecord(ctx->ev_hot0, s));
-  k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status,
+  k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(hv, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, hot_tab, d_status,
                                               n_d, n_r, t);
   CK(cudaEventRecord(ctx->ev_hot1, s));
   ctx->hot_recorded = true;

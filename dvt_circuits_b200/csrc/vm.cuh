@@ -71,6 +71,7 @@ DKGV_NI void vm_copy3(OpFile f, int d, int a) {
   for (int i = 0; i < 9; i++) f.base[(size_t)(d * 3 + i) * f.stride] = f.base[(size_t)(a * 3 + i) * f.stride];
 }
 DKGV_NI bool vm_eq(OpFile f, int a, int b) { return eq(of_load(f, a), of_load(f, b)); }
+DKGV_NI void vm_neg(OpFile f, int d, int a) { of_store(f, d, neg(of_load(f, a))); }
 
 // ---- slot map --------------------------------------------------------------------------------
 enum : int { AX = 0, AY, AZ, BX, BY, BZ, T0, T1, T2, T3, T4, T5, T6, VM_SLOTS };
@@ -171,21 +172,63 @@ DKGV_NI void vm_g1_madd(OpFile f, int p) {
   vm_add(f, Z1, Z1, T0);
 }
 
-// A <- [k]A, small public scalar, warp-uniform control flow (left-to-right binary, top bit free)
-DKGV_HD void vm_g1_mul_small(const OpFile& f, uint32_t k) {
-  if (k == 0) {
+// Signed-digit chain for the small public scalar (recipient id): [k]P = sum d_i 2^i P with
+// d_i in {-1, 0, +1}.  The non-adjacent form has ~1/3 non-zero digits instead of ~1/2, so
+// fewer point additions (12 M each) at the price of at most one more doubling (8 M); whichever of
+// plain binary and NAF is cheaper for this k is used.  Exact arithmetic either way - only the
+// addition chain changes.  Warp-uniform: every lane of a warp shares k.
+struct SmallChain {
+  unsigned long long pos, neg;  // digit masks
+  int top;                      // index of the leading (+1) digit; -1 for k == 0
+};
+DKGV_HD int chain_cost(unsigned long long pos, unsigned long long neg, int top) {
+  int nz = 0;
+  for (int i = 0; i <= top; i++) nz += (int)(((pos | neg) >> i) & 1);
+  return 8 * top + 12 * (nz - 1);
+}
+DKGV_HD SmallChain make_small_chain(uint32_t k) {
+  SmallChain c;
+  c.pos = k;
+  c.neg = 0;
+  c.top = -1;
+  if (k == 0) return c;
+  int tb = 31;
+  while (!((k >> tb) & 1)) tb--;
+  c.top = tb;
+  unsigned long long k3 = 3ull * k, kk = k;
+  unsigned long long np = (k3 & ~kk) >> 1, nn = (~k3 & kk) >> 1;
+  int tn = 33;
+  while (!((np >> tn) & 1)) tn--;
+  if (chain_cost(np, nn, tn) < chain_cost(c.pos, 0, tb)) {
+    c.pos = np;
+    c.neg = nn;
+    c.top = tn;
+  }
+  return c;
+}
+
+// A <- [k]A along the chain; uses B as the base copy (BY is negated in place when the digit sign flips)
+DKGV_HD void vm_g1_mul_chain(const OpFile& f, const SmallChain& c) {
+  if (c.top < 0) {
     vm_set_point(f, AX, g1_identity());
     return;
   }
-  if ((k & (k - 1)) != 0) vm_copy3(f, BX, AX);
-  int top = 31;
-  while (!((k >> top) & 1)) top--;
+  if (((c.pos | c.neg) & ~(1ull << c.top)) != 0) vm_copy3(f, BX, AX);
+  bool b_neg = false;
 #pragma unroll 1
-  for (int b = top - 1; b >= 0; b--) {
+  for (int b = c.top - 1; b >= 0; b--) {
     vm_g1_dbl(f);
-    if ((k >> b) & 1) vm_g1_add(f);
+    bool p = (c.pos >> b) & 1, n = (c.neg >> b) & 1;
+    if (p || n) {
+      if (n != b_neg) {
+        vm_neg(f, BY, BY);
+        b_neg = n;
+      }
+      vm_g1_add(f);
+    }
   }
 }
+DKGV_HD void vm_g1_mul_small(const OpFile& f, uint32_t k) { vm_g1_mul_chain(f, make_small_chain(k)); }
 
 // coefficient k of dealer d -> projective point at slots (s, s+1, s+2); identity -> (0 : 1 : 0)
 DKGV_HD void vm_load_coeff(const OpFile& f, int s, const VVView& v, uint32_t k, uint32_t d) {
@@ -200,9 +243,10 @@ DKGV_HD void vm_feldman_eval(const OpFile& f, const VVView& v, uint32_t t, uint3
     return;
   }
   vm_load_coeff(f, AX, v, t - 1, d);
+  SmallChain chain = make_small_chain(id);
 #pragma unroll 1
   for (int k = (int)t - 2; k >= 0; k--) {
-    vm_g1_mul_small(f, id);
+    vm_g1_mul_chain(f, chain);
     vm_load_coeff(f, BX, v, (uint32_t)k, d);
     vm_g1_add(f);
   }
