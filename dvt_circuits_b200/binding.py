@@ -62,6 +62,13 @@ DECLARED_SYMBOLS = {
     "dkgv_g1_fixed_base_mul": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_g1_decompress_check": (ctypes.c_int, [_vp, _u32, _vp, _vp]),
     "dkgv_fr_poly_eval": (ctypes.c_int, [_vp, _u32, _u32, _vp, _u32, _vp, _vp]),
+    "dkgv_agg_final_keys": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "dkgv_lagrange_at_zero": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_eval_points": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp]),
+    "dkgv_g2_decompress_check": (ctypes.c_int, [_vp, _u32, _vp, _vp]),
+    "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
+    "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -188,3 +195,63 @@ class Verifier:
         out = np.empty((n_d, ids.shape[0], 32), dtype=np.uint8)
         self._ck(self._lib.dkgv_fr_poly_eval(self._h, n_d, t, _p(coeffs), ids.shape[0], _p(ids), _p(out)))
         return out
+
+    # ---- aggregation / Lagrange -----------------------------------------------------------------
+    def agg_final_keys(self, vv, ids, want_coeffs=True):
+        """vv [n, t, 48], ids [m] -> (status, coeffs [t,48], keys [m,48])"""
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        n, t = vv.shape[0], vv.shape[1]
+        ids = _host(ids, np.uint32)
+        co = np.zeros((t, 48), dtype=np.uint8)
+        keys = np.zeros((ids.shape[0], 48), dtype=np.uint8)
+        st = ctypes.c_uint8(0)
+        self._ck(self._lib.dkgv_agg_final_keys(self._h, n, t, _p(vv), _p(ids), ids.shape[0], _p(co) if want_coeffs else None, _p(keys),
+                                               ctypes.cast(ctypes.byref(st), _vp)))
+        return int(st.value), co, keys
+
+    def lagrange_at_zero(self, pts, ids):
+        pts = np.ascontiguousarray(pts, dtype=np.uint8).reshape(-1, 48)
+        ids = _host(ids, np.uint32)
+        out = np.zeros((48,), dtype=np.uint8)
+        st = ctypes.c_uint8(0)
+        k = ids.shape[0]
+        if pts.shape[0] != k:
+            return int(Status.ERR_LEN), bytes(48)
+        self._ck(self._lib.dkgv_lagrange_at_zero(self._h, k, _p(pts), _p(ids), _p(out), ctypes.cast(ctypes.byref(st), _vp)))
+        return int(st.value), out.tobytes()
+
+    def eval_points(self, coeffs, ids):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8).reshape(-1, 48)
+        ids = _host(ids, np.uint32)
+        out = np.zeros((ids.shape[0], 48), dtype=np.uint8)
+        st = ctypes.c_uint8(0)
+        self._ck(self._lib.dkgv_eval_points(self._h, coeffs.shape[0], _p(coeffs), _p(ids), ids.shape[0], _p(out),
+                                            ctypes.cast(ctypes.byref(st), _vp)))
+        return int(st.value), out
+
+    # ---- BLS checks --------------------------------------------------------------------------------
+    def g2_decompress_check(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.uint8).reshape(-1, 96)
+        st = np.empty((pts.shape[0],), dtype=np.uint8)
+        self._ck(self._lib.dkgv_g2_decompress_check(self._h, pts.shape[0], _p(pts), _p(st)))
+        return st
+
+    def hash_to_g2(self, msgs):
+        """list of bytes -> [m, 96] compressed G2 points"""
+        offs = np.zeros((len(msgs) + 1,), dtype=np.uint32)
+        for i, m in enumerate(msgs):
+            offs[i + 1] = offs[i] + len(m)
+        blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8).copy()
+        out = np.zeros((len(msgs), 96), dtype=np.uint8)
+        self._ck(self._lib.dkgv_hash_to_g2(self._h, len(msgs), _p(blob), _p(offs), _p(out)))
+        return out
+
+    def bls_verify_batch(self, pk, sig, hm, hm_idx=None):
+        pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(-1, 48)
+        sig = np.ascontiguousarray(sig, dtype=np.uint8).reshape(-1, 96)
+        hm = np.ascontiguousarray(hm, dtype=np.uint8).reshape(-1, 96)
+        idx = _host(hm_idx, np.uint32) if hm_idx is not None else None
+        st = np.empty((pk.shape[0],), dtype=np.uint8)
+        self._ck(self._lib.dkgv_bls_verify_batch(self._h, pk.shape[0], _p(pk), _p(sig), hm.shape[0], _p(hm),
+                                                 _p(idx) if idx is not None else None, _p(st)))
+        return st

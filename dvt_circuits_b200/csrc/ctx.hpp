@@ -1,0 +1,57 @@
+// Shared host-side definitions of the C ABI implementation (ctx, error macro, device buffers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/dkgv.h"
+
+namespace dkgv_host {
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace dkgv_host
+
+struct dkgv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t* gtab = nullptr;
+  uint32_t* gtab30 = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+  dkgv_host::DevBuf vv_limbs, vv_inf, dealer_bad;      // session scratch (decoded verification vectors)
+  dkgv_host::DevBuf in_a, in_b, in_c, out_a, out_b;    // staging for the host-pointer entry points
+  dkgv_host::DevBuf scratch_a, scratch_b, scratch_c;   // intermediates of the aggregation / pairing paths
+  cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
+  bool hot_recorded = false;
+  bool stack_set = false;
+};
+
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) {                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+      return -2;                                                     \
+    }                                                                \
+  } while (0)
+
+static inline int dkgv_fail(dkgv_ctx* ctx, const char* msg) {
+  ctx->err = msg;
+  return -1;
+}

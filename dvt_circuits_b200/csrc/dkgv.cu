@@ -195,55 +195,13 @@ k_fr_poly_eval(const uint8_t* __restrict__ coeffs, const uint32_t* __restrict__ 
 }
 
 // ============================================================================ host side
+#include "ctx.hpp"
+using dkgv_host::DevBuf;
 namespace {
 thread_local std::string g_create_error;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-}  // namespace
-
-struct dkgv_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  uint32_t* gtab = nullptr;
-  uint32_t* gtab30 = nullptr;
-  uint64_t launches = 0;
-  std::string err;
-  DevBuf vv_limbs, vv_inf, dealer_bad;           // session scratch (decoded verification vectors)
-  DevBuf in_a, in_b, in_c, out_a, out_b;         // staging for the host-pointer entry points
-  cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;  // bracket the hot kernel (roofline timing)
-  bool hot_recorded = false;
-};
-
-#define CK(call)                                                                          \
-  do {                                                                                    \
-    cudaError_t e_ = (call);                                                              \
-    if (e_ != cudaSuccess) {                                                              \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
-      return -2;                                                                          \
-    }                                                                                     \
-  } while (0)
-
-static int fail(dkgv_ctx* ctx, const char* msg) {
-  ctx->err = msg;
-  return -1;
 }
+
+static int fail(dkgv_ctx* ctx, const char* msg) { return dkgv_fail(ctx, msg); }
 
 extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   if (!out) return -1;
@@ -292,7 +250,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b})
+  for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
+                    &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c})
     b->release();
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);

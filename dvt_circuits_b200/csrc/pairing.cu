@@ -1,0 +1,163 @@
+// BLS partial-signature checks on the GPU (C ABI part 2): G2 decoding, hash-to-G2 and the batched
+// pairing-equality kernel.  Replaces crates/dkg/src/crypto/bls_common.rs:11-40 and the signature
+// loop of verify_generation_hashes (crates/dkg/src/verification.rs:237-248).
+#include "ctx.hpp"
+#include "h2c.cuh"
+
+using namespace dkgv;
+
+// one thread per hashed message: decode (subgroup-checked) into an affine struct in global memory
+__global__ void __launch_bounds__(32) k_g2_decode(const uint8_t* __restrict__ in, G2Aff* __restrict__ out, uint8_t* __restrict__ st,
+                                                  uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G2Aff a;
+  uint32_t s = g2_decompress(in + (size_t)i * 96, &a, true);
+  out[i] = a;
+  st[i] = (uint8_t)s;
+}
+
+__global__ void __launch_bounds__(32) k_g2_decompress_check(const uint8_t* __restrict__ in, uint8_t* __restrict__ st, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G2Aff a;
+  st[i] = (uint8_t)g2_decompress(in + (size_t)i * 96, &a, true);
+}
+
+// one thread per message; msgs are concatenated, offsets[i]..offsets[i+1]
+__global__ void __launch_bounds__(32) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ offsets,
+                                                   uint8_t* __restrict__ out, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G2Aff h;
+  hash_to_g2(&h, msgs + offsets[i], offsets[i + 1] - offsets[i]);
+  uint8_t enc[96];
+  g2_compress(&h, enc);
+  for (int k = 0; k < 96; k++) out[(size_t)i * 96 + k] = enc[k];
+}
+
+// one thread per check: status = OK | SLASHABLE_SIG_INVALID (pairing equality false)
+//                               | PANIC_BAD_G1 (pk undecodable) | PANIC_BAD_G2 (signature undecodable)
+// (the caller maps the decode failures to the reference's exit for its call site:
+//  .expect -> panic in verify_generation_hashes, slashable in prove_wrong_final_key_generation)
+__global__ void __launch_bounds__(32)
+k_bls_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ sig, const G2Aff* __restrict__ hm,
+             const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  // decode order of the reference: signature first, then key (verification.rs:238-241)
+  G2Aff s;
+  G1Aff p;
+  uint32_t ds = g2_decompress(sig + (size_t)i * 96, &s, true);
+  uint32_t dp = g1_decompress(pk + (size_t)i * 48, &p, true);
+  uint8_t st;
+  if (ds != G1_DEC_OK) {
+    st = DKGV_PANIC_BAD_G2;
+  } else if (dp != G1_DEC_OK) {
+    st = DKGV_PANIC_BAD_G1;
+  } else {
+    G2Aff h = hm[hm_idx ? hm_idx[i] : 0];
+    st = bls_verify_precomputed(&p, &s, &h) ? DKGV_OK : DKGV_SLASHABLE_SIG_INVALID;
+  }
+  status[i] = st;
+}
+
+static int ensure_stack(dkgv_ctx* ctx) {
+  if (!ctx->stack_set) {
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+    ctx->stack_set = true;
+  }
+  return 0;
+}
+
+extern "C" int dkgv_g2_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!in || !decode_status) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_stack(ctx)) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve((size_t)m * 96));
+  CK(ctx->out_b.reserve(m));
+  CK(cudaMemcpyAsync(ctx->in_a.p, in, (size_t)m * 96, cudaMemcpyHostToDevice, s));
+  k_g2_decompress_check<<<(m + 31) / 32, 32, 0, s>>>((const uint8_t*)ctx->in_a.p, (uint8_t*)ctx->out_b.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(decode_status, ctx->out_b.p, m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_hash_to_g2(dkgv_ctx* ctx, uint32_t m, const uint8_t* msgs, const uint32_t* offsets, uint8_t* out) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!offsets || !out) return dkgv_fail(ctx, "null pointer argument");
+  size_t total = offsets[m];
+  if (total && !msgs) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_stack(ctx)) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve(total ? total : 1));
+  CK(ctx->in_b.reserve((size_t)(m + 1) * 4));
+  CK(ctx->out_a.reserve((size_t)m * 96));
+  if (total) CK(cudaMemcpyAsync(ctx->in_a.p, msgs, total, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, offsets, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, s));
+  k_hash_to_g2<<<(m + 31) / 32, 32, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)m * 96, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
+                                         const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status, void* stream) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!d_pk || !d_sig || !d_hm || !d_status || n_hm == 0) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_stack(ctx)) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  CK(ctx->scratch_a.reserve((size_t)n_hm * sizeof(G2Aff)));
+  CK(ctx->scratch_b.reserve(n_hm));
+  k_g2_decode<<<(n_hm + 31) / 32, 32, 0, s>>>(d_hm, (G2Aff*)ctx->scratch_a.p, (uint8_t*)ctx->scratch_b.p, n_hm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  k_bls_verify<<<(m + 31) / 32, 32, 0, s>>>(d_pk, d_sig, (const G2Aff*)ctx->scratch_a.p, d_hm_idx, d_status, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pk, const uint8_t* sig, uint32_t n_hm,
+                                     const uint8_t* hm, const uint32_t* hm_idx, uint8_t* status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!pk || !sig || !hm || !status || n_hm == 0) return dkgv_fail(ctx, "null pointer argument");
+  if (hm_idx)
+    for (uint32_t i = 0; i < m; i++)
+      if (hm_idx[i] >= n_hm) return dkgv_fail(ctx, "hm_idx out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve((size_t)m * 48));
+  CK(ctx->in_b.reserve((size_t)m * 96));
+  CK(ctx->in_c.reserve((size_t)n_hm * 96));
+  CK(ctx->out_a.reserve(hm_idx ? (size_t)m * 4 : 4));
+  CK(ctx->out_b.reserve(m));
+  CK(cudaMemcpyAsync(ctx->in_a.p, pk, (size_t)m * 48, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, sig, (size_t)m * 96, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_c.p, hm, (size_t)n_hm * 96, cudaMemcpyHostToDevice, s));
+  if (hm_idx) CK(cudaMemcpyAsync(ctx->out_a.p, hm_idx, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+  int rc = dkgv_bls_verify_batch_dev(ctx, m, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, n_hm, (const uint8_t*)ctx->in_c.p,
+                                     hm_idx ? (const uint32_t*)ctx->out_a.p : nullptr, (uint8_t*)ctx->out_b.p, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(status, ctx->out_b.p, m, cudaMemcpyDeviceToHost, s));
+  // an undecodable hashed message is a caller bug, not an item outcome
+  uint8_t hst[16];
+  uint32_t chk = n_hm < 16 ? n_hm : 16;
+  CK(cudaMemcpyAsync(hst, ctx->scratch_b.p, chk, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (uint32_t i = 0; i < chk; i++)
+    if (hst[i]) return dkgv_fail(ctx, "hashed message is not a valid G2 encoding");
+  return 0;
+}

@@ -99,6 +99,35 @@ int dkgv_g1_fixed_base_mul(dkgv_ctx* ctx, uint32_t m, const uint8_t* scalars, ui
 /* ---- G1 decoding with subgroup check (to_g1_affine, crypto/bls_common.rs:108-112) ----------- */
 int dkgv_g1_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status);
 
+/* ---- final / partial key aggregation (crates/dkg/src/dkg_math.rs:178-248) -------------------- */
+/* agg_coefficients: vv [n][t][48] (t = vv[0].len(); ragged inputs are the caller's PANIC_INDEX),
+ * coeff_out [t][48] = column sums C_k (may be NULL), keys_out [n_ids][48] = evaluate_polynomial(C, ids[j]).
+ * *status: OK / PANIC_BAD_G1 (some coefficient undecodable; outputs are then meaningless).       */
+int dkgv_agg_final_keys(dkgv_ctx* ctx, uint32_t n, uint32_t t, const uint8_t* vv, const uint32_t* ids, uint32_t n_ids,
+                        uint8_t* coeff_out, uint8_t* keys_out, uint8_t* status);
+/* lagrange_interpolation at 0 over (ids[i], pts[i]); ids are u32 scalars (bls_id_from_u32).
+ * *status: OK / ERR_LEN (k == 0) / ERR_ZERO_ID / ERR_DUP_ID / PANIC_BAD_G1; k == 1 returns pts[0]. */
+int dkgv_lagrange_at_zero(dkgv_ctx* ctx, uint32_t k, const uint8_t* pts, const uint32_t* ids, uint8_t* out, uint8_t* status);
+/* evaluate_polynomial over an arbitrary point vector: out[j] = sum_k coeffs[k] * ids[j]^k          */
+int dkgv_eval_points(dkgv_ctx* ctx, uint32_t t, const uint8_t* coeffs, const uint32_t* ids, uint32_t n_ids, uint8_t* out,
+                     uint8_t* status);
+
+/* ---- BLS partial-signature checks (crates/dkg/src/crypto/bls_common.rs:11-40) ----------------- */
+/* G2 decoding with subgroup check (BlsSignature::from_bytes, crypto/bls_keys.rs:165-176)          */
+int dkgv_g2_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status);
+/* hash_message_to_g2 for m messages: msgs = concatenation, offsets [m+1]; out [m][96] compressed  */
+int dkgv_hash_to_g2(dkgv_ctx* ctx, uint32_t m, const uint8_t* msgs, const uint32_t* offsets, uint8_t* out);
+/* bls_verify_precomputed_hash for m (pk, sig) pairs: e(pk, H) == e(G1, sig), H = hm[hm_idx[i]]
+ * (hm_idx NULL: all use hm[0]).  hm [n_hm][96] compressed hashed messages.
+ * status[i]: OK / SLASHABLE_SIG_INVALID (equality false) / PANIC_BAD_G2 (sig undecodable; checked
+ * first, as verification.rs:238-241) / PANIC_BAD_G1 (pk undecodable).  Callers map the decode
+ * outcomes to their call site's exit (panic in verify_generation_hashes, slashable in
+ * prove_wrong_final_key_generation, unslashable-invalid in verification.rs:243-248).              */
+int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pk, const uint8_t* sig, uint32_t n_hm, const uint8_t* hm,
+                          const uint32_t* hm_idx, uint8_t* status);
+int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
+                              const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status, void* stream);
+
 /* ---- dealer-side helper for building synthetic ceremonies (not a verification step) --------- */
 /* out[d][j] = sum_k coeffs[d][k] * ids[j]^k mod r ; coeffs [n_dealers][t][32] BE (< r), out BE   */
 int dkgv_fr_poly_eval(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* coeffs, uint32_t n_ids,

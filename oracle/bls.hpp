@@ -212,8 +212,8 @@ struct FrTag {};
 typedef Mont<6, FpTag> Fp;
 typedef Mont<4, FrTag> Fr;
 
-static const char* P_HEX = "1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab";
-static const char* R_HEX = "73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001";
+[[maybe_unused]] static const char* P_HEX = "1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab";
+[[maybe_unused]] static const char* R_HEX = "73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001";
 static const u64 X_ABS = 0xd201000000010000ull;  // |x|, x < 0
 
 struct Consts;

@@ -152,3 +152,50 @@ void he_fp30_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t
   fp30_to_canonical(fp30_mul_small<12>(fp30_add(fp30_add(x, y), fp30_sub<32>(y, x))), o.l); fp_raw_to_be48(m12_48, o.l);
 }
 }
+
+// ---- tower / pairing / hash-to-G2 (tower.cuh, h2c.cuh) -------------------------------------------
+#include "../../dvt_circuits_b200/csrc/h2c.cuh"
+extern "C" {
+uint32_t he_g2_decompress(const uint8_t* in96, uint8_t* out96) {
+  G2Aff a;
+  uint32_t st = g2_decompress(in96, &a, true);
+  if (st == G1_DEC_OK) g2_compress(&a, out96);
+  return st;
+}
+void he_hash_to_g2(const uint8_t* msg, size_t len, uint8_t* out96) {
+  G2Aff h;
+  hash_to_g2(&h, msg, len);
+  g2_compress(&h, out96);
+}
+// 1 valid, 0 invalid, negative: -48 bad pk, -49 bad sig/hm
+int he_bls_verify_hm(const uint8_t* pk48, const uint8_t* sig96, const uint8_t* hm96) {
+  G1Aff pk;
+  G2Aff sig, hm;
+  if (g1_decompress(pk48, &pk, true) != G1_DEC_OK) return -48;
+  if (g2_decompress(sig96, &sig, true) != G1_DEC_OK) return -49;
+  if (g2_decompress(hm96, &hm, true) != G1_DEC_OK) return -49;
+  return bls_verify_precomputed(&pk, &sig, &hm) ? 1 : 0;
+}
+// e(P,Q)^3 as 576 canonical big-endian bytes, same layout as orc_pairing_bytes
+int he_pairing_bytes(const uint8_t* p48, const uint8_t* q96, uint8_t* out576) {
+  G1Aff p;
+  G2Aff q;
+  if (g1_decompress(p48, &p, true) != G1_DEC_OK || g2_decompress(q96, &q, true) != G1_DEC_OK) return -1;
+  Fp12 f = fp12_one(), e;
+  miller_loop_acc(&f, &p, &q);
+  fp12_conj(&f, &f);
+  final_exponentiation(&e, &f);
+  const Fp* c = &e.c0.c0.c0;
+  for (int i = 0; i < 12; i++) {
+    Fp v = from_mont(c[i]);
+    fp_raw_to_be48(out576 + 48 * i, v.l);
+  }
+  return 0;
+}
+void he_sha256(const uint8_t* msg, size_t len, uint8_t* out32) {
+  Sha256 s;
+  sha_init(&s);
+  sha_update(&s, msg, len);
+  sha_finish(&s, out32);
+}
+}

@@ -1,0 +1,103 @@
+"""-m gpu parity tests of the finalization path through the C ABI: key aggregation, Lagrange at 0,
+hash-to-G2, G2 decoding and the batched BLS pairing checks - against the reference's own KATs
+(crates/dkg/src/dkg_math.rs:259-375) and the CPU oracle on seeded random inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_oracle import (EVAL_PKS, EVAL_TARGET, KAT_BAD_SIG, KAT_MSG, KAT_PK, KAT_SIG, KAT_WRONG_PK, LAG_PKS, LAG_TARGET, pts)
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+INF1, INF2 = bytes([0xC0]) + bytes(47), bytes([0xC0]) + bytes(95)
+
+
+def test_hash_to_g2(verifier):
+    msgs = [b"Sign with new partial key", KAT_MSG, b"", b"x" * 300, b"hello"]
+    out = verifier.hash_to_g2(msgs)
+    for m, o in zip(msgs, out):
+        assert bytes(o) == O.hash_to_g2(m)
+
+
+def test_g2_decompress(verifier):
+    cases = [KAT_SIG, KAT_BAD_SIG, INF2, bytes(96), bytes([0xE0]) + bytes(95), O.hash_to_g2(b"abc")]
+    st = verifier.g2_decompress_check(np.array([list(c) for c in cases], dtype=np.uint8))
+    assert st.tolist() == [O.g2_decompress(c)[0] for c in cases]
+    assert st.tolist()[:3] == [0, 0, 0]
+
+
+def test_kat_bls_verify(verifier):
+    # dkg_math.rs:259-278 incl. the three negatives, + identity semantics
+    hm = [O.hash_to_g2(KAT_MSG), O.hash_to_g2(b"\x00")]
+    pk = [KAT_PK, KAT_PK, KAT_WRONG_PK, KAT_PK, INF1, INF1, KAT_PK, bytes(48), KAT_PK]
+    sig = [KAT_SIG, KAT_SIG, KAT_SIG, KAT_BAD_SIG, INF2, KAT_SIG, INF2, KAT_SIG, bytes(96)]
+    idx = [0, 1, 0, 0, 0, 0, 0, 0, 0]
+    st = verifier.bls_verify_batch(np.array([list(x) for x in pk], dtype=np.uint8), np.array([list(x) for x in sig], dtype=np.uint8),
+                                   np.array([list(x) for x in hm], dtype=np.uint8), idx)
+    assert st.tolist() == [0, 7, 7, 7, 0, 7, 7, 48, 49]
+
+
+def test_bls_batch_random(verifier):
+    rng = np.random.default_rng(5)
+    m = 40
+    msg = b"Sign with new partial key"
+    hm = O.hash_to_g2(msg)
+    sks = [int.from_bytes(rng.bytes(31), "big") + 1 for _ in range(m)]
+    pks = [O.g1_fixed_base(s.to_bytes(32, "big"))[1] for s in sks]
+    # sig_i = sk_i * H(m): computed with the pure-Python restatement (G2 scalar multiplication)
+    from oracle.pyref import bls12_381 as B
+    hpt = B.g2_decompress(hm)
+    sigs = [B.g2_compress(B.g2_mul(hpt, s)) for s in sks]
+    for i in range(0, m, 5):  # corrupt every 5th: wrong key for that signature
+        pks[i] = pks[(i + 1) % m]
+    st = verifier.bls_verify_batch(np.array([list(x) for x in pks], dtype=np.uint8), np.array([list(x) for x in sigs], dtype=np.uint8),
+                                   np.array([list(hm)], dtype=np.uint8))
+    exp = O.bls_verify_batch(np.array([list(x) for x in pks], dtype=np.uint8), np.array([list(x) for x in sigs], dtype=np.uint8), hm, threads=4)
+    assert st.tolist() == [0 if e == 1 else 7 for e in exp.tolist()]
+    assert st.tolist().count(7) == m // 5
+
+
+def test_kat_lagrange(verifier):
+    assert verifier.lagrange_at_zero(pts(LAG_PKS), [1, 2, 3, 4, 5]) == (0, H(LAG_TARGET))
+    assert verifier.lagrange_at_zero(pts(LAG_PKS[4:] + LAG_PKS[:4]), [5, 1, 2, 3, 4]) == (0, H(LAG_TARGET))
+    st, out = verifier.lagrange_at_zero(pts([LAG_PKS[1], LAG_PKS[0]] + LAG_PKS[2:]), [1, 2, 3, 4, 5])
+    assert st == 0 and out != H(LAG_TARGET)
+    assert verifier.lagrange_at_zero(pts(LAG_PKS), [1, 2, 0, 4, 5])[0] == 36
+    assert verifier.lagrange_at_zero(pts(LAG_PKS), [1, 2, 2, 4, 5])[0] == 37
+    assert verifier.lagrange_at_zero(pts(LAG_PKS[:1]), [9]) == (0, H(LAG_PKS[0]))
+    assert verifier.lagrange_at_zero(np.zeros((0, 48), dtype=np.uint8), [])[0] == 32
+    bad = pts(LAG_PKS).copy()
+    bad[2] = 0
+    assert verifier.lagrange_at_zero(bad, [1, 2, 3, 4, 5])[0] == 48
+
+
+def test_kat_eval_points(verifier):
+    st, out = verifier.eval_points(pts(EVAL_PKS), [1, 0, 7])
+    assert st == 0 and bytes(out[0]).hex() == EVAL_TARGET
+    assert bytes(out[1]) == H(EVAL_PKS[0])  # id 0 -> C_0
+    assert bytes(out[2]) == O.evaluate_polynomial(b"".join(H(h) for h in EVAL_PKS), 3, 7)[1]
+
+
+@pytest.mark.parametrize("n,t", [(3, 2), (7, 5), (40, 9), (33, 1)])
+def test_agg_final_keys_vs_oracle(verifier, n, t):
+    from dvt_circuits_b200 import synthetic
+    s = synthetic.make_session(verifier, n, n, t, seed=99 + n)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    st, co, keys = verifier.agg_final_keys(s["vv"], ids)
+    ost, oco, okeys = O.agg_coefficients(s["vv"], ids, O.FAST)
+    assert st == ost == 0
+    assert (co == oco).all() and (keys == okeys).all()
+    # size-independent property: Lagrange at 0 over the final keys returns the aggregate C_0
+    lst, agg = verifier.lagrange_at_zero(keys, ids)
+    if n >= t:
+        assert lst == 0 and agg == bytes(co[0])
+    assert O.lagrange(keys, ids, O.FAST) == (lst, agg)
+
+
+def test_agg_bad_point(verifier):
+    from dvt_circuits_b200 import synthetic
+    s = synthetic.make_session(verifier, 4, 4, 3)
+    vv = s["vv"].copy()
+    vv[2, 1] = 0
+    st, _, _ = verifier.agg_final_keys(vv, [1, 2, 3, 4])
+    assert st == 48
