@@ -69,6 +69,10 @@ DECLARED_SYMBOLS = {
     "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    # include/dkgh.h
+    "dkgh_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                    ctypes.c_char_p, ctypes.c_size_t]),
+    "dkgh_initial_commitment_hash": (None, [_vp, ctypes.c_uint8, ctypes.c_uint8, _vp, _u32, _vp]),
 }
 
 
@@ -255,3 +259,23 @@ class Verifier:
         self._ck(self._lib.dkgv_bls_verify_batch(self._h, pk.shape[0], _p(pk), _p(sig), hm.shape[0], _p(hm),
                                                  _p(idx) if idx is not None else None, _p(st)))
         return st
+
+    # ---- dkg_prover_host `execute` contract (include/dkgh.h) ------------------------------------------
+    def execute(self, type_, json_text, auth=False, bls_identity=False):
+        """-> (exit_code, status, message)"""
+        st = ctypes.c_int(0)
+        msg = ctypes.create_string_buffer(512)
+        if isinstance(json_text, str):
+            json_text = json_text.encode()
+        code = self._lib.dkgh_execute(self._h, type_.encode(), json_text, int(auth), int(bls_identity), ctypes.byref(st), msg, 512)
+        return int(code), int(st.value), msg.value.decode(errors="replace")
+
+
+def initial_commitment_hash(gen_id, n, k, base_pubkeys):
+    """compute_initial_commitment_hash (verification.rs:151-175); base_pubkeys [count, 48] u8"""
+    lib = load_library()
+    pk = np.ascontiguousarray(base_pubkeys, dtype=np.uint8).reshape(-1, 48)
+    gid = np.frombuffer(bytes(gen_id), dtype=np.uint8)
+    out = np.zeros((32,), dtype=np.uint8)
+    lib.dkgh_initial_commitment_hash(_p(gid), n & 0xFF, k & 0xFF, _p(pk) if pk.size else None, pk.shape[0], _p(out))
+    return out.tobytes()

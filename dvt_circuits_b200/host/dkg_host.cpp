@@ -1,0 +1,420 @@
+// Host-side mirror of the reference's `dkg` crate API on top of the C ABI (include/dkgv.h).
+// Same function names, argument meaning and outcome classes as
+//   crates/dkg/src/verification.rs  (verify_seed_exchange_commitment :68, verify_generations :262,
+//                                    prove_wrong_final_key_generation :422, compute_initial_commitment_hash :151)
+// and the guests' pre-checks / exit mapping
+//   crates/bad_share_exchange_prove/src/main.rs:16-82, crates/finalization_prove/src/main.rs:7-33,
+//   crates/bad_parial_key_prove/src/main.rs:16-51,
+// reading the dkg_prover_host JSON input format (crates/dkg/src/types.rs:27-203).
+// All group / field / pairing arithmetic runs on the GPU through dkgv_*; the host does hashing,
+// sorting, the identity-signature check and the control flow.  Every reference exit (Ok, Slashable,
+// Unslashable, io::Error, panic!) becomes one dkgv_status code; `exit code` follows script/run.sh.
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+#include "../../include/dkgv.h"
+#include "util.hpp"
+
+namespace dkgh {
+
+typedef std::vector<uint8_t> Bytes;
+
+struct Panic {
+  int code;
+};
+struct Settings {
+  uint8_t n = 0, k = 0;
+  Bytes gen_id;
+};
+struct Setup {
+  bool auth = false;          // cargo feature auth_commitment
+  bool bls_identity = false;  // BlsDkgWithBlsCommitment (48/96-byte identity keys) vs secp256k1 (33/64)
+  size_t id_pk() const { return bls_identity ? 48 : 33; }
+  size_t id_sig() const { return bls_identity ? 96 : 64; }
+};
+
+static Settings parse_settings(const Json& j) {
+  Settings s;
+  s.n = json_u8(j.at("n"), "n");
+  s.k = json_u8(j.at("k"), "k");
+  s.gen_id = hex_fixed(j.at("gen_id"), 16, "gen_id");
+  return s;
+}
+static std::vector<Bytes> parse_hex_list(const Json& j, size_t n, const char* what) {
+  if (j.kind != Json::Arr) throw std::runtime_error(std::string(what) + ": expected an array");
+  std::vector<Bytes> out;
+  for (auto& e : j.arr) out.push_back(hex_fixed(e, n, what));
+  return out;
+}
+struct Commitment {
+  Bytes hash, pubkey, signature;
+};
+static Commitment parse_commitment(const Json& j, const Setup& su) {
+  Commitment c;
+  c.pubkey = hex_fixed(j.at("pubkey"), su.id_pk(), "commitment.pubkey");
+  if (su.auth) {  // the fields only exist under the auth_commitment feature (types.rs:71-78)
+    c.hash = hex_fixed(j.at("hash"), 32, "commitment.hash");
+    c.signature = hex_fixed(j.at("signature"), su.id_sig(), "commitment.signature");
+  }
+  return c;
+}
+
+// verification.rs:151-175
+static Bytes compute_initial_commitment_hash(const Settings& st, const std::vector<Bytes>& base_pubkeys) {
+  Sha256 h;
+  h.update(st.gen_id);
+  uint8_t hdr[3] = {st.n, st.k, (uint8_t)base_pubkeys.size()};
+  h.update(hdr, 3);
+  for (auto& p : base_pubkeys) h.update(p);
+  return h.finish();
+}
+
+struct Host {
+  dkgv_ctx* ctx;
+  Setup su;
+  Secp256k1 secp;
+  std::string detail;  // expected / got keys for messages
+
+  void ck(int rc) {
+    if (rc != 0) throw std::runtime_error(std::string("dkgv: ") + dkgv_last_error(ctx));
+  }
+  // verification.rs:364-374 and :478-493: true = signature valid; undecodable key or signature panics
+  bool verify_identity_sig(const Commitment& c) {
+    if (!su.bls_identity) {
+      SecpPoint pk;
+      U256 r, s;
+      if (!secp.parse_pubkey(c.pubkey.data(), &pk)) throw Panic{DKGV_PANIC_BAD_IDENTITY};
+      if (!secp.parse_sig(c.signature.data(), &r, &s)) throw Panic{DKGV_PANIC_BAD_IDENTITY};
+      return secp.verify(pk, c.hash.data(), r, s);
+    }
+    // BLS identity: PublicKey::verify_signature(hash bytes, sig) = hash_to_g2 + pairing equality
+    uint32_t offs[2] = {0, 32};
+    uint8_t hm[96], st = 0;
+    ck(dkgv_hash_to_g2(ctx, 1, c.hash.data(), offs, hm));
+    ck(dkgv_bls_verify_batch(ctx, 1, c.pubkey.data(), c.signature.data(), 1, hm, nullptr, &st));
+    if (st == DKGV_PANIC_BAD_G1 || st == DKGV_PANIC_BAD_G2) throw Panic{st};
+    return st == DKGV_OK;
+  }
+
+  // ---- verify_seed_exchange_commitment (verification.rs:68-149)
+  int verify_seed_exchange_commitment(const std::vector<Bytes>& hashes, const Json& seed_exchange, const std::vector<Bytes>& base_pubkeys) {
+    Commitment c = parse_commitment(seed_exchange.at("commitment"), su);
+    Bytes ich = hex_fixed(seed_exchange.at("initial_commitment_hash"), 32, "initial_commitment_hash");
+    const Json& ss = seed_exchange.at("ssecret");
+    Bytes dst = hex_fixed(ss.at("dst_base_hash"), 32, "dst_base_hash");
+    Bytes secret = hex_fixed(ss.at("shared_secret"), 32, "shared_secret");
+    if (su.auth && !verify_identity_sig(c)) return DKGV_UNSLASHABLE_COMMIT_SIG;
+    // secret < r ?  (bls_keys.rs:98-114) - decided on the GPU together with G*s below; but the
+    // reference tests the range BEFORE the hash check, so ask the device first
+    uint8_t pk[48], pst = 0;
+    ck(dkgv_g1_fixed_base_mul(ctx, 1, secret.data(), pk, &pst));
+    if (pst == DKGV_SLASHABLE_SECRET_RANGE) return DKGV_SLASHABLE_SECRET_RANGE;
+    if (su.auth) {  // compute_seed_exchange_hash, verification.rs:29-48,101-114
+      Sha256 h;
+      h.update(ich);
+      h.update(secret);  // sk.to_bytes() of an in-range scalar is the input itself
+      h.update(dst);
+      if (h.finish() != c.hash) return DKGV_SLASHABLE_COMMIT_HASH;
+    }
+    // get_index_in_commitments, verification.rs:50-66
+    std::vector<Bytes> sorted = hashes;
+    std::sort(sorted.begin(), sorted.end());
+    int idx = -1;
+    for (size_t i = 0; i < sorted.size(); i++)
+      if (sorted[i] == dst) {
+        idx = (int)i;
+        break;
+      }
+    if (idx < 0) return DKGV_SLASHABLE_DST_NOT_FOUND;
+    uint32_t id = (uint32_t)idx + 1;
+    // Feldman check on the GPU: 1 dealer x 1 recipient
+    Bytes vv;
+    for (auto& p : base_pubkeys) vv.insert(vv.end(), p.begin(), p.end());
+    uint8_t st = 0;
+    ck(dkgv_share_matrix_verify(ctx, 1, 1, (uint32_t)base_pubkeys.size(), vv.data(), &id, secret.data(), &st));
+    if (st == DKGV_PANIC_BAD_G1) throw Panic{DKGV_PANIC_BAD_G1};
+    return st;
+  }
+
+  // ---- guest 1 (crates/bad_share_exchange_prove/src/main.rs:16-82)
+  int guest_bad_share(const Json& data) {
+    std::vector<Bytes> hashes = parse_hex_list(data.at("base_hashes"), 32, "base_hashes");
+    const Json& ic = data.at("initial_commitment");
+    Settings st = parse_settings(ic.at("settings"));
+    Bytes ihash = hex_fixed(ic.at("hash"), 32, "initial_commitment.hash");
+    std::vector<Bytes> base_pubkeys = parse_hex_list(ic.at("base_pubkeys"), 48, "base_pubkeys");
+    const Json& se = data.at("seeds_exchange_commitment");
+    // serde deserialises the whole struct before the guest runs: force the field checks now
+    (void)parse_commitment(se.at("commitment"), su);
+    (void)hex_fixed(se.at("initial_commitment_hash"), 32, "initial_commitment_hash");
+    (void)hex_fixed(se.at("ssecret").at("dst_base_hash"), 32, "dst_base_hash");
+    (void)hex_fixed(se.at("ssecret").at("shared_secret"), 32, "shared_secret");
+    if (hashes.size() != st.n) throw Panic{DKGV_PANIC_PRECHECK};
+    if (st.n < st.k) throw Panic{DKGV_PANIC_PRECHECK};
+    if (std::find(hashes.begin(), hashes.end(), ihash) == hashes.end()) throw Panic{DKGV_PANIC_PRECHECK};
+    if (compute_initial_commitment_hash(st, base_pubkeys) != ihash) throw Panic{DKGV_PANIC_PRECHECK};
+    return verify_seed_exchange_commitment(hashes, se, base_pubkeys);
+  }
+
+  struct Generation {
+    std::vector<Bytes> vv;
+    Bytes base_hash, partial_pubkey, message_signature;
+    std::string message;
+  };
+  static Generation parse_generation(const Json& g, bool full) {
+    Generation r;
+    r.vv = parse_hex_list(g.at("base_pubkeys"), 48, "base_pubkeys");
+    r.base_hash = hex_fixed(g.at("base_hash"), 32, "base_hash");
+    if (full) {
+      r.partial_pubkey = hex_fixed(g.at("partial_pubkey"), 48, "partial_pubkey");
+      const Json& m = g.at("message_cleartext");
+      if (m.kind != Json::Str) throw std::runtime_error("message_cleartext: expected a string");
+      r.message = m.str;
+      r.message_signature = hex_fixed(g.at("message_signature"), 96, "message_signature");
+    }
+    return r;
+  }
+
+  // sorted (stable, by base_hash) verification vectors -> agg_coefficients on the GPU.
+  // ragged vectors: shorter than vv[0] -> index panic, longer -> tail ignored (dkg_math.rs:235-239)
+  void agg(const std::vector<const Generation*>& sorted, const std::vector<uint32_t>& ids, Bytes* coeffs, Bytes* keys) {
+    size_t t = sorted[0]->vv.size();
+    Bytes flat;
+    for (auto* g : sorted) {
+      if (g->vv.size() < t) throw Panic{DKGV_PANIC_INDEX};
+      for (size_t k = 0; k < t; k++) flat.insert(flat.end(), g->vv[k].begin(), g->vv[k].end());
+    }
+    coeffs->assign(t * 48, 0);
+    keys->assign(ids.size() * 48, 0);
+    uint8_t st = 0;
+    ck(dkgv_agg_final_keys(ctx, (uint32_t)sorted.size(), (uint32_t)t, flat.data(), ids.data(), (uint32_t)ids.size(), coeffs->data(),
+                           keys->data(), &st));
+    if (st != DKGV_OK) throw Panic{st};
+  }
+  // every coefficient of every generation must decode - also the tail the aggregation ignores
+  // (verification.rs:282-291 maps Point::from_bytes(...).expect over all of them)
+  void expect_all_points(const std::vector<const Generation*>& gens) {
+    Bytes flat;
+    for (auto* g : gens)
+      for (auto& p : g->vv) flat.insert(flat.end(), p.begin(), p.end());
+    if (flat.empty()) return;
+    std::vector<uint8_t> st(flat.size() / 48);
+    ck(dkgv_g1_decompress_check(ctx, (uint32_t)st.size(), flat.data(), st.data()));
+    for (uint8_t s : st)
+      if (s) throw Panic{DKGV_PANIC_BAD_G1};
+  }
+
+  // ---- verify_generations (verification.rs:262-331) incl. verify_generation_hashes (:211-260)
+  int verify_generations(const std::vector<Generation>& gens, const Settings& st, const Bytes& agg_key) {
+    if (gens.size() != st.n) return DKGV_ERR_LEN;
+    if (gens.empty()) return DKGV_ERR_LEN;
+    for (size_t i = 1; i < gens.size(); i++)
+      if (gens[i].message != gens[0].message) return DKGV_ERR_MSG_MISMATCH;
+    // one hash-to-G2, then all signature checks in one batch
+    uint32_t offs[2] = {0, (uint32_t)gens[0].message.size()};
+    uint8_t hm[96];
+    ck(dkgv_hash_to_g2(ctx, 1, (const uint8_t*)gens[0].message.data(), offs, hm));
+    Bytes pks, sigs;
+    for (auto& g : gens) {
+      pks.insert(pks.end(), g.partial_pubkey.begin(), g.partial_pubkey.end());
+      sigs.insert(sigs.end(), g.message_signature.begin(), g.message_signature.end());
+    }
+    std::vector<uint8_t> vst(gens.size());
+    ck(dkgv_bls_verify_batch(ctx, (uint32_t)gens.size(), pks.data(), sigs.data(), 1, hm, nullptr, vst.data()));
+    // input order, first failure wins; per generation: decode (panic), signature, then hash
+    for (size_t i = 0; i < gens.size(); i++) {
+      if (vst[i] == DKGV_PANIC_BAD_G2 || vst[i] == DKGV_PANIC_BAD_G1) throw Panic{vst[i]};
+      if (vst[i] != DKGV_OK) return DKGV_UNSLASHABLE_SIG_INVALID;
+      if (compute_initial_commitment_hash(st, gens[i].vv) != gens[i].base_hash) return DKGV_UNSLASHABLE_GEN_HASH;
+    }
+    std::vector<const Generation*> sorted;
+    for (auto& g : gens) sorted.push_back(&g);
+    std::stable_sort(sorted.begin(), sorted.end(), [](const Generation* a, const Generation* b) { return a->base_hash < b->base_hash; });
+    expect_all_points(sorted);
+    std::vector<uint32_t> ids;
+    for (size_t i = 0; i < sorted.size(); i++) ids.push_back((uint32_t)i + 1);
+    Bytes coeffs, keys;
+    agg(sorted, ids, &coeffs, &keys);
+    uint8_t lst = 0, computed[48];
+    ck(dkgv_lagrange_at_zero(ctx, (uint32_t)ids.size(), keys.data(), ids.data(), computed, &lst));
+    if (lst != DKGV_OK) return lst;
+    if (memcmp(computed, agg_key.data(), 48) != 0) return DKGV_ERR_AGG_MISMATCH_VV;
+    Bytes ppk;
+    for (auto* g : sorted) ppk.insert(ppk.end(), g->partial_pubkey.begin(), g->partial_pubkey.end());
+    ck(dkgv_lagrange_at_zero(ctx, (uint32_t)ids.size(), ppk.data(), ids.data(), computed, &lst));
+    if (lst == DKGV_PANIC_BAD_G1) throw Panic{lst};
+    if (lst != DKGV_OK) return lst;
+    if (memcmp(computed, agg_key.data(), 48) != 0) return DKGV_ERR_AGG_MISMATCH_PK;
+    return DKGV_OK;
+  }
+
+  // ---- guest 4 (crates/finalization_prove/src/main.rs:7-33); always BlsDkgWithBlsCommitment
+  int guest_finalization(const Json& data) {
+    Settings st = parse_settings(data.at("settings"));
+    const Json& gj = data.at("generations");
+    if (gj.kind != Json::Arr) throw std::runtime_error("generations: expected an array");
+    std::vector<Generation> gens;
+    for (auto& g : gj.arr) gens.push_back(parse_generation(g, true));
+    Bytes agg_key = hex_fixed(data.at("aggregate_pubkey"), 48, "aggregate_pubkey");
+    uint8_t dst = 0;
+    ck(dkgv_g1_decompress_check(ctx, 1, agg_key.data(), &dst));
+    if (dst) throw Panic{DKGV_PANIC_BAD_G1};
+    return verify_generations(gens, st, agg_key);
+  }
+
+  // ---- prove_wrong_final_key_generation (verification.rs:422-466)
+  int prove_wrong_final_key_generation(const Json& data) {
+    Settings st = parse_settings(data.at("settings"));
+    const Json& gj = data.at("generations");
+    if (gj.kind != Json::Arr) throw std::runtime_error("generations: expected an array");
+    std::vector<Generation> gens;
+    for (auto& g : gj.arr) gens.push_back(parse_generation(g, false));
+    const Json& bpj = data.at("bad_partial");
+    (void)parse_settings(bpj.at("settings"));  // deserialised but never read
+    Generation bp = parse_generation(bpj.at("data"), true);
+    Commitment c = parse_commitment(bpj.at("commitment"), su);
+    if (su.auth) {  // verify_commitment_signature, :468-496 with compute_partial_share_hash :333-362
+      Sha256 h;
+      h.update(st.gen_id);
+      uint8_t hdr[3] = {st.n, st.k, (uint8_t)bp.vv.size()};
+      h.update(hdr, 3);
+      for (auto& p : bp.vv) h.update(p);
+      h.update(bp.base_hash);
+      h.update(bp.partial_pubkey);
+      uint8_t ml = (uint8_t)bp.message.size();
+      h.update(&ml, 1);
+      h.update((const uint8_t*)bp.message.data(), bp.message.size());
+      h.update(bp.message_signature);
+      if (h.finish() != c.hash) return DKGV_UNSLASHABLE_COMMIT_HASH;
+      if (!verify_identity_sig(c)) return DKGV_UNSLASHABLE_COMMIT_SIG;
+    }
+    for (auto& g : gens)  // verify_generation_base_hashes :376-397
+      if (compute_initial_commitment_hash(st, g.vv) != g.base_hash) return DKGV_UNSLASHABLE_GEN_HASH;
+    std::vector<const Generation*> sorted;
+    for (auto& g : gens) sorted.push_back(&g);
+    std::stable_sort(sorted.begin(), sorted.end(), [](const Generation* a, const Generation* b) { return a->base_hash < b->base_hash; });
+    int perp = -1;  // last match wins (:506-510)
+    for (size_t i = 0; i < sorted.size(); i++)
+      if (sorted[i]->base_hash == bp.base_hash) perp = (int)i;
+    if (perp < 0) return DKGV_UNSLASHABLE_PERP_NOT_FOUND;
+    uint8_t dst = 0;
+    ck(dkgv_g1_decompress_check(ctx, 1, bp.partial_pubkey.data(), &dst));
+    if (dst) return DKGV_SLASHABLE_BAD_PK;
+    ck(dkgv_g2_decompress_check(ctx, 1, bp.message_signature.data(), &dst));
+    if (dst) return DKGV_SLASHABLE_BAD_SIG;
+    uint32_t offs[2] = {0, (uint32_t)bp.message.size()};
+    uint8_t hm[96], vst = 0;
+    ck(dkgv_hash_to_g2(ctx, 1, (const uint8_t*)bp.message.data(), offs, hm));
+    ck(dkgv_bls_verify_batch(ctx, 1, bp.partial_pubkey.data(), bp.message_signature.data(), 1, hm, nullptr, &vst));
+    if (vst != DKGV_OK) return DKGV_SLASHABLE_SIG_INVALID;
+    // verify_expected_key -> compute_pubkey_share (:399-420, :523-551), quirk Q1 kept: Horner over the K_j
+    if (sorted.empty()) throw Panic{DKGV_PANIC_INDEX};
+    expect_all_points(sorted);
+    std::vector<uint32_t> ids;
+    for (size_t i = 0; i < sorted.size(); i++) ids.push_back((uint32_t)i + 1);
+    Bytes coeffs, keys;
+    agg(sorted, ids, &coeffs, &keys);
+    uint32_t pid = (uint32_t)perp + 1;
+    uint8_t expected[48], est = 0;
+    ck(dkgv_eval_points(ctx, (uint32_t)ids.size(), keys.data(), &pid, 1, expected, &est));
+    if (est != DKGV_OK) throw Panic{est};
+    if (memcmp(expected, bp.partial_pubkey.data(), 48) != 0) return DKGV_SLASHABLE_KEY_MISMATCH;
+    return DKGV_OK;
+  }
+};
+
+static bool is_slashable(int s) { return s >= 1 && s < 16; }
+
+}  // namespace dkgh
+
+extern "C" {
+// `dkg_prover_host execute --type <type> --input-file <json>` semantics on the GPU.
+//   type: "bad-share" | "finalization" | "bad-partial-key";  auth: feature auth_commitment;
+//   bls_identity: 1 = BlsDkgWithBlsCommitment (always used by finalization, as the reference does)
+// returns the process exit code of the reference (0 = misbehaviour proven / ceremony valid, 1 = anything
+// else), *status = the dkgv_status reached (255 = input rejected by the JSON / hex layer, as serde would)
+int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg, size_t msg_cap) {
+  using namespace dkgh;
+  int st = 255;
+  std::string m;
+  int code = 1;
+  try {
+    std::string text(json_text);
+    Json data = JsonParser(text).parse();
+    Host h{ctx, Setup{auth != 0, bls_identity != 0}, Secp256k1(), ""};
+    std::string ty(type);
+    if (ty == "bad-share") {
+      st = h.guest_bad_share(data);
+      code = is_slashable(st) ? 0 : 1;
+    } else if (ty == "finalization") {
+      h.su.bls_identity = true;
+      st = h.guest_finalization(data);
+      code = st == DKGV_OK ? 0 : 1;
+    } else if (ty == "bad-partial-key") {
+      st = h.prove_wrong_final_key_generation(data);
+      code = is_slashable(st) ? 0 : 1;
+    } else {
+      m = "unknown type";
+    }
+  } catch (const dkgh::Panic& p) {
+    st = p.code;
+    code = 1;
+  } catch (const std::exception& e) {
+    m = e.what();
+    code = 1;
+  }
+  if (status) *status = st;
+  if (msg && msg_cap) {
+    snprintf(msg, msg_cap, "%s", m.c_str());
+  }
+  return code;
+}
+// compute_initial_commitment_hash (verification.rs:151-175) for callers that build inputs
+void dkgh_initial_commitment_hash(const uint8_t* gen_id16, uint8_t n, uint8_t k, const uint8_t* base_pubkeys, uint32_t count, uint8_t* out32) {
+  dkgh::Settings st;
+  st.n = n;
+  st.k = k;
+  st.gen_id.assign(gen_id16, gen_id16 + 16);
+  std::vector<dkgh::Bytes> pk;
+  for (uint32_t i = 0; i < count; i++) pk.emplace_back(base_pubkeys + (size_t)i * 48, base_pubkeys + (size_t)(i + 1) * 48);
+  dkgh::Bytes h = dkgh::compute_initial_commitment_hash(st, pk);
+  memcpy(out32, h.data(), 32);
+}
+}
+
+#ifdef DKGH_MAIN
+// dkg_prover_host-compatible command line: execute --type T --input-file F [--auth] [--bls-identity]
+int main(int argc, char** argv) {
+  std::string type, file;
+  int auth = 0, bls = 0;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a.rfind("--type=", 0) == 0) type = a.substr(7);
+    else if (a == "--type" && i + 1 < argc) type = argv[++i];
+    else if (a.rfind("--input-file=", 0) == 0) file = a.substr(13);
+    else if ((a == "--input-file" || a == "-i") && i + 1 < argc) file = argv[++i];
+    else if (a == "--auth") auth = 1;
+    else if (a == "--bls-identity") bls = 1;
+  }
+  std::ifstream in(file);
+  if (!in) {
+    fprintf(stderr, "cannot read %s\n", file.c_str());
+    return 1;
+  }
+  std::stringstream ss;
+  ss << in.rdbuf();
+  dkgv_ctx* ctx = nullptr;
+  if (dkgv_ctx_create(0, &ctx) != 0) {
+    fprintf(stderr, "no CUDA device: %s\n", dkgv_last_error(nullptr));
+    return 1;
+  }
+  int status = 0;
+  char msg[512];
+  int code = dkgh_execute(ctx, type.c_str(), ss.str().c_str(), auth, bls, &status, msg, sizeof msg);
+  printf("status=%d exit=%d %s\n", status, code, msg);
+  dkgv_ctx_destroy(ctx);
+  return code;
+}
+#endif
