@@ -69,6 +69,7 @@ DECLARED_SYMBOLS = {
     "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_g2_mul_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     # include/dkgh.h
     "dkgh_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                     ctypes.c_char_p, ctypes.c_size_t]),
@@ -259,6 +260,13 @@ class Verifier:
         self._ck(self._lib.dkgv_bls_verify_batch(self._h, pk.shape[0], _p(pk), _p(sig), hm.shape[0], _p(hm),
                                                  _p(idx) if idx is not None else None, _p(st)))
         return st
+
+    def g2_mul_batch(self, base96, scalars):
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1, 32)
+        base = np.frombuffer(bytes(base96), dtype=np.uint8)
+        out = np.zeros((scalars.shape[0], 96), dtype=np.uint8)
+        self._ck(self._lib.dkgv_g2_mul_batch(self._h, scalars.shape[0], _p(base), _p(scalars), _p(out)))
+        return out
 
     # ---- dkg_prover_host `execute` contract (include/dkgh.h) ------------------------------------------
     def execute(self, type_, json_text, auth=False, bls_identity=False):

@@ -62,6 +62,28 @@ k_bls_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ sig, co
   status[i] = st;
 }
 
+// signer-side helper for synthetic ceremonies (not a verification step): out[i] = [scalars[i]] * base
+struct LimbArr {
+  const uint32_t* w;
+  DKGV_HD uint32_t operator()(int i) const { return w[i]; }
+};
+__global__ void __launch_bounds__(32) k_g2_mul_batch(const uint8_t* __restrict__ base96, const uint8_t* __restrict__ scalars,
+                                                     uint8_t* __restrict__ out, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G2Aff b;
+  g2_decompress(base96, &b, false);
+  uint32_t s[8];
+  fr_raw_from_be32(s, scalars + (size_t)i * 32);
+  G2Proj p = g2_from_affine(b), r;
+  g2_mul_public(&r, &p, LimbArr{s}, 8);
+  G2Aff a;
+  g2_to_affine(&a, &r);
+  uint8_t enc[96];
+  g2_compress(&a, enc);
+  for (int k = 0; k < 96; k++) out[(size_t)i * 96 + k] = enc[k];
+}
+
 static int ensure_stack(dkgv_ctx* ctx) {
   if (!ctx->stack_set) {
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
@@ -159,5 +181,25 @@ extern "C" int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* p
   CK(cudaStreamSynchronize(s));
   for (uint32_t i = 0; i < chk; i++)
     if (hst[i]) return dkgv_fail(ctx, "hashed message is not a valid G2 encoding");
+  return 0;
+}
+
+extern "C" int dkgv_g2_mul_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* base96, const uint8_t* scalars, uint8_t* out) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!base96 || !scalars || !out) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_stack(ctx)) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve(96));
+  CK(ctx->in_b.reserve((size_t)m * 32));
+  CK(ctx->out_a.reserve((size_t)m * 96));
+  CK(cudaMemcpyAsync(ctx->in_a.p, base96, 96, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, scalars, (size_t)m * 32, cudaMemcpyHostToDevice, s));
+  k_g2_mul_batch<<<(m + 31) / 32, 32, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)m * 96, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }

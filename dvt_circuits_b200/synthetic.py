@@ -54,3 +54,23 @@ def corrupt_shares(shares, p_bad, seed=DEFAULT_SEED):
             out[d, j] = 0xFF
             expected[d, j] = 1
     return out, expected
+
+
+def make_finalization(verifier, n, t, seed=DEFAULT_SEED, message=b"Sign with new partial key"):
+    """Config 4: partial secret S_j = sum_i s_{i,j}, partial_pubkey_j = G*S_j,
+    sig_j = S_j * H(m).  -> dict(vv, ids, partial_pubkeys [n,48], signatures [n,96], hm [96], message)"""
+    s = make_session(verifier, n, n, t, seed)
+    sh = s["shares"]
+    sums = []
+    for j in range(n):
+        acc = 0
+        for i in range(n):
+            acc += int.from_bytes(sh[i, j].tobytes(), "big")
+        sums.append((acc % R_INT).to_bytes(32, "big"))
+    sk = np.frombuffer(b"".join(sums), dtype=np.uint8).reshape(n, 32)
+    pks, st = verifier.g1_fixed_base_mul(sk)
+    assert not st.any()
+    hm = verifier.hash_to_g2([message])[0]
+    sigs = verifier.g2_mul_batch(hm.tobytes(), sk)
+    s.update({"partial_pubkeys": pks, "signatures": sigs, "hm": hm, "message": message, "partial_secrets": sk})
+    return s

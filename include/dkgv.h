@@ -132,6 +132,8 @@ int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, co
 /* out[d][j] = sum_k coeffs[d][k] * ids[j]^k mod r ; coeffs [n_dealers][t][32] BE (< r), out BE   */
 int dkgv_fr_poly_eval(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* coeffs, uint32_t n_ids,
                       const uint32_t* ids, uint8_t* out);
+/* signer-side helper: out[i] = compress([scalars[i]] * base), base a compressed G2 point (e.g. H(m)) */
+int dkgv_g2_mul_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* base96, const uint8_t* scalars, uint8_t* out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,54 @@
+"""CPU-only: the C-ABI library loads without a GPU, exports every symbol include/*.h declares, and the
+product path fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import dvt_circuits_b200 as dk
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = set()
+    for h in ("dkgv.h", "dkgh.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(dkg[vh]_\w+)\s*\(", text))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = dk.load_library()
+    decl = declared_functions()
+    assert decl, "no declarations found"
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported by libdkgv.so"
+    assert decl == set(dk.DECLARED_SYMBOLS), decl ^ set(dk.DECLARED_SYMBOLS)
+
+
+def test_status_codes_match_header():
+    text = open(os.path.join(ROOT, "include", "dkgv.h")).read()
+    for name, val in re.findall(r"DKGV_(\w+) = (\d+)", text):
+        if name.startswith("DEC_"):
+            continue
+        assert dk.Status[name] == int(val)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dk.DkgvError):
+        dk.Verifier(0)
+
+
+def test_product_never_touches_the_oracle():
+    """nothing under dvt_circuits_b200/ or bench's b200 arm may import / link oracle/"""
+    for base, _, files in os.walk(os.path.join(ROOT, "dvt_circuits_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle/" not in text.replace("never the oracle/", "") and "liboracle" not in text and "oracle_lib" not in text, f

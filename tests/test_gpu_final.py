@@ -101,3 +101,41 @@ def test_agg_bad_point(verifier):
     vv[2, 1] = 0
     st, _, _ = verifier.agg_final_keys(vv, [1, 2, 3, 4])
     assert st == 48
+
+
+@pytest.mark.parametrize("n,t", [(8, 5), (48, 17)])
+def test_synthetic_finalization_properties(verifier, n, t):
+    """size-independent properties of a whole synthetic ceremony (config 4): every partial signature
+    verifies, the partial public keys equal the final keys K_j, and both Lagrange interpolations give
+    the aggregate key C_0 - then the same through the JSON flow (n <= 255 fits the reference format)."""
+    import json
+    import dvt_circuits_b200 as dk
+    from dvt_circuits_b200 import synthetic
+    f = synthetic.make_finalization(verifier, n, t)
+    st = verifier.bls_verify_batch(f["partial_pubkeys"], f["signatures"], f["hm"])
+    assert not st.any()
+    ast, co, keys = verifier.agg_final_keys(f["vv"], f["ids"])
+    assert ast == 0 and (keys == f["partial_pubkeys"]).all()
+    assert verifier.lagrange_at_zero(keys, f["ids"]) == (0, bytes(co[0]))
+    # a corrupted signature set: swap two signatures -> exactly those two checks fail
+    sig = f["signatures"].copy()
+    sig[[0, 1]] = sig[[1, 0]]
+    st = verifier.bls_verify_batch(f["partial_pubkeys"], sig, f["hm"])
+    assert st.tolist() == [7, 7] + [0] * (n - 2)
+    # JSON flow
+    gen_id = bytes(range(16))
+    gens = []
+    for i in range(n):
+        gens.append({"base_pubkeys": [bytes(p).hex() for p in f["vv"][i]],
+                     "base_hash": dk.initial_commitment_hash(gen_id, n, t, f["vv"][i]).hex(),
+                     "partial_pubkey": "", "message_cleartext": f["message"].decode(), "message_signature": ""})
+    # recipient ids follow the sorted base hashes: generation at sorted position p owns id p+1
+    order = sorted(range(n), key=lambda i: bytes.fromhex(gens[i]["base_hash"]))
+    for pos, i in enumerate(order):
+        gens[i]["partial_pubkey"] = bytes(f["partial_pubkeys"][pos]).hex()
+        gens[i]["message_signature"] = bytes(f["signatures"][pos]).hex()
+    # the aggregate key does not depend on which id a dealer holds
+    data = {"settings": {"n": n, "k": t, "gen_id": gen_id.hex()}, "generations": gens, "aggregate_pubkey": bytes(co[0]).hex()}
+    assert verifier.execute("finalization", json.dumps(data))[:2] == (0, 0)
+    data["aggregate_pubkey"] = bytes(co[1]).hex()
+    assert verifier.execute("finalization", json.dumps(data))[:2] == (1, 34)

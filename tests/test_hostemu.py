@@ -1,0 +1,124 @@
+"""CPU-only: the per-thread logic of the CUDA kernels (dvt_circuits_b200/csrc/*.cuh compiled for the
+host by tests/hostemu) against the oracles - field arithmetic, G1 formulas and codecs, the operand-file
+(vm.cuh) and 30-bit (vm30.cuh, with static bound checking) formulations of the share check, the tower,
+pairing and hash-to-G2.  The PTX carry-chain product itself is pinned by the -m gpu tests."""
+import ctypes
+import hashlib
+import os
+import random
+import subprocess
+
+import pytest
+
+import oracle_lib as O
+from oracle.pyref import bls12_381 as B
+from test_oracle import EVAL_PKS, EVAL_TARGET, KAT_BAD_SIG, KAT_MSG, KAT_PK, KAT_SIG
+
+H = bytes.fromhex
+
+
+@pytest.fixture(scope="module")
+def L():
+    path = os.path.join(O.ROOT, "tests", "hostemu", "libhostemu.so")
+    src = os.path.join(O.ROOT, "tests", "hostemu", "hostemu.cpp")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", path, src])
+    return ctypes.CDLL(path)
+
+
+def buf(n):
+    return ctypes.create_string_buffer(n)
+
+
+def test_field_ops(L):
+    rnd = random.Random(7)
+    for it in range(100):
+        a, b = rnd.randrange(B.P), rnd.randrange(B.P)
+        if it == 0:
+            a = 0
+        if it == 1:
+            a = b = B.P - 1
+        m, ad, sb, iv = buf(48), buf(48), buf(48), buf(48)
+        L.he_fp_ops(a.to_bytes(48, "big"), b.to_bytes(48, "big"), m, ad, sb, iv)
+        assert int.from_bytes(m.raw, "big") == a * b % B.P
+        assert int.from_bytes(ad.raw, "big") == (a + b) % B.P
+        assert int.from_bytes(sb.raw, "big") == (a - b) % B.P
+        assert int.from_bytes(iv.raw, "big") == pow(a, B.P - 2, B.P)
+        o = [buf(48) for _ in range(4)]
+        L.he_fp30_ops(a.to_bytes(48, "big"), b.to_bytes(48, "big"), *o)
+        assert int.from_bytes(o[0].raw, "big") == a * b % B.P
+        assert int.from_bytes(o[1].raw, "big") == (a + b) % B.P
+        assert int.from_bytes(o[2].raw, "big") == (a - b) % B.P
+        assert int.from_bytes(o[3].raw, "big") == 12 * ((a + b) + (b - a)) % B.P
+        x, y, r = rnd.randrange(B.R), rnd.randrange(B.R), buf(32)
+        L.he_fr_mul(x.to_bytes(32, "big"), y.to_bytes(32, "big"), r)
+        assert int.from_bytes(r.raw, "big") == x * y % B.R
+
+
+def test_g1_formulas_and_codec(L):
+    rnd = random.Random(3)
+    for it in range(6):
+        p = B.g1_mul(B.G1, rnd.randrange(B.R))
+        q = B.g1_mul(B.G1, rnd.randrange(B.R))
+        for x, y in [(p, q), (p, p), (p, B.E1.neg(p)), (None, q), (p, None), (None, None)]:
+            k = rnd.choice([0, 1, 2, 3, 5, 1023, 1024, 0xFFFFFFFF, rnd.randrange(2 ** 32)])
+            o = [buf(48) for _ in range(4)]
+            assert L.he_g1_ops(B.g1_compress(x), B.g1_compress(y), k, *o) == 0
+            assert o[0].raw == B.g1_compress(B.g1_add(x, y)) == o[1].raw
+            assert o[2].raw == B.g1_compress(B.g1_add(x, x))
+            assert o[3].raw == B.g1_compress(B.g1_mul(x, k))
+    o = buf(48)
+    for enc in (KAT_PK, bytes([0xC0]) + bytes(47), bytes(48), bytes([0xE0]) + bytes(47)):
+        assert L.he_g1_decompress(enc, o) == O.g1_decompress(enc)[0]
+    pb = bytearray(B.P.to_bytes(48, "big"))
+    pb[0] |= 0x80
+    assert L.he_g1_decompress(bytes(pb), o) == 2
+    x = 1
+    while True:  # on the curve, outside the subgroup (cf. report-1-bad-aggregate-pubkey)
+        yy = B.fp_sqrt((x ** 3 + 4) % B.P)
+        if yy is not None and not B.g1_in_subgroup((x, yy)):
+            break
+        x += 1
+    assert L.he_g1_decompress(B.g1_compress((x, yy)), o) == 4
+
+
+def test_share_check_all_formulations(L):
+    """he_share_check runs the inlined, operand-file and 30-bit variants and returns >= 0x100 on any
+    disagreement between them"""
+    ev, pk = buf(48), buf(48)
+    vv = b"".join(H(h) for h in EVAL_PKS)
+    assert L.he_share_check(vv, 3, 1, (5).to_bytes(32, "big"), ev, pk) == 4
+    assert ev.raw.hex() == EVAL_TARGET  # dkg_math.rs:281-298
+    assert pk.raw == B.g1_compress(B.g1_mul(B.G1, 5))
+    rnd = random.Random(11)
+    for t in (0, 1, 2, 6):
+        coef = [rnd.randrange(B.R) for _ in range(t)]
+        vv = b"".join(B.g1_compress(B.g1_mul(B.G1, c)) for c in coef)
+        for i in (0, 1, 2, 7, 1023, 1024, 0xFFFFFFFF):
+            s = sum(c * pow(i, k, B.R) for k, c in enumerate(coef)) % B.R
+            assert L.he_share_check(vv, t, i, s.to_bytes(32, "big"), ev, pk) == 0, (t, i)
+            assert L.he_share_check(vv, t, i, ((s + 1) % B.R).to_bytes(32, "big"), ev, pk) == 4
+        assert L.he_share_check(vv, t, 3, B.R.to_bytes(32, "big"), ev, pk) == 1
+
+
+def test_tower_pairing_h2c(L):
+    for m in (b"", b"abc", bytes(range(200))):
+        o = buf(32)
+        L.he_sha256(m, ctypes.c_size_t(len(m)), o)
+        assert o.raw == hashlib.sha256(m).digest()
+    for m in (b"Sign with new partial key", KAT_MSG, b"", b"x" * 300):
+        o = buf(96)
+        L.he_hash_to_g2(m, ctypes.c_size_t(len(m)), o)
+        assert o.raw == O.hash_to_g2(m)
+    o = buf(96)
+    assert L.he_g2_decompress(KAT_SIG, o) == 0 and o.raw == KAT_SIG
+    assert L.he_g2_decompress(bytes(96), o) == 1
+    hm = O.hash_to_g2(KAT_MSG)
+    assert L.he_bls_verify_hm(KAT_PK, KAT_SIG, hm) == 1  # dkg_math.rs:259-278
+    assert L.he_bls_verify_hm(KAT_PK, KAT_BAD_SIG, hm) == 0
+    assert L.he_bls_verify_hm(KAT_PK, KAT_SIG, O.hash_to_g2(b"\x00")) == 0
+    inf1, inf2 = bytes([0xC0]) + bytes(47), bytes([0xC0]) + bytes(95)
+    assert L.he_bls_verify_hm(inf1, inf2, hm) == 1 and L.he_bls_verify_hm(inf1, KAT_SIG, hm) == 0
+    a = buf(576)
+    assert L.he_pairing_bytes(KAT_PK, KAT_SIG, a) == 0
+    assert O.pairing_bytes(KAT_PK, KAT_SIG) == (0, a.raw)

@@ -1,0 +1,55 @@
+"""CPU-only, world_size 2 over gloo: the host-side sharding logic of the N>1 path - row-block
+partition of the dealer matrix, deterministic per-dealer synthetic rows, all-gather of the verdict
+bytes into the full matrix (what bench.py does with NCCL on the GPUs)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, n, t, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dvt_circuits_b200 import synthetic
+    rows = n // world
+    # each rank builds only its dealers' coefficient rows; they must equal the single-process rows
+    mine = synthetic.make_coefficients(rows, t, dealer_offset=rank * rows)
+    full = synthetic.make_coefficients(n, t)
+    ok = bool((mine == full[rank * rows:(rank + 1) * rows]).all())
+    # verdict bytes: rank r reports (dealer + recipient) % 7 for its rows; gather in rank order
+    d = np.arange(rank * rows, (rank + 1) * rows)[:, None]
+    local = torch.from_numpy(((d + np.arange(n)[None, :]) % 7).astype(np.uint8))
+    out = torch.empty((n, n), dtype=torch.uint8)
+    dist.all_gather_into_tensor(out, local)
+    exp = ((np.arange(n)[:, None] + np.arange(n)[None, :]) % 7).astype(np.uint8)
+    ok = ok and bool((out.numpy() == exp).all())
+    # max-over-ranks timing reduction used by bench.py
+    tms = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ok = ok and float(tms.item()) == 10.0 + world - 1
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_row_block_sharding_and_gather():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 8, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
