@@ -46,7 +46,8 @@ def corrupt_shares(shares, p_bad, seed=DEFAULT_SEED):
         if k == 0 or n_d == 1 and k == 1:
             b = int(bit[d, j])
             out[d, j, 31 - b // 8] ^= 1 << (b % 8)
-            expected[d, j] = 4
+            # a flipped bit can push the value past r (probability ~1e-4): then the range check fires first
+            expected[d, j] = 4 if int.from_bytes(out[d, j].tobytes(), "big") < R_INT else 1
         elif k == 1:
             out[d, j] = shares[(d + 1) % n_d, j]
             expected[d, j] = 4 if (shares[(d + 1) % n_d, j] != shares[d, j]).any() else 0
