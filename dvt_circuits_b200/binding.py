@@ -24,6 +24,7 @@ class Status(enum.IntEnum):
     SLASHABLE_BAD_SIG = 6
     SLASHABLE_SIG_INVALID = 7
     SLASHABLE_KEY_MISMATCH = 8
+    SLASHABLE_BAD_ENCRYPTED_MSG = 9
     UNSLASHABLE_COMMIT_SIG = 16
     UNSLASHABLE_COMMIT_HASH = 17
     UNSLASHABLE_GEN_HASH = 18
@@ -61,6 +62,7 @@ DECLARED_SYMBOLS = {
     "dkgv_feldman_eval": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_g1_fixed_base_mul": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_g1_decompress_check": (ctypes.c_int, [_vp, _u32, _vp, _vp]),
+    "dkgv_g1_mul_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_fr_poly_eval": (ctypes.c_int, [_vp, _u32, _u32, _vp, _u32, _vp, _vp]),
     "dkgv_agg_final_keys": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_lagrange_at_zero": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp, _vp]),
@@ -70,6 +72,7 @@ DECLARED_SYMBOLS = {
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_g2_mul_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
+    "dkgv_initial_commitment_hashes": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, ctypes.c_uint8, ctypes.c_uint8, _vp]),
     # include/dkgh.h
     "dkgh_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                     ctypes.c_char_p, ctypes.c_size_t]),
@@ -186,6 +189,14 @@ class Verifier:
         self._ck(self._lib.dkgv_g1_fixed_base_mul(self._h, m, _p(scalars), _p(out), _p(st)))
         return out, st
 
+    def g1_mul_batch(self, pts, scalars):
+        pts = np.ascontiguousarray(pts, dtype=np.uint8).reshape(-1, 48)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1, 32)
+        out = np.zeros((pts.shape[0], 48), dtype=np.uint8)
+        st = np.zeros((pts.shape[0],), dtype=np.uint8)
+        self._ck(self._lib.dkgv_g1_mul_batch(self._h, pts.shape[0], _p(pts), _p(scalars), _p(out), _p(st)))
+        return out, st
+
     def g1_decompress_check(self, pts):
         pts = _host(pts, np.uint8)
         m = pts.shape[0]
@@ -260,6 +271,14 @@ class Verifier:
         self._ck(self._lib.dkgv_bls_verify_batch(self._h, pk.shape[0], _p(pk), _p(sig), hm.shape[0], _p(hm),
                                                  _p(idx) if idx is not None else None, _p(st)))
         return st
+
+    def initial_commitment_hashes(self, vv, gen_id, n, k):
+        """base hashes of all dealers at once: vv [n_d, t, 48] -> [n_d, 32]"""
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        gid = np.frombuffer(bytes(gen_id), dtype=np.uint8)
+        out = np.zeros((vv.shape[0], 32), dtype=np.uint8)
+        self._ck(self._lib.dkgv_initial_commitment_hashes(self._h, vv.shape[0], vv.shape[1], _p(vv), _p(gid), n & 0xFF, k & 0xFF, _p(out)))
+        return out
 
     def g2_mul_batch(self, base96, scalars):
         scalars = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1, 32)

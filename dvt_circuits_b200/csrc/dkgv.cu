@@ -109,6 +109,10 @@ k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_
   uint32_t d = blockIdx.x * 32 + lane;
   uint32_t j = blockIdx.y * (SVM_NT / 32) + warp;
   if (j >= n_r) return;
+  // blocks are dispatched in increasing blockIdx; recipient ids usually ascend (1..n) and the chain
+  // for a larger id is longer, so walk the columns from the back: expensive units first, cheap ones
+  // fill the tail of the last wave (longest-processing-time-first)
+  j = n_r - 1 - j;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
 #ifdef DKGV_HOT_FP30

@@ -67,7 +67,7 @@ DKGV_D void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
 #endif
 
 template <class PR>
-struct Mont {
+struct alignas(16) Mont {
   static constexpr int N = PR::N;
   uint32_t l[N];
 };

@@ -171,6 +171,36 @@ k_lagrange_terms(const uint8_t* __restrict__ pts, const uint32_t* __restrict__ w
   }
 }
 
+// BlsG1::mul_scalar (crates/dkg/src/dkg_math.rs:122-127) for m independent (point, scalar) pairs:
+// out[i] = compress([s_i] P_i); status OK / PANIC_BAD_G1 (P_i undecodable) / PANIC_BAD_SCALAR (s_i >= r)
+__global__ void __launch_bounds__(64)
+k_g1_mul_batch(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, uint8_t* __restrict__ out, uint8_t* __restrict__ status,
+               uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G1Aff y;
+  uint32_t s[8];
+  bool pt_ok = g1_decompress(pts + (size_t)i * 48, &y, true) == G1_DEC_OK;
+  bool sc_ok = fr_raw_from_be32(s, scalars + (size_t)i * 32);
+  G1Proj base = g1_from_affine(y), acc = g1_identity();
+  bool started = false;
+#pragma unroll 1
+  for (int l = 7; l >= 0; l--) {
+#pragma unroll 1
+    for (int b = 31; b >= 0; b--) {
+      if (started) acc = g1_dbl(acc);
+      if ((s[l] >> b) & 1) {
+        acc = started ? g1_add(acc, base) : base;
+        started = true;
+      }
+    }
+  }
+  uint8_t enc[48];
+  g1_compress(g1_to_affine(acc), enc);
+  for (int k = 0; k < 48; k++) out[(size_t)i * 48 + k] = (pt_ok && sc_ok) ? enc[k] : 0;
+  status[i] = !sc_ok ? DKGV_PANIC_BAD_SCALAR : (!pt_ok ? DKGV_PANIC_BAD_G1 : DKGV_OK);
+}
+
 // sum of k projective points (one warp) -> 48-byte encoding
 __global__ void __launch_bounds__(32) k_sum_points(const uint32_t* __restrict__ partial, uint32_t k, uint8_t* __restrict__ out) {
   uint32_t lane = threadIdx.x;
@@ -300,4 +330,26 @@ extern "C" int dkgv_eval_points(dkgv_ctx* ctx, uint32_t t, const uint8_t* coeffs
   if ((t && !coeffs) || !ids || !out) return dkgv_fail(ctx, "null pointer argument");
   // a one-"dealer" session: decode + column sum over a single row is the identity map
   return dkgv_agg_final_keys(ctx, 1, t, coeffs, ids, n_ids, nullptr, out, status);
+}
+
+extern "C" int dkgv_g1_mul_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pts, const uint8_t* scalars, uint8_t* out, uint8_t* status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (!pts || !scalars || !out || !status) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  CK(ctx->in_a.reserve((size_t)m * 48));
+  CK(ctx->in_b.reserve((size_t)m * 32));
+  CK(ctx->out_a.reserve((size_t)m * 48));
+  CK(ctx->out_b.reserve(m));
+  CK(cudaMemcpyAsync(ctx->in_a.p, pts, (size_t)m * 48, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, scalars, (size_t)m * 32, cudaMemcpyHostToDevice, s));
+  k_g1_mul_batch<<<(m + 63) / 64, 64, 0, s>>>((const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p,
+                                             (uint8_t*)ctx->out_b.p, m);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)m * 48, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status, ctx->out_b.p, m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
 }

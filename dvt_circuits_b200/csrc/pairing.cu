@@ -1,6 +1,8 @@
 // BLS partial-signature checks on the GPU (C ABI part 2): G2 decoding, hash-to-G2 and the batched
 // pairing-equality kernel.  Replaces crates/dkg/src/crypto/bls_common.rs:11-40 and the signature
 // loop of verify_generation_hashes (crates/dkg/src/verification.rs:237-248).
+#include <cstring>
+
 #include "ctx.hpp"
 #include "h2c.cuh"
 
@@ -82,6 +84,29 @@ __global__ void __launch_bounds__(32) k_g2_mul_batch(const uint8_t* __restrict__
   uint8_t enc[96];
   g2_compress(&a, enc);
   for (int k = 0; k < 96; k++) out[(size_t)i * 96 + k] = enc[k];
+}
+
+// base_hash_d = SHA-256(gen_id(16) || n || k || len as u8 || vv[d][0..t))  (verification.rs:151-175);
+// one thread per dealer, 48*t + 19 byte preimage streamed from HBM
+__global__ void __launch_bounds__(64) k_initial_commitment_hashes(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t,
+                                                                  const uint8_t* __restrict__ hdr19, uint8_t* __restrict__ out) {
+  uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_d) return;
+  Sha256 s;
+  sha_init(&s);
+  uint8_t h[19];
+  for (int i = 0; i < 19; i++) h[i] = hdr19[i];
+  sha_update(&s, h, 19);
+  const uint8_t* row = vv + (size_t)d * t * 48;
+  uint8_t chunk[48];
+#pragma unroll 1
+  for (uint32_t k = 0; k < t; k++) {
+    for (int i = 0; i < 48; i++) chunk[i] = row[(size_t)k * 48 + i];
+    sha_update(&s, chunk, 48);
+  }
+  uint8_t dg[32];
+  sha_finish(&s, dg);
+  for (int i = 0; i < 32; i++) out[(size_t)d * 32 + i] = dg[i];
 }
 
 static int ensure_stack(dkgv_ctx* ctx) {
@@ -200,6 +225,34 @@ extern "C" int dkgv_g2_mul_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* base9
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)m * 96, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_initial_commitment_hashes(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* vv, const uint8_t* gen_id16,
+                                              uint8_t n, uint8_t k, uint8_t* out) {
+  if (!ctx) return -1;
+  if (n_dealers == 0) return 0;
+  if ((t && !vv) || !gen_id16 || !out) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure_stack(ctx)) return rc;
+  cudaStream_t s = ctx->stream;
+  size_t vvb = (size_t)n_dealers * t * 48;
+  uint8_t hdr[19];
+  memcpy(hdr, gen_id16, 16);
+  hdr[16] = n;
+  hdr[17] = k;
+  hdr[18] = (uint8_t)t;  // `len as u8` truncation of the reference
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->in_b.reserve(32));
+  CK(ctx->out_a.reserve((size_t)n_dealers * 32));
+  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, hdr, 19, cudaMemcpyHostToDevice, s));
+  k_initial_commitment_hashes<<<(n_dealers + 63) / 64, 64, 0, s>>>((const uint8_t*)ctx->in_a.p, n_dealers, t, (const uint8_t*)ctx->in_b.p,
+                                                                 (uint8_t*)ctx->out_a.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)n_dealers * 32, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
 }

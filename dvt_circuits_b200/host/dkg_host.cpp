@@ -325,6 +325,127 @@ struct Host {
   }
 };
 
+// RFC 8439 ChaCha20 keystream XOR (32-byte key, 12-byte nonce, counter from 0), as the `chacha20` crate
+static void chacha20_xor(const uint8_t* key, const uint8_t* nonce, Bytes& data) {
+  auto rotl = [](uint32_t v, int n) { return (v << n) | (v >> (32 - n)); };
+  auto ld = [](const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; };
+  uint32_t init[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+  for (int i = 0; i < 8; i++) init[4 + i] = ld(key + 4 * i);
+  for (int i = 0; i < 3; i++) init[13 + i] = ld(nonce + 4 * i);
+  for (size_t blk = 0; blk * 64 < data.size(); blk++) {
+    init[12] = (uint32_t)blk;
+    uint32_t x[16];
+    memcpy(x, init, sizeof x);
+    auto qr = [&](int a, int b, int c, int d) {
+      x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16);
+      x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+      x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
+      x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    };
+    for (int r = 0; r < 10; r++) {
+      qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+      qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) {
+      uint32_t w = x[i] + init[i];
+      for (int b = 0; b < 4; b++) {
+        size_t pos = blk * 64 + 4 * i + b;
+        if (pos < data.size()) data[pos] ^= (uint8_t)(w >> (8 * b));
+      }
+    }
+  }
+}
+
+// ---- guest 3 (crates/bad_encrypted_share_prove/src/main.rs:281-405), quirk Q2 kept:
+// once the decrypted message parses, every path ends in the final panic (exit 1)
+static int guest_bad_encrypted_share(Host& h, const Json& data, int* exit_code) {
+  *exit_code = 1;
+  const Setup& su = h.su;
+  (void)hex_fixed(data.at("sender_pubkey"), su.id_pk(), "sender_pubkey");  // deserialised, never read
+  Bytes sender_encr_pubkey = hex_fixed(data.at("sender_encr_pubkey"), 48, "sender_encr_pubkey");
+  Bytes receiver_sk = hex_fixed(data.at("receiver_encr_seckey"), 32, "receiver_encr_seckey");
+  const Json& ej = data.at("encrypted_data");
+  if (ej.kind != Json::Str) throw std::runtime_error("encrypted_data: expected a string");
+  Settings st = parse_settings(data.at("settings"));
+  std::vector<Bytes> hashes = parse_hex_list(data.at("base_hashes"), 32, "base_hashes");
+  std::vector<Bytes> sender_pks = parse_hex_list(data.at("sender_base_pubkeys"), 48, "sender_base_pubkeys");
+  std::vector<Bytes> receiver_pks = parse_hex_list(data.at("receiver_base_pubkeys"), 48, "receiver_base_pubkeys");
+  Bytes sender_hash = compute_initial_commitment_hash(st, sender_pks);
+  if (std::find(hashes.begin(), hashes.end(), sender_hash) == hashes.end()) throw Panic{DKGV_PANIC_PRECHECK};
+  Bytes receiver_hash = compute_initial_commitment_hash(st, receiver_pks);
+  if (std::find(hashes.begin(), hashes.end(), receiver_hash) == hashes.end()) throw Panic{DKGV_PANIC_PRECHECK};
+  uint8_t rpk[48], pst = 0;
+  h.ck(dkgv_g1_fixed_base_mul(h.ctx, 1, receiver_sk.data(), rpk, &pst));
+  if (pst != DKGV_OK) throw Panic{DKGV_PANIC_BAD_SCALAR};  // .expect("Invalid seckey")
+  if (receiver_pks.empty()) throw Panic{DKGV_PANIC_INDEX};
+  if (Bytes(rpk, rpk + 48) != *std::max_element(receiver_pks.begin(), receiver_pks.end())) throw Panic{DKGV_PANIC_PRECHECK};
+  if (sender_pks.empty()) throw Panic{DKGV_PANIC_INDEX};
+  if (sender_encr_pubkey != *std::max_element(sender_pks.begin(), sender_pks.end())) throw Panic{DKGV_PANIC_PRECHECK};
+  if (hashes.size() != st.n || st.n < st.k) throw Panic{DKGV_PANIC_PRECHECK};
+  // ECDH on the GPU: P = their * our
+  uint8_t shared[48], mst = 0;
+  h.ck(dkgv_g1_mul_batch(h.ctx, 1, sender_encr_pubkey.data(), receiver_sk.data(), shared, &mst));
+  if (mst != DKGV_OK) throw Panic{mst};
+  Sha256 kh;
+  kh.update(shared, 48);
+  Bytes digest = kh.finish();  // key = digest, nonce = its first 12 bytes (salts are commented out upstream)
+  const std::string& hexs = ej.str;
+  if (hexs.size() % 2) throw Panic{DKGV_PANIC_PRECHECK};
+  Bytes msg(hexs.size() / 2);
+  for (size_t i = 0; i < msg.size(); i++) {
+    int a = hexv(hexs[2 * i]), b = hexv(hexs[2 * i + 1]);
+    if (a < 0 || b < 0) throw Panic{DKGV_PANIC_PRECHECK};  // hex::decode(...).expect
+    msg[i] = (uint8_t)(a * 16 + b);
+  }
+  chacha20_xor(digest.data(), digest.data(), msg);
+  size_t want = 16 + 1 + 32 + (su.auth ? 32 + su.id_pk() + su.id_sig() : su.id_pk());
+  if (msg.size() < want) {  // ReadError -> commit + return
+    *exit_code = 0;
+    return DKGV_SLASHABLE_BAD_ENCRYPTED_MSG;
+  }
+  if (msg.size() > want) throw Panic{DKGV_PANIC_PRECHECK};  // stream.finalize() assert
+  if (!std::equal(st.gen_id.begin(), st.gen_id.end(), msg.begin()) || msg[16] != 3) {
+    *exit_code = 0;
+    return DKGV_SLASHABLE_BAD_ENCRYPTED_MSG;
+  }
+  // rebuild the SharedData the guest hands to verify_seed_exchange_commitment
+  auto hexs_of = [](const uint8_t* p, size_t n) {
+    static const char* d = "0123456789abcdef";
+    std::string o;
+    for (size_t i = 0; i < n; i++) {
+      o += d[p[i] >> 4];
+      o += d[p[i] & 15];
+    }
+    return o;
+  };
+  Json se;
+  se.kind = Json::Obj;
+  auto S = [](const std::string& v) {
+    Json j;
+    j.kind = Json::Str;
+    j.str = v;
+    return j;
+  };
+  Json ss;
+  ss.kind = Json::Obj;
+  ss.obj.emplace_back("shared_secret", S(hexs_of(msg.data() + 17, 32)));
+  ss.obj.emplace_back("dst_base_hash", S(hexs_of(receiver_hash.data(), 32)));
+  Json cm;
+  cm.kind = Json::Obj;
+  if (su.auth) {
+    cm.obj.emplace_back("hash", S(hexs_of(msg.data() + 49, 32)));
+    cm.obj.emplace_back("pubkey", S(hexs_of(msg.data() + 81, su.id_pk())));
+    cm.obj.emplace_back("signature", S(hexs_of(msg.data() + 81 + su.id_pk(), su.id_sig())));
+  } else {
+    cm.obj.emplace_back("pubkey", S(hexs_of(msg.data() + 49, su.id_pk())));
+  }
+  se.obj.emplace_back("initial_commitment_hash", S(hexs_of(sender_hash.data(), 32)));
+  se.obj.emplace_back("ssecret", ss);
+  se.obj.emplace_back("commitment", cm);
+  // verify_initial_commitment_hash is true by construction (the hash was just computed from these fields)
+  return h.verify_seed_exchange_commitment(hashes, se, sender_pks);  // exit stays 1 (Q2)
+}
+
 static bool is_slashable(int s) { return s >= 1 && s < 16; }
 
 }  // namespace dkgh
@@ -355,6 +476,8 @@ int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int aut
     } else if (ty == "bad-partial-key") {
       st = h.prove_wrong_final_key_generation(data);
       code = is_slashable(st) ? 0 : 1;
+    } else if (ty == "bad-encrypted-share") {
+      st = guest_bad_encrypted_share(h, data, &code);
     } else {
       m = "unknown type";
     }

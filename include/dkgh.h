@@ -16,6 +16,7 @@ extern "C" {
  *   type = "bad-share"        crates/bad_share_exchange_prove/src/main.rs:16-82
  *        | "finalization"     crates/finalization_prove/src/main.rs:7-33   (BLS identity setup, as the reference)
  *        | "bad-partial-key"  crates/bad_parial_key_prove/src/main.rs:16-51
+ *        | "bad-encrypted-share" crates/bad_encrypted_share_prove/src/main.rs:281-405 (incl. quirk Q2)
  *   auth = cargo feature auth_commitment; bls_identity = BlsDkgWithBlsCommitment instead of secp256k1.
  * Returns the reference's process exit code (0 = misbehaviour proven / ceremony valid, 1 otherwise);
  * *status = dkgv_status reached, or 255 when the input is rejected while parsing (serde error).   */

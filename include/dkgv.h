@@ -38,6 +38,7 @@ enum dkgv_status {
   DKGV_SLASHABLE_BAD_SIG = 6,        /* verification.rs:448-454 message_signature undecodable    */
   DKGV_SLASHABLE_SIG_INVALID = 7,    /* verification.rs:456-461 pairing check false              */
   DKGV_SLASHABLE_KEY_MISMATCH = 8,   /* verification.rs:413-418 expected key != partial key (Q1) */
+  DKGV_SLASHABLE_BAD_ENCRYPTED_MSG = 9, /* bad_encrypted_share_prove/main.rs:359-369 decrypted message does not parse */
   DKGV_UNSLASHABLE_COMMIT_SIG = 16,  /* verification.rs:76-89, 488-493 identity signature        */
   DKGV_UNSLASHABLE_COMMIT_HASH = 17, /* verification.rs:470-477                                  */
   DKGV_UNSLASHABLE_GEN_HASH = 18,    /* verification.rs:250-257, 388-393                         */
@@ -96,6 +97,11 @@ int dkgv_feldman_eval(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_ids, uint32_
 /* out[i] = compress(G * scalars[i]); status OK / SLASHABLE_SECRET_RANGE (scalar >= r)           */
 int dkgv_g1_fixed_base_mul(dkgv_ctx* ctx, uint32_t m, const uint8_t* scalars, uint8_t* out, uint8_t* status);
 
+/* ---- P * s (BlsG1::mul_scalar, crates/dkg/src/dkg_math.rs:122-127; the ECDH step of
+ *      crates/bad_encrypted_share_prove/src/main.rs:339-342), m independent pairs ----------------- */
+/* out[i] = compress([scalars[i]] pts[i]); status OK / PANIC_BAD_G1 / PANIC_BAD_SCALAR (scalar >= r) */
+int dkgv_g1_mul_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pts, const uint8_t* scalars, uint8_t* out, uint8_t* status);
+
 /* ---- G1 decoding with subgroup check (to_g1_affine, crypto/bls_common.rs:108-112) ----------- */
 int dkgv_g1_decompress_check(dkgv_ctx* ctx, uint32_t m, const uint8_t* in, uint8_t* decode_status);
 
@@ -127,6 +133,11 @@ int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pk, const ui
                           const uint32_t* hm_idx, uint8_t* status);
 int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
                               const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status, void* stream);
+
+/* ---- initial-commitment hashes (crates/dkg/src/verification.rs:151-175) on the GPU ------------- */
+/* out[d] = SHA-256(gen_id(16) || n || k || (t as u8) || vv[d][0..t)), one per dealer, out [n_dealers][32] */
+int dkgv_initial_commitment_hashes(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* vv, const uint8_t* gen_id16,
+                                   uint8_t n, uint8_t k, uint8_t* out);
 
 /* ---- dealer-side helper for building synthetic ceremonies (not a verification step) --------- */
 /* out[d][j] = sum_k coeffs[d][k] * ids[j]^k mod r ; coeffs [n_dealers][t][32] BE (< r), out BE   */

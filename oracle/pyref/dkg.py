@@ -423,3 +423,94 @@ def guest_bad_partial_key(setup, data, detail=None):
     except Panic as e:
         return e.code, 1
     return s, (0 if is_slashable(s) else 1)
+
+
+# ----------------------------------------------------------------------------- bad-encrypted-share guest
+SLASHABLE_BAD_ENCRYPTED_MSG = 9
+STATUS_NAMES[SLASHABLE_BAD_ENCRYPTED_MSG] = "SLASHABLE_BAD_ENCRYPTED_MSG"
+
+
+def chacha20_xor(key, nonce, data, counter=0):
+    """RFC 8439 ChaCha20 (32-byte key, 12-byte nonce, 32-bit block counter)."""
+    def rotl(v, n):
+        return ((v << n) & 0xFFFFFFFF) | (v >> (32 - n))
+
+    def qr(s, a, b, c, d):
+        s[a] = (s[a] + s[b]) & 0xFFFFFFFF; s[d] = rotl(s[d] ^ s[a], 16)
+        s[c] = (s[c] + s[d]) & 0xFFFFFFFF; s[b] = rotl(s[b] ^ s[c], 12)
+        s[a] = (s[a] + s[b]) & 0xFFFFFFFF; s[d] = rotl(s[d] ^ s[a], 8)
+        s[c] = (s[c] + s[d]) & 0xFFFFFFFF; s[b] = rotl(s[b] ^ s[c], 7)
+
+    out = bytearray()
+    k = [int.from_bytes(key[4 * i:4 * i + 4], "little") for i in range(8)]
+    nn = [int.from_bytes(nonce[4 * i:4 * i + 4], "little") for i in range(3)]
+    for blk in range((len(data) + 63) // 64):
+        init = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + k + [(counter + blk) & 0xFFFFFFFF] + nn
+        s = list(init)
+        for _ in range(10):
+            qr(s, 0, 4, 8, 12); qr(s, 1, 5, 9, 13); qr(s, 2, 6, 10, 14); qr(s, 3, 7, 11, 15)
+            qr(s, 0, 5, 10, 15); qr(s, 1, 6, 11, 12); qr(s, 2, 7, 8, 13); qr(s, 3, 4, 9, 14)
+        ks = b"".join(((s[i] + init[i]) & 0xFFFFFFFF).to_bytes(4, "little") for i in range(16))
+        chunk = data[64 * blk:64 * blk + 64]
+        out += bytes(x ^ y for x, y in zip(chunk, ks))
+    return bytes(out)
+
+
+def guest_bad_encrypted_share(setup, data, detail=None):
+    """crates/bad_encrypted_share_prove/src/main.rs:281-405 -> (status, exit_code).
+    Quirk Q2 kept: once the message parses, every path ends in the final panic (exit 1)."""
+    try:
+        st = data["settings"]
+        sender_hash = compute_initial_commitment_hash(st, data["sender_base_pubkeys"])
+        hashes = [hx(h) for h in data["base_hashes"]]
+        if sender_hash not in hashes:
+            raise Panic(PANIC_PRECHECK)
+        receiver_hash = compute_initial_commitment_hash(st, data["receiver_base_pubkeys"])
+        if receiver_hash not in hashes:
+            raise Panic(PANIC_PRECHECK)
+        sk = B.fr_from_be(hx(data["receiver_encr_seckey"]))
+        if sk is None:
+            raise Panic(PANIC_BAD_SCALAR)
+        rpk = B.g1_compress(B.g1_mul(B.G1, sk))
+        if not data["receiver_base_pubkeys"]:
+            raise Panic(PANIC_INDEX)
+        if rpk != max(hx(p) for p in data["receiver_base_pubkeys"]):
+            raise Panic(PANIC_PRECHECK)
+        if not data["sender_base_pubkeys"]:
+            raise Panic(PANIC_INDEX)
+        if hx(data["sender_encr_pubkey"]) != max(hx(p) for p in data["sender_base_pubkeys"]):
+            raise Panic(PANIC_PRECHECK)
+        if len(hashes) != st["n"] or st["n"] < st["k"]:
+            raise Panic(PANIC_PRECHECK)
+        their = g1_from_bytes_expect(hx(data["sender_encr_pubkey"]))
+        shared = B.g1_compress(B.g1_mul(their, sk))
+        digest = hashlib.sha256(shared).digest()
+        try:
+            enc = bytes.fromhex(data["encrypted_data"])
+        except ValueError:
+            raise Panic(PANIC_PRECHECK)
+        msg = chacha20_xor(digest, digest[:12], enc)
+        if detail is not None:
+            detail["ecdh"] = shared.hex()
+            detail["plaintext_prefix"] = msg[:17].hex()
+        idlen = 33 if setup.identity == "secp256k1" else 48
+        siglen = 64 if setup.identity == "secp256k1" else 96
+        want = 16 + 1 + 32 + (32 + idlen + siglen if setup.auth else idlen)
+        if len(msg) < want:
+            return SLASHABLE_BAD_ENCRYPTED_MSG, 0          # ReadError -> commit + return
+        if len(msg) > want:
+            raise Panic(PANIC_PRECHECK)                    # stream.finalize() assert
+        gen_id, mtype, secret = msg[:16], msg[16], msg[17:49]
+        if gen_id != hx(st["gen_id"]) or mtype != 3:
+            return SLASHABLE_BAD_ENCRYPTED_MSG, 0
+        if setup.auth:
+            commitment = {"hash": msg[49:81].hex(), "pubkey": msg[81:81 + idlen].hex(), "signature": msg[81 + idlen:].hex()}
+        else:
+            commitment = {"pubkey": msg[49:].hex()}
+        seed = {"initial_commitment_hash": sender_hash.hex(),
+                "ssecret": {"shared_secret": secret.hex(), "dst_base_hash": receiver_hash.hex()}, "commitment": commitment}
+        ic = {"hash": sender_hash.hex(), "settings": st, "base_pubkeys": data["sender_base_pubkeys"]}
+        s = verify_seed_exchange_commitment(setup, data["base_hashes"], seed, ic, detail)
+        return s, 1                                        # Q2: falls through to the final panic
+    except Panic as e:
+        return e.code, 1

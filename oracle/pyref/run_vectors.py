@@ -21,6 +21,8 @@ def run_one(kind, auth, scenario, identity):
         st, code = D.guest_finalization(setup, scenario, detail)
     elif kind == "wrong_final_key_generation":
         st, code = D.guest_bad_partial_key(setup, scenario, detail)
+    elif kind == "bad_encrypted_share":
+        st, code = D.guest_bad_encrypted_share(setup, scenario, detail)
     else:
         raise KeyError(kind)
     return st, code, detail
@@ -30,8 +32,10 @@ def main(ref_root, out_path):
     out = {"vectors": [], "examples": []}
     bad = 0
     for mode in ("auth", "no_auth"):
-        for kind in ("share", "finalization", "wrong_final_key_generation"):
+        for kind in ("share", "finalization", "wrong_final_key_generation", "bad_encrypted_share"):
             d = os.path.join(ref_root, "test_vectors", mode, kind)
+            if not os.path.isdir(d):
+                continue
             for fn in sorted(os.listdir(d)):
                 j = json.load(open(os.path.join(d, fn)))
                 t = time.time()

@@ -139,3 +139,17 @@ def test_synthetic_finalization_properties(verifier, n, t):
     assert verifier.execute("finalization", json.dumps(data))[:2] == (0, 0)
     data["aggregate_pubkey"] = bytes(co[1]).hex()
     assert verifier.execute("finalization", json.dumps(data))[:2] == (1, 34)
+
+
+def test_initial_commitment_hashes(verifier):
+    import hashlib
+    import dvt_circuits_b200 as dk
+    from dvt_circuits_b200 import synthetic
+    gen_id = bytes(range(16))
+    for n, t in ((5, 3), (70, 43), (3, 300)):
+        vv = synthetic.make_session(verifier, n, 1, t)["vv"]
+        out = verifier.initial_commitment_hashes(vv, gen_id, n, t)
+        for d in range(n):
+            exp = hashlib.sha256(gen_id + bytes([n & 0xFF, t & 0xFF, t & 0xFF]) + vv[d].tobytes()).digest()
+            assert bytes(out[d]) == exp
+            assert dk.initial_commitment_hash(gen_id, n, t, vv[d]) == exp

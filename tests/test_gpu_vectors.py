@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VEC = os.path.join(ROOT, "tests", "golden", "reference_vectors")
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "vector_outcomes.json")))
-TYPE = {"share": "bad-share", "finalization": "finalization", "wrong_final_key_generation": "bad-partial-key"}
+TYPE = {"share": "bad-share", "finalization": "finalization", "wrong_final_key_generation": "bad-partial-key",
+        "bad_encrypted_share": "bad-encrypted-share"}
 
 
 @pytest.mark.parametrize("entry", GOLD["vectors"], ids=lambda e: e["file"])
