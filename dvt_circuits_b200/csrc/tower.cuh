@@ -51,54 +51,56 @@ template <uint32_t (*F0)(int), uint32_t (*F1)(int)>
 DKGV_HD Fp2 fp2_const() {
   return Fp2{fp_const<F0>(), fp_const<F1>()};
 }
+// The Fp2 layer computes in registers: each routine loads its operands once, runs the (independent)
+// Fp products with the inlined carry-chain code - three of them interleave in fp2_mul - and stores
+// once.  Only Fp2 values travel through local memory; profiles/r1_bls_verify.md has the before/after.
 DKGV_NI2 void fp2_add(Fp2* r, const Fp2* a, const Fp2* b) {
-  fpa(&r->c0, &a->c0, &b->c0);
-  fpa(&r->c1, &a->c1, &b->c1);
+  Fp x = add(a->c0, b->c0), y = add(a->c1, b->c1);
+  r->c0 = x;
+  r->c1 = y;
 }
 DKGV_NI2 void fp2_sub(Fp2* r, const Fp2* a, const Fp2* b) {
-  fps(&r->c0, &a->c0, &b->c0);
-  fps(&r->c1, &a->c1, &b->c1);
+  Fp x = sub(a->c0, b->c0), y = sub(a->c1, b->c1);
+  r->c0 = x;
+  r->c1 = y;
 }
 DKGV_NI2 void fp2_neg(Fp2* r, const Fp2* a) {
-  Fp z = zero<FpParams>();
-  fps(&r->c0, &z, &a->c0);
-  fps(&r->c1, &z, &a->c1);
+  Fp x = neg(a->c0), y = neg(a->c1);
+  r->c0 = x;
+  r->c1 = y;
 }
-DKGV_NI2 void fp2_dbl(Fp2* r, const Fp2* a) { fp2_add(r, a, a); }
+DKGV_NI2 void fp2_dbl(Fp2* r, const Fp2* a) {
+  Fp x = dbl(a->c0), y = dbl(a->c1);
+  r->c0 = x;
+  r->c1 = y;
+}
 DKGV_NI2 void fp2_mul(Fp2* r, const Fp2* a, const Fp2* b) {  // Karatsuba, 3 M
-  Fp t0, t1, t2, s0, s1;
-  fpm(&t0, &a->c0, &b->c0);
-  fpm(&t1, &a->c1, &b->c1);
-  fpa(&s0, &a->c0, &a->c1);
-  fpa(&s1, &b->c0, &b->c1);
-  fpm(&t2, &s0, &s1);
-  fps(&r->c0, &t0, &t1);
-  fps(&t2, &t2, &t0);
-  fps(&r->c1, &t2, &t1);
+  Fp a0 = a->c0, a1 = a->c1, b0 = b->c0, b1 = b->c1;
+  Fp t0 = mul(a0, b0), t1 = mul(a1, b1), t2 = mul(add(a0, a1), add(b0, b1));
+  r->c0 = sub(t0, t1);
+  r->c1 = sub(sub(t2, t0), t1);
 }
 DKGV_NI2 void fp2_sqr(Fp2* r, const Fp2* a) {  // (c0+c1)(c0-c1), 2 c0 c1
-  Fp s, d, m;
-  fpa(&s, &a->c0, &a->c1);
-  fps(&d, &a->c0, &a->c1);
-  fpm(&m, &a->c0, &a->c1);
-  fpm(&r->c0, &s, &d);
-  fpa(&r->c1, &m, &m);
+  Fp a0 = a->c0, a1 = a->c1;
+  Fp x = mul(add(a0, a1), sub(a0, a1)), m = mul(a0, a1);
+  r->c0 = x;
+  r->c1 = dbl(m);
 }
 DKGV_NI2 void fp2_scale(Fp2* r, const Fp2* a, const Fp* s) {
-  fpm(&r->c0, &a->c0, s);
-  fpm(&r->c1, &a->c1, s);
+  Fp k = *s;
+  Fp x = mul(a->c0, k), y = mul(a->c1, k);
+  r->c0 = x;
+  r->c1 = y;
 }
 DKGV_NI2 void fp2_conj(Fp2* r, const Fp2* a) {
-  Fp z = zero<FpParams>();
-  r->c0 = a->c0;
-  fps(&r->c1, &z, &a->c1);
+  Fp x = a->c0, y = neg(a->c1);
+  r->c0 = x;
+  r->c1 = y;
 }
 DKGV_NI2 void fp2_mul_xi(Fp2* r, const Fp2* a) {  // * (1 + u)
-  Fp t0, t1;
-  fps(&t0, &a->c0, &a->c1);
-  fpa(&t1, &a->c0, &a->c1);
-  r->c0 = t0;
-  r->c1 = t1;
+  Fp a0 = a->c0, a1 = a->c1;
+  r->c0 = sub(a0, a1);
+  r->c1 = add(a0, a1);
 }
 DKGV_NI2 void fp2_inv(Fp2* r, const Fp2* a) {
   Fp n, t, z = zero<FpParams>();
