@@ -63,6 +63,28 @@ DKGV_D void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
                  : "r"(a[j]), "r"(b), "r"(acc[j + 2]), "r"(acc[j + 3]));
   asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(acc[n - 2]), "=r"(acc[n - 1]) : "r"(a[n - 2]), "r"(b));
 }
+// EXPERIMENT (-DDKGV_RED_TWO_PIPE, off by default: measured slower, profiles/r1_fp30_experiment.md).
+// Reduction row on TWO pipes.  m * mod[k] + E[k] never overflows 64 bits, so the 12 products are
+// carry-free wide multiply-adds (IMAD.WIDE.U32 at the full FMA-pipe rate, bench/imad_carry.cu) whose
+// low words ARE the new E[k]; the high words are folded into the next column by one add/addc chain
+// on the otherwise idle ALU pipe.  E: column-aligned array (12 limbs), O: one column up; the row
+// m * mod spans columns 0..12, so the last high word and the chain's carry land in O[N-1].
+// Same sums as cmad_mod<PR,1>(O, m); cmad_mod<PR,0>(E, m); addc O[N-1].
+template <class PR>
+DKGV_D void red_row_alu(uint32_t* E, uint32_t* O, uint32_t m) {
+  constexpr int N = PR::N;
+  uint32_t hi[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    unsigned long long w = (unsigned long long)m * PR::mod(k) + E[k];
+    E[k] = (uint32_t)w;
+    hi[k] = (uint32_t)(w >> 32);
+  }
+  asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[1]) : "r"(hi[0]));
+#pragma unroll
+  for (int k = 2; k < N; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(E[k]) : "r"(hi[k - 1]));
+  asm volatile("addc.u32 %0, %0, %1;" : "+r"(O[N - 1]) : "r"(hi[N - 1]));
+}
 }  // namespace ptx
 #endif
 
@@ -220,9 +242,13 @@ DKGV_HD Mont<PR> mul(const Mont<PR>& a, const Mont<PR>& b) {
     }
     {
       uint32_t m = ev[0] * PR::INV;
+#ifndef DKGV_RED_TWO_PIPE
       ptx::cmad_mod<PR, 1>(od, m);
       ptx::cmad_mod<PR, 0>(ev, m);
       asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[N - 1]));
+#else
+      ptx::red_row_alu<PR>(ev, od, m);
+#endif
     }
     // ---- row i+1 : roles swapped (od is column-aligned)
     asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(od[0]) : "r"(ev[1]));
@@ -231,9 +257,13 @@ DKGV_HD Mont<PR> mul(const Mont<PR>& a, const Mont<PR>& b) {
     asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[N - 1]));
     {
       uint32_t m = od[0] * PR::INV;
+#ifndef DKGV_RED_TWO_PIPE
       ptx::cmad_mod<PR, 1>(ev, m);
       ptx::cmad_mod<PR, 0>(od, m);
       asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[N - 1]));
+#else
+      ptx::red_row_alu<PR>(od, ev, m);
+#endif
     }
   }
   // merge: the last row (index N-1, odd) ran with `od` column-aligned, so od[0] == 0 is the
