@@ -54,6 +54,26 @@ def executed_modmul_per_share(n, t):
         k3 = 3 * j
         tot += min(cost(j, 0), cost((k3 & ~j) >> 1, (~k3 & j) >> 1)) + 12
     return (t - 1) * tot / n + 33 * 11 + 4
+
+
+def canonical_horner_modmul(t, x):
+    """SURVEY.md 8(d) W_eval for one evaluation at |x| (binary chain, mixed add); f(0) = C_0 is free"""
+    x = abs(x)
+    return 0 if x == 0 else (t - 1) * (8 * (x.bit_length() - 1) + 12 * (bin(x).count("1") - 1) + 11)
+
+
+def executed_horner_modmul(t, x):
+    """what fd_seed_eval / vm_feldman_eval execute at |x|: signed-digit chain + a full addition per step"""
+    x = abs(x)
+    if x == 0:
+        return 0
+    def cost(pos, neg):
+        m = pos | neg
+        return 8 * (m.bit_length() - 1) + 12 * (bin(m).count("1") - 1)
+    k3 = 3 * x
+    return (t - 1) * (min(cost(x, 0), cost((k3 & ~x) >> 1, (~k3 & x) >> 1)) + 12)
+
+
 PAPER_PEAK_MAC = 148 * 64 * 1.965e9
 METRIC = "verified shares/sec (n=1024,t=683)"
 
@@ -68,6 +88,8 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
+                    help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")
     return ap.parse_args()
 
 
@@ -217,6 +239,7 @@ def run_b200(args):
     rows = n // world
 
     v = dk.Verifier(local)
+    v.set_share_path({"auto": v.PATH_AUTO, "horner": v.PATH_HORNER, "fdiff": v.PATH_FDIFF}[args.share_path])
     sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
     ts = torch.cuda.Stream(device=dev)
     stream = ts.cuda_stream
@@ -261,7 +284,7 @@ def run_b200(args):
         if rank == 0:
             sampler.start()
         launches0 = v.launch_count
-        step_ms, hot_ms = [], []
+        step_ms, hot_ms, phase_ms = [], [], []
         barrier()
         wall0 = time.perf_counter()
         for _ in range(args.steps):
@@ -273,6 +296,8 @@ def run_b200(args):
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
             hot_ms.append(v.last_hot_kernel_ms())
+            if v.last_share_path == v.PATH_FDIFF:
+                phase_ms.append(v.last_share_phases_ms())
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
@@ -338,34 +363,65 @@ def run_b200(args):
         shares = n * n
         value = shares / (ms_per_step * 1e-3)
         hot = statistics.mean(hot_ms)
-        units_per_launch = rows * n
         MODMUL_PER_SHARE = canonical_modmul_per_share(n, t)
-        achieved = units_per_launch * MODMUL_PER_SHARE * MAC_PER_MODMUL / (hot * 1e-3)
-        executed = units_per_launch * executed_modmul_per_share(n, t) * MAC_PER_MODMUL / (hot * 1e-3)
-        algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        fdiff = v.last_share_path == v.PATH_FDIFF
+        if fdiff:
+            # dominant kernel: k_fd_seed = t Horner evaluations per dealer at the plan's seed points
+            plan = dk.share_fd_plan(t, n)
+            seeds = range(plan["lo"], plan["hi"] + 1)
+            kernel = "k_fd_seed"
+            units_per_launch = rows * t
+            canon_unit = sum(canonical_horner_modmul(t, x) for x in seeds) / t
+            exec_unit = sum(executed_horner_modmul(t, x) for x in seeds) / t
+            algo_bytes = rows * t * 100 + rows * t * 144  # decoded vv read once + projective evaluations written
+        else:
+            plan = None
+            kernel = "k_share_verify"
+            units_per_launch = rows * n
+            canon_unit = MODMUL_PER_SHARE
+            exec_unit = executed_modmul_per_share(n, t)
+            algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        achieved = units_per_launch * canon_unit * MAC_PER_MODMUL / (hot * 1e-3)
+        executed = units_per_launch * exec_unit * MAC_PER_MODMUL / (hot * 1e-3)
+        step_mean = statistics.mean(step_ms)
+        # whole path: canonical per-share work (84 314 modmul) of every verified share per second of step time
+        path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / (step_mean * 1e-3)
+        roof = {"bound": "int_pipe", "kernel": kernel, "achieved": achieved / 1e9, "peak": peak["imad_wide"] / 1e9,
+                "unit": "G wide-MAC/s (32x32->64)", "frac": achieved / peak["imad_wide"], "peak_source": peak["source"],
+                "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
+                "frac_of_carry_chain_peak": (achieved / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                "executed_gmac_per_s": executed / 1e9,
+                "executed_frac_of_carry_chain_peak": (executed / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                "executed_modmul_per_unit": exec_unit,
+                "kernel_ms": hot, "kernel_share_of_step": hot / step_mean,
+                "units_per_launch": units_per_launch, "unit_is": "one Horner evaluation (dealer, seed point)" if fdiff else "one share",
+                "modmul_per_unit": canon_unit, "mac_per_modmul": MAC_PER_MODMUL,
+                "traffic": None,
+                "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
+                               "modmul_per_share_canonical": MODMUL_PER_SHARE,
+                               "note": "canonical per-share Horner work of all verified shares / step time; finite differences "
+                                       "execute fewer products than that, so this exceeds the kernel's own utilisation"},
+                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (hot * 1e-3) / 1e9,
+                        "note": "integer-bound path: HBM use is a rounding error"}}
+        if fdiff:
+            ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
+            roof["fdiff"] = {"seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
+                             "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "gs_compare": ph[3]},
+                             "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs (381-bit Montgomery Fp, 255-bit Fr)", "data": "synthetic",
             "config": {"workload": f"synthetic DKG n={n}, t={t}: full {n}x{n} share-matrix verification, dealer row blocks over {world} GPU(s)",
                        "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
+                       "share_path": "finite differences (t Horner seeds per dealer + differences)" if fdiff else "Horner per share",
                        "parallelism": f"row-block x{world}, NCCL all-gather of verdict bytes" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",
                     "h2d_bytes_per_step": int(h_vv.numel() + h_sh.numel() + h_ids.numel() * 4) * world,
                     "d2h_bytes_per_step": int(h_st.numel()) * world, "timing": "host wall clock around dkgv_share_matrix_verify, max over ranks"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "int_pipe", "kernel": "k_share_verify", "achieved": achieved / 1e9, "peak": peak["imad_wide"] / 1e9,
-                         "unit": "G wide-MAC/s (32x32->64)", "frac": achieved / peak["imad_wide"], "peak_source": peak["source"],
-                         "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
-                         "frac_of_carry_chain_peak": (achieved / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                         "executed_gmac_per_s": executed / 1e9, "executed_frac_of_carry_chain_peak": (executed / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                         "executed_modmul_per_unit": executed_modmul_per_share(n, t),
-                         "kernel_ms": hot, "kernel_share_of_step": hot / statistics.mean(step_ms),
-                         "units_per_launch": units_per_launch, "modmul_per_unit": MODMUL_PER_SHARE, "mac_per_modmul": MAC_PER_MODMUL,
-                         "traffic": None,
-                         "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (hot * 1e-3) / 1e9,
-                                 "note": "integer-bound path: HBM use is a rounding error"}},
+            "roofline": roof,
             "pairing": {"metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
                         "checks_per_step": m_total, "ms_per_step": pair_ms_step, "bad_verdicts": pair_bad,
                         "note": "e(pk,H(m)) == e(G1,sig) as 2 Miller loops + 1 final exponentiation per check, incl. G1/G2 decoding with subgroup checks"},

@@ -59,6 +59,11 @@ DECLARED_SYMBOLS = {
     "dkgv_last_hot_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_set_share_path": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dkgv_last_share_path": (ctypes.c_int, [_vp]),
+    "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                          ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "dkgv_last_share_phases_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_feldman_eval": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_g1_fixed_base_mul": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_g1_decompress_check": (ctypes.c_int, [_vp, _u32, _vp, _vp]),
@@ -155,6 +160,22 @@ class Verifier:
 
     def sync(self):
         self._ck(self._lib.dkgv_sync(self._h))
+
+    # share-matrix evaluation strategy (enum dkgv_share_path)
+    PATH_AUTO, PATH_HORNER, PATH_FDIFF = 0, 1, 2
+
+    def set_share_path(self, mode):
+        self._ck(self._lib.dkgv_set_share_path(self._h, int(mode)))
+
+    @property
+    def last_share_path(self):
+        return int(self._lib.dkgv_last_share_path(self._h))
+
+    def last_share_phases_ms(self):
+        """(seed Horner, differences, extension, G*s compare) device ms of the last finite-difference run"""
+        ms = (ctypes.c_float * 4)()
+        self._ck(self._lib.dkgv_last_share_phases_ms(self._h, ms))
+        return [float(x) for x in ms]
 
     # ---- share verification ------------------------------------------------------------------
     def share_matrix_verify(self, vv, ids, shares):
@@ -296,6 +317,15 @@ class Verifier:
             json_text = json_text.encode()
         code = self._lib.dkgh_execute(self._h, type_.encode(), json_text, int(auth), int(bls_identity), ctypes.byref(st), msg, 512)
         return int(code), int(st.value), msg.value.decode(errors="replace")
+
+
+def share_fd_plan(t, n_recipients):
+    """dkgv_share_fd_plan -> dict(use, lo, hi, steps, modmul_fd, modmul_horner) (per dealer, evaluation only)"""
+    lib = load_library()
+    lo, hi, steps = ctypes.c_int32(), ctypes.c_int32(), _u32()
+    cf, ch = ctypes.c_uint64(), ctypes.c_uint64()
+    use = lib.dkgv_share_fd_plan(t, n_recipients, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(steps), ctypes.byref(cf), ctypes.byref(ch))
+    return {"use": bool(use), "lo": lo.value, "hi": hi.value, "steps": steps.value, "modmul_fd": cf.value, "modmul_horner": ch.value}
 
 
 def initial_commitment_hash(gen_id, n, k, base_pubkeys):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/dkgv.h"
 
@@ -40,6 +41,13 @@ struct dkgv_ctx {
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
   bool hot_recorded = false;
   bool stack_set = false;
+  // finite-difference share path (share_fd.cu)
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx;
+  std::vector<int32_t> fd_seed_host;
+  cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
+  bool fd_recorded = false;
+  int share_path = 0;       // DKGV_SHARE_PATH_* requested
+  int last_share_path = 0;  // path taken by the most recent share-matrix call
 };
 
 #define CK(call)                                                     \

@@ -7,10 +7,18 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "vm30.cuh"
+#include "fdiff.cuh"
 
 using namespace dkgv;
+
+// share_fd.cu
+int dkgv_fd_setup(dkgv_ctx* ctx);
+bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r);
+int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
 
 // ============================================================================ kernels
 // Offset fixed-base table of the generator (layout in feldman.cuh).
@@ -238,6 +246,11 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
     return bail("cudaFuncSetAttribute smem", e);
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
     return bail("cudaFuncSetAttribute carveout", e);
+  if (dkgv_fd_setup(ctx) != 0) {
+    g_create_error = "finite-difference path setup: " + ctx->err;
+    dkgv_ctx_destroy(ctx);
+    return -2;
+  }
   k_build_gtab<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
   ctx->launches++;
 #ifdef DKGV_HOT_FP30
@@ -255,8 +268,11 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
-                    &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c})
+                    &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
+                    &ctx->fd_db, &ctx->fd_seedx})
     b->release();
+  for (cudaEvent_t ev : ctx->ev_fd)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
@@ -310,13 +326,36 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
   return 0;
 }
 
-extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
-                                            const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, void* stream) {
+extern "C" int dkgv_set_share_path(dkgv_ctx* ctx, int mode) {
   if (!ctx) return -1;
-  if (n_d == 0 || n_r == 0) return 0;
-  if (!d_ids || !d_shares || !d_status || (t && !d_vv)) return fail(ctx, "null pointer argument");
+  if (mode < DKGV_SHARE_PATH_AUTO || mode > DKGV_SHARE_PATH_FDIFF) return fail(ctx, "unknown share path");
+  ctx->share_path = mode;
+  return 0;
+}
+extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, int32_t* lo, int32_t* hi, uint32_t* steps, uint64_t* modmul_fd,
+                                  uint64_t* modmul_horner) {
+  FdPlan p = fd_make_plan(t, n_r);
+  if (lo) *lo = p.lo;
+  if (hi) *hi = p.hi;
+  if (steps) *steps = p.steps;
+  if (modmul_fd) *modmul_fd = p.cost_fd;
+  if (modmul_horner) *modmul_horner = p.cost_horner;
+  return p.use ? 1 : 0;
+}
+extern "C" int dkgv_last_share_path(const dkgv_ctx* ctx) { return ctx ? ctx->last_share_path : -1; }
+extern "C" int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4) {
+  if (!ctx || !ms4) return -1;
+  if (!ctx->fd_recorded) return fail(ctx, "no finite-difference share verification launched yet");
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  CK(cudaEventSynchronize(ctx->ev_fd[4]));
+  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(ms4 + i, ctx->ev_fd[i], ctx->ev_fd[i + 1]));
+  return 0;
+}
+
+// h_ids: host copy of the ids when the caller has one (else fetched from the device when the path
+// selection needs it)
+static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
+                                 const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
   VVView view;
   uint32_t n_pad;
 #ifdef DKGV_HOT_FP30
@@ -325,11 +364,33 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   HotView hv{view.limbs, view.inf, view.n_pad};
   const uint32_t* hot_tab = ctx->gtab30;
 #else
+  // Recipient ids that are the consecutive ranks 1..n_r (always the case for a ceremony,
+  // verification.rs:50-66,129) allow t Horner evaluations + finite differences per dealer.
+  bool use_fd = false;
+  FdPlan plan{};
+  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r > t && n_r <= 65535) {
+    std::vector<uint32_t> fetched;
+    if (!h_ids) {  // device-pointer entry: fetch the (tiny) id list before any work is queued
+      fetched.resize(n_r);
+      CK(cudaMemcpyAsync(fetched.data(), d_ids, (size_t)n_r * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      h_ids = fetched.data();
+    }
+    if (dkgv_fd_ids_consecutive(h_ids, n_r)) {
+      plan = fd_make_plan(t, n_r);
+      use_fd = plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF;
+    }
+  }
   int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false);
   if (rc) return rc;
+  if (use_fd) {
+    ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;
+    return dkgv_share_matrix_fd(ctx, view, n_d, n_r, t, plan, d_ids, d_shares, d_status, s);
+  }
   HotView hv = view;
   const uint32_t* hot_tab = ctx->gtab;
 #endif
+  ctx->last_share_path = DKGV_SHARE_PATH_HORNER;
   dim3 grid(n_pad / 32, (n_r + SVM_NT / 32 - 1) / (SVM_NT / 32));
   CK(cudaEventRecord(ctx->ev_hot0, s));
   k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(hv, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, hot_tab, d_status,
@@ -339,6 +400,16 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
+                                            const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, void* stream) {
+  if (!ctx) return -1;
+  if (n_d == 0 || n_r == 0) return 0;
+  if (!d_ids || !d_shares || !d_status || (t && !d_vv)) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  return share_matrix_dev_impl(ctx, n_d, n_r, t, d_vv, d_ids, nullptr, d_shares, d_status, s);
 }
 
 extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* vv,
@@ -356,8 +427,8 @@ extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_
   if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->in_c.p, shares, shb, cudaMemcpyHostToDevice, s));
-  int rc = dkgv_share_matrix_verify_dev(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p,
-                                        (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, s);
+  int rc = share_matrix_dev_impl(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, ids,
+                                 (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, s);
   if (rc) return rc;
   CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

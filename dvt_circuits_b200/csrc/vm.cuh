@@ -17,7 +17,7 @@
 #include "feldman.cuh"
 
 #if defined(__CUDACC__)
-#define DKGV_NI __host__ __device__ __noinline__
+#define DKGV_NI static __host__ __device__ __noinline__
 #else
 #define DKGV_NI static
 #endif

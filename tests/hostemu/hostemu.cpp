@@ -9,6 +9,7 @@
 
 #define DKGV_BOUND_CHECK 1
 #include "../../dvt_circuits_b200/csrc/vm30.cuh"
+#include "../../dvt_circuits_b200/csrc/fdiff.cuh"
 
 using namespace dkgv;
 
@@ -150,6 +151,70 @@ void he_fp30_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t
   fp30_to_canonical(fp30_add(x, y), o.l); fp_raw_to_be48(add48, o.l);
   fp30_to_canonical(fp30_sub<8>(x, y), o.l); fp_raw_to_be48(sub48, o.l);
   fp30_to_canonical(fp30_mul_small<12>(fp30_add(fp30_add(x, y), fp30_sub<32>(y, x))), o.l); fp_raw_to_be48(m12_48, o.l);
+}
+}
+
+// ---- finite-difference share path (fdiff.cuh): the exact sequence of k_fd_seed / k_fd_init /
+// k_fd_ext items share_fd.cu launches, for one dealer sitting in lane `d` of a 32-dealer plane.
+extern "C" {
+// plan[0..3] = use, lo, hi, steps.  lo_force != 0x7fffffff overrides the planned window start.
+// out48[j] = compress(f(j + 1)), j = 0..n_r-1.  Returns 0, or < 0 when the shape is not applicable.
+int he_fd_row(const uint8_t* vv, uint32_t t, uint32_t n_r, int32_t lo_force, int32_t* plan4, uint8_t* out48) {
+  const uint32_t n_pad = 32, d = 5;
+  FdPlan plan = fd_make_plan(t, n_r);
+  plan4[0] = plan.use;
+  plan4[1] = plan.lo;
+  plan4[2] = plan.hi;
+  plan4[3] = (int32_t)plan.steps;
+  if (t < 2 || n_r <= t) return -1;
+  if (lo_force != 0x7fffffff) {
+    plan.lo = lo_force;
+    plan.hi = lo_force + (int32_t)t - 1;
+    if (plan.lo > 1 || plan.hi < 1) return -2;
+    plan.steps = n_r - (uint32_t)plan.hi;
+  }
+  std::vector<uint32_t> limbs((size_t)t * 24 * n_pad, 0);
+  std::vector<uint8_t> inf((size_t)t * n_pad, 1);
+  for (uint32_t k = 0; k < t; k++) {
+    G1Aff a;
+    if (g1_decompress(vv + (size_t)k * 48, &a, true) != G1_DEC_OK) return -3;
+    vv_store(limbs.data(), inf.data(), n_pad, k, d, a);
+  }
+  VVView view{limbs.data(), inf.data(), n_pad};
+  const uint32_t NT = 4, me = 1;
+  std::vector<U4> file((size_t)VM_SLOTS * 3 * NT);
+  OpFile f{file.data() + me, NT};
+  const size_t ent = (size_t)36 * n_pad;
+  const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
+  std::vector<uint32_t> evals(n_evals * ent, 0xdeadbeef), p0((size_t)t * ent), p1((size_t)t * ent), da((size_t)t * ent),
+      db((size_t)t * ent);
+  for (int32_t x = plan.lo; x <= plan.hi; x++) {
+    fd_seed_eval(f, view, t, d, x);
+    fd_store(f, AX, fd_entry(evals.data(), n_pad, (size_t)(x - plan.lo), d), n_pad);
+  }
+  const size_t e_hi = (size_t)(plan.hi - plan.lo);
+  memcpy(da.data(), evals.data() + e_hi * ent, ent * 4);
+  memcpy(db.data(), evals.data() + e_hi * ent, ent * 4);
+  uint32_t* pp[2] = {p0.data(), p1.data()};
+  const uint32_t* src = evals.data();
+  for (uint32_t r = 1; r < t; r++) {
+    uint32_t* dst = pp[r & 1];
+    for (uint32_t i = 0; i + r < t; i++) fd_init_item(f, src, dst, da.data(), db.data(), n_pad, t, r, i, d);
+    src = dst;
+  }
+  uint32_t* dd[2] = {da.data(), db.data()};
+  for (uint32_t tick = 1; tick <= plan.steps + t - 2; tick++) {
+    int32_t k_lo, k_hi;
+    fd_ext_band(t, plan.steps, tick, &k_lo, &k_hi);
+    // items of one tick are independent: run them in descending order to catch any accidental
+    // dependence on the ascending order
+    for (int32_t k = k_hi; k >= k_lo; k--) fd_ext_item(f, dd[(tick & 1) ^ 1], dd[tick & 1], evals.data(), n_pad, t, tick, (uint32_t)k, e_hi, d);
+  }
+  for (uint32_t j = 0; j < n_r; j++) {
+    fd_load(f, AX, fd_entry(evals.data(), n_pad, (size_t)((int64_t)(j + 1) - plan.lo), d), n_pad);
+    g1_compress(g1_to_affine(vm_get_point(f, AX)), out48 + (size_t)j * 48);
+  }
+  return 0;
 }
 }
 

@@ -122,3 +122,26 @@ def test_tower_pairing_h2c(L):
     a = buf(576)
     assert L.he_pairing_bytes(KAT_PK, KAT_SIG, a) == 0
     assert O.pairing_bytes(KAT_PK, KAT_SIG) == (0, a.raw)
+
+
+def test_finite_difference_row(L):
+    """fdiff.cuh: seeds by Horner on a window around 0, backward differences, wavefront extension -
+    every f(1..n) must equal the oracle's evaluate_polynomial (dkg_math.rs:160-174)"""
+    rnd = random.Random(5)
+    for t, n_r, lo in [(2, 5, None), (3, 9, None), (3, 9, 1), (3, 9, -1), (5, 12, None), (5, 12, -3), (5, 6, 1), (8, 20, None)]:
+        coef = [rnd.randrange(B.R) for _ in range(t)]
+        if t == 5:
+            coef[2] = 0  # an identity coefficient
+        vv = b"".join(B.g1_compress(B.g1_mul(B.G1, c)) for c in coef)
+        plan = (ctypes.c_int32 * 4)()
+        out = buf(48 * n_r)
+        rc = L.he_fd_row(vv, t, n_r, ctypes.c_int32(0x7FFFFFFF if lo is None else lo), plan, out)
+        assert rc == 0, (t, n_r, lo, rc)
+        assert plan[2] - plan[1] + 1 == t and plan[1] <= 1 <= plan[2] and plan[3] == n_r - plan[2]
+        for j in range(n_r):
+            want = B.g1_compress(B.g1_mul(B.G1, sum(c * pow(j + 1, k, B.R) for k, c in enumerate(coef)) % B.R))
+            assert out.raw[48 * j:48 * j + 48] == want, (t, n_r, lo, j)
+    plan = (ctypes.c_int32 * 4)()
+    assert L.he_fd_row(bytes(48), 1, 5, ctypes.c_int32(0x7FFFFFFF), plan, buf(48 * 5)) == -1 and plan[0] == 0
+    L.he_fd_row(bytes(48 * 683), 683, 1024, ctypes.c_int32(0x7FFFFFFF), plan, buf(48))  # plan only (vv undecodable -> -3)
+    assert plan[0] == 1 and plan[1] < 0 < plan[2] and plan[2] - plan[1] == 682
