@@ -88,6 +88,7 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
     ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
                     help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")
     return ap.parse_args()
@@ -239,6 +240,7 @@ def run_b200(args):
     rows = n // world
 
     v = dk.Verifier(local)
+    v.set_share_parts(args.parts)
     v.set_share_path({"auto": v.PATH_AUTO, "horner": v.PATH_HORNER, "fdiff": v.PATH_FDIFF}[args.share_path])
     sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
     ts = torch.cuda.Stream(device=dev)
@@ -367,13 +369,14 @@ def run_b200(args):
         fdiff = v.last_share_path == v.PATH_FDIFF
         if fdiff:
             # dominant kernel: k_fd_seed = t Horner evaluations per dealer at the plan's seed points
-            plan = dk.share_fd_plan(t, n)
+            plan = dk.share_fd_plan(t, n, args.parts)
+            m_parts, h_part = plan["parts"], plan["h"]
             seeds = range(plan["lo"], plan["hi"] + 1)
             kernel = "k_fd_seed"
-            units_per_launch = rows * t
-            canon_unit = sum(canonical_horner_modmul(t, x) for x in seeds) / t
-            exec_unit = sum(executed_horner_modmul(t, x) for x in seeds) / t
-            algo_bytes = rows * t * 100 + rows * t * 144  # decoded vv read once + projective evaluations written
+            units_per_launch = rows * m_parts * h_part
+            canon_unit = sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part
+            exec_unit = sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part
+            algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144  # decoded vv read once + projective evaluations written
         else:
             plan = None
             kernel = "k_share_verify"
@@ -394,7 +397,7 @@ def run_b200(args):
                 "executed_frac_of_carry_chain_peak": (executed / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
                 "executed_modmul_per_unit": exec_unit,
                 "kernel_ms": hot, "kernel_share_of_step": hot / step_mean,
-                "units_per_launch": units_per_launch, "unit_is": "one Horner evaluation (dealer, seed point)" if fdiff else "one share",
+                "units_per_launch": units_per_launch, "unit_is": "one Horner evaluation (dealer, part, seed point)" if fdiff else "one share",
                 "modmul_per_unit": canon_unit, "mac_per_modmul": MAC_PER_MODMUL,
                 "traffic": None,
                 "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
@@ -405,8 +408,10 @@ def run_b200(args):
                         "note": "integer-bound path: HBM use is a rounding error"}}
         if fdiff:
             ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
-            roof["fdiff"] = {"seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
-                             "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "gs_compare": ph[3]},
+            roof["fdiff"] = {"parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
+                             "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
+                             "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "recombine_gs_compare": ph[3]},
+                             "phase_share_of_step": {k: v_ / step_mean for k, v_ in zip(("seed_horner", "differences", "extension", "recombine_gs_compare"), ph)},
                              "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -414,7 +419,8 @@ def run_b200(args):
             "dtype": "u32 limbs (381-bit Montgomery Fp, 255-bit Fr)", "data": "synthetic",
             "config": {"workload": f"synthetic DKG n={n}, t={t}: full {n}x{n} share-matrix verification, dealer row blocks over {world} GPU(s)",
                        "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
-                       "share_path": "finite differences (t Horner seeds per dealer + differences)" if fdiff else "Horner per share",
+                       "share_path": (f"finite differences: {plan['parts']} parts x {plan['h']} coefficients per dealer, "
+                                      f"{plan['h']} Horner seeds per part, differences, recombination") if fdiff else "Horner per share",
                        "parallelism": f"row-block x{world}, NCCL all-gather of verdict bytes" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",

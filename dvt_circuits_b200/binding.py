@@ -61,8 +61,10 @@ DECLARED_SYMBOLS = {
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_set_share_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_path": (ctypes.c_int, [_vp]),
-    "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
-                                          ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "dkgv_set_share_parts": (ctypes.c_int, [_vp, _u32]),
+    "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
+                                          ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
+                                          ctypes.POINTER(ctypes.c_uint64)]),
     "dkgv_last_share_phases_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_feldman_eval": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_g1_fixed_base_mul": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
@@ -166,6 +168,10 @@ class Verifier:
 
     def set_share_path(self, mode):
         self._ck(self._lib.dkgv_set_share_path(self._h, int(mode)))
+
+    def set_share_parts(self, parts):
+        """parts per dealer polynomial on the finite-difference path (0 = planner's choice)"""
+        self._ck(self._lib.dkgv_set_share_parts(self._h, int(parts)))
 
     @property
     def last_share_path(self):
@@ -319,13 +325,15 @@ class Verifier:
         return int(code), int(st.value), msg.value.decode(errors="replace")
 
 
-def share_fd_plan(t, n_recipients):
-    """dkgv_share_fd_plan -> dict(use, lo, hi, steps, modmul_fd, modmul_horner) (per dealer, evaluation only)"""
+def share_fd_plan(t, n_recipients, parts=0):
+    """dkgv_share_fd_plan -> dict(use, parts, h, lo, hi, steps, modmul_fd, modmul_horner) (per dealer, evaluation only)"""
     lib = load_library()
-    lo, hi, steps = ctypes.c_int32(), ctypes.c_int32(), _u32()
+    m, h, lo, hi, steps = _u32(), _u32(), ctypes.c_int32(), ctypes.c_int32(), _u32()
     cf, ch = ctypes.c_uint64(), ctypes.c_uint64()
-    use = lib.dkgv_share_fd_plan(t, n_recipients, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(steps), ctypes.byref(cf), ctypes.byref(ch))
-    return {"use": bool(use), "lo": lo.value, "hi": hi.value, "steps": steps.value, "modmul_fd": cf.value, "modmul_horner": ch.value}
+    use = lib.dkgv_share_fd_plan(t, n_recipients, parts, ctypes.byref(m), ctypes.byref(h), ctypes.byref(lo), ctypes.byref(hi),
+                                 ctypes.byref(steps), ctypes.byref(cf), ctypes.byref(ch))
+    return {"use": use == 1, "exists": use >= 0, "parts": m.value, "h": h.value, "lo": lo.value, "hi": hi.value, "steps": steps.value,
+            "modmul_fd": cf.value, "modmul_horner": ch.value}
 
 
 def initial_commitment_hash(gen_id, n, k, base_pubkeys):

@@ -42,11 +42,12 @@ struct dkgv_ctx {
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)
-  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx;
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top;
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
   bool fd_recorded = false;
   int share_path = 0;       // DKGV_SHARE_PATH_* requested
+  uint32_t share_parts = 0; // 0: planner's choice of parts per dealer; else forced
   int last_share_path = 0;  // path taken by the most recent share-matrix call
 };
 

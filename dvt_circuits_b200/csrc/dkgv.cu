@@ -269,7 +269,7 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
-                    &ctx->fd_db, &ctx->fd_seedx})
+                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top})
     b->release();
   for (cudaEvent_t ev : ctx->ev_fd)
     if (ev) cudaEventDestroy(ev);
@@ -332,15 +332,23 @@ extern "C" int dkgv_set_share_path(dkgv_ctx* ctx, int mode) {
   ctx->share_path = mode;
   return 0;
 }
-extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, int32_t* lo, int32_t* hi, uint32_t* steps, uint64_t* modmul_fd,
-                                  uint64_t* modmul_horner) {
-  FdPlan p = fd_make_plan(t, n_r);
+extern "C" int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts) {
+  if (!ctx) return -1;
+  if (parts > FD_MAX_PARTS) return fail(ctx, "too many parts");
+  ctx->share_parts = parts;
+  return 0;
+}
+extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo, int32_t* hi,
+                                  uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner) {
+  FdPlan p = fd_make_plan(t, n_r, parts_force);
+  if (parts) *parts = p.m;
+  if (h) *h = p.h;
   if (lo) *lo = p.lo;
   if (hi) *hi = p.hi;
   if (steps) *steps = p.steps;
   if (modmul_fd) *modmul_fd = p.cost_fd;
   if (modmul_horner) *modmul_horner = p.cost_horner;
-  return p.use ? 1 : 0;
+  return p.cost_fd == ~0ull ? -1 : (p.use ? 1 : 0);
 }
 extern "C" int dkgv_last_share_path(const dkgv_ctx* ctx) { return ctx ? ctx->last_share_path : -1; }
 extern "C" int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4) {
@@ -368,7 +376,7 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
   // verification.rs:50-66,129) allow t Horner evaluations + finite differences per dealer.
   bool use_fd = false;
   FdPlan plan{};
-  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r > t && n_r <= 65535) {
+  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r >= 3 && n_r <= 65535 && t <= 65535 * FD_MAX_PARTS) {
     std::vector<uint32_t> fetched;
     if (!h_ids) {  // device-pointer entry: fetch the (tiny) id list before any work is queued
       fetched.resize(n_r);
@@ -377,8 +385,8 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
       h_ids = fetched.data();
     }
     if (dkgv_fd_ids_consecutive(h_ids, n_r)) {
-      plan = fd_make_plan(t, n_r);
-      use_fd = plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF;
+      plan = fd_make_plan(t, n_r, ctx->share_parts);
+      use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
     }
   }
   int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false);

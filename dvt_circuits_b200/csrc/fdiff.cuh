@@ -13,6 +13,13 @@
 //   extension   E_s[k] = nabla^k f(hi + s):  E_s[k] = E_{s-1}[k] + E_s[k+1],  E_s[t-1] = D[t-1]
 //               run as a wavefront: at tick tau thread k computes step s = tau - (t-2-k)
 //
+// Splitting.  The seeds cost t Horner chains of t-1 steps each - quadratic in t.  Writing
+//   f(x) = sum_{i<m} y^i f_i(x),   y = x^h mod r,   f_i(x) = sum_{k<h} C_{ih+k} x^k,   h = ceil(t/m)
+// turns one dealer into m "virtual dealers" of degree h-1: m*h = t seeds of h-1 steps (m times less
+// work), the same t-1 additions per extended point, and one joint double-and-add (Straus, NAF digits
+// of the public scalars y^i shared by every dealer of the warp) per share to recombine.  [y]P = [x^h]P
+// because every decoded commitment lies in the order-r subgroup (the decoder's subgroup check).
+//
 // Exact group arithmetic throughout (same complete RCB formulas), so every evaluation is the same
 // projective-equivalent point Horner would give and the verdicts are bit-identical.
 //
@@ -54,24 +61,33 @@ DKGV_HD void fd_store(const OpFile& f, int s, uint32_t* ent, uint32_t n_pad) {
   }
 }
 
-// A <- f_d(x) for a small signed x (Horner with the signed-digit chain of |x|; [-x]P = -([x]P))
-DKGV_HD void fd_seed_eval(const OpFile& f, const VVView& v, uint32_t t, uint32_t d, int32_t x) {
-  if (t == 0) {
+// coefficient k of dealer d; beyond the vector's end the padding coefficient is the identity
+DKGV_HD void fd_load_coeff(const OpFile& f, int s, const VVView& v, uint32_t t, uint32_t k, uint32_t d) {
+  if (k < t)
+    vm_load_coeff(f, s, v, k, d);
+  else
+    vm_set_point(f, s, g1_identity());
+}
+
+// A <- sum_{k<h} C_{k0+k} x^k for a small signed x (Horner with the signed-digit chain of |x|;
+// [-x]P = -([x]P)).  k0 = 0, h = t evaluates the whole polynomial.
+DKGV_HD void fd_seed_eval(const OpFile& f, const VVView& v, uint32_t t, uint32_t d, int32_t x, uint32_t k0, uint32_t h) {
+  if (h == 0) {
     vm_set_point(f, AX, g1_identity());
     return;
   }
   if (x == 0) {
-    vm_load_coeff(f, AX, v, 0, d);
+    fd_load_coeff(f, AX, v, t, k0, d);
     return;
   }
   bool negx = x < 0;
   SmallChain chain = make_small_chain(negx ? (uint32_t)(-(int64_t)x) : (uint32_t)x);
-  vm_load_coeff(f, AX, v, t - 1, d);
+  fd_load_coeff(f, AX, v, t, k0 + h - 1, d);
 #pragma unroll 1
-  for (int k = (int)t - 2; k >= 0; k--) {
+  for (int k = (int)h - 2; k >= 0; k--) {
     vm_g1_mul_chain(f, chain);
     if (negx) vm_neg(f, AY, AY);
-    vm_load_coeff(f, BX, v, (uint32_t)k, d);
+    fd_load_coeff(f, BX, v, t, k0 + (uint32_t)k, d);
     vm_g1_add(f);
   }
 }
@@ -109,14 +125,93 @@ DKGV_HD void fd_ext_band(uint32_t t, uint32_t steps, uint32_t tick, int32_t* k_l
   *k_hi = hi > (int32_t)t - 2 ? (int32_t)t - 2 : hi;
 }
 
-// compare the evaluation (an evals entry) with G * s: the tail of verify_seed_exchange_commitment
+// ---- recombination of the m parts ---------------------------------------------------------------
+constexpr uint32_t FD_MAX_PARTS = 16;
+constexpr uint32_t FD_DIG_WORDS = 16;  // per (x, i): 8 words of +1 digits, 8 words of -1 digits (NAF, 256 positions)
+
+// NAF digit masks of the public scalars y^i (i = 1..m-1), y = x^h mod r; returns the highest digit
+// position over all i (-1 if every scalar is zero).  dig: (m-1) * FD_DIG_WORDS words.
+DKGV_HD int fd_comb_digits(uint32_t x, uint32_t h, uint32_t m, uint32_t* dig) {
+  Fr xm = zero<FrParams>();
+  xm.l[0] = x;
+  xm = to_mont(xm);
+  Fr y = one<FrParams>();
+  for (int b = 31; b >= 0; b--) {
+    y = mul(y, y);
+    if ((h >> b) & 1) y = mul(y, xm);
+  }
+  Fr p = y;
+  int top = -1;
+  for (uint32_t i = 1; i < m; i++) {
+    Fr s = from_mont(p);
+    uint32_t s3[9];
+    uint64_t c = 0;
+    for (int w = 0; w < 8; w++) {
+      c += (uint64_t)s.l[w] * 3;
+      s3[w] = (uint32_t)c;
+      c >>= 32;
+    }
+    s3[8] = (uint32_t)c;
+    uint32_t* pos = dig + (size_t)(i - 1) * FD_DIG_WORDS;
+    uint32_t* neg = pos + 8;
+    for (int w = 0; w < 8; w++) {
+      uint32_t sw = s.l[w], sn = w < 7 ? s.l[w + 1] : 0u;
+      uint32_t plo = s3[w] & ~sw, phi = s3[w + 1] & ~sn;  // bits of (3s & ~s), this word and the next
+      uint32_t nlo = ~s3[w] & sw, nhi = ~s3[w + 1] & sn;
+      pos[w] = (plo >> 1) | (phi << 31);
+      neg[w] = (nlo >> 1) | (nhi << 31);
+      uint32_t any = pos[w] | neg[w];
+      for (int b = 31; b >= 0; b--)
+        if ((any >> b) & 1) {
+          if (32 * w + b > top) top = 32 * w + b;
+          break;
+        }
+    }
+    p = mul(p, y);
+  }
+  return top;
+}
+
+// A <- sum_i [y^i] f_i(x): entries of the m virtual dealers (part i of dealer d sits at column
+// i * n_pad + d of a plane n_padv = m * n_pad wide), joint double-and-add over the NAF digits.
+// Control flow depends on (x, h, m) only - warp-uniform when all lanes share the recipient.
+DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e,
+                             uint32_t d, const uint32_t* dig, int top) {
+  bool started = false;
+#pragma unroll 1
+  for (int b = top; b >= 0; b--) {
+    if (started) vm_g1_dbl(f);
+#pragma unroll 1
+    for (uint32_t i = 1; i < m; i++) {
+      const uint32_t* pos = dig + (size_t)(i - 1) * FD_DIG_WORDS;
+      bool p = (pos[b >> 5] >> (b & 31)) & 1, n = (pos[8 + (b >> 5)] >> (b & 31)) & 1;
+      if (!(p || n)) continue;
+      fd_load(f, BX, fd_entry(evals, n_padv, e, i * n_pad + d), n_padv);
+      if (n) vm_neg(f, BY, BY);
+      if (started) {
+        vm_g1_add(f);
+      } else {
+        vm_copy3(f, AX, BX);
+        started = true;
+      }
+    }
+  }
+  fd_load(f, BX, fd_entry(evals, n_padv, e, d), n_padv);
+  if (started)
+    vm_g1_add(f);
+  else
+    vm_copy3(f, AX, BX);
+}
+
+// recombine, then compare with G * s: the tail of verify_seed_exchange_commitment
 // (crates/dkg/src/verification.rs:92-99,138-146), same status contract as vm_share_check
-DKGV_HD uint8_t fd_compare_item(const OpFile& f, const uint32_t* ent, uint32_t n_pad, const uint8_t* secret_be,
-                                const uint32_t* gtab, bool dealer_bad) {
+DKGV_HD uint8_t fd_combine_compare_item(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e,
+                                        uint32_t d, const uint32_t* dig, int top, const uint8_t* secret_be, const uint32_t* gtab,
+                                        bool dealer_bad) {
+  fd_combine_eval(f, evals, n_padv, n_pad, m, e, d, dig, top);
   uint32_t s[8];
   bool in_range = fr_raw_from_be32(s, secret_be);
   vm_fixed_base_mul(f, gtab, s);
-  fd_load(f, AX, ent, n_pad);
   uint8_t st = vm_g1_eq_ab(f) ? DKGV_OK : DKGV_SLASHABLE_SHARE_MISMATCH;
   if (dealer_bad) st = DKGV_PANIC_BAD_G1;
   if (!in_range) st = DKGV_SLASHABLE_SECRET_RANGE;
@@ -133,36 +228,57 @@ inline uint64_t fd_horner_cost(uint32_t t, uint32_t ax) {
 
 struct FdPlan {
   bool use;          // finite differences pay off for this shape
-  int32_t lo, hi;    // seed points lo..hi (hi - lo + 1 == t, lo <= 1 <= hi)
+  uint32_t m, h;     // parts per dealer and coefficients per part (m * h >= t)
+  int32_t lo, hi;    // seed points lo..hi (hi - lo + 1 == h, lo <= 1 <= hi)
   uint32_t steps;    // extension steps: n_r - hi
   uint64_t cost_fd, cost_horner;  // field products per dealer, both ways (excluding G*s)
 };
 
-// ids must already be known to be a permutation of 1..n_r
-inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r) {
-  FdPlan p{};
-  p.use = false;
-  for (uint32_t j = 1; j <= n_r; j++) p.cost_horner += fd_horner_cost(t, j);
-  if (t < 2 || n_r <= t) return p;
-  // window of t consecutive integers containing 1 with the cheapest Horner total + extension length
-  uint64_t* pre = new uint64_t[t + 1];  // pre[a] = sum_{x=1..a} cost(x)
+// cheapest window of h consecutive integers containing 1 for polynomials of h coefficients
+inline uint64_t fd_best_window(uint32_t h, uint32_t n_r, int32_t* lo_out) {
+  uint64_t* pre = new uint64_t[h + 1];  // pre[a] = sum_{x=1..a} cost(x)
   pre[0] = 0;
-  for (uint32_t a = 1; a <= t; a++) pre[a] = pre[a - 1] + fd_horner_cost(t, a);
+  for (uint32_t a = 1; a <= h; a++) pre[a] = pre[a - 1] + fd_horner_cost(h, a);
   uint64_t best = ~0ull;
-  for (int32_t lo = 2 - (int32_t)t; lo <= 1; lo++) {
-    int32_t hi = lo + (int32_t)t - 1;
+  for (int32_t lo = 2 - (int32_t)h; lo <= 1; lo++) {
+    int32_t hi = lo + (int32_t)h - 1;
     uint64_t c = pre[hi] + (lo < 0 ? pre[-lo] : 0);
-    c += (uint64_t)t * (t - 1) / 2 * 12 + (uint64_t)(n_r - (uint32_t)hi) * (t - 1) * 12;
+    c += (uint64_t)h * (h - 1) / 2 * 12 + (uint64_t)(n_r - (uint32_t)hi) * (h - 1) * 12;
     if (c < best) {
       best = c;
-      p.lo = lo;
-      p.hi = hi;
+      *lo_out = lo;
     }
   }
   delete[] pre;
+  return best;
+}
+
+// ids must already be known to be a permutation of 1..n_r.  m_force != 0 fixes the number of parts.
+inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0) {
+  FdPlan p{};
+  p.use = false;
+  p.m = 1;
+  p.h = t;
+  p.cost_fd = ~0ull;
+  for (uint32_t j = 1; j <= n_r; j++) p.cost_horner += fd_horner_cost(t, j);
+  for (uint32_t m = 1; m <= FD_MAX_PARTS; m++) {
+    if (m_force && m != m_force) continue;
+    uint32_t h = (t + m - 1) / m;
+    if (h < 2 || n_r <= h || (m > 1 && (uint64_t)(m - 1) * h >= t)) continue;  // every part must hold a coefficient
+    int32_t lo = 1;
+    uint64_t c = (uint64_t)m * fd_best_window(h, n_r, &lo);
+    if (m > 1) c += (uint64_t)n_r * (255 * 8 + (uint64_t)(m - 1) * 85 * 12 + 12);  // joint NAF double-and-add per share
+    if (c < p.cost_fd) {
+      p.cost_fd = c;
+      p.m = m;
+      p.h = h;
+      p.lo = lo;
+      p.hi = lo + (int32_t)h - 1;
+    }
+  }
+  if (p.cost_fd == ~0ull) return p;
   p.steps = n_r - (uint32_t)p.hi;
-  p.cost_fd = best;
-  p.use = best * 10 < p.cost_horner * 9;
+  p.use = p.cost_fd * 10 < p.cost_horner * 9;
   return p;
 }
 

@@ -88,18 +88,21 @@ int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_r
                                  uint8_t* d_status, void* stream);
 
 /* Evaluation strategy of the share-matrix entry points.  AUTO (default): when the recipient ids are a
- * permutation of 1..n_recipients (always so for a ceremony: verification.rs:50-66,129) and
- * n_recipients > t, evaluate t points per dealer by Horner and the rest by finite differences
- * (exact group arithmetic, identical verdicts); otherwise Horner per share.                       */
+ * permutation of 1..n_recipients (always so for a ceremony: verification.rs:50-66,129), split every
+ * dealer polynomial into `parts` pieces of h coefficients, evaluate h points per piece by Horner, all
+ * further points by finite differences, and recombine per share (exact group arithmetic, identical
+ * verdicts); otherwise, or when that is not cheaper, Horner per share.                              */
 enum dkgv_share_path { DKGV_SHARE_PATH_AUTO = 0, DKGV_SHARE_PATH_HORNER = 1, DKGV_SHARE_PATH_FDIFF = 2 };
 int dkgv_set_share_path(dkgv_ctx* ctx, int mode); /* FDIFF: use it whenever applicable, even if not cheaper */
+int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts); /* 0 = planner's choice (default), else 1..16 */
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
-/* the plan AUTO would use for ids 1..n_recipients: Horner seed points lo..hi (hi - lo + 1 == t), extension
- * steps, field products per dealer by finite differences and by per-share Horner (evaluation only, G*s
- * excluded).  Returns 1 when finite differences are chosen, 0 otherwise.  Pure host function.      */
-int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, int32_t* lo, int32_t* hi, uint32_t* steps, uint64_t* modmul_fd,
-                       uint64_t* modmul_horner);
-/* device times of the last finite-difference run: seed Horner, differences, extension, G*s compare */
+/* the plan for ids 1..n_recipients (parts_force 0 = cheapest): parts, h = ceil(t / parts), Horner seed points
+ * lo..hi (hi - lo + 1 == h), extension steps, field products per dealer by this plan and by per-share Horner
+ * (evaluation only, G*s excluded).  Returns 1 when AUTO would take this plan, 0 when Horner per share is
+ * cheaper, -1 when no plan exists for the shape.  Pure host function.                                */
+int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo,
+                       int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner);
+/* device times of the last finite-difference run: seed Horner, differences, extension, recombine + G*s compare */
 int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4);
 
 /* ---- evaluate_polynomial (crates/dkg/src/dkg_math.rs:160-174), batched ---------------------- */

@@ -155,22 +155,27 @@ void he_fp30_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t
 }
 
 // ---- finite-difference share path (fdiff.cuh): the exact sequence of k_fd_seed / k_fd_init /
-// k_fd_ext items share_fd.cu launches, for one dealer sitting in lane `d` of a 32-dealer plane.
+// k_fd_ext / k_fd_digits / k_fd_combine items share_fd.cu launches, for one dealer sitting in lane
+// `d` of a 32-dealer plane.
 extern "C" {
-// plan[0..3] = use, lo, hi, steps.  lo_force != 0x7fffffff overrides the planned window start.
-// out48[j] = compress(f(j + 1)), j = 0..n_r-1.  Returns 0, or < 0 when the shape is not applicable.
-int he_fd_row(const uint8_t* vv, uint32_t t, uint32_t n_r, int32_t lo_force, int32_t* plan4, uint8_t* out48) {
+// plan6 = use, parts, h, lo, hi, steps.  m_force 0 = planner's choice; lo_force != 0x7fffffff overrides
+// the planned window start.  out48[j] = compress(f(j + 1)), j = 0..n_r-1.  Returns 0, or < 0 when no
+// plan exists for the shape.
+int he_fd_row(const uint8_t* vv, uint32_t t, uint32_t n_r, uint32_t m_force, int32_t lo_force, int32_t* plan6, uint8_t* out48) {
   const uint32_t n_pad = 32, d = 5;
-  FdPlan plan = fd_make_plan(t, n_r);
-  plan4[0] = plan.use;
-  plan4[1] = plan.lo;
-  plan4[2] = plan.hi;
-  plan4[3] = (int32_t)plan.steps;
-  if (t < 2 || n_r <= t) return -1;
+  FdPlan plan = fd_make_plan(t, n_r, m_force);
+  plan6[0] = plan.use;
+  plan6[1] = (int32_t)plan.m;
+  plan6[2] = (int32_t)plan.h;
+  plan6[3] = plan.lo;
+  plan6[4] = plan.hi;
+  plan6[5] = (int32_t)plan.steps;
+  if (plan.cost_fd == ~0ull) return -1;
+  const uint32_t m = plan.m, h = plan.h;
   if (lo_force != 0x7fffffff) {
     plan.lo = lo_force;
-    plan.hi = lo_force + (int32_t)t - 1;
-    if (plan.lo > 1 || plan.hi < 1) return -2;
+    plan.hi = lo_force + (int32_t)h - 1;
+    if (plan.lo > 1 || plan.hi < 1 || (uint32_t)plan.hi >= n_r) return -2;
     plan.steps = n_r - (uint32_t)plan.hi;
   }
   std::vector<uint32_t> limbs((size_t)t * 24 * n_pad, 0);
@@ -184,37 +189,57 @@ int he_fd_row(const uint8_t* vv, uint32_t t, uint32_t n_r, int32_t lo_force, int
   const uint32_t NT = 4, me = 1;
   std::vector<U4> file((size_t)VM_SLOTS * 3 * NT);
   OpFile f{file.data() + me, NT};
-  const size_t ent = (size_t)36 * n_pad;
+  const uint32_t n_padv = n_pad * m;
+  const size_t ent = (size_t)36 * n_padv;
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
-  std::vector<uint32_t> evals(n_evals * ent, 0xdeadbeef), p0((size_t)t * ent), p1((size_t)t * ent), da((size_t)t * ent),
-      db((size_t)t * ent);
-  for (int32_t x = plan.lo; x <= plan.hi; x++) {
-    fd_seed_eval(f, view, t, d, x);
-    fd_store(f, AX, fd_entry(evals.data(), n_pad, (size_t)(x - plan.lo), d), n_pad);
-  }
+  std::vector<uint32_t> evals(n_evals * ent, 0xdeadbeef), p0((size_t)h * ent), p1((size_t)h * ent), da((size_t)h * ent),
+      db((size_t)h * ent);
+  for (uint32_t part = 0; part < m; part++)
+    for (int32_t x = plan.lo; x <= plan.hi; x++) {
+      fd_seed_eval(f, view, t, d, x, part * h, h);
+      fd_store(f, AX, fd_entry(evals.data(), n_padv, (size_t)(x - plan.lo), part * n_pad + d), n_padv);
+    }
   const size_t e_hi = (size_t)(plan.hi - plan.lo);
   memcpy(da.data(), evals.data() + e_hi * ent, ent * 4);
   memcpy(db.data(), evals.data() + e_hi * ent, ent * 4);
   uint32_t* pp[2] = {p0.data(), p1.data()};
-  const uint32_t* src = evals.data();
-  for (uint32_t r = 1; r < t; r++) {
-    uint32_t* dst = pp[r & 1];
-    for (uint32_t i = 0; i + r < t; i++) fd_init_item(f, src, dst, da.data(), db.data(), n_pad, t, r, i, d);
-    src = dst;
-  }
   uint32_t* dd[2] = {da.data(), db.data()};
-  for (uint32_t tick = 1; tick <= plan.steps + t - 2; tick++) {
-    int32_t k_lo, k_hi;
-    fd_ext_band(t, plan.steps, tick, &k_lo, &k_hi);
-    // items of one tick are independent: run them in descending order to catch any accidental
-    // dependence on the ascending order
-    for (int32_t k = k_hi; k >= k_lo; k--) fd_ext_item(f, dd[(tick & 1) ^ 1], dd[tick & 1], evals.data(), n_pad, t, tick, (uint32_t)k, e_hi, d);
+  for (uint32_t part = 0; part < m; part++) {  // a virtual dealer = one column of the planes
+    const uint32_t vd = part * n_pad + d;
+    const uint32_t* src = evals.data();
+    for (uint32_t r = 1; r < h; r++) {
+      uint32_t* dst = pp[r & 1];
+      for (uint32_t i = 0; i + r < h; i++) fd_init_item(f, src, dst, da.data(), db.data(), n_padv, h, r, i, vd);
+      src = dst;
+    }
+    for (uint32_t tick = 1; tick <= plan.steps + h - 2; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
+      // items of one tick are independent: run them in descending order to catch any accidental
+      // dependence on the ascending order
+      for (int32_t k = k_hi; k >= k_lo; k--)
+        fd_ext_item(f, dd[(tick & 1) ^ 1], dd[tick & 1], evals.data(), n_padv, h, tick, (uint32_t)k, e_hi, vd);
+    }
   }
+  std::vector<uint32_t> dig((size_t)(m > 1 ? m - 1 : 1) * FD_DIG_WORDS);
   for (uint32_t j = 0; j < n_r; j++) {
-    fd_load(f, AX, fd_entry(evals.data(), n_pad, (size_t)((int64_t)(j + 1) - plan.lo), d), n_pad);
+    int top = m > 1 ? fd_comb_digits(j + 1, h, m, dig.data()) : -1;
+    fd_combine_eval(f, evals.data(), n_padv, n_pad, m, (size_t)((int64_t)(j + 1) - plan.lo), d, dig.data(), top);
     g1_compress(g1_to_affine(vm_get_point(f, AX)), out48 + (size_t)j * 48);
   }
   return 0;
+}
+
+// NAF digits of x^(h i) mod r as signed bytes: out[(i-1) * 256 + b] in {-1, 0, 1}; returns top
+int he_fd_digits(uint32_t x, uint32_t h, uint32_t m, int8_t* out) {
+  std::vector<uint32_t> dig((size_t)(m - 1) * FD_DIG_WORDS);
+  int top = fd_comb_digits(x, h, m, dig.data());
+  for (uint32_t i = 1; i < m; i++)
+    for (int b = 0; b < 256; b++) {
+      const uint32_t* pos = dig.data() + (size_t)(i - 1) * FD_DIG_WORDS;
+      out[(i - 1) * 256 + b] = (int8_t)(((pos[b >> 5] >> (b & 31)) & 1) - ((pos[8 + (b >> 5)] >> (b & 31)) & 1));
+    }
+  return top;
 }
 }
 

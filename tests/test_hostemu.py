@@ -125,23 +125,42 @@ def test_tower_pairing_h2c(L):
 
 
 def test_finite_difference_row(L):
-    """fdiff.cuh: seeds by Horner on a window around 0, backward differences, wavefront extension -
-    every f(1..n) must equal the oracle's evaluate_polynomial (dkg_math.rs:160-174)"""
+    """fdiff.cuh: polynomial split into m parts, seeds by Horner on a window around 0, backward
+    differences, wavefront extension, joint double-and-add recombination - every f(1..n) must equal the
+    oracle's evaluate_polynomial (dkg_math.rs:160-174)"""
     rnd = random.Random(5)
-    for t, n_r, lo in [(2, 5, None), (3, 9, None), (3, 9, 1), (3, 9, -1), (5, 12, None), (5, 12, -3), (5, 6, 1), (8, 20, None)]:
+    NONE = 0x7FFFFFFF
+    cases = [(2, 5, 1, None), (3, 9, 1, None), (3, 9, 1, 1), (3, 9, 1, -1), (5, 12, 1, None), (5, 12, 1, -3), (5, 6, 1, 1), (8, 20, 0, None),
+             (8, 20, 2, None), (9, 20, 2, 0), (7, 7, 2, None), (12, 9, 3, None), (12, 30, 4, None), (13, 16, 5, 1)]
+    for t, n_r, m, lo in cases:
         coef = [rnd.randrange(B.R) for _ in range(t)]
         if t == 5:
             coef[2] = 0  # an identity coefficient
         vv = b"".join(B.g1_compress(B.g1_mul(B.G1, c)) for c in coef)
-        plan = (ctypes.c_int32 * 4)()
+        plan = (ctypes.c_int32 * 6)()
         out = buf(48 * n_r)
-        rc = L.he_fd_row(vv, t, n_r, ctypes.c_int32(0x7FFFFFFF if lo is None else lo), plan, out)
-        assert rc == 0, (t, n_r, lo, rc)
-        assert plan[2] - plan[1] + 1 == t and plan[1] <= 1 <= plan[2] and plan[3] == n_r - plan[2]
+        rc = L.he_fd_row(vv, t, n_r, m, ctypes.c_int32(NONE if lo is None else lo), plan, out)
+        assert rc == 0, (t, n_r, m, lo, rc)
+        _, pm, ph, plo, phi, steps = list(plan)
+        assert (m == 0 or pm == m) and ph == -(-t // pm) and phi - plo + 1 == ph and plo <= 1 <= phi and steps == n_r - phi
         for j in range(n_r):
             want = B.g1_compress(B.g1_mul(B.G1, sum(c * pow(j + 1, k, B.R) for k, c in enumerate(coef)) % B.R))
-            assert out.raw[48 * j:48 * j + 48] == want, (t, n_r, lo, j)
-    plan = (ctypes.c_int32 * 4)()
-    assert L.he_fd_row(bytes(48), 1, 5, ctypes.c_int32(0x7FFFFFFF), plan, buf(48 * 5)) == -1 and plan[0] == 0
-    L.he_fd_row(bytes(48 * 683), 683, 1024, ctypes.c_int32(0x7FFFFFFF), plan, buf(48))  # plan only (vv undecodable -> -3)
-    assert plan[0] == 1 and plan[1] < 0 < plan[2] and plan[2] - plan[1] == 682
+            assert out.raw[48 * j:48 * j + 48] == want, (t, n_r, m, lo, j)
+    plan = (ctypes.c_int32 * 6)()
+    assert L.he_fd_row(bytes(48), 1, 5, 0, ctypes.c_int32(NONE), plan, buf(48 * 5)) == -1 and plan[0] == 0
+    L.he_fd_row(bytes(48 * 683), 683, 1024, 0, ctypes.c_int32(NONE), plan, buf(48))  # plan only (vv undecodable -> -3)
+    assert plan[0] == 1 and plan[1] > 1 and plan[3] < 0 < plan[4]
+
+
+def test_recombination_digits(L):
+    """fd_comb_digits: signed digits of x^(h i) mod r are a non-adjacent form of the right value"""
+    out = (ctypes.c_int8 * (256 * 5))()
+    for x, h, m in [(1, 7, 2), (2, 114, 6), (1024, 114, 6), (777, 1, 3), (0xFFFFFFFF, 65535, 4)]:
+        top = L.he_fd_digits(x, h, m, out)
+        tops = []
+        for i in range(1, m):
+            dg = [out[(i - 1) * 256 + b] for b in range(256)]
+            assert sum(dv << b for b, dv in enumerate(dg)) == pow(x, h * i, B.R)
+            assert all(not (dg[b] and dg[b + 1]) for b in range(255))
+            tops.append(max([b for b in range(256) if dg[b]], default=-1))
+        assert top == max(tops)
