@@ -19,6 +19,16 @@ __global__ void __launch_bounds__(32) k_g2_decode(const uint8_t* __restrict__ in
   st[i] = (uint8_t)s;
 }
 
+// one thread per hashed message: its 68 Miller-loop lines, shared by every check against that message
+__global__ void __launch_bounds__(32) k_g2_prepare(const G2Aff* __restrict__ hm, const uint8_t* __restrict__ st, G2Line* __restrict__ lines,
+                                                   uint32_t n_hm) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_hm) return;
+  G2Aff a = hm[i];
+  if (st[i] != G1_DEC_OK || a.inf) return;  // never read: the check is skipped / the pair is the Gt identity
+  g2_prepare(lines + (size_t)i * G2_PREP_LINES, &a);
+}
+
 __global__ void __launch_bounds__(32) k_g2_decompress_check(const uint8_t* __restrict__ in, uint8_t* __restrict__ st, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -44,7 +54,7 @@ __global__ void __launch_bounds__(32) k_hash_to_g2(const uint8_t* __restrict__ m
 //  .expect -> panic in verify_generation_hashes, slashable in prove_wrong_final_key_generation)
 __global__ void __launch_bounds__(32)
 k_bls_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ sig, const G2Aff* __restrict__ hm,
-             const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status, uint32_t m) {
+             const G2Line* __restrict__ hm_lines, const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   // decode order of the reference: signature first, then key (verification.rs:238-241)
@@ -58,8 +68,10 @@ k_bls_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ sig, co
   } else if (dp != G1_DEC_OK) {
     st = DKGV_PANIC_BAD_G1;
   } else {
-    G2Aff h = hm[hm_idx ? hm_idx[i] : 0];
-    st = bls_verify_precomputed(&p, &s, &h) ? DKGV_OK : DKGV_SLASHABLE_SIG_INVALID;
+    uint32_t hi = hm_idx ? hm_idx[i] : 0;
+    G2Aff h = hm[hi];
+    st = bls_verify_prepared(&p, &s, &h, hm_lines ? hm_lines + (size_t)hi * G2_PREP_LINES : nullptr) ? DKGV_OK
+                                                                                                       : DKGV_SLASHABLE_SIG_INVALID;
   }
   status[i] = st;
 }
@@ -170,7 +182,17 @@ extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_
   k_g2_decode<<<(n_hm + 31) / 32, 32, 0, s>>>(d_hm, (G2Aff*)ctx->scratch_a.p, (uint8_t*)ctx->scratch_b.p, n_hm);
   ctx->launches++;
   CK(cudaGetLastError());
-  k_bls_verify<<<(m + 31) / 32, 32, 0, s>>>(d_pk, d_sig, (const G2Aff*)ctx->scratch_a.p, d_hm_idx, d_status, m);
+  // messages shared by several checks: their lines are computed once (19.6 KB per message)
+  const G2Line* lines = nullptr;
+  if ((size_t)n_hm * 4 <= m && (size_t)n_hm * G2_PREP_LINES * sizeof(G2Line) <= ((size_t)256 << 20)) {
+    CK(ctx->scratch_c.reserve((size_t)n_hm * G2_PREP_LINES * sizeof(G2Line)));
+    k_g2_prepare<<<(n_hm + 31) / 32, 32, 0, s>>>((const G2Aff*)ctx->scratch_a.p, (const uint8_t*)ctx->scratch_b.p, (G2Line*)ctx->scratch_c.p,
+                                                 n_hm);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    lines = (const G2Line*)ctx->scratch_c.p;
+  }
+  k_bls_verify<<<(m + 31) / 32, 32, 0, s>>>(d_pk, d_sig, (const G2Aff*)ctx->scratch_a.p, lines, d_hm_idx, d_status, m);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

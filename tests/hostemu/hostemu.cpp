@@ -264,7 +264,14 @@ int he_bls_verify_hm(const uint8_t* pk48, const uint8_t* sig96, const uint8_t* h
   if (g1_decompress(pk48, &pk, true) != G1_DEC_OK) return -48;
   if (g2_decompress(sig96, &sig, true) != G1_DEC_OK) return -49;
   if (g2_decompress(hm96, &hm, true) != G1_DEC_OK) return -49;
-  return bls_verify_precomputed(&pk, &sig, &hm) ? 1 : 0;
+  int plain = bls_verify_precomputed(&pk, &sig, &hm) ? 1 : 0;
+  if (!hm.inf) {  // the prepared-lines route of k_bls_verify must agree
+    std::vector<G2Line> lines(G2_PREP_LINES);
+    g2_prepare(lines.data(), &hm);
+    int prep = bls_verify_prepared(&pk, &sig, &hm, lines.data()) ? 1 : 0;
+    if (prep != plain) return -100;
+  }
+  return plain;
 }
 // e(P,Q)^3 as 576 canonical big-endian bytes, same layout as orc_pairing_bytes
 int he_pairing_bytes(const uint8_t* p48, const uint8_t* q96, uint8_t* out576) {
