@@ -300,12 +300,26 @@ def run_b200(args):
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
             hot_ms.append(v.last_hot_kernel_ms())
-            if v.last_share_path == v.PATH_FDIFF:
-                phase_ms.append(v.last_share_phases_ms())
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
         clocks = sampler.stop() if rank == 0 else None
+        if v.last_share_path == v.PATH_FDIFF:
+            # per-kernel times: the timed steps above run the parts on concurrent streams, where single
+            # phases have no duration of their own; repeat the same steps phase after phase on one stream
+            v.set_share_overlap(False)
+            serial_ms = []
+            for _ in range(args.steps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ts)
+                step_device()
+                e1.record(ts)
+                e1.synchronize()
+                serial_ms.append(e0.elapsed_time(e1))
+                phase_ms.append(v.last_share_phases_ms())
+            v.set_share_overlap(True)
+            barrier()
 
         total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -369,51 +383,66 @@ def run_b200(args):
         hot = statistics.mean(hot_ms)
         MODMUL_PER_SHARE = canonical_modmul_per_share(n, t)
         fdiff = v.last_share_path == v.PATH_FDIFF
-        if fdiff:
-            # dominant kernel: k_fd_seed = t Horner evaluations per dealer at the plan's seed points
-            plan = dk.share_fd_plan(t, n, args.parts)
-            m_parts, h_part = plan["parts"], plan["h"]
-            seeds = range(plan["lo"], plan["hi"] + 1)
-            kernel = "k_fd_seed"
-            units_per_launch = rows * m_parts * h_part
-            canon_unit = sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part
-            exec_unit = sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part
-            algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144  # decoded vv read once + projective evaluations written
-        else:
-            plan = None
-            kernel = "k_share_verify"
-            units_per_launch = rows * n
-            canon_unit = MODMUL_PER_SHARE
-            exec_unit = executed_modmul_per_share(n, t)
-            algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
-        achieved = units_per_launch * canon_unit * MAC_PER_MODMUL / (hot * 1e-3)
-        executed = units_per_launch * exec_unit * MAC_PER_MODMUL / (hot * 1e-3)
         step_mean = statistics.mean(step_ms)
         # whole path: canonical per-share work (84 314 modmul) of every verified share per second of step time
         path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / (step_mean * 1e-3)
-        roof = {"bound": "int_pipe", "kernel": kernel, "achieved": achieved / 1e9, "peak": peak["imad_wide"] / 1e9,
-                "unit": "G wide-MAC/s (32x32->64)", "frac": achieved / peak["imad_wide"], "peak_source": peak["source"],
+
+        def kernel_entry(name, units, unit_is, canon_unit, exec_unit, ms, ref_ms):
+            a, e = units * canon_unit * MAC_PER_MODMUL / (ms * 1e-3), units * exec_unit * MAC_PER_MODMUL / (ms * 1e-3)
+            return {"kernel": name, "achieved": a / 1e9, "frac": a / peak["imad_wide"],
+                    "frac_of_carry_chain_peak": (a / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                    "executed_gmac_per_s": e / 1e9,
+                    "executed_frac_of_carry_chain_peak": (e / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                    "kernel_ms": ms, "kernel_share_of_step": ms / ref_ms, "units_per_launch_total": units, "unit_is": unit_is,
+                    "modmul_per_unit": canon_unit, "executed_modmul_per_unit": exec_unit}
+
+        if fdiff:
+            plan = dk.share_fd_plan(t, n, args.parts)
+            m_parts, h_part = plan["parts"], plan["h"]
+            seeds = range(plan["lo"], plan["hi"] + 1)
+            ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
+            ref = statistics.mean(serial_ms)
+            comb_canon = (255 * 8 + (m_parts - 1) * 85 * 12 + 12 if m_parts > 1 else 0) + 33 * 11 + 4
+            kernels = [
+                kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
+                             sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
+                             sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part, ph[0], ref),
+                kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, 12, ph[1], ref),
+                kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, 12, ph[2], ref),
+                kernel_entry("k_fd_combine", rows * n, "one share: joint double-and-add over the parts, G*s, compare", comb_canon, comb_canon,
+                             ph[3], ref),
+            ]
+            top = max(kernels, key=lambda k_: k_["kernel_ms"])
+            algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144
+        else:
+            plan = None
+            kernels = [kernel_entry("k_share_verify", rows * n, "one share", MODMUL_PER_SHARE, executed_modmul_per_share(n, t), hot, step_mean)]
+            top = kernels[0]
+            algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        roof = {"bound": "int_pipe", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak["imad_wide"] / 1e9,
+                "unit": "G wide-MAC/s (32x32->64)", "frac": top["frac"], "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
-                "frac_of_carry_chain_peak": (achieved / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                "executed_gmac_per_s": executed / 1e9,
-                "executed_frac_of_carry_chain_peak": (executed / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                "executed_modmul_per_unit": exec_unit,
-                "kernel_ms": hot, "kernel_share_of_step": hot / step_mean,
-                "units_per_launch": units_per_launch, "unit_is": "one Horner evaluation (dealer, part, seed point)" if fdiff else "one share",
-                "modmul_per_unit": canon_unit, "mac_per_modmul": MAC_PER_MODMUL,
+                "frac_of_carry_chain_peak": top["frac_of_carry_chain_peak"],
+                "executed_gmac_per_s": top["executed_gmac_per_s"],
+                "executed_frac_of_carry_chain_peak": top["executed_frac_of_carry_chain_peak"],
+                "kernel_ms": top["kernel_ms"], "kernel_share_of_step": top["kernel_share_of_step"],
+                "units_per_launch": top["units_per_launch_total"], "unit_is": top["unit_is"],
+                "modmul_per_unit": top["modmul_per_unit"], "mac_per_modmul": MAC_PER_MODMUL,
                 "traffic": None,
+                "kernels": kernels,
                 "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
                                "modmul_per_share_canonical": MODMUL_PER_SHARE,
                                "note": "canonical per-share Horner work of all verified shares / step time; finite differences "
-                                       "execute fewer products than that, so this exceeds the kernel's own utilisation"},
-                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (hot * 1e-3) / 1e9,
+                                       "execute fewer products than that, so this exceeds the kernels' own utilisation"},
+                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
         if fdiff:
-            ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
             roof["fdiff"] = {"parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
                              "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
                              "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "recombine_gs_compare": ph[3]},
-                             "phase_share_of_step": {k: v_ / step_mean for k, v_ in zip(("seed_horner", "differences", "extension", "recombine_gs_compare"), ph)},
+                             "serial_step_ms": ref, "overlapped_step_ms": step_mean,
+                             "note": "phase times from extra steps run phase-after-phase on one stream; the timed steps behind `value` "
+                                     "run the parts on concurrent streams",
                              "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -62,6 +62,7 @@ DECLARED_SYMBOLS = {
     "dkgv_set_share_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_path": (ctypes.c_int, [_vp]),
     "dkgv_set_share_parts": (ctypes.c_int, [_vp, _u32]),
+    "dkgv_set_share_overlap": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
                                           ctypes.POINTER(ctypes.c_uint64)]),
@@ -168,6 +169,10 @@ class Verifier:
 
     def set_share_path(self, mode):
         self._ck(self._lib.dkgv_set_share_path(self._h, int(mode)))
+
+    def set_share_overlap(self, on):
+        """True (default): one internal stream per part; False: one stream, phase after phase"""
+        self._ck(self._lib.dkgv_set_share_overlap(self._h, int(bool(on))))
 
     def set_share_parts(self, parts):
         """parts per dealer polynomial on the finite-difference path (0 = planner's choice)"""

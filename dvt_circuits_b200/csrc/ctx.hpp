@@ -46,6 +46,9 @@ struct dkgv_ctx {
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
   bool fd_recorded = false;
+  bool fd_overlap = true;  // one stream per part (default) or everything on the caller's stream
+  cudaStream_t fd_streams[16] = {};
+  cudaEvent_t fd_fork = nullptr, fd_join[16] = {};
   int share_path = 0;       // DKGV_SHARE_PATH_* requested
   uint32_t share_parts = 0; // 0: planner's choice of parts per dealer; else forced
   int last_share_path = 0;  // path taken by the most recent share-matrix call

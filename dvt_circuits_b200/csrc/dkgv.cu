@@ -273,6 +273,11 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     b->release();
   for (cudaEvent_t ev : ctx->ev_fd)
     if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 16; i++) {
+    if (ctx->fd_streams[i]) cudaStreamSynchronize(ctx->fd_streams[i]), cudaStreamDestroy(ctx->fd_streams[i]);
+    if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
+  }
+  if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
@@ -336,6 +341,11 @@ extern "C" int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts) {
   if (!ctx) return -1;
   if (parts > FD_MAX_PARTS) return fail(ctx, "too many parts");
   ctx->share_parts = parts;
+  return 0;
+}
+extern "C" int dkgv_set_share_overlap(dkgv_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->fd_overlap = on != 0;
   return 0;
 }
 extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo, int32_t* hi,

@@ -21,32 +21,31 @@ constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_seed(VVView vv, const int32_t* __restrict__ seed_x, int32_t lo, uint32_t* __restrict__ evals, uint32_t n_d, uint32_t t,
-          uint32_t h) {
+          uint32_t h, uint32_t part0, uint32_t n_padv) {
   extern __shared__ U4 opfile[];
   uint32_t d = blockIdx.x * 32 + threadIdx.x;
   int32_t x = seed_x[blockIdx.y];  // most expensive points first
-  uint32_t part = blockIdx.z;
+  uint32_t part = part0 + blockIdx.z;
   uint32_t dd = d < n_d ? d : n_d - 1;
   OpFile f{opfile + threadIdx.x, FD_NT};
   fd_seed_eval(f, vv, t, dd, x, part * h, h);
-  uint32_t n_padv = vv.n_pad * gridDim.z;
   fd_store(f, AX, fd_entry(evals, n_padv, (size_t)(x - lo), part * vv.n_pad + d), n_padv);
 }
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_init(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t* __restrict__ da, uint32_t* __restrict__ db,
-          uint32_t n_pad, uint32_t t, uint32_t r) {
+          uint32_t n_pad, uint32_t t, uint32_t r, uint32_t col0) {
   extern __shared__ U4 opfile[];
-  uint32_t d = blockIdx.x * 32 + threadIdx.x;
+  uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
   fd_init_item(f, src, dst, da, db, n_pad, t, r, blockIdx.y, d);
 }
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_ext(const uint32_t* __restrict__ old, uint32_t* __restrict__ cur, uint32_t* __restrict__ evals, uint32_t n_pad, uint32_t t,
-         uint32_t tick, uint32_t k_lo, size_t e_hi) {
+         uint32_t tick, uint32_t k_lo, size_t e_hi, uint32_t col0) {
   extern __shared__ U4 opfile[];
-  uint32_t d = blockIdx.x * 32 + threadIdx.x;
+  uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
   fd_ext_item(f, old, cur, evals, n_pad, t, tick, k_lo + blockIdx.y, e_hi, d);
 }
@@ -81,6 +80,11 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
+  CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
+  for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
+    CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->fd_join[i], cudaEventDisableTiming));
+  }
   return 0;
 }
 
@@ -123,38 +127,78 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   CK(cudaMemcpyAsync(ctx->fd_seedx.p, ctx->fd_seed_host.data(), (size_t)h * 4, cudaMemcpyHostToDevice, s));
 
   const unsigned gx = n_pad / 32, gxv = n_padv / 32;
+  const size_t e_hi = (size_t)(plan.hi - plan.lo);  // == h - 1
+  const uint32_t ticks = plan.steps + h - 2;
+  const bool overlap = ctx->fd_overlap && m > 1;
   CK(cudaEventRecord(ctx->ev_fd[0], s));
   CK(cudaEventRecord(ctx->ev_hot0, s));
-  k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h);
-  CK(cudaEventRecord(ctx->ev_hot1, s));
-  CK(cudaEventRecord(ctx->ev_fd[1], s));
+  if (!overlap) {
+    // one stream, phase after phase over all parts at once (also the mode that yields per-phase times)
+    k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv);
+    CK(cudaEventRecord(ctx->ev_hot1, s));
+    CK(cudaEventRecord(ctx->ev_fd[1], s));
+    ctx->launches++;
+    // backward differences of every part at hi
+    CK(cudaMemcpyAsync(dd[0], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(dd[1], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
+    const uint32_t* src = evals;
+    for (uint32_t r = 1; r < h; r++) {
+      uint32_t* dst = pp[r & 1];
+      k_fd_init<<<dim3(gxv, h - r), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0);
+      ctx->launches++;
+      src = dst;
+    }
+    CK(cudaEventRecord(ctx->ev_fd[2], s));
+    // wavefront extension hi+1 .. n_r
+    for (uint32_t tick = 1; tick <= ticks; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
+      if (k_lo > k_hi) continue;
+      k_fd_ext<<<dim3(gxv, (unsigned)(k_hi - k_lo + 1)), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
+                                                                            (uint32_t)k_lo, e_hi, 0);
+      ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev_fd[3], s));
+  } else {
+    // The parts are independent until the recombination: each runs its seed -> differences -> extension
+    // chain on its own stream, so the tail of one part's kernel is filled by blocks of the others
+    // (no grid-wide barrier per round / tick; matters when a rank holds few dealers).
+    CK(cudaEventRecord(ctx->fd_fork, s));
+    for (uint32_t p = 0; p < m; p++) {
+      cudaStream_t sp = ctx->fd_streams[p];
+      CK(cudaStreamWaitEvent(sp, ctx->fd_fork, 0));
+      k_fd_seed<<<dim3(gx, h, 1), FD_NT, FD_SMEM, sp>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, p, n_padv);
+      ctx->launches++;
+      const size_t w = (size_t)n_pad * 4, pitch = (size_t)n_padv * 4;
+      const uint32_t* col = evals + e_hi * ent_words + (size_t)p * n_pad;
+      CK(cudaMemcpy2DAsync(dd[0] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
+      CK(cudaMemcpy2DAsync(dd[1] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
+    }
+    for (uint32_t r = 1; r < h; r++)
+      for (uint32_t p = 0; p < m; p++) {
+        k_fd_init<<<dim3(gx, h - r), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0], dd[1], n_padv,
+                                                                          h, r, p * n_pad);
+        ctx->launches++;
+      }
+    for (uint32_t tick = 1; tick <= ticks; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
+      if (k_lo > k_hi) continue;
+      for (uint32_t p = 0; p < m; p++) {
+        k_fd_ext<<<dim3(gx, (unsigned)(k_hi - k_lo + 1)), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals,
+                                                                                               n_padv, h, tick, (uint32_t)k_lo, e_hi,
+                                                                                               p * n_pad);
+        ctx->launches++;
+      }
+    }
+    for (uint32_t p = 0; p < m; p++) {
+      CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
+      CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
+    }
+    CK(cudaEventRecord(ctx->ev_hot1, s));
+    for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
+  }
   ctx->hot_recorded = true;
-  ctx->launches++;
-
-  // backward differences of every part at hi
-  const size_t e_hi = (size_t)(plan.hi - plan.lo);  // == h - 1
-  CK(cudaMemcpyAsync(dd[0], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(dd[1], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
-  const uint32_t* src = evals;
-  for (uint32_t r = 1; r < h; r++) {
-    uint32_t* dst = pp[r & 1];
-    k_fd_init<<<dim3(gxv, h - r), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r);
-    ctx->launches++;
-    src = dst;
-  }
-  CK(cudaEventRecord(ctx->ev_fd[2], s));
-
-  // wavefront extension hi+1 .. n_r
-  const uint32_t ticks = plan.steps + h - 2;
-  for (uint32_t tick = 1; tick <= ticks; tick++) {
-    int32_t k_lo, k_hi;
-    fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
-    if (k_lo > k_hi) continue;
-    k_fd_ext<<<dim3(gxv, (unsigned)(k_hi - k_lo + 1)), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
-                                                                          (uint32_t)k_lo, e_hi);
-    ctx->launches++;
-  }
-  CK(cudaEventRecord(ctx->ev_fd[3], s));
 
   if (m > 1) {
     k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (uint32_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);

@@ -95,6 +95,9 @@ int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_r
 enum dkgv_share_path { DKGV_SHARE_PATH_AUTO = 0, DKGV_SHARE_PATH_HORNER = 1, DKGV_SHARE_PATH_FDIFF = 2 };
 int dkgv_set_share_path(dkgv_ctx* ctx, int mode); /* FDIFF: use it whenever applicable, even if not cheaper */
 int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts); /* 0 = planner's choice (default), else 1..16 */
+/* on (default): the parts of the finite-difference path run on one internal stream each and join before the
+ * recombination; off: everything on the caller's stream, phase after phase (gives per-phase device times) */
+int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
 /* the plan for ids 1..n_recipients (parts_force 0 = cheapest): parts, h = ceil(t / parts), Horner seed points
  * lo..hi (hi - lo + 1 == h), extension steps, field products per dealer by this plan and by per-share Horner
@@ -102,7 +105,8 @@ int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the l
  * cheaper, -1 when no plan exists for the shape.  Pure host function.                                */
 int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo,
                        int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner);
-/* device times of the last finite-difference run: seed Horner, differences, extension, recombine + G*s compare */
+/* device times of the last finite-difference run: seed Horner, differences, extension, recombine + G*s compare;
+ * with overlap on the first three run concurrently and only ms4[0] (their total) and ms4[3] are meaningful */
 int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4);
 
 /* ---- evaluate_polynomial (crates/dkg/src/dkg_math.rs:160-174), batched ---------------------- */
