@@ -402,14 +402,15 @@ def run_b200(args):
             seeds = range(plan["lo"], plan["hi"] + 1)
             ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
             ref = statistics.mean(serial_ms)
-            comb_canon = (255 * 8 + (m_parts - 1) * 85 * 12 + 12 if m_parts > 1 else 0) + 33 * 11 + 4
+            # 128 shared doublings (GLV), per point: table 3P/5P/7P (44) + 2 x 128/5 additions + 128/5 products by beta; + part 0; + G*s, compare
+            comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
                              sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part, ph[0], ref),
                 kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, 12, ph[1], ref),
                 kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, 12, ph[2], ref),
-                kernel_entry("k_fd_combine", rows * n, "one share: joint double-and-add over the parts, G*s, compare", comb_canon, comb_canon,
+                kernel_entry("k_fd_combine", rows * n, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare", comb_canon, comb_canon,
                              ph[3], ref),
             ]
             top = max(kernels, key=lambda k_: k_["kernel_ms"])

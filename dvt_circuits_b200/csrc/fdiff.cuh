@@ -16,8 +16,8 @@
 // Splitting.  The seeds cost t Horner chains of t-1 steps each - quadratic in t.  Writing
 //   f(x) = sum_{i<m} y^i f_i(x),   y = x^h mod r,   f_i(x) = sum_{k<h} C_{ih+k} x^k,   h = ceil(t/m)
 // turns one dealer into m "virtual dealers" of degree h-1: m*h = t seeds of h-1 steps (m times less
-// work), the same t-1 additions per extended point, and one joint double-and-add (Straus, NAF digits
-// of the public scalars y^i shared by every dealer of the warp) per share to recombine.  [y]P = [x^h]P
+// work), the same t-1 additions per extended point, and one joint double-and-add (Straus with GLV halves
+// and width-4 signed digits of the public scalars y^i, shared by every dealer of the warp) per share.  [y]P = [x^h]P
 // because every decoded commitment lies in the order-r subgroup (the decoder's subgroup check).
 //
 // Exact group arithmetic throughout (same complete RCB formulas), so every evaluation is the same
@@ -126,12 +126,78 @@ DKGV_HD void fd_ext_band(uint32_t t, uint32_t steps, uint32_t tick, int32_t* k_l
 }
 
 // ---- recombination of the m parts ---------------------------------------------------------------
+// sum_i [k_i] P_i with k_i = y^i mod r (public, the same for every dealer) and P_i = f_i(x):
+//  * GLV: z^2 P = -phi(P) = (beta X : -Y : Z) on G1 (z the curve parameter, r = z^4 - z^2 + 1; the same
+//    endomorphism the subgroup check of g1.cuh uses), so k = k1 + k2 z^2 with k2 = k div z^2, k1 = k mod z^2
+//    (both < 2^128, no lattice rounding needed) halves the doublings: [k]P = [k1]P + [k2](-phi(P));
+//  * width-4 signed windows: digits in {+-1, +-3, +-5, +-7}, one non-zero digit in five on average, against
+//    a per-share table {P, 3P, 5P, 7P} (phi is applied to the table entry on the fly: one product).
 constexpr uint32_t FD_MAX_PARTS = 16;
-constexpr uint32_t FD_DIG_WORDS = 16;  // per (x, i): 8 words of +1 digits, 8 words of -1 digits (NAF, 256 positions)
+constexpr uint32_t FD_GLV_DIGITS = 132;   // positions per half scalar (at most 130 used)
+constexpr uint32_t FD_TAB_SLOTS = 4;      // per point: 2P (scratch), 3P, 5P, 7P
+DKGV_HD size_t fd_dig_bytes(uint32_t m) { return (size_t)(m > 1 ? m - 1 : 1) * 2 * FD_GLV_DIGITS; }
 
-// NAF digit masks of the public scalars y^i (i = 1..m-1), y = x^h mod r; returns the highest digit
-// position over all i (-1 if every scalar is zero).  dig: (m-1) * FD_DIG_WORDS words.
-DKGV_HD int fd_comb_digits(uint32_t x, uint32_t h, uint32_t m, uint32_t* dig) {
+// width-4 NAF of a value of at most 129 bits (5 limbs, destroyed); returns the top non-zero position or -1
+DKGV_HD int fd_wnaf4(uint32_t* k, int8_t* out) {
+  int top = -1;
+  for (uint32_t b = 0; b < FD_GLV_DIGITS; b++) {
+    int dgt = 0;
+    if (k[0] & 1) {
+      dgt = (int)(k[0] & 15);
+      if (dgt >= 8) dgt -= 16;
+      // k -= dgt
+      uint64_t c;
+      if (dgt > 0) {
+        uint64_t br = (uint64_t)dgt;
+        for (int w = 0; w < 5; w++) {
+          uint64_t v = (uint64_t)k[w] - br;
+          k[w] = (uint32_t)v;
+          br = (v >> 32) & 1;
+        }
+      } else {
+        c = (uint64_t)(-dgt);
+        for (int w = 0; w < 5; w++) {
+          c += k[w];
+          k[w] = (uint32_t)c;
+          c >>= 32;
+        }
+      }
+      top = (int)b;
+    }
+    out[b] = (int8_t)dgt;
+    for (int w = 0; w < 4; w++) k[w] = (k[w] >> 1) | (k[w + 1] << 31);
+    k[4] >>= 1;
+  }
+  return top;
+}
+
+// k (canonical, 8 limbs, < r) -> k1 = k mod z^2, k2 = k div z^2 (5-limb buffers, top limb 0)
+DKGV_HD void fd_glv_split(const uint32_t* k, uint32_t* k1, uint32_t* k2) {
+  const uint32_t Z2[5] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u, 0u};  // z^2, z = -0xd201000000010000
+  uint32_t rem[5] = {0, 0, 0, 0, 0};
+  for (int w = 0; w < 5; w++) k2[w] = 0;
+  for (int b = 255; b >= 0; b--) {
+    for (int w = 4; w > 0; w--) rem[w] = (rem[w] << 1) | (rem[w - 1] >> 31);
+    rem[0] = (rem[0] << 1) | ((k[b >> 5] >> (b & 31)) & 1);
+    uint32_t tmp[5];
+    uint64_t br = 0;
+    for (int w = 0; w < 5; w++) {
+      uint64_t v = (uint64_t)rem[w] - Z2[w] - br;
+      tmp[w] = (uint32_t)v;
+      br = (v >> 32) & 1;
+    }
+    if (!br) {
+      for (int w = 0; w < 5; w++) rem[w] = tmp[w];
+      if (b < 160) k2[b >> 5] |= 1u << (b & 31);  // b < 128 whenever the quotient bit is set (k < r < 2^255, z^2 > 2^127)
+    }
+  }
+  for (int w = 0; w < 5; w++) k1[w] = rem[w];
+}
+
+// Signed digits of the recombination scalars y^i (i = 1..m-1), y = x^h mod r:
+//   dig[((i-1)*2 + half) * FD_GLV_DIGITS + b], half 0 = k1 (acts on P_i), half 1 = k2 (acts on -phi(P_i)).
+// Returns the highest non-zero position over all of them (-1 if none).
+DKGV_HD int fd_comb_digits(uint32_t x, uint32_t h, uint32_t m, int8_t* dig) {
   Fr xm = zero<FrParams>();
   xm.l[0] = x;
   xm = to_mont(xm);
@@ -144,50 +210,68 @@ DKGV_HD int fd_comb_digits(uint32_t x, uint32_t h, uint32_t m, uint32_t* dig) {
   int top = -1;
   for (uint32_t i = 1; i < m; i++) {
     Fr s = from_mont(p);
-    uint32_t s3[9];
-    uint64_t c = 0;
-    for (int w = 0; w < 8; w++) {
-      c += (uint64_t)s.l[w] * 3;
-      s3[w] = (uint32_t)c;
-      c >>= 32;
-    }
-    s3[8] = (uint32_t)c;
-    uint32_t* pos = dig + (size_t)(i - 1) * FD_DIG_WORDS;
-    uint32_t* neg = pos + 8;
-    for (int w = 0; w < 8; w++) {
-      uint32_t sw = s.l[w], sn = w < 7 ? s.l[w + 1] : 0u;
-      uint32_t plo = s3[w] & ~sw, phi = s3[w + 1] & ~sn;  // bits of (3s & ~s), this word and the next
-      uint32_t nlo = ~s3[w] & sw, nhi = ~s3[w + 1] & sn;
-      pos[w] = (plo >> 1) | (phi << 31);
-      neg[w] = (nlo >> 1) | (nhi << 31);
-      uint32_t any = pos[w] | neg[w];
-      for (int b = 31; b >= 0; b--)
-        if ((any >> b) & 1) {
-          if (32 * w + b > top) top = 32 * w + b;
-          break;
-        }
-    }
+    uint32_t k1[5], k2[5];
+    fd_glv_split(s.l, k1, k2);
+    int t1 = fd_wnaf4(k1, dig + (size_t)((i - 1) * 2) * FD_GLV_DIGITS);
+    int t2 = fd_wnaf4(k2, dig + (size_t)((i - 1) * 2 + 1) * FD_GLV_DIGITS);
+    if (t1 > top) top = t1;
+    if (t2 > top) top = t2;
     p = mul(p, y);
   }
   return top;
 }
 
+DKGV_NI void vm_mul_beta(OpFile f, int d, int a) {
+  Fp beta;
+#pragma unroll
+  for (int i = 0; i < 12; i++) beta.l[i] = consts::BETA_M(i);
+  of_store(f, d, mul(of_load(f, a), beta));
+}
+
 // A <- sum_i [y^i] f_i(x): entries of the m virtual dealers (part i of dealer d sits at column
-// i * n_pad + d of a plane n_padv = m * n_pad wide), joint double-and-add over the NAF digits.
-// Control flow depends on (x, h, m) only - warp-uniform when all lanes share the recipient.
-DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e,
-                             uint32_t d, const uint32_t* dig, int top) {
+// i * n_pad + d of a plane n_padv = m * n_pad wide).  tab: this share's table plane, entry
+// (i-1) * FD_TAB_SLOTS + slot for column d of a plane n_pad wide.  Control flow depends on (x, h, m)
+// only - warp-uniform when all lanes share the recipient.
+DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e, uint32_t d,
+                             const int8_t* dig, int top, uint32_t* tab) {
+  // odd multiples 3P, 5P, 7P of every point that has a non-trivial scalar
+  if (top >= 0) {
+#pragma unroll 1
+    for (uint32_t i = 1; i < m; i++) {
+      const uint32_t* pi = fd_entry(evals, n_padv, e, i * n_pad + d);
+      uint32_t* t2 = fd_entry(tab, n_pad, (size_t)(i - 1) * FD_TAB_SLOTS, d);
+      fd_load(f, AX, pi, n_padv);
+      vm_g1_dbl(f);
+      fd_store(f, AX, t2, n_pad);
+      fd_load(f, BX, pi, n_padv);
+#pragma unroll 1
+      for (uint32_t sl = 1; sl < FD_TAB_SLOTS; sl++) {
+        vm_g1_add(f);
+        fd_store(f, AX, fd_entry(tab, n_pad, (size_t)(i - 1) * FD_TAB_SLOTS + sl, d), n_pad);
+        if (sl + 1 < FD_TAB_SLOTS) fd_load(f, BX, t2, n_pad);
+      }
+    }
+  }
   bool started = false;
 #pragma unroll 1
   for (int b = top; b >= 0; b--) {
     if (started) vm_g1_dbl(f);
 #pragma unroll 1
-    for (uint32_t i = 1; i < m; i++) {
-      const uint32_t* pos = dig + (size_t)(i - 1) * FD_DIG_WORDS;
-      bool p = (pos[b >> 5] >> (b & 31)) & 1, n = (pos[8 + (b >> 5)] >> (b & 31)) & 1;
-      if (!(p || n)) continue;
-      fd_load(f, BX, fd_entry(evals, n_padv, e, i * n_pad + d), n_padv);
-      if (n) vm_neg(f, BY, BY);
+    for (uint32_t ih = 0; ih < 2 * (m - 1); ih++) {
+      int dg = dig[(size_t)ih * FD_GLV_DIGITS + b];
+      if (dg == 0) continue;
+      uint32_t i = 1 + (ih >> 1);
+      bool half = ih & 1, ng = dg < 0;
+      uint32_t a = (uint32_t)(ng ? -dg : dg);
+      if (a == 1)
+        fd_load(f, BX, fd_entry(evals, n_padv, e, i * n_pad + d), n_padv);
+      else
+        fd_load(f, BX, fd_entry(tab, n_pad, (size_t)(i - 1) * FD_TAB_SLOTS + (a >> 1), d), n_pad);
+      if (half) {  // -phi(P) = (beta X : -Y : Z)
+        vm_mul_beta(f, BX, BX);
+        ng = !ng;
+      }
+      if (ng) vm_neg(f, BY, BY);
       if (started) {
         vm_g1_add(f);
       } else {
@@ -206,9 +290,9 @@ DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_
 // recombine, then compare with G * s: the tail of verify_seed_exchange_commitment
 // (crates/dkg/src/verification.rs:92-99,138-146), same status contract as vm_share_check
 DKGV_HD uint8_t fd_combine_compare_item(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e,
-                                        uint32_t d, const uint32_t* dig, int top, const uint8_t* secret_be, const uint32_t* gtab,
-                                        bool dealer_bad) {
-  fd_combine_eval(f, evals, n_padv, n_pad, m, e, d, dig, top);
+                                        uint32_t d, const int8_t* dig, int top, uint32_t* tab, const uint8_t* secret_be,
+                                        const uint32_t* gtab, bool dealer_bad) {
+  fd_combine_eval(f, evals, n_padv, n_pad, m, e, d, dig, top, tab);
   uint32_t s[8];
   bool in_range = fr_raw_from_be32(s, secret_be);
   vm_fixed_base_mul(f, gtab, s);
@@ -225,6 +309,10 @@ inline uint64_t fd_horner_cost(uint32_t t, uint32_t ax) {
   SmallChain c = make_small_chain(ax);
   return (uint64_t)(t - 1) * (uint64_t)(chain_cost(c.pos, c.neg, c.top) + 12);
 }
+
+// field products of one recombination: 128 shared doublings, per point a table (1 doubling + 3 additions),
+// 2 * 128/5 additions and 128/5 products by beta; one more addition for part 0
+inline uint64_t fd_comb_cost(uint32_t m) { return m > 1 ? 128 * 8 + (uint64_t)(m - 1) * (44 + 52 * 12 + 26) + 12 : 0; }
 
 struct FdPlan {
   bool use;          // finite differences pay off for this shape
@@ -267,7 +355,7 @@ inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0) {
     if (h < 2 || n_r <= h || (m > 1 && (uint64_t)(m - 1) * h >= t)) continue;  // every part must hold a coefficient
     int32_t lo = 1;
     uint64_t c = (uint64_t)m * fd_best_window(h, n_r, &lo);
-    if (m > 1) c += (uint64_t)n_r * (255 * 8 + (uint64_t)(m - 1) * 85 * 12 + 12);  // joint NAF double-and-add per share
+    if (m > 1) c += (uint64_t)n_r * fd_comb_cost(m);
     if (c < p.cost_fd) {
       p.cost_fd = c;
       p.m = m;

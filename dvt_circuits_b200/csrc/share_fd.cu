@@ -51,26 +51,30 @@ k_fd_ext(const uint32_t* __restrict__ old, uint32_t* __restrict__ cur, uint32_t*
 }
 
 __global__ void __launch_bounds__(128)
-k_fd_digits(uint32_t n_r, uint32_t h, uint32_t m, uint32_t* __restrict__ dig, int32_t* __restrict__ top) {
+k_fd_digits(uint32_t n_r, uint32_t h, uint32_t m, int8_t* __restrict__ dig, int32_t* __restrict__ top) {
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (x > n_r) return;
-  top[x - 1] = fd_comb_digits(x, h, m, dig + (size_t)(x - 1) * (m - 1) * FD_DIG_WORDS);
+  top[x - 1] = fd_comb_digits(x, h, m, dig + (size_t)(x - 1) * fd_dig_bytes(m));
 }
 
+// recipients j0 .. j0 + gridDim.y - 1; tab holds one table plane per (recipient of this launch, point, slot)
 __global__ void __launch_bounds__(FD_NT)
-k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const uint32_t* __restrict__ dig, const int32_t* __restrict__ top,
+k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
              const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab,
-             const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t n_pad, uint32_t n_d, uint32_t n_r) {
+             const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t* __restrict__ tab, uint32_t n_pad,
+             uint32_t n_d, uint32_t n_r, uint32_t j0) {
   extern __shared__ U4 opfile[];
   uint32_t d = blockIdx.x * 32 + threadIdx.x;
-  uint32_t j = blockIdx.y;
+  uint32_t j = j0 + blockIdx.y;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
   OpFile f{opfile + threadIdx.x, FD_NT};
   uint32_t x = ids[j];
   size_t e = (size_t)((int64_t)x - lo);
-  uint8_t st = fd_combine_compare_item(f, evals, n_pad * m, n_pad, m, e, dd, dig + (size_t)(x - 1) * (m - 1) * FD_DIG_WORDS,
-                                       m > 1 ? top[x - 1] : -1, shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
+  uint32_t* my_tab = tab + (size_t)blockIdx.y * (m - 1) * FD_TAB_SLOTS * 36 * n_pad;  // column d, not dd: private to this thread
+  uint8_t st = fd_combine_compare_item(f, evals, n_pad * m, n_pad, m, e, dd, dig + (size_t)(x - 1) * fd_dig_bytes(m),
+                                       m > 1 ? top[x - 1] : -1, my_tab + (d - dd), shares + ((size_t)dd * n_r + j) * 32, gtab,
+                                       dealer_bad[dd] != 0);
   if (active) status[(size_t)d * n_r + j] = st;
 }
 
@@ -111,7 +115,14 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   CK(ctx->fd_da.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_db.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_seedx.reserve((size_t)h * 4));
-  CK(ctx->fd_dig.reserve((size_t)n_r * (m > 1 ? m - 1 : 1) * FD_DIG_WORDS * 4));
+  CK(ctx->fd_dig.reserve((size_t)n_r * fd_dig_bytes(m)));
+  // per-share tables of the recombination: recipients are processed in chunks that fit the budget
+  const size_t tab_per_recipient = (size_t)(m > 1 ? m - 1 : 0) * FD_TAB_SLOTS * 36 * n_pad * 4;
+  const size_t tab_budget = (size_t)4 << 30;
+  uint32_t chunk_r = n_r;
+  if (tab_per_recipient && tab_per_recipient * chunk_r > tab_budget) chunk_r = (uint32_t)(tab_budget / tab_per_recipient);
+  if (chunk_r == 0) chunk_r = 1;
+  CK(ctx->fd_tab.reserve(tab_per_recipient ? tab_per_recipient * chunk_r : 16));
   CK(ctx->fd_top.reserve((size_t)n_r * 4));
   uint32_t* evals = (uint32_t*)ctx->fd_evals.p;
   uint32_t* pp[2] = {(uint32_t*)ctx->fd_p0.p, (uint32_t*)ctx->fd_p1.p};
@@ -201,13 +212,16 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   ctx->hot_recorded = true;
 
   if (m > 1) {
-    k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (uint32_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
+    k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
     ctx->launches++;
   }
-  k_fd_combine<<<dim3(gx, n_r), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const uint32_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p,
-                                                     d_ids, d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status, n_pad,
-                                                     n_d, n_r);
-  ctx->launches++;
+  for (uint32_t j0 = 0; j0 < n_r; j0 += chunk_r) {
+    uint32_t nj = n_r - j0 < chunk_r ? n_r - j0 : chunk_r;
+    k_fd_combine<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
+                                                      d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status,
+                                                      (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, j0);
+    ctx->launches++;
+  }
   CK(cudaEventRecord(ctx->ev_fd[4], s));
   ctx->fd_recorded = true;
   CK(cudaGetLastError());

@@ -221,26 +221,18 @@ int he_fd_row(const uint8_t* vv, uint32_t t, uint32_t n_r, uint32_t m_force, int
         fd_ext_item(f, dd[(tick & 1) ^ 1], dd[tick & 1], evals.data(), n_padv, h, tick, (uint32_t)k, e_hi, vd);
     }
   }
-  std::vector<uint32_t> dig((size_t)(m > 1 ? m - 1 : 1) * FD_DIG_WORDS);
+  std::vector<int8_t> dig(fd_dig_bytes(m));
+  std::vector<uint32_t> tab((size_t)(m > 1 ? m - 1 : 1) * FD_TAB_SLOTS * 36 * n_pad, 0xdeadbeef);
   for (uint32_t j = 0; j < n_r; j++) {
     int top = m > 1 ? fd_comb_digits(j + 1, h, m, dig.data()) : -1;
-    fd_combine_eval(f, evals.data(), n_padv, n_pad, m, (size_t)((int64_t)(j + 1) - plan.lo), d, dig.data(), top);
+    fd_combine_eval(f, evals.data(), n_padv, n_pad, m, (size_t)((int64_t)(j + 1) - plan.lo), d, dig.data(), top, tab.data());
     g1_compress(g1_to_affine(vm_get_point(f, AX)), out48 + (size_t)j * 48);
   }
   return 0;
 }
 
-// NAF digits of x^(h i) mod r as signed bytes: out[(i-1) * 256 + b] in {-1, 0, 1}; returns top
-int he_fd_digits(uint32_t x, uint32_t h, uint32_t m, int8_t* out) {
-  std::vector<uint32_t> dig((size_t)(m - 1) * FD_DIG_WORDS);
-  int top = fd_comb_digits(x, h, m, dig.data());
-  for (uint32_t i = 1; i < m; i++)
-    for (int b = 0; b < 256; b++) {
-      const uint32_t* pos = dig.data() + (size_t)(i - 1) * FD_DIG_WORDS;
-      out[(i - 1) * 256 + b] = (int8_t)(((pos[b >> 5] >> (b & 31)) & 1) - ((pos[8 + (b >> 5)] >> (b & 31)) & 1));
-    }
-  return top;
-}
+// signed digits of x^(h i) mod r: out[((i-1)*2 + half) * 132 + b]; returns top
+int he_fd_digits(uint32_t x, uint32_t h, uint32_t m, int8_t* out) { return fd_comb_digits(x, h, m, out); }
 }
 
 // ---- tower / pairing / hash-to-G2 (tower.cuh, h2c.cuh) -------------------------------------------

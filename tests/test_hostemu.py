@@ -153,14 +153,25 @@ def test_finite_difference_row(L):
 
 
 def test_recombination_digits(L):
-    """fd_comb_digits: signed digits of x^(h i) mod r are a non-adjacent form of the right value"""
-    out = (ctypes.c_int8 * (256 * 5))()
-    for x, h, m in [(1, 7, 2), (2, 114, 6), (1024, 114, 6), (777, 1, 3), (0xFFFFFFFF, 65535, 4)]:
-        top = L.he_fd_digits(x, h, m, out)
+    """fd_comb_digits: k = x^(h i) mod r splits as k1 + k2 z^2 (GLV), each half in width-4 signed digits"""
+    Z2 = 0xD201000000010000 ** 2
+    out = (ctypes.c_int8 * (132 * 2 * 5))()
+    for x, h, m in [(1, 7, 2), (2, 114, 6), (1024, 114, 6), (777, 1, 3), (0xFFFFFFFF, 65535, 4), (3, (B.R - 1) // 2, 2)]:
+        top = L.he_fd_digits(x, h & 0xFFFFFFFF, m, out)
         tops = []
         for i in range(1, m):
-            dg = [out[(i - 1) * 256 + b] for b in range(256)]
-            assert sum(dv << b for b, dv in enumerate(dg)) == pow(x, h * i, B.R)
-            assert all(not (dg[b] and dg[b + 1]) for b in range(255))
-            tops.append(max([b for b in range(256) if dg[b]], default=-1))
+            ks = []
+            for half in (0, 1):
+                dg = [out[((i - 1) * 2 + half) * 132 + b] for b in range(132)]
+                assert all(dv == 0 or (dv % 2 and abs(dv) <= 7) for dv in dg)
+                nz = [b for b in range(132) if dg[b]]
+                assert all(b2 - b1 >= 4 for b1, b2 in zip(nz, nz[1:]))
+                tops.append(max(nz, default=-1))
+                ks.append(sum(dv << b for b, dv in enumerate(dg)))
+            assert 0 <= ks[0] < Z2 and 0 <= ks[1] < 2 ** 128
+            assert ks[0] + ks[1] * Z2 == pow(x, (h & 0xFFFFFFFF) * i, B.R)
         assert top == max(tops)
+    # z^2 acts as -phi on G1: [z^2](x, y) = (beta x, -y)
+    p = B.g1_mul(B.G1, 12345)
+    q = B.g1_mul(p, Z2 % B.R)
+    assert q[1] == (-p[1]) % B.P and pow(q[0] * pow(p[0], -1, B.P) % B.P, 3, B.P) == 1
