@@ -88,6 +88,7 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
     ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
                     help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")
@@ -278,7 +279,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    peak = measured_int_peak() if rank == 0 else None
+    peak = None
+    if rank == 0:
+        peak = measured_int_peak() if not args.no_peak else {"imad_wide": PAPER_PEAK_MAC, "imad_wide_x": None, "fp_mul_per_s": None,
+                                                            "source": "paper peak 148 SM x 64 lanes x 1.965 GHz (--no-peak)"}
 
     with torch.cuda.stream(ts):
         for _ in range(args.warmup):
@@ -429,7 +433,7 @@ def run_b200(args):
                 "kernel_ms": top["kernel_ms"], "kernel_share_of_step": top["kernel_share_of_step"],
                 "units_per_launch": top["units_per_launch_total"], "unit_is": top["unit_is"],
                 "modmul_per_unit": top["modmul_per_unit"], "mac_per_modmul": MAC_PER_MODMUL,
-                "traffic": None,
+                "traffic": None, "traffic_ref": "profiles/ (ncu --set full captures: DRAM bytes per launch are negligible on this integer-bound path)",
                 "kernels": kernels,
                 "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
                                "modmul_per_share_canonical": MODMUL_PER_SHARE,
