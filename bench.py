@@ -89,6 +89,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2], help="dkgv_set_share_overlap mode of the timed steps")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
     ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
                     help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")
@@ -244,6 +245,7 @@ def run_b200(args):
 
     v = dk.Verifier(local)
     v.set_share_parts(args.parts)
+    v.set_share_overlap(args.overlap)
     v.set_share_path({"auto": v.PATH_AUTO, "horner": v.PATH_HORNER, "fdiff": v.PATH_FDIFF}[args.share_path])
     sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
     ts = torch.cuda.Stream(device=dev)
@@ -322,7 +324,7 @@ def run_b200(args):
                 e1.synchronize()
                 serial_ms.append(e0.elapsed_time(e1))
                 phase_ms.append(v.last_share_phases_ms())
-            v.set_share_overlap(True)
+            v.set_share_overlap(args.overlap)
             barrier()
 
         total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)

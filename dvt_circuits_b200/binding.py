@@ -171,8 +171,9 @@ class Verifier:
         self._ck(self._lib.dkgv_set_share_path(self._h, int(mode)))
 
     def set_share_overlap(self, on):
-        """True (default): one internal stream per part; False: one stream, phase after phase"""
-        self._ck(self._lib.dkgv_set_share_overlap(self._h, int(bool(on))))
+        """1 / True (default): one internal stream per part; 2: plus recombination pipelined behind the extension;
+        0 / False: one stream, phase after phase"""
+        self._ck(self._lib.dkgv_set_share_overlap(self._h, int(on)))
 
     def set_share_parts(self, parts):
         """parts per dealer polynomial on the finite-difference path (0 = planner's choice)"""

@@ -18,7 +18,7 @@ using namespace dkgv;
 int dkgv_fd_setup(dkgv_ctx* ctx);
 bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r);
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
+                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
 
 // ============================================================================ kernels
 // Offset fixed-base table of the generator (layout in feldman.cuh).
@@ -269,7 +269,7 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
-                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab})
+                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols})
     b->release();
   for (cudaEvent_t ev : ctx->ev_fd)
     if (ev) cudaEventDestroy(ev);
@@ -278,6 +278,9 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
+  if (ctx->fd_comb_stream) cudaStreamSynchronize(ctx->fd_comb_stream), cudaStreamDestroy(ctx->fd_comb_stream);
+  if (ctx->fd_comb_done) cudaEventDestroy(ctx->fd_comb_done);
+  for (cudaEvent_t ev : ctx->fd_chunk_ev) cudaEventDestroy(ev);
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
@@ -346,6 +349,7 @@ extern "C" int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts) {
 extern "C" int dkgv_set_share_overlap(dkgv_ctx* ctx, int on) {
   if (!ctx) return -1;
   ctx->fd_overlap = on != 0;
+  ctx->fd_pipeline = on == 2;
   return 0;
 }
 extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo, int32_t* hi,
@@ -386,8 +390,8 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
   // verification.rs:50-66,129) allow t Horner evaluations + finite differences per dealer.
   bool use_fd = false;
   FdPlan plan{};
+  std::vector<uint32_t> fetched;  // must outlive the finite-difference call (it reads the ids again)
   if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r >= 3 && n_r <= 65535 && t <= 65535 * FD_MAX_PARTS) {
-    std::vector<uint32_t> fetched;
     if (!h_ids) {  // device-pointer entry: fetch the (tiny) id list before any work is queued
       fetched.resize(n_r);
       CK(cudaMemcpyAsync(fetched.data(), d_ids, (size_t)n_r * 4, cudaMemcpyDeviceToHost, s));
@@ -403,7 +407,7 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
   if (rc) return rc;
   if (use_fd) {
     ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;
-    return dkgv_share_matrix_fd(ctx, view, n_d, n_r, t, plan, d_ids, d_shares, d_status, s);
+    return dkgv_share_matrix_fd(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, s);
   }
   HotView hv = view;
   const uint32_t* hot_tab = ctx->gtab;

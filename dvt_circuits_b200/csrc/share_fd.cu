@@ -57,21 +57,22 @@ k_fd_digits(uint32_t n_r, uint32_t h, uint32_t m, int8_t* __restrict__ dig, int3
   top[x - 1] = fd_comb_digits(x, h, m, dig + (size_t)(x - 1) * fd_dig_bytes(m));
 }
 
-// recipients j0 .. j0 + gridDim.y - 1; tab holds one table plane per (recipient of this launch, point, slot)
+// recipients: columns j0 .. j0 + gridDim.y - 1, or (cols != nullptr) cols[j0 ..] = columns in ascending-id order;
+// tab holds one table plane per (tab_r0 + blockIdx.y, point, slot)
 __global__ void __launch_bounds__(FD_NT)
 k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
              const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab,
              const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t* __restrict__ tab, uint32_t n_pad,
-             uint32_t n_d, uint32_t n_r, uint32_t j0) {
+             uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0) {
   extern __shared__ U4 opfile[];
   uint32_t d = blockIdx.x * 32 + threadIdx.x;
-  uint32_t j = j0 + blockIdx.y;
+  uint32_t j = cols ? cols[j0 + blockIdx.y] : j0 + blockIdx.y;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
   OpFile f{opfile + threadIdx.x, FD_NT};
   uint32_t x = ids[j];
   size_t e = (size_t)((int64_t)x - lo);
-  uint32_t* my_tab = tab + (size_t)blockIdx.y * (m - 1) * FD_TAB_SLOTS * 36 * n_pad;  // column d, not dd: private to this thread
+  uint32_t* my_tab = tab + (size_t)(tab_r0 + blockIdx.y) * (m - 1) * FD_TAB_SLOTS * 36 * n_pad;  // column d, not dd: private to this thread
   uint8_t st = fd_combine_compare_item(f, evals, n_pad * m, n_pad, m, e, dd, dig + (size_t)(x - 1) * fd_dig_bytes(m),
                                        m > 1 ? top[x - 1] : -1, my_tab + (d - dd), shares + ((size_t)dd * n_r + j) * 32, gtab,
                                        dealer_bad[dd] != 0);
@@ -85,10 +86,16 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   }
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
+  // the extension is a long dependent chain of small launches: its streams get the highest priority so
+  // that recombination blocks (comb stream, lowest priority) only fill the slots it leaves idle
+  int prio_least = 0, prio_greatest = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
-    CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&ctx->fd_streams[i], cudaStreamNonBlocking, prio_greatest));
     CK(cudaEventCreateWithFlags(&ctx->fd_join[i], cudaEventDisableTiming));
   }
+  CK(cudaStreamCreateWithPriority(&ctx->fd_comb_stream, cudaStreamNonBlocking, prio_least));
+  CK(cudaEventCreateWithFlags(&ctx->fd_comb_done, cudaEventDisableTiming));
   return 0;
 }
 
@@ -103,8 +110,11 @@ bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
   return true;
 }
 
+static inline const uint32_t* evals_c(dkgv_ctx* ctx) { return (const uint32_t*)ctx->fd_evals.p; }
+constexpr uint32_t FD_COMB_CHUNKS = 8;  // recombination launches pipelined behind the extension
+
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
+                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
   const uint32_t n_pad = view.n_pad, m = plan.m, h = plan.h;
   const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
   const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
@@ -123,6 +133,40 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   if (tab_per_recipient && tab_per_recipient * chunk_r > tab_budget) chunk_r = (uint32_t)(tab_budget / tab_per_recipient);
   if (chunk_r == 0) chunk_r = 1;
   CK(ctx->fd_tab.reserve(tab_per_recipient ? tab_per_recipient * chunk_r : 16));
+  // columns in ascending-id order: the extension produces f(x) in that order, so the recombination of a
+  // range of ids can start as soon as the wavefront has passed it
+  const bool pipelined = ctx->fd_overlap && ctx->fd_pipeline && m > 1 && chunk_r == n_r;
+  if (pipelined) {
+    ctx->fd_cols_host.resize(n_r);
+    for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
+    CK(ctx->fd_cols.reserve((size_t)n_r * 4));
+    CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
+    while (ctx->fd_chunk_ev.size() < (size_t)(FD_COMB_CHUNKS + 1) * FD_MAX_PARTS) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      ctx->fd_chunk_ev.push_back(ev);
+    }
+  }
+  auto launch_combine = [&](cudaStream_t cs, uint32_t r0, uint32_t nj, const uint32_t* cols, uint32_t tab_r0) {
+    k_fd_combine<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
+                                                               (const int32_t*)ctx->fd_top.p, d_ids, d_shares, ctx->gtab,
+                                                               (const uint8_t*)ctx->dealer_bad.p, d_status, (uint32_t*)ctx->fd_tab.p,
+                                                               n_pad, n_d, n_r, r0, cols, tab_r0);
+    ctx->launches++;
+  };
+  // recombination of the ids (x0, x1] on the comb stream once every part stream has produced them
+  uint32_t chunk_no = 0, next_chunk = 1;
+  auto chunk_end = [&](uint32_t c) { return (uint32_t)(((uint64_t)plan.steps * c + FD_COMB_CHUNKS - 1) / FD_COMB_CHUNKS); };
+  auto combine_after_parts = [&](uint32_t x0, uint32_t x1) -> int {
+    for (uint32_t p = 0; p < m; p++) {
+      cudaEvent_t ev = ctx->fd_chunk_ev[(size_t)chunk_no * FD_MAX_PARTS + p];
+      CK(cudaEventRecord(ev, ctx->fd_streams[p]));
+      CK(cudaStreamWaitEvent(ctx->fd_comb_stream, ev, 0));
+    }
+    chunk_no++;
+    if (x1 > x0) launch_combine(ctx->fd_comb_stream, x0, x1 - x0, (const uint32_t*)ctx->fd_cols.p, x0);
+    return 0;
+  };
   CK(ctx->fd_top.reserve((size_t)n_r * 4));
   uint32_t* evals = (uint32_t*)ctx->fd_evals.p;
   uint32_t* pp[2] = {(uint32_t*)ctx->fd_p0.p, (uint32_t*)ctx->fd_p1.p};
@@ -175,6 +219,11 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
     // chain on its own stream, so the tail of one part's kernel is filled by blocks of the others
     // (no grid-wide barrier per round / tick; matters when a rank holds few dealers).
     CK(cudaEventRecord(ctx->fd_fork, s));
+    if (pipelined) {
+      CK(cudaStreamWaitEvent(ctx->fd_comb_stream, ctx->fd_fork, 0));
+      k_fd_digits<<<(n_r + 127) / 128, 128, 0, ctx->fd_comb_stream>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
+      ctx->launches++;
+    }
     for (uint32_t p = 0; p < m; p++) {
       cudaStream_t sp = ctx->fd_streams[p];
       CK(cudaStreamWaitEvent(sp, ctx->fd_fork, 0));
@@ -185,6 +234,8 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
       CK(cudaMemcpy2DAsync(dd[0] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
       CK(cudaMemcpy2DAsync(dd[1] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
     }
+    if (pipelined)  // ids 1..hi are seed values
+      if (int rc = combine_after_parts(0, (uint32_t)plan.hi)) return rc;
     for (uint32_t r = 1; r < h; r++)
       for (uint32_t p = 0; p < m; p++) {
         k_fd_init<<<dim3(gx, h - r), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0], dd[1], n_padv,
@@ -201,26 +252,35 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
                                                                                                p * n_pad);
         ctx->launches++;
       }
+      if (pipelined && tick >= h - 1) {  // step tick - (h - 2) of every part is queued: ids up to hi + that step exist after it
+        uint32_t sdone = tick - (h - 2);
+        while (next_chunk <= FD_COMB_CHUNKS && chunk_end(next_chunk) <= sdone) {
+          uint32_t s_beg = chunk_end(next_chunk - 1), s_end = chunk_end(next_chunk);
+          next_chunk++;
+          if (s_end > s_beg)
+            if (int rc = combine_after_parts((uint32_t)plan.hi + s_beg, (uint32_t)plan.hi + s_end)) return rc;
+        }
+      }
     }
     for (uint32_t p = 0; p < m; p++) {
       CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
       CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
+    }
+    if (pipelined) {
+      CK(cudaEventRecord(ctx->fd_comb_done, ctx->fd_comb_stream));
+      CK(cudaStreamWaitEvent(s, ctx->fd_comb_done, 0));
     }
     CK(cudaEventRecord(ctx->ev_hot1, s));
     for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
   }
   ctx->hot_recorded = true;
 
-  if (m > 1) {
-    k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
-    ctx->launches++;
-  }
-  for (uint32_t j0 = 0; j0 < n_r; j0 += chunk_r) {
-    uint32_t nj = n_r - j0 < chunk_r ? n_r - j0 : chunk_r;
-    k_fd_combine<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
-                                                      d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status,
-                                                      (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, j0);
-    ctx->launches++;
+  if (!pipelined) {
+    if (m > 1) {
+      k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
+      ctx->launches++;
+    }
+    for (uint32_t j0 = 0; j0 < n_r; j0 += chunk_r) launch_combine(s, j0, n_r - j0 < chunk_r ? n_r - j0 : chunk_r, nullptr, 0);
   }
   CK(cudaEventRecord(ctx->ev_fd[4], s));
   ctx->fd_recorded = true;

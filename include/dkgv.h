@@ -95,8 +95,10 @@ int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_r
 enum dkgv_share_path { DKGV_SHARE_PATH_AUTO = 0, DKGV_SHARE_PATH_HORNER = 1, DKGV_SHARE_PATH_FDIFF = 2 };
 int dkgv_set_share_path(dkgv_ctx* ctx, int mode); /* FDIFF: use it whenever applicable, even if not cheaper */
 int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts); /* 0 = planner's choice (default), else 1..16 */
-/* on (default): the parts of the finite-difference path run on one internal stream each and join before the
- * recombination; off: everything on the caller's stream, phase after phase (gives per-phase device times) */
+/* 1 (default): the parts of the finite-difference path run on one internal stream each and join before the
+ * recombination; 2: additionally the recombination of an id range starts as soon as the extension has passed
+ * it (measured neutral to slightly slower on a full GPU, kept as an option for ranks with few dealers);
+ * 0: everything on the caller's stream, phase after phase (gives per-phase device times)              */
 int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
 /* the plan for ids 1..n_recipients (parts_force 0 = cheapest): parts, h = ceil(t / parts), Horner seed points
