@@ -7,7 +7,7 @@
 One "step" = one pass of the hot path (decode + subgroup-check the verification vectors, Feldman
 evaluation in the exponent for every (dealer, recipient), G*s, compare) over the whole share matrix.
 With N ranks the ONE ceremony is sharded by dealer row blocks (strong scaling, as BASELINE.json names
-it); the only exchange is an NCCL all-gather of the per-share verdict bytes, inside the timed region.
+it); the only exchange is an NCCL all-gather of the per-share verdict bitmask, inside the timed region.
 
 `value`     device-timed, inputs resident in HBM, max over ranks.
 `e2e`       same metric through the reference-facing C ABI with HOST (pinned) buffers:
@@ -255,7 +255,9 @@ def run_b200(args):
         d_ids = torch.from_numpy(sess["ids"].view(np.int32)).to(dev)
         d_sh = torch.from_numpy(sess["shares"]).to(dev)
         d_st = torch.empty((rows, n), dtype=torch.uint8, device=dev)
-        d_all = torch.empty((n, n), dtype=torch.uint8, device=dev) if world > 1 else d_st
+        # ranks exchange the verdict BITMASK (1 bit per share), not the status bytes
+        d_bits = torch.zeros(((rows * n + 31) // 32,), dtype=torch.int32, device=dev)
+        d_all = torch.zeros((world * d_bits.numel(),), dtype=torch.int32, device=dev) if world > 1 else d_st
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # pinned host copies for the end-to-end leg
     h_vv = torch.from_numpy(sess["vv"]).pin_memory()
@@ -266,14 +268,16 @@ def run_b200(args):
     def step_device():
         v.share_matrix_verify_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh.data_ptr(), d_st.data_ptr(), stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_st)
+            v.pack_verdicts_dev(rows * n, d_st.data_ptr(), d_bits.data_ptr(), stream)
+            dist.all_gather_into_tensor(d_all, d_bits)
 
     def step_e2e():
         rc = v._lib.dkgv_share_matrix_verify(v._h, rows, n, t, h_vv.data_ptr(), h_ids.data_ptr(), h_sh.data_ptr(), h_st.data_ptr())
         v._ck(rc)
         if world > 1:
             d_st.copy_(h_st, non_blocking=True)
-            dist.all_gather_into_tensor(d_all, d_st)
+            v.pack_verdicts_dev(rows * n, d_st.data_ptr(), d_bits.data_ptr(), stream)
+            dist.all_gather_into_tensor(d_all, d_bits)
 
     def barrier():
         torch.cuda.synchronize()
@@ -459,7 +463,7 @@ def run_b200(args):
                        "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
                        "share_path": (f"finite differences: {plan['parts']} parts x {plan['h']} coefficients per dealer, "
                                       f"{plan['h']} Horner seeds per part, differences, recombination") if fdiff else "Horner per share",
-                       "parallelism": f"row-block x{world}, NCCL all-gather of verdict bytes" if world > 1 else "single GPU"},
+                       "parallelism": f"row-block x{world}, NCCL all-gather of the verdict bitmask ({n * n // 8} B)" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",
                     "h2d_bytes_per_step": int(h_vv.numel() + h_sh.numel() + h_ids.numel() * 4) * world,

@@ -5,4 +5,4 @@ This package is a thin ctypes binding over the C ABI in include/dkgv.h (libdkgv.
 CUDA for sm_100a).  There is NO CPU fallback: importing works without a GPU (so symbol/ABI tests can
 run), but creating a `Verifier` raises when the library or a CUDA device is missing.
 """
-from .binding import (DkgvError, Verifier, Status, lib_path, load_library, DECLARED_SYMBOLS, initial_commitment_hash, share_fd_plan)  # noqa: F401
+from .binding import (DkgvError, Verifier, Status, lib_path, load_library, DECLARED_SYMBOLS, initial_commitment_hash, share_fd_plan, verdict_bits_to_matrix)  # noqa: F401

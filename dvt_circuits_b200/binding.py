@@ -59,6 +59,8 @@ DECLARED_SYMBOLS = {
     "dkgv_last_hot_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_items_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_pack_verdicts_dev": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "dkgv_set_share_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_path": (ctypes.c_int, [_vp]),
     "dkgv_set_share_parts": (ctypes.c_int, [_vp, _u32]),
@@ -205,6 +207,22 @@ class Verifier:
         """device pointers (ints); asynchronous"""
         self._ck(self._lib.dkgv_share_matrix_verify_dev(self._h, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, stream))
 
+    def share_items_verify(self, vv, ids, item_dealer, item_recipient, secrets):
+        """sparse (dealer, recipient-column) items of one session -> status [m] u8"""
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        n_d, t = vv.shape[0], vv.shape[1]
+        ids = _host(ids, np.uint32)
+        it_d, it_r = _host(item_dealer, np.uint32), _host(item_recipient, np.uint32)
+        m = it_d.shape[0]
+        secrets = _host(secrets, np.uint8, (m, 32))
+        status = np.empty((m,), dtype=np.uint8)
+        self._ck(self._lib.dkgv_share_items_verify(self._h, n_d, ids.shape[0], t, _p(vv), _p(ids), m, _p(it_d), _p(it_r), _p(secrets), _p(status)))
+        return status
+
+    def pack_verdicts_dev(self, n, d_status, d_bits, stream=None):
+        """device pointers; bit i of d_bits (u32 words) = status[i] != OK; asynchronous"""
+        self._ck(self._lib.dkgv_pack_verdicts_dev(self._h, int(n), d_status, d_bits, stream))
+
     def feldman_eval(self, vv, ids):
         vv = np.ascontiguousarray(vv, dtype=np.uint8)
         n_d, t = vv.shape[0], vv.shape[1]
@@ -329,6 +347,15 @@ class Verifier:
             json_text = json_text.encode()
         code = self._lib.dkgh_execute(self._h, type_.encode(), json_text, int(auth), int(bls_identity), ctypes.byref(st), msg, 512)
         return int(code), int(st.value), msg.value.decode(errors="replace")
+
+
+def verdict_bits_to_matrix(words, n_dealers, n_recipients):
+    """Unpack the bitmask of dkgv_pack_verdicts_dev (u32 words, bit i%32 of word i//32 = share i is NOT ok,
+    shares in row-major (dealer, recipient) order) into a bool matrix [n_dealers, n_recipients]; the
+    bad-participant list of the share proof type is `np.nonzero(m.any(axis=1))[0]`."""
+    w = np.ascontiguousarray(words).view(np.uint8)
+    bits = np.unpackbits(w, bitorder="little")[:n_dealers * n_recipients]
+    return bits.reshape(n_dealers, n_recipients).astype(bool)
 
 
 def share_fd_plan(t, n_recipients, parts=0):

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -133,6 +134,35 @@ k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_
   if (active) status[(size_t)d * n_r + j] = st;
 }
 
+// Sparse item list over one session: a warp = up to 32 items that share ONE recipient (the host sorts
+// the items by recipient), so the chain over the id bits stays warp-uniform; dealers differ per lane.
+__global__ void __launch_bounds__(32)
+k_share_items(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ s_dealer,
+              const uint32_t* __restrict__ s_col, const uint32_t* __restrict__ s_orig, const uint32_t* __restrict__ warp_first,
+              const uint8_t* __restrict__ secrets, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status, uint32_t t) {
+  extern __shared__ U4 opfile[];
+  uint32_t first = warp_first[blockIdx.x], cnt = warp_first[blockIdx.x + 1] - first;
+  bool active = threadIdx.x < cnt;
+  uint32_t it = first + (active ? threadIdx.x : cnt - 1);
+  uint32_t d = s_dealer[it], id = ids[s_col[first]], orig = s_orig[it];
+  OpFile f{opfile + threadIdx.x, 32};
+  uint8_t st = vm_share_check(f, vv, t, d, id, secrets + (size_t)orig * 32, gtab, dealer_bad[d] != 0);
+  if (active) status[orig] = st;
+}
+
+// bit i of bits = (status[i] != DKGV_OK), little-endian within each 32-bit word; n_words = ceil(n / 32)
+__global__ void __launch_bounds__(256) k_pack_verdicts(const uint8_t* __restrict__ status, uint32_t* __restrict__ bits, size_t n) {
+  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w * 32 >= n) return;
+  uint32_t v = 0;
+#pragma unroll 4
+  for (int b = 0; b < 32; b++) {
+    size_t i = w * 32 + b;
+    if (i < n && status[i] != DKGV_OK) v |= 1u << b;
+  }
+  bits[w] = v;
+}
+
 // evaluate_polynomial for every (dealer, id) with compressed output
 __global__ void __launch_bounds__(SV_WARPS * 32)
 k_feldman_eval(VVView vv, const uint32_t* __restrict__ ids, uint8_t* __restrict__ out, uint32_t n_d, uint32_t n_r, uint32_t t) {
@@ -245,6 +275,8 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVM_SMEM)) != cudaSuccess)
     return bail("cudaFuncSetAttribute smem", e);
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute carveout", e);
+  if ((e = cudaFuncSetAttribute(k_share_items, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
     return bail("cudaFuncSetAttribute carveout", e);
   if (dkgv_fd_setup(ctx) != 0) {
     g_create_error = "finite-difference path setup: " + ctx->err;
@@ -454,6 +486,71 @@ extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_
   if (rc) return rc;
   CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_pack_verdicts_dev(dkgv_ctx* ctx, uint64_t n, const uint8_t* d_status, uint32_t* d_bits, void* stream) {
+  if (!ctx) return -1;
+  if (n == 0) return 0;
+  if (!d_status || !d_bits) return fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  size_t words = (size_t)((n + 31) / 32);
+  k_pack_verdicts<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_status, d_bits, (size_t)n);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dkgv_share_items_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* vv, const uint32_t* ids,
+                                       uint32_t m, const uint32_t* item_dealer, const uint32_t* item_recipient, const uint8_t* secrets,
+                                       uint8_t* status) {
+  if (!ctx) return -1;
+  if (m == 0) return 0;
+  if (n_d == 0 || n_r == 0) return fail(ctx, "items given for an empty session");
+  if (!ids || !item_dealer || !item_recipient || !secrets || !status || (t && !vv)) return fail(ctx, "null pointer argument");
+  for (uint32_t i = 0; i < m; i++)
+    if (item_dealer[i] >= n_d || item_recipient[i] >= n_r) return fail(ctx, "item index out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // sort by recipient column (stable: dealers stay in caller order), cut into warps of one recipient each
+  std::vector<uint32_t> perm(m);
+  for (uint32_t i = 0; i < m; i++) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return item_recipient[a] < item_recipient[b]; });
+  std::vector<uint32_t> sd(m), sc(m), wf;
+  for (uint32_t i = 0; i < m; i++) {
+    sd[i] = item_dealer[perm[i]];
+    sc[i] = item_recipient[perm[i]];
+    if (i == 0 || sc[i] != sc[i - 1] || i - wf.back() == 32) wf.push_back(i);
+  }
+  uint32_t n_warps = (uint32_t)wf.size();
+  wf.push_back(m);
+  size_t vvb = (size_t)n_d * t * 48;
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->in_b.reserve((size_t)n_r * 4));
+  CK(ctx->in_c.reserve((size_t)m * 32));
+  CK(ctx->out_a.reserve(m));
+  CK(ctx->scratch_a.reserve((size_t)m * 12 + (size_t)(n_warps + 1) * 4));
+  uint32_t* d_sd = (uint32_t*)ctx->scratch_a.p;
+  uint32_t *d_sc = d_sd + m, *d_so = d_sc + m, *d_wf = d_so + m;
+  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_c.p, secrets, (size_t)m * 32, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_sd, sd.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_sc, sc.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_so, perm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_wf, wf.data(), (size_t)(n_warps + 1) * 4, cudaMemcpyHostToDevice, s));
+  VVView view;
+  uint32_t n_pad;
+  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, nullptr, s, &view, &n_pad, false);
+  if (rc) return rc;
+  k_share_items<<<n_warps, 32, (size_t)VM_SLOTS * 3 * 32 * sizeof(U4), s>>>(view, (const uint8_t*)ctx->dealer_bad.p,
+                                                                           (const uint32_t*)ctx->in_b.p, d_sd, d_sc, d_so, d_wf,
+                                                                           (const uint8_t*)ctx->in_c.p, ctx->gtab, (uint8_t*)ctx->out_a.p, t);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(status, ctx->out_a.p, m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));  // also keeps the host vectors alive until the copies are done
   return 0;
 }
 

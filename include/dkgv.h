@@ -87,6 +87,16 @@ int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_r
                                  const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
                                  uint8_t* d_status, void* stream);
 
+/* Sparse item list over one session (e.g. only the complained-about shares): item i is the pair
+ * (item_dealer[i] < n_dealers, item_recipient[i] < n_recipients = column into ids) with secret secrets[i][32];
+ * status[i] as in the matrix call.  Horner per item; the items are grouped by recipient internally.   */
+int dkgv_share_items_verify(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t, const uint8_t* vv,
+                            const uint32_t* ids, uint32_t m, const uint32_t* item_dealer, const uint32_t* item_recipient,
+                            const uint8_t* secrets, uint8_t* status);
+/* verdict bitmask of a status array on the device: bit (i % 32) of word i / 32 is set when status[i] != OK
+ * (ceil(n / 32) words; what the ranks exchange instead of the status bytes).  Asynchronous on `stream`. */
+int dkgv_pack_verdicts_dev(dkgv_ctx* ctx, uint64_t n, const uint8_t* d_status, uint32_t* d_bits, void* stream);
+
 /* Evaluation strategy of the share-matrix entry points.  AUTO (default): when the recipient ids are a
  * permutation of 1..n_recipients (always so for a ceremony: verification.rs:50-66,129), split every
  * dealer polynomial into `parts` pieces of h coefficients, evaluate h points per piece by Horner, all

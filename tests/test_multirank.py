@@ -31,6 +31,18 @@ def _worker(rank, world, port, n, t, q):
     dist.all_gather_into_tensor(out, local)
     exp = ((np.arange(n)[:, None] + np.arange(n)[None, :]) % 7).astype(np.uint8)
     ok = ok and bool((out.numpy() == exp).all())
+    # verdict bitmask (what bench.py exchanges at N > 1): each rank packs its rows like k_pack_verdicts, the
+    # gathered words unpack into the full (dealer, recipient) matrix
+    import dvt_circuits_b200 as dk
+    bits = np.packbits((local.numpy().reshape(-1) != 0).astype(np.uint8), bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, dtype=np.uint8)]).view(np.int32)
+    lw = torch.from_numpy(bits.copy())
+    allw = torch.empty((world * lw.numel(),), dtype=torch.int32)
+    dist.all_gather_into_tensor(allw, lw)
+    per = lw.numel()
+    got = np.concatenate([dk.verdict_bits_to_matrix(allw.numpy()[r * per:(r + 1) * per], rows, n) for r in range(world)])
+    ok = ok and bool((got == (exp != 0)).all())
+    ok = ok and sorted(np.nonzero(got.any(axis=1))[0].tolist()) == sorted(np.nonzero((exp != 0).any(axis=1))[0].tolist())
     # max-over-ranks timing reduction used by bench.py
     tms = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
