@@ -9,6 +9,7 @@
 //   k_fd_digits   NAF digits of the public recombination scalars x^(h i) mod r, one thread per id
 //   k_fd_combine  sum_i [y^i] f_i(x) by joint double-and-add, G * s, compare: one thread per share
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ctx.hpp"
@@ -16,6 +17,7 @@
 
 using namespace dkgv;
 
+static uint32_t g_fd_ipb_force = 0;  // items per block of the difference / extension launches, DKGV_FD_IPB (experiments)
 constexpr int FD_NT = 32;  // one warp per block: 32 consecutive dealers, one entry (cf. SVM_NT in dkgv.cu)
 constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
 
@@ -34,20 +36,23 @@ k_fd_seed(VVView vv, const int32_t* __restrict__ seed_x, int32_t lo, uint32_t* _
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_init(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t* __restrict__ da, uint32_t* __restrict__ db,
-          uint32_t n_pad, uint32_t t, uint32_t r, uint32_t col0) {
+          uint32_t n_pad, uint32_t t, uint32_t r, uint32_t col0, uint32_t ipb) {
   extern __shared__ U4 opfile[];
   uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
-  fd_init_item(f, src, dst, da, db, n_pad, t, r, blockIdx.y, d);
+#pragma unroll 1
+  for (uint32_t i = blockIdx.y * ipb; i < (blockIdx.y + 1) * ipb && i + r < t; i++) fd_init_item(f, src, dst, da, db, n_pad, t, r, i, d);
 }
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_ext(const uint32_t* __restrict__ old, uint32_t* __restrict__ cur, uint32_t* __restrict__ evals, uint32_t n_pad, uint32_t t,
-         uint32_t tick, uint32_t k_lo, size_t e_hi, uint32_t col0) {
+         uint32_t tick, uint32_t k_lo, uint32_t k_hi, size_t e_hi, uint32_t col0, uint32_t ipb) {
   extern __shared__ U4 opfile[];
   uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
-  fd_ext_item(f, old, cur, evals, n_pad, t, tick, k_lo + blockIdx.y, e_hi, d);
+#pragma unroll 1
+  for (uint32_t k = k_lo + blockIdx.y * ipb; k < k_lo + (blockIdx.y + 1) * ipb && k <= k_hi; k++)
+    fd_ext_item(f, old, cur, evals, n_pad, t, tick, k, e_hi, d);
 }
 
 __global__ void __launch_bounds__(128)
@@ -84,6 +89,7 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
+  if (const char* e = getenv("DKGV_FD_IPB")) g_fd_ipb_force = (uint32_t)atoi(e);
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
   // the extension is a long dependent chain of small launches: its streams get the highest priority so
@@ -111,6 +117,10 @@ bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
 }
 
 static inline const uint32_t* evals_c(dkgv_ctx* ctx) { return (const uint32_t*)ctx->fd_evals.p; }
+// Items (point additions) per block of the difference / extension launches.  One per block is the
+// measured optimum on B200 (n=1024, t=683, N=1: extension 336 ms with 1, 344 ms with 2, 367 ms with 4 items):
+// block scheduling is not what the one-addition blocks lose time on.  DKGV_FD_IPB overrides (experiments).
+static inline uint32_t items_per_block(uint32_t, uint32_t) { return g_fd_ipb_force ? g_fd_ipb_force : 1; }
 constexpr uint32_t FD_COMB_CHUNKS = 8;  // recombination launches pipelined behind the extension
 
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
@@ -199,7 +209,8 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
     const uint32_t* src = evals;
     for (uint32_t r = 1; r < h; r++) {
       uint32_t* dst = pp[r & 1];
-      k_fd_init<<<dim3(gxv, h - r), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0);
+      uint32_t ipb = items_per_block(gxv, h - r);
+      k_fd_init<<<dim3(gxv, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0, ipb);
       ctx->launches++;
       src = dst;
     }
@@ -209,8 +220,9 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
       int32_t k_lo, k_hi;
       fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
       if (k_lo > k_hi) continue;
-      k_fd_ext<<<dim3(gxv, (unsigned)(k_hi - k_lo + 1)), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
-                                                                            (uint32_t)k_lo, e_hi, 0);
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
+      k_fd_ext<<<dim3(gxv, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
+                                                                      (uint32_t)k_lo, (uint32_t)k_hi, e_hi, 0, ipb);
       ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev_fd[3], s));
@@ -236,20 +248,23 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
     }
     if (pipelined)  // ids 1..hi are seed values
       if (int rc = combine_after_parts(0, (uint32_t)plan.hi)) return rc;
-    for (uint32_t r = 1; r < h; r++)
+    for (uint32_t r = 1; r < h; r++) {
+      uint32_t ipb = items_per_block(gxv, h - r);
       for (uint32_t p = 0; p < m; p++) {
-        k_fd_init<<<dim3(gx, h - r), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0], dd[1], n_padv,
-                                                                          h, r, p * n_pad);
+        k_fd_init<<<dim3(gx, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0],
+                                                                                            dd[1], n_padv, h, r, p * n_pad, ipb);
         ctx->launches++;
       }
+    }
     for (uint32_t tick = 1; tick <= ticks; tick++) {
       int32_t k_lo, k_hi;
       fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
       if (k_lo > k_hi) continue;
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
       for (uint32_t p = 0; p < m; p++) {
-        k_fd_ext<<<dim3(gx, (unsigned)(k_hi - k_lo + 1)), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals,
-                                                                                               n_padv, h, tick, (uint32_t)k_lo, e_hi,
-                                                                                               p * n_pad);
+        k_fd_ext<<<dim3(gx, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h,
+                                                                                         tick, (uint32_t)k_lo, (uint32_t)k_hi, e_hi,
+                                                                                         p * n_pad, ipb);
         ctx->launches++;
       }
       if (pipelined && tick >= h - 1) {  // step tick - (h - 2) of every part is queued: ids up to hi + that step exist after it
