@@ -23,15 +23,15 @@ constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_seed(VVView vv, const int32_t* __restrict__ seed_x, int32_t lo, uint32_t* __restrict__ evals, uint32_t n_d, uint32_t t,
-          uint32_t h, uint32_t part0, uint32_t n_padv) {
+          uint32_t h, uint32_t part0, uint32_t n_padv, uint32_t d0, uint32_t n_cols) {
   extern __shared__ U4 opfile[];
-  uint32_t d = blockIdx.x * 32 + threadIdx.x;
-  int32_t x = seed_x[blockIdx.y];  // most expensive points first
+  uint32_t d = blockIdx.x * 32 + threadIdx.x;  // column of this dealer chunk; dealer d0 + d
+  int32_t x = seed_x[blockIdx.y];              // most expensive points first
   uint32_t part = part0 + blockIdx.z;
-  uint32_t dd = d < n_d ? d : n_d - 1;
+  uint32_t dd = d0 + d < n_d ? d0 + d : n_d - 1;
   OpFile f{opfile + threadIdx.x, FD_NT};
   fd_seed_eval(f, vv, t, dd, x, part * h, h);
-  fd_store(f, AX, fd_entry(evals, n_padv, (size_t)(x - lo), part * vv.n_pad + d), n_padv);
+  fd_store(f, AX, fd_entry(evals, n_padv, (size_t)(x - lo), part * n_cols + d), n_padv);
 }
 
 __global__ void __launch_bounds__(FD_NT)
@@ -68,20 +68,21 @@ __global__ void __launch_bounds__(FD_NT)
 k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
              const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab,
              const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t* __restrict__ tab, uint32_t n_pad,
-             uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0) {
+             uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0, uint32_t d0) {
   extern __shared__ U4 opfile[];
-  uint32_t d = blockIdx.x * 32 + threadIdx.x;
+  uint32_t d = blockIdx.x * 32 + threadIdx.x;  // column of this dealer chunk (n_pad columns); dealer d0 + d
   uint32_t j = cols ? cols[j0 + blockIdx.y] : j0 + blockIdx.y;
-  bool active = d < n_d;
-  uint32_t dd = active ? d : n_d - 1;
+  bool active = d0 + d < n_d;
+  uint32_t dd = active ? d : n_d - 1 - d0;  // column whose data an inactive lane borrows
+  uint32_t gd = d0 + dd;
   OpFile f{opfile + threadIdx.x, FD_NT};
   uint32_t x = ids[j];
   size_t e = (size_t)((int64_t)x - lo);
   uint32_t* my_tab = tab + (size_t)(tab_r0 + blockIdx.y) * (m - 1) * FD_TAB_SLOTS * 36 * n_pad;  // column d, not dd: private to this thread
   uint8_t st = fd_combine_compare_item(f, evals, n_pad * m, n_pad, m, e, dd, dig + (size_t)(x - 1) * fd_dig_bytes(m),
-                                       m > 1 ? top[x - 1] : -1, my_tab + (d - dd), shares + ((size_t)dd * n_r + j) * 32, gtab,
-                                       dealer_bad[dd] != 0);
-  if (active) status[(size_t)d * n_r + j] = st;
+                                       m > 1 ? top[x - 1] : -1, my_tab + (d - dd), shares + ((size_t)gd * n_r + j) * 32, gtab,
+                                       dealer_bad[gd] != 0);
+  if (active) status[(size_t)gd * n_r + j] = st;
 }
 
 int dkgv_fd_setup(dkgv_ctx* ctx) {
@@ -123,9 +124,11 @@ static inline const uint32_t* evals_c(dkgv_ctx* ctx) { return (const uint32_t*)c
 static inline uint32_t items_per_block(uint32_t, uint32_t) { return g_fd_ipb_force ? g_fd_ipb_force : 1; }
 constexpr uint32_t FD_COMB_CHUNKS = 8;  // recombination launches pipelined behind the extension
 
-int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
-  const uint32_t n_pad = view.n_pad, m = plan.m, h = plan.h;
+// dealers d0 .. d0 + n_pad - 1 (n_pad a multiple of 32: the column count of this chunk's planes)
+static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad, uint32_t n_d, uint32_t n_r, uint32_t t,
+                  const FdPlan& plan, const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status,
+                  cudaStream_t s) {
+  const uint32_t m = plan.m, h = plan.h;
   const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
   const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
@@ -161,7 +164,7 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
     k_fd_combine<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
                                                                (const int32_t*)ctx->fd_top.p, d_ids, d_shares, ctx->gtab,
                                                                (const uint8_t*)ctx->dealer_bad.p, d_status, (uint32_t*)ctx->fd_tab.p,
-                                                               n_pad, n_d, n_r, r0, cols, tab_r0);
+                                                               n_pad, n_d, n_r, r0, cols, tab_r0, d0);
     ctx->launches++;
   };
   // recombination of the ids (x0, x1] on the comb stream once every part stream has produced them
@@ -199,7 +202,7 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   CK(cudaEventRecord(ctx->ev_hot0, s));
   if (!overlap) {
     // one stream, phase after phase over all parts at once (also the mode that yields per-phase times)
-    k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv);
+    k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv, d0, n_pad);
     CK(cudaEventRecord(ctx->ev_hot1, s));
     CK(cudaEventRecord(ctx->ev_fd[1], s));
     ctx->launches++;
@@ -239,7 +242,8 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
     for (uint32_t p = 0; p < m; p++) {
       cudaStream_t sp = ctx->fd_streams[p];
       CK(cudaStreamWaitEvent(sp, ctx->fd_fork, 0));
-      k_fd_seed<<<dim3(gx, h, 1), FD_NT, FD_SMEM, sp>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, p, n_padv);
+      k_fd_seed<<<dim3(gx, h, 1), FD_NT, FD_SMEM, sp>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, p, n_padv, d0,
+                                                        n_pad);
       ctx->launches++;
       const size_t w = (size_t)n_pad * 4, pitch = (size_t)n_padv * 4;
       const uint32_t* col = evals + e_hi * ent_words + (size_t)p * n_pad;
@@ -300,5 +304,21 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   CK(cudaEventRecord(ctx->ev_fd[4], s));
   ctx->fd_recorded = true;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// Dealers are independent, so a ceremony whose planes would not fit the memory budget is processed in
+// dealer chunks (multiples of 32 columns).  (1024, 683) on one GPU needs 1.5 GB of planes + 3.6 GB of tables.
+int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
+  const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
+  const size_t bytes_per_col = (n_evals + 4 * (size_t)plan.h) * 36 * plan.m * 4;
+  size_t budget = (size_t)12 << 30;
+  if (const char* e = getenv("DKGV_FD_PLANE_BUDGET_MB")) budget = (size_t)atoll(e) << 20;  // tests force several chunks
+  uint32_t chunk = (uint32_t)std::min<size_t>(view.n_pad, std::max<size_t>(32, (budget / bytes_per_col) & ~(size_t)31));
+  for (uint32_t d0 = 0; d0 < view.n_pad && d0 < n_d; d0 += chunk) {
+    uint32_t cols = std::min(chunk, view.n_pad - d0);
+    if (int rc = fd_run(ctx, view, d0, cols, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, s)) return rc;
+  }
   return 0;
 }
