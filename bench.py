@@ -88,6 +88,7 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-finalization", action="store_true", help="skip the config-4 finalization leg")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2], help="dkgv_set_share_overlap mode of the timed steps")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
@@ -387,6 +388,29 @@ def run_b200(args):
         pair_ms_step = float(pair_total.item()) / len(pair_ms)
         pair_bad = int(d_pall.count_nonzero().item())
 
+        # BASELINE config 4: finalization of the whole ceremony through the host-pointer C ABI (rank 0, one GPU):
+        # agg_coefficients + the n final keys, two Lagrange interpolations at 0, n partial-signature checks
+        fin_line = None
+        if rank == 0 and not args.no_finalization:
+            ff = synthetic.make_finalization(v, n, t)
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                ast, co, keys = v.agg_final_keys(ff["vv"], ff["ids"])
+                t1 = time.perf_counter()
+                l1 = v.lagrange_at_zero(keys, ff["ids"])
+                l2 = v.lagrange_at_zero(ff["partial_pubkeys"], ff["ids"])
+                t2 = time.perf_counter()
+                st_f = v.bls_verify_batch(ff["partial_pubkeys"], ff["signatures"], ff["hm"])
+                t3 = time.perf_counter()
+                ok = bool(ast == 0 and (keys == ff["partial_pubkeys"]).all() and l1 == (0, bytes(co[0])) and l2 == l1 and not st_f.any())
+                cur = {"metric": "finalization of one ceremony (host buffers, wall clock)", "n": n, "t": t, "total_ms": (t3 - t0) * 1e3,
+                       "agg_final_keys_ms": (t1 - t0) * 1e3, "lagrange_x2_ms": (t2 - t1) * 1e3, "partial_signature_checks_ms": (t3 - t2) * 1e3,
+                       "final_keys_per_s": n / (t1 - t0), "all_checks_hold": ok}
+                if best is None or cur["total_ms"] < best["total_ms"]:
+                    best = cur
+            fin_line = best
+
     if rank == 0:
         shares = n * n
         value = shares / (ms_per_step * 1e-3)
@@ -473,6 +497,7 @@ def run_b200(args):
             "pairing": {"metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
                         "checks_per_step": m_total, "ms_per_step": pair_ms_step, "bad_verdicts": pair_bad,
                         "note": "e(pk,H(m)) == e(G1,sig) as 2 Miller loops + 1 final exponentiation per check, incl. G1/G2 decoding with subgroup checks"},
+            "finalization": fin_line,
             "parity": {"bad_verdicts_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
             "wall_s_timed_region": wall,
         }

@@ -20,6 +20,8 @@ int dkgv_fd_setup(dkgv_ctx* ctx);
 bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r);
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
                          const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
+int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s);
 
 // ============================================================================ kernels
 // Offset fixed-base table of the generator (layout in feldman.cuh).
@@ -571,9 +573,19 @@ extern "C" int dkgv_feldman_eval(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_ids, ui
   uint32_t n_pad;
   int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, nullptr, s, &view, &n_pad);
   if (rc) return rc;
-  dim3 grid(n_pad / 32, (n_ids + SV_WARPS - 1) / SV_WARPS);
-  k_feldman_eval<<<grid, SV_WARPS * 32, 0, s>>>(view, (const uint32_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, n_d, n_ids, t);
-  ctx->launches++;
+  FdPlan plan{};
+  bool use_fd = false;
+  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_ids >= 3 && n_ids <= 65535 && dkgv_fd_ids_consecutive(ids, n_ids)) {
+    plan = fd_make_plan(t, n_ids, ctx->share_parts);
+    use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
+  }
+  if (use_fd) {
+    if (int rc2 = dkgv_feldman_eval_fd(ctx, view, n_d, n_ids, t, plan, (const uint32_t*)ctx->in_b.p, ids, (uint8_t*)ctx->out_a.p, s)) return rc2;
+  } else {
+    dim3 grid(n_pad / 32, (n_ids + SV_WARPS - 1) / SV_WARPS);
+    k_feldman_eval<<<grid, SV_WARPS * 32, 0, s>>>(view, (const uint32_t*)ctx->in_b.p, (uint8_t*)ctx->out_a.p, n_d, n_ids, t);
+    ctx->launches++;
+  }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, ctx->out_a.p, ob, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(row_status, ctx->dealer_bad.p, n_d, cudaMemcpyDeviceToHost, s));

@@ -5,9 +5,14 @@
 // These run once per ceremony on n, t ~ 10^3 inputs: thread-per-output kernels with the inlined
 // formulas of g1.cuh; the verification vectors come decoded in the limb-planar layout of feldman.cuh.
 #include "ctx.hpp"
-#include "feldman.cuh"
+#include "fdiff.cuh"
 
 using namespace dkgv;
+
+// share_fd.cu
+bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r);
+int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s);
 
 namespace {
 struct ExpRm2 {
@@ -90,6 +95,21 @@ k_column_sums(VVView vv, uint32_t t, uint32_t* __restrict__ coeffs25, uint8_t* _
       for (int i = 0; i < 48; i++) enc_out[(size_t)warp * 48 + i] = enc[i];
     }
   }
+}
+
+// the column sums as the verification vector of ONE dealer (column 0 of a 32-wide plane, the rest identity):
+// input of the finite-difference evaluation of the final keys
+__global__ void __launch_bounds__(128)
+k_coeffs_to_planar(const uint32_t* __restrict__ coeffs25, uint32_t t, uint32_t* __restrict__ limbs, uint8_t* __restrict__ inf) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= t * 32) return;
+  uint32_t k = p >> 5, d = p & 31;
+  G1Aff a;
+  a.x = zero<FpParams>();
+  a.y = zero<FpParams>();
+  a.inf = 1;
+  if (d == 0) a = load_affine25(coeffs25 + (size_t)k * 25);
+  vv_store(limbs, inf, 32, k, d, a);
 }
 
 // K_j = sum_k C_k id_j^k (Horner from the top, dkg_math.rs:160-174); one thread per id
@@ -258,9 +278,27 @@ extern "C" int dkgv_agg_final_keys(dkgv_ctx* ctx, uint32_t n, uint32_t t, const 
     CK(cudaGetLastError());
   }
   if (n_ids) {
-    k_eval_points_at_ids<<<(n_ids + 63) / 64, 64, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (const uint32_t*)ctx->in_b.p, n_ids,
-                                                         (uint8_t*)ctx->out_b.p);
-    ctx->launches++;
+    // ids 1..n_ids (the ranks of a ceremony): the n final keys come from t-ish Horner seeds + finite differences
+    // (csrc/fdiff.cuh) instead of n Horner chains of t-1 steps; same points, same encodings
+    FdPlan plan{};
+    bool use_fd = false;
+    if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_ids >= 3 && n_ids <= 65535 && dkgv_fd_ids_consecutive(ids, n_ids)) {
+      plan = fd_make_plan(t, n_ids, ctx->share_parts);
+      use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
+    }
+    if (use_fd) {
+      CK(ctx->scratch_b.reserve((size_t)t * 24 * 32 * 4));
+      CK(ctx->scratch_c.reserve((size_t)t * 32));
+      k_coeffs_to_planar<<<(t * 32 + 127) / 128, 128, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (uint32_t*)ctx->scratch_b.p,
+                                                              (uint8_t*)ctx->scratch_c.p);
+      ctx->launches++;
+      VVView one{(const uint32_t*)ctx->scratch_b.p, (const uint8_t*)ctx->scratch_c.p, 32};
+      if (int rc = dkgv_feldman_eval_fd(ctx, one, 1, n_ids, t, plan, (const uint32_t*)ctx->in_b.p, ids, (uint8_t*)ctx->out_b.p, s)) return rc;
+    } else {
+      k_eval_points_at_ids<<<(n_ids + 63) / 64, 64, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (const uint32_t*)ctx->in_b.p, n_ids,
+                                                           (uint8_t*)ctx->out_b.p);
+      ctx->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(keys_out, ctx->out_b.p, (size_t)n_ids * 48, cudaMemcpyDeviceToHost, s));
   }

@@ -85,8 +85,34 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
   if (active) status[(size_t)gd * n_r + j] = st;
 }
 
+// evaluate_polynomial output instead of the share comparison: out[dealer][column j] = compress(f_d(ids[j]))
+__global__ void __launch_bounds__(FD_NT)
+k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
+                 const uint32_t* __restrict__ ids, uint8_t* __restrict__ out48, uint32_t* __restrict__ tab, uint32_t n_pad, uint32_t n_d,
+                 uint32_t n_r, uint32_t j0, uint32_t tab_r0, uint32_t d0) {
+  extern __shared__ U4 opfile[];
+  uint32_t d = blockIdx.x * 32 + threadIdx.x;
+  uint32_t j = j0 + blockIdx.y;
+  bool active = d0 + d < n_d;
+  uint32_t dd = active ? d : n_d - 1 - d0;
+  OpFile f{opfile + threadIdx.x, FD_NT};
+  uint32_t x = ids[j];
+  size_t e = (size_t)((int64_t)x - lo);
+  uint32_t* my_tab = tab + (size_t)(tab_r0 + blockIdx.y) * (m - 1) * FD_TAB_SLOTS * 36 * n_pad;
+  fd_combine_eval(f, evals, n_pad * m, n_pad, m, e, dd, dig + (size_t)(x - 1) * fd_dig_bytes(m), m > 1 ? top[x - 1] : -1,
+                  my_tab + (d - dd));
+  uint8_t enc[48];
+  g1_compress(g1_to_affine(vm_get_point(f, AX)), enc);
+  if (active) {
+    uint8_t* o = out48 + ((size_t)(d0 + d) * n_r + j) * 48;
+#pragma unroll
+    for (int i = 0; i < 48; i++) o[i] = enc[i];
+  }
+}
+
 int dkgv_fd_setup(dkgv_ctx* ctx) {
-  for (const void* k : {(const void*)k_fd_seed, (const void*)k_fd_init, (const void*)k_fd_ext, (const void*)k_fd_combine}) {
+  for (const void* k : {(const void*)k_fd_seed, (const void*)k_fd_init, (const void*)k_fd_ext, (const void*)k_fd_combine,
+                        (const void*)k_fd_combine_out}) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
@@ -127,7 +153,7 @@ constexpr uint32_t FD_COMB_CHUNKS = 8;  // recombination launches pipelined behi
 // dealers d0 .. d0 + n_pad - 1 (n_pad a multiple of 32: the column count of this chunk's planes)
 static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad, uint32_t n_d, uint32_t n_r, uint32_t t,
                   const FdPlan& plan, const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status,
-                  cudaStream_t s) {
+                  uint8_t* d_out48, cudaStream_t s) {
   const uint32_t m = plan.m, h = plan.h;
   const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
   const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
@@ -148,7 +174,7 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   CK(ctx->fd_tab.reserve(tab_per_recipient ? tab_per_recipient * chunk_r : 16));
   // columns in ascending-id order: the extension produces f(x) in that order, so the recombination of a
   // range of ids can start as soon as the wavefront has passed it
-  const bool pipelined = ctx->fd_overlap && ctx->fd_pipeline && m > 1 && chunk_r == n_r;
+  const bool pipelined = ctx->fd_overlap && ctx->fd_pipeline && m > 1 && chunk_r == n_r && !d_out48;
   if (pipelined) {
     ctx->fd_cols_host.resize(n_r);
     for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
@@ -161,6 +187,13 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     }
   }
   auto launch_combine = [&](cudaStream_t cs, uint32_t r0, uint32_t nj, const uint32_t* cols, uint32_t tab_r0) {
+    if (d_out48) {  // evaluation output (cols == nullptr: this mode is never pipelined)
+      k_fd_combine_out<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
+                                                                     (const int32_t*)ctx->fd_top.p, d_ids, d_out48,
+                                                                     (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, tab_r0, d0);
+      ctx->launches++;
+      return;
+    }
     k_fd_combine<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
                                                                (const int32_t*)ctx->fd_top.p, d_ids, d_shares, ctx->gtab,
                                                                (const uint8_t*)ctx->dealer_bad.p, d_status, (uint32_t*)ctx->fd_tab.p,
@@ -309,8 +342,9 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
 
 // Dealers are independent, so a ceremony whose planes would not fit the memory budget is processed in
 // dealer chunks (multiples of 32 columns).  (1024, 683) on one GPU needs 1.5 GB of planes + 3.6 GB of tables.
-int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
+static int fd_run_chunks(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, uint8_t* d_out48,
+                         cudaStream_t s) {
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
   const size_t bytes_per_col = (n_evals + 4 * (size_t)plan.h) * 36 * plan.m * 4;
   size_t budget = (size_t)12 << 30;
@@ -318,7 +352,20 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
   uint32_t chunk = (uint32_t)std::min<size_t>(view.n_pad, std::max<size_t>(32, (budget / bytes_per_col) & ~(size_t)31));
   for (uint32_t d0 = 0; d0 < view.n_pad && d0 < n_d; d0 += chunk) {
     uint32_t cols = std::min(chunk, view.n_pad - d0);
-    if (int rc = fd_run(ctx, view, d0, cols, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, s)) return rc;
+    if (int rc = fd_run(ctx, view, d0, cols, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, d_out48, s)) return rc;
   }
   return 0;
+}
+
+int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
+  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, nullptr, s);
+}
+
+// evaluate_polynomial (dkg_math.rs:160-174) of every dealer at every id, ids a permutation of 1..n_r:
+// d_out48[d][j] = compress(f_d(ids[j])).  Used for the final keys K_j of agg_coefficients (one "dealer": the
+// column sums) and the batched dkgv_feldman_eval.
+int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
+                         const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s) {
+  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, nullptr, nullptr, d_out48, s);
 }
