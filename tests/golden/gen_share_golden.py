@@ -85,12 +85,24 @@ def mut_identity_eval(vv, pts, shares, bad):
         shares[0][j] = bytes(32)
 
 
+def mut_ranks_split(vv, pts, shares, bad):
+    s = bytearray(shares[0][5]); s[0] ^= 0x40; shares[0][5] = bytes(s)   # may leave the range or just mismatch
+    shares[1][0] = shares[2][0]
+    shares[2][11] = bytes(32)
+    vv[1][4] = B.g1_compress(None)       # identity coefficient in the middle of a part
+    vv[2][8] = vv[2][7]                  # repeated coefficient
+
+
 out = {"sessions": [
     session("main", 5, 3, [1, 2, 3, 4, 5, 37], mut_main),
     session("t1", 2, 1, [1, 2, 9], mut_none),
     session("t0", 2, 0, [1, 2], mut_none),
     session("ragged-n", 33, 2, [1, 2, 1024, 0], mut_none),
     session("identity", 2, 3, [1, 6], mut_identity_eval),
+    # recipient ids = the ranks 1..n in arbitrary column order (what a ceremony always has): the shape that
+    # takes the finite-difference route of the share matrix (csrc/fdiff.cuh)
+    session("ranks", 5, 3, [4, 1, 6, 2, 5, 3], mut_main),
+    session("ranks-split", 3, 9, [7, 12, 1, 3, 10, 2, 9, 4, 11, 6, 8, 5], mut_ranks_split),
 ]}
 # fixed-base G*s known answers incl. edge scalars
 ks = [0, 1, 2, 255, 256, B.R - 1, prng("fb", 0) % B.R, prng("fb", 1) % B.R, 1 << 248, (1 << 255) % B.R]
