@@ -355,8 +355,8 @@ def run_b200(args):
         bad_e2e = int(h_st.count_nonzero().item())
 
         # second BASELINE metric: BLS pairing checks/s (bls_verify_precomputed_hash, one common message),
-        # 65536 checks sharded over the ranks, inputs resident in HBM, verdict bytes all-gathered
-        m_total = 65536
+        # 262144 checks (a batch that saturates the GPU) sharded over the ranks, inputs resident in HBM, verdict bytes all-gathered
+        m_total = 262144
         m_loc = m_total // world
         fin = synthetic.make_finalization(v, 64, 8)
         reps = (m_loc + 63) // 64

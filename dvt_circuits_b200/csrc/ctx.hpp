@@ -38,6 +38,7 @@ struct dkgv_ctx {
   dkgv_host::DevBuf vv_limbs, vv_inf, dealer_bad;      // session scratch (decoded verification vectors)
   dkgv_host::DevBuf in_a, in_b, in_c, out_a, out_b;    // staging for the host-pointer entry points
   dkgv_host::DevBuf scratch_a, scratch_b, scratch_c;   // intermediates of the aggregation / pairing paths
+  dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
   bool hot_recorded = false;
   bool stack_set = false;

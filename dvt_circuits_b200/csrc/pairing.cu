@@ -1,6 +1,7 @@
 // BLS partial-signature checks on the GPU (C ABI part 2): G2 decoding, hash-to-G2 and the batched
 // pairing-equality kernel.  Replaces crates/dkg/src/crypto/bls_common.rs:11-40 and the signature
 // loop of verify_generation_hashes (crates/dkg/src/verification.rs:237-248).
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.hpp"
@@ -48,26 +49,43 @@ __global__ void __launch_bounds__(32) k_hash_to_g2(const uint8_t* __restrict__ m
   for (int k = 0; k < 96; k++) out[(size_t)i * 96 + k] = enc[k];
 }
 
+// G1 decode (subgroup-checked) into an affine struct in global memory, one thread per key
+__global__ void __launch_bounds__(64) k_g1_decode(const uint8_t* __restrict__ in, G1Aff* __restrict__ out, uint8_t* __restrict__ st,
+                                                  uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  G1Aff a;
+  uint32_t s = g1_decompress(in + (size_t)i * 48, &a, true);
+  out[i] = a;
+  st[i] = (uint8_t)s;
+}
+
 // one thread per check: status = OK | SLASHABLE_SIG_INVALID (pairing equality false)
 //                               | PANIC_BAD_G1 (pk undecodable) | PANIC_BAD_G2 (signature undecodable)
 // (the caller maps the decode failures to the reference's exit for its call site:
-//  .expect -> panic in verify_generation_hashes, slashable in prove_wrong_final_key_generation)
-__global__ void __launch_bounds__(32)
-k_bls_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ sig, const G2Aff* __restrict__ hm,
-             const G2Line* __restrict__ hm_lines, const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status, uint32_t m) {
+//  .expect -> panic in verify_generation_hashes, slashable in prove_wrong_final_key_generation).
+// Keys and signatures arrive decoded (k_g1_decode / k_g2_decode): the decoders' code (square roots, subgroup
+// checks, ~200 KB of SASS) stays out of this kernel, whose working set of instructions is the Miller loop and
+// the final exponentiation only - with everything in one kernel ncu showed a 79 % instruction-cache hit rate and
+// 22 % of the issue stalls on instruction fetch (profiles/r1_bls_verify.md).
+#ifndef DKGV_BLS_MINB
+#define DKGV_BLS_MINB 1
+#endif
+__global__ void __launch_bounds__(32, DKGV_BLS_MINB)
+k_bls_verify(const G1Aff* __restrict__ pk, const uint8_t* __restrict__ pk_st, const G2Aff* __restrict__ sig,
+             const uint8_t* __restrict__ sig_st, const G2Aff* __restrict__ hm, const G2Line* __restrict__ hm_lines,
+             const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   // decode order of the reference: signature first, then key (verification.rs:238-241)
-  G2Aff s;
-  G1Aff p;
-  uint32_t ds = g2_decompress(sig + (size_t)i * 96, &s, true);
-  uint32_t dp = g1_decompress(pk + (size_t)i * 48, &p, true);
   uint8_t st;
-  if (ds != G1_DEC_OK) {
+  if (sig_st[i] != G1_DEC_OK) {
     st = DKGV_PANIC_BAD_G2;
-  } else if (dp != G1_DEC_OK) {
+  } else if (pk_st[i] != G1_DEC_OK) {
     st = DKGV_PANIC_BAD_G1;
   } else {
+    G2Aff s = sig[i];
+    G1Aff p = pk[i];
     uint32_t hi = hm_idx ? hm_idx[i] : 0;
     G2Aff h = hm[hi];
     st = bls_verify_prepared(&p, &s, &h, hm_lines ? hm_lines + (size_t)hi * G2_PREP_LINES : nullptr) ? DKGV_OK
@@ -192,7 +210,24 @@ extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_
     CK(cudaGetLastError());
     lines = (const G2Line*)ctx->scratch_c.p;
   }
-  k_bls_verify<<<(m + 31) / 32, 32, 0, s>>>(d_pk, d_sig, (const G2Aff*)ctx->scratch_a.p, lines, d_hm_idx, d_status, m);
+  // decode keys and signatures in their own kernels
+  CK(ctx->bls_pk.reserve((size_t)m * sizeof(G1Aff)));
+  CK(ctx->bls_sig.reserve((size_t)m * sizeof(G2Aff)));
+  CK(ctx->bls_st.reserve((size_t)m * 2));
+  uint8_t* pk_st = (uint8_t*)ctx->bls_st.p;
+  uint8_t* sig_st = pk_st + m;
+  k_g2_decode<<<(m + 31) / 32, 32, 0, s>>>(d_sig, (G2Aff*)ctx->bls_sig.p, sig_st, m);
+  k_g1_decode<<<(m + 63) / 64, 64, 0, s>>>(d_pk, (G1Aff*)ctx->bls_pk.p, pk_st, m);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  static int cap_kb = -1;  // experiment: DKGV_BLS_SMEM_KB of unused dynamic shared memory per block caps the resident checks per SM
+  if (cap_kb < 0) {
+    const char* e = getenv("DKGV_BLS_SMEM_KB");
+    cap_kb = e ? atoi(e) : 0;
+    if (cap_kb > 48) CK(cudaFuncSetAttribute(k_bls_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_kb * 1024));
+  }
+  k_bls_verify<<<(m + 31) / 32, 32, (size_t)cap_kb * 1024, s>>>((const G1Aff*)ctx->bls_pk.p, pk_st, (const G2Aff*)ctx->bls_sig.p, sig_st,
+                                            (const G2Aff*)ctx->scratch_a.p, lines, d_hm_idx, d_status, m);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
