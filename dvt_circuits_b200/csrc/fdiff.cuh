@@ -221,11 +221,12 @@ DKGV_HD int fd_comb_digits(uint32_t x, uint32_t h, uint32_t m, int8_t* dig) {
   return top;
 }
 
-DKGV_NI void vm_mul_beta(OpFile f, int d, int a) {
+// slot <- beta (the cube root of unity of phi); a constant store instead of a third copy of the product routine
+DKGV_NI void vm_set_beta(OpFile f, int d) {
   Fp beta;
 #pragma unroll
   for (int i = 0; i < 12; i++) beta.l[i] = consts::BETA_M(i);
-  of_store(f, d, mul(of_load(f, a), beta));
+  of_store(f, d, beta);
 }
 
 // A <- sum_i [y^i] f_i(x): entries of the m virtual dealers (part i of dealer d sits at column
@@ -268,7 +269,8 @@ DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_
       else
         fd_load(f, BX, fd_entry(tab, n_pad, (size_t)(i - 1) * FD_TAB_SLOTS + (a >> 1), d), n_pad);
       if (half) {  // -phi(P) = (beta X : -Y : Z)
-        vm_mul_beta(f, BX, BX);
+        vm_set_beta(f, T6);
+        vm_mul(f, BX, BX, T6);
         ng = !ng;
       }
       if (ng) vm_neg(f, BY, BY);

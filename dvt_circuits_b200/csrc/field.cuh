@@ -304,6 +304,66 @@ DKGV_HD Mont<PR> mul(const Mont<PR>& a, const Mont<PR>& b) {
   return r;
 }
 
+// (a*b + c*d) * R^-1 mod p with ONE interleaved Montgomery reduction: per row the two multiplicand rows
+// a*b_i and c*d_i are accumulated before the single reduction row m*p, i.e. 3 x N^2 + N wide products
+// instead of the 4 x N^2 + 2N of two separate products and an addition (444 vs 600 for Fp).  The running
+// value stays below 3p + 1 (a, c < p), which the spare top bits of both moduli absorb: 3 * 0x1a0111eb < 2^32
+// for Fp, so no chain can carry out of the top limb; two conditional subtractions bring the result below p.
+// Same value as add(mul(a, b), mul(c, d)) - used for the "sum of two products" lines of the RCB formulas.
+template <class PR>
+DKGV_HD Mont<PR> mul2add(const Mont<PR>& a, const Mont<PR>& b, const Mont<PR>& c, const Mont<PR>& d) {
+#if defined(__CUDA_ARCH__)
+  constexpr int N = PR::N;
+  Mont<PR> r;
+  uint32_t ev[N], od[N];
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    // ---- row i : ev is column-aligned
+    if (i == 0) {
+      ptx::mul_n<N>(od, a.l + 1, b.l[0]);
+      ptx::mul_n<N>(ev, a.l, b.l[0]);
+    } else {
+      asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(ev[0]) : "r"(od[1]));
+      ptx::madc_n_rshift<N>(od, a.l + 1, b.l[i]);
+      ptx::cmad_n<N>(ev, a.l, b.l[i]);
+      asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[N - 1]));
+    }
+    ptx::cmad_n<N>(od, c.l + 1, d.l[i]);
+    ptx::cmad_n<N>(ev, c.l, d.l[i]);
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[N - 1]));
+    {
+      uint32_t m = ev[0] * PR::INV;
+      ptx::cmad_mod<PR, 1>(od, m);
+      ptx::cmad_mod<PR, 0>(ev, m);
+      asm volatile("addc.u32 %0, %0, 0;" : "+r"(od[N - 1]));
+    }
+    // ---- row i+1 : roles swapped (od is column-aligned)
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(od[0]) : "r"(ev[1]));
+    ptx::madc_n_rshift<N>(ev, a.l + 1, b.l[i + 1]);
+    ptx::cmad_n<N>(od, a.l, b.l[i + 1]);
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[N - 1]));
+    ptx::cmad_n<N>(ev, c.l + 1, d.l[i + 1]);
+    ptx::cmad_n<N>(od, c.l, d.l[i + 1]);
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[N - 1]));
+    {
+      uint32_t m = od[0] * PR::INV;
+      ptx::cmad_mod<PR, 1>(ev, m);
+      ptx::cmad_mod<PR, 0>(od, m);
+      asm volatile("addc.u32 %0, %0, 0;" : "+r"(ev[N - 1]));
+    }
+  }
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(od[1]), "r"(ev[0]));
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.l[k]) : "r"(od[k + 1]), "r"(ev[k]));
+  asm volatile("addc.u32 %0, %1, 0;" : "=r"(r.l[N - 1]) : "r"(ev[N - 1]));
+  cond_sub_mod<PR>(r.l, 0);
+  cond_sub_mod<PR>(r.l, 0);
+  return r;
+#else
+  return add(mul(a, b), mul(c, d));
+#endif
+}
+
 template <class PR>
 DKGV_HD Mont<PR> sqr(const Mont<PR>& a) {
   return mul(a, a);
