@@ -49,11 +49,7 @@ def executed_modmul_per_share(n, t):
     def cost(pos, neg):
         m = pos | neg
         return 8 * (m.bit_length() - 1) + 12 * (bin(m).count("1") - 1)
-    tot = 0
-    for j in range(1, n + 1):
-        k3 = 3 * j
-        tot += min(cost(j, 0), cost((k3 & ~j) >> 1, (~k3 & j) >> 1)) + 12
-    return (t - 1) * tot / n + 33 * 11 + 4
+    return sum(executed_horner_modmul(t, j) for j in range(1, n + 1)) / n + 33 * EXEC_MADD + 4
 
 
 def canonical_horner_modmul(t, x):
@@ -62,16 +58,23 @@ def canonical_horner_modmul(t, x):
     return 0 if x == 0 else (t - 1) * (8 * (x.bit_length() - 1) + 12 * (bin(x).count("1") - 1) + 11)
 
 
+# executed product-equivalents (300 wide MACs each) of the vm.cuh formulas: the fused sum-of-two-products routine
+# (mul2add, 444 MACs) replaces three pairs in the additions and one in the doubling
+EXEC_ADD, EXEC_DBL, EXEC_MADD = 6 + 3 * 444 / 300, 6 + 444 / 300, 5 + 3 * 444 / 300
+
+
 def executed_horner_modmul(t, x):
-    """what fd_seed_eval / vm_feldman_eval execute at |x|: signed-digit chain + a full addition per step"""
+    """what fd_seed_eval / vm_feldman_eval execute at |x|: signed-digit chain (chosen with the canonical 8 / 12
+    weights, vm.cuh make_small_chain) + a full addition per step, in executed product-equivalents"""
     x = abs(x)
     if x == 0:
         return 0
-    def cost(pos, neg):
+    def shape(pos, neg):
         m = pos | neg
-        return 8 * (m.bit_length() - 1) + 12 * (bin(m).count("1") - 1)
+        return m.bit_length() - 1, bin(m).count("1") - 1
     k3 = 3 * x
-    return (t - 1) * (min(cost(x, 0), cost((k3 & ~x) >> 1, (~k3 & x) >> 1)) + 12)
+    dbl, adds = min((shape(x, 0), shape((k3 & ~x) >> 1, (~k3 & x) >> 1)), key=lambda s_: 8 * s_[0] + 12 * s_[1])
+    return (t - 1) * (EXEC_DBL * dbl + EXEC_ADD * adds + EXEC_ADD)
 
 
 PAPER_PEAK_MAC = 148 * 64 * 1.965e9
@@ -438,13 +441,15 @@ def run_b200(args):
             ref = statistics.mean(serial_ms)
             # 128 shared doublings (GLV), per point: table 3P/5P/7P (44) + 2 x 128/5 additions + 128/5 products by beta; + part 0; + G*s, compare
             comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
+            comb_exec = ((128 * EXEC_DBL + (m_parts - 1) * (EXEC_DBL + 3 * EXEC_ADD + 52 * EXEC_ADD + 26) + EXEC_ADD if m_parts > 1 else 0)
+                         + 33 * EXEC_MADD + 4)
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
                              sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part, ph[0], ref),
-                kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, 12, ph[1], ref),
-                kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, 12, ph[2], ref),
-                kernel_entry("k_fd_combine", rows * n, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare", comb_canon, comb_canon,
+                kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, EXEC_ADD, ph[1], ref),
+                kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, EXEC_ADD, ph[2], ref),
+                kernel_entry("k_fd_combine", rows * n, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare", comb_canon, comb_exec,
                              ph[3], ref),
             ]
             top = max(kernels, key=lambda k_: k_["kernel_ms"])
