@@ -91,6 +91,8 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-shortcut", dest="shortcut", action="store_false",
+                    help="evaluate every id in the group even when the scalar-side consistency conditions hold (dkgv_set_share_shortcut 0)")
     ap.add_argument("--no-finalization", action="store_true", help="skip the config-4 finalization leg")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2], help="dkgv_set_share_overlap mode of the timed steps")
@@ -250,6 +252,7 @@ def run_b200(args):
     v = dk.Verifier(local)
     v.set_share_parts(args.parts)
     v.set_share_overlap(args.overlap)
+    v.set_share_shortcut(args.shortcut)
     v.set_share_path({"auto": v.PATH_AUTO, "horner": v.PATH_HORNER, "fdiff": v.PATH_FDIFF}[args.share_path])
     sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
     ts = torch.cuda.Stream(device=dev)
@@ -318,6 +321,7 @@ def run_b200(args):
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
         clocks = sampler.stop() if rank == 0 else None
+        continued = bool(v.last_share_continued) if v.last_share_path == v.PATH_FDIFF else False
         if v.last_share_path == v.PATH_FDIFF:
             # per-kernel times: the timed steps above run the parts on concurrent streams, where single
             # phases have no duration of their own; repeat the same steps phase after phase on one stream
@@ -356,6 +360,30 @@ def run_b200(args):
             dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
         e2e_s_per_step = float(e2e_total.item()) / args.steps
         bad_e2e = int(h_st.count_nonzero().item())
+
+        # BASELINE config 5: the same matrix with half of the shares corrupted (one flipped bit each): every dealer group
+        # takes the full evaluation; verdicts must flag exactly the corrupted shares
+        rng = np.random.Generator(np.random.PCG64([0xBAD, rank]))
+        mask = rng.random((rows, n)) < 0.5
+        sh_bad = sess["shares"].copy()
+        sh_bad[mask, 31] ^= 1
+        d_sh_bad = torch.from_numpy(sh_bad).to(dev)
+        mixed_ms = []
+        for i in range(1 + max(1, args.steps - 1)):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            v.share_matrix_verify_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh_bad.data_ptr(), d_st.data_ptr(), stream)
+            e1.record(ts)
+            e1.synchronize()
+            if i:
+                mixed_ms.append(e0.elapsed_time(e1))
+        mixed_ok = bool(((d_st != 0) == torch.from_numpy(mask).to(dev)).all().item())
+        mixed_total = torch.tensor([sum(mixed_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mixed_total, op=dist.ReduceOp.MAX)
+        mixed_ms_step = float(mixed_total.item()) / len(mixed_ms)
+        del d_sh_bad
 
         # second BASELINE metric: BLS pairing checks/s (bls_verify_precomputed_hash, one common message),
         # 262144 checks (a batch that saturates the GPU) sharded over the ranks, inputs resident in HBM, verdict bytes all-gathered
@@ -443,14 +471,18 @@ def run_b200(args):
             comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
             comb_exec = ((128 * EXEC_DBL + (m_parts - 1) * (EXEC_DBL + 3 * EXEC_ADD + 52 * EXEC_ADD + 26) + EXEC_ADD if m_parts > 1 else 0)
                          + 33 * EXEC_MADD + 4)
+            # consistency shortcut (honest ceremony): only the ids 1..t are evaluated in the group
+            short = args.shortcut and n > t and not continued
+            ids_eval = t if short else n
+            ext_steps = max(0, ids_eval - plan["hi"]) if short else plan["steps"]
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
                              sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part, ph[0], ref),
                 kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, EXEC_ADD, ph[1], ref),
-                kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, EXEC_ADD, ph[2], ref),
-                kernel_entry("k_fd_combine", rows * n, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare", comb_canon, comb_exec,
-                             ph[3], ref),
+                kernel_entry("k_fd_ext", rows * m_parts * ext_steps * (h_part - 1), "one point addition (all ticks)", 12, EXEC_ADD, ph[2], ref),
+                kernel_entry("k_fd_combine", rows * ids_eval, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare",
+                             comb_canon, comb_exec, ph[3], ref),
             ]
             top = max(kernels, key=lambda k_: k_["kernel_ms"])
             algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144
@@ -477,7 +509,8 @@ def run_b200(args):
                 "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
         if fdiff:
-            roof["fdiff"] = {"parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
+            roof["fdiff"] = {"consistency_shortcut": bool(short), "ids_evaluated_in_the_group": ids_eval, "extension_steps_run": ext_steps,
+                             "parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
                              "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
                              "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "recombine_gs_compare": ph[3]},
                              "serial_step_ms": ref, "overlapped_step_ms": step_mean,
@@ -502,6 +535,9 @@ def run_b200(args):
             "pairing": {"metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
                         "checks_per_step": m_total, "ms_per_step": pair_ms_step, "bad_verdicts": pair_bad,
                         "note": "e(pk,H(m)) == e(G1,sig) as 2 Miller loops + 1 final exponentiation per check, incl. G1/G2 decoding with subgroup checks"},
+            "mixed_items": {"metric": "verified shares/sec, 50 % of the shares corrupted (BASELINE config 5)", "value": shares / (mixed_ms_step * 1e-3),
+                            "unit": "shares/s", "ms_per_step": mixed_ms_step, "verdicts_flag_exactly_the_corrupted_shares": mixed_ok,
+                            "note": "every dealer group fails the consistency conditions and takes the full evaluation"},
             "finalization": fin_line,
             "parity": {"bad_verdicts_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
             "wall_s_timed_region": wall,

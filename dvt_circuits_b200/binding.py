@@ -65,6 +65,8 @@ DECLARED_SYMBOLS = {
     "dkgv_last_share_path": (ctypes.c_int, [_vp]),
     "dkgv_set_share_parts": (ctypes.c_int, [_vp, _u32]),
     "dkgv_set_share_overlap": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dkgv_set_share_shortcut": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dkgv_last_share_continued": (ctypes.c_int, [_vp]),
     "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
                                           ctypes.POINTER(ctypes.c_uint64)]),
@@ -173,9 +175,16 @@ class Verifier:
         self._ck(self._lib.dkgv_set_share_path(self._h, int(mode)))
 
     def set_share_overlap(self, on):
-        """1 / True (default): one internal stream per part; 2: plus recombination pipelined behind the extension;
-        0 / False: one stream, phase after phase"""
+        """1 / True (default): one internal stream per part; 0 / False: one stream, phase after phase"""
         self._ck(self._lib.dkgv_set_share_overlap(self._h, int(on)))
+
+    def set_share_shortcut(self, on):
+        """True (default): ids beyond t only for dealer groups that fail the scalar-side consistency conditions"""
+        self._ck(self._lib.dkgv_set_share_shortcut(self._h, int(bool(on))))
+
+    @property
+    def last_share_continued(self):
+        return int(self._lib.dkgv_last_share_continued(self._h))
 
     def set_share_parts(self, parts):
         """parts per dealer polynomial on the finite-difference path (0 = planner's choice)"""

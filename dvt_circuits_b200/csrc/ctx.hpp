@@ -43,17 +43,18 @@ struct dkgv_ctx {
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)
-  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols;
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom;
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
   bool fd_recorded = false;
   bool fd_overlap = true;  // one stream per part (default) or everything on the caller's stream
-  bool fd_pipeline = false;  // also start recombining id ranges while the extension is still running
+  bool fd_polycheck = true;  // consistency shortcut: ids beyond t only for dealer groups that fail the scalar-side conditions
+  uint32_t fd_binom_t = 0;   // t the cached binomial coefficients belong to
+  bool fd_last_need = false; // the last finite-difference run had to continue beyond t for some dealer group
   cudaStream_t fd_streams[16] = {};
   cudaEvent_t fd_fork = nullptr, fd_join[16] = {};
-  cudaStream_t fd_comb_stream = nullptr;  // recombination launches, pipelined behind the extension
+  cudaStream_t fd_comb_stream = nullptr;  // scalar-side checks of the shortcut, concurrent with the seeds
   cudaEvent_t fd_comb_done = nullptr;
-  std::vector<cudaEvent_t> fd_chunk_ev;
   std::vector<uint32_t> fd_cols_host;
   int share_path = 0;       // DKGV_SHARE_PATH_* requested
   uint32_t share_parts = 0; // 0: planner's choice of parts per dealer; else forced

@@ -303,7 +303,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
-                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols, &ctx->bls_pk, &ctx->bls_sig, &ctx->bls_st})
+                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols, &ctx->fd_sl, &ctx->fd_flags, &ctx->fd_binom, &ctx->bls_pk,
+                    &ctx->bls_sig, &ctx->bls_st})
     b->release();
   for (cudaEvent_t ev : ctx->ev_fd)
     if (ev) cudaEventDestroy(ev);
@@ -314,7 +315,6 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
   if (ctx->fd_comb_stream) cudaStreamSynchronize(ctx->fd_comb_stream), cudaStreamDestroy(ctx->fd_comb_stream);
   if (ctx->fd_comb_done) cudaEventDestroy(ctx->fd_comb_done);
-  for (cudaEvent_t ev : ctx->fd_chunk_ev) cudaEventDestroy(ev);
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
@@ -383,8 +383,14 @@ extern "C" int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts) {
 extern "C" int dkgv_set_share_overlap(dkgv_ctx* ctx, int on) {
   if (!ctx) return -1;
   ctx->fd_overlap = on != 0;
-  ctx->fd_pipeline = on == 2;
   return 0;
+}
+extern "C" int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->fd_polycheck = on != 0;
+  return 0;
+}
+extern "C" int dkgv_last_share_continued(const dkgv_ctx* ctx) { return ctx ? (ctx->fd_last_need ? 1 : 0) : -1;
 }
 extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo, int32_t* hi,
                                   uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner) {

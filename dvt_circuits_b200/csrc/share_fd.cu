@@ -6,8 +6,10 @@
 //   k_fd_seed     h Horner evaluations of h-1 steps per virtual dealer (LPT order)
 //   k_fd_init     h-1 rounds of pairwise differences           (1 point addition per item)
 //   k_fd_ext      steps + h - 2 wavefront ticks                (1 point addition per item)
-//   k_fd_digits   NAF digits of the public recombination scalars x^(h i) mod r, one thread per id
+//   k_fd_digits   signed digits of the public recombination scalars x^(h i) mod r, one thread per id
 //   k_fd_combine  sum_i [y^i] f_i(x) by joint double-and-add, G * s, compare: one thread per share
+// plus the consistency shortcut (k_fd_binom / k_fd_share_limbs / k_fd_polycheck / k_fd_need / k_fd_fill_ok, see below):
+// only the ids 1..t go through the group arithmetic unless a dealer group fails the scalar-side conditions.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -46,8 +48,10 @@ k_fd_init(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_ext(const uint32_t* __restrict__ old, uint32_t* __restrict__ cur, uint32_t* __restrict__ evals, uint32_t n_pad, uint32_t t,
-         uint32_t tick, uint32_t k_lo, uint32_t k_hi, size_t e_hi, uint32_t col0, uint32_t ipb) {
+         uint32_t tick, uint32_t k_lo, uint32_t k_hi, size_t e_hi, uint32_t col0, uint32_t ipb, const uint8_t* __restrict__ need_group,
+         uint32_t groups) {
   extern __shared__ U4 opfile[];
+  if (need_group && !need_group[(col0 / 32 + blockIdx.x) % groups]) return;  // continuation only for dealer groups that need it
   uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
 #pragma unroll 1
@@ -68,8 +72,10 @@ __global__ void __launch_bounds__(FD_NT)
 k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
              const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab,
              const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t* __restrict__ tab, uint32_t n_pad,
-             uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0, uint32_t d0) {
+             uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0, uint32_t d0,
+             const uint8_t* __restrict__ need_group) {
   extern __shared__ U4 opfile[];
+  if (need_group && !need_group[blockIdx.x]) return;
   uint32_t d = blockIdx.x * 32 + threadIdx.x;  // column of this dealer chunk (n_pad columns); dealer d0 + d
   uint32_t j = cols ? cols[j0 + blockIdx.y] : j0 + blockIdx.y;
   bool active = d0 + d < n_d;
@@ -85,14 +91,129 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
   if (active) status[(size_t)gd * n_r + j] = st;
 }
 
+// ---- consistency shortcut -------------------------------------------------------------------------------
+// All n shares of a dealer are valid  <=>  (1) every share is < r, (2) the shares s(1..n) lie on a polynomial of
+// degree <= t-1 over Fr, and (3) G*s(x) == f(x) at t distinct ids x.  (The commitments C_k = a_k G define
+// A(x) = sum a_k x^k of degree <= t-1 with f(x) = A(x) G; (3) makes A agree with the polynomial of (2) at t
+// points, hence everywhere.)  (2) is pure scalar arithmetic: the t-th forward differences of the share sequence,
+// sum_j (-1)^j C(t,j) s(x+j), must vanish for x = 1..n-t.  So only the ids 1..t go through the group arithmetic;
+// a dealer (group of 32) that fails any of the three conditions continues with the full path, which yields the
+// exact per-share verdicts.  Exact, deterministic - no random linear combination.
+
+// c[j] = (-1)^j C(t, j) mod r in Montgomery form, j = 0..t  (one thread per j: products + one inversion)
+__global__ void __launch_bounds__(128) k_fd_binom(uint32_t t, uint32_t* __restrict__ c) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > t) return;
+  Fr num = one<FrParams>(), den = one<FrParams>();
+  for (uint32_t i = 1; i <= j; i++) {
+    Fr a = zero<FrParams>(), b = zero<FrParams>();
+    a.l[0] = t - i + 1;
+    b.l[0] = i;
+    num = mul(num, to_mont(a));
+    den = mul(den, to_mont(b));
+  }
+  // den^(r-2)
+  Fr inv = one<FrParams>();
+  for (int l = 7; l >= 0; l--) {
+    uint32_t w = consts::R_MINUS_2(l);
+    for (int b = 31; b >= 0; b--) {
+      inv = mul(inv, inv);
+      if ((w >> b) & 1) inv = mul(inv, den);
+    }
+  }
+  Fr v = mul(num, inv);
+  if (j & 1) v = neg(v);
+  for (int l = 0; l < 8; l++) c[(size_t)j * 8 + l] = v.l[l];
+}
+
+// shares of one dealer chunk as little-endian limbs in ascending-id order: sl[d - d0][x - 1][8]; poly_ok[d] = 0 when a share is >= r
+__global__ void __launch_bounds__(128)
+k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict__ cols, uint32_t* __restrict__ sl, uint8_t* __restrict__ poly_ok,
+                 uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r) {
+  uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
+  if (xi >= n_r || d0 + dl >= n_d) return;
+  uint32_t l[8];
+  bool ok = fr_raw_from_be32(l, shares + ((size_t)(d0 + dl) * n_r + cols[xi]) * 32);
+  if (!ok) poly_ok[d0 + dl] = 0;
+  uint32_t* o = sl + ((size_t)dl * n_r + xi) * 8;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o[i] = l[i];
+}
+
+// condition (2): one block per dealer, one thread per window x = w + 1; poly_ok[d] = 0 when a t-th difference is non-zero
+__global__ void __launch_bounds__(256)
+k_fd_polycheck(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ c, uint8_t* __restrict__ poly_ok, uint32_t d0, uint32_t n_d,
+               uint32_t n_r, uint32_t t) {
+  uint32_t dl = blockIdx.x;
+  if (d0 + dl >= n_d) return;
+  const uint32_t* row = sl + (size_t)dl * n_r * 8;
+  bool bad = false;
+  for (uint32_t w = threadIdx.x; w + t < n_r; w += blockDim.x) {
+    Fr acc = zero<FrParams>();
+#pragma unroll 1
+    for (uint32_t j = 0; j <= t; j++) {
+      Fr sv, cv;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        sv.l[i] = row[(size_t)(w + j) * 8 + i];
+        cv.l[i] = c[(size_t)j * 8 + i];
+      }
+      acc = add(acc, mul(sv, cv));  // canonical share x Montgomery coefficient = canonical product
+    }
+    bad |= !is_zero(acc);
+  }
+  if (bad) poly_ok[d0 + dl] = 0;
+}
+
+// need_group[g] = 1 when some dealer of the 32-dealer group g (of this chunk) fails a condition: undecodable
+// commitment, (1)/(2) failed, or a verdict other than OK among the ids 1..t_lim
+__global__ void __launch_bounds__(128)
+k_fd_need(const uint8_t* __restrict__ status, const uint32_t* __restrict__ cols, const uint8_t* __restrict__ poly_ok,
+          const uint8_t* __restrict__ dealer_bad, uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r, uint32_t t_lim,
+          uint8_t* __restrict__ need_group, uint32_t* __restrict__ any_need) {
+  uint32_t dl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dl >= n_cols || d0 + dl >= n_d) return;
+  uint32_t d = d0 + dl;
+  bool need = dealer_bad[d] != 0 || poly_ok[d] == 0;
+  for (uint32_t xi = 0; xi < t_lim && !need; xi++) need = status[(size_t)d * n_r + cols[xi]] != DKGV_OK;
+  if (need) {
+    need_group[dl / 32] = 1;
+    atomicOr(any_need, 1u);
+  }
+}
+
+// verdict OK for the ids beyond t_lim of every dealer group that met the three conditions
+__global__ void __launch_bounds__(128)
+k_fd_fill_ok(uint8_t* __restrict__ status, const uint32_t* __restrict__ cols, const uint8_t* __restrict__ need_group, uint32_t d0,
+             uint32_t n_cols, uint32_t n_d, uint32_t n_r, uint32_t t_lim) {
+  uint32_t xi = t_lim + blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
+  if (xi >= n_r || d0 + dl >= n_d || need_group[dl / 32]) return;
+  status[(size_t)(d0 + dl) * n_r + cols[xi]] = DKGV_OK;
+}
+
+// both copies of the extension state <- the latest value of every item after a phase of `cnt` steps
+// (item k finished at tick cnt + h-2-k, whose parity says which copy holds it)
+__global__ void __launch_bounds__(128)
+k_fd_sync_state(uint32_t* __restrict__ da, uint32_t* __restrict__ db, uint32_t n_padv, uint32_t h, uint32_t cnt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per = (size_t)36 * n_padv;
+  if (i >= per * (h - 1)) return;
+  uint32_t k = (uint32_t)(i / per);
+  bool in_b = ((cnt + h - 2 - k) & 1) != 0;  // tick tau writes copy tau & 1: 1 = db
+  if (in_b)
+    da[i] = db[i];
+  else
+    db[i] = da[i];
+}
+
 // evaluate_polynomial output instead of the share comparison: out[dealer][column j] = compress(f_d(ids[j]))
 __global__ void __launch_bounds__(FD_NT)
 k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
                  const uint32_t* __restrict__ ids, uint8_t* __restrict__ out48, uint32_t* __restrict__ tab, uint32_t n_pad, uint32_t n_d,
-                 uint32_t n_r, uint32_t j0, uint32_t tab_r0, uint32_t d0) {
+                 uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0, uint32_t d0) {
   extern __shared__ U4 opfile[];
   uint32_t d = blockIdx.x * 32 + threadIdx.x;
-  uint32_t j = j0 + blockIdx.y;
+  uint32_t j = cols ? cols[j0 + blockIdx.y] : j0 + blockIdx.y;
   bool active = d0 + d < n_d;
   uint32_t dd = active ? d : n_d - 1 - d0;
   OpFile f{opfile + threadIdx.x, FD_NT};
@@ -119,15 +240,11 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   if (const char* e = getenv("DKGV_FD_IPB")) g_fd_ipb_force = (uint32_t)atoi(e);
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
-  // the extension is a long dependent chain of small launches: its streams get the highest priority so
-  // that recombination blocks (comb stream, lowest priority) only fill the slots it leaves idle
-  int prio_least = 0, prio_greatest = 0;
-  CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
-    CK(cudaStreamCreateWithPriority(&ctx->fd_streams[i], cudaStreamNonBlocking, prio_greatest));
+    CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->fd_join[i], cudaEventDisableTiming));
   }
-  CK(cudaStreamCreateWithPriority(&ctx->fd_comb_stream, cudaStreamNonBlocking, prio_least));
+  CK(cudaStreamCreateWithFlags(&ctx->fd_comb_stream, cudaStreamNonBlocking));  // scalar-side checks, concurrent with the seeds
   CK(cudaEventCreateWithFlags(&ctx->fd_comb_done, cudaEventDisableTiming));
   return 0;
 }
@@ -143,12 +260,10 @@ bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
   return true;
 }
 
-static inline const uint32_t* evals_c(dkgv_ctx* ctx) { return (const uint32_t*)ctx->fd_evals.p; }
 // Items (point additions) per block of the difference / extension launches.  One per block is the
 // measured optimum on B200 (n=1024, t=683, N=1: extension 336 ms with 1, 344 ms with 2, 367 ms with 4 items):
 // block scheduling is not what the one-addition blocks lose time on.  DKGV_FD_IPB overrides (experiments).
 static inline uint32_t items_per_block(uint32_t, uint32_t) { return g_fd_ipb_force ? g_fd_ipb_force : 1; }
-constexpr uint32_t FD_COMB_CHUNKS = 8;  // recombination launches pipelined behind the extension
 
 // dealers d0 .. d0 + n_pad - 1 (n_pad a multiple of 32: the column count of this chunk's planes)
 static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad, uint32_t n_d, uint32_t n_r, uint32_t t,
@@ -156,8 +271,13 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
                   uint8_t* d_out48, cudaStream_t s) {
   const uint32_t m = plan.m, h = plan.h;
   const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
+  const uint32_t groups = n_pad / 32;
   const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
+  // the consistency shortcut: ids 1..t through the group arithmetic, the rest only for dealer groups that need it
+  const bool shortcut = ctx->fd_polycheck && d_shares && !d_out48 && n_r > t;
+  const uint32_t t_lim = shortcut ? t : n_r;
+  const uint32_t steps1 = t_lim > (uint32_t)plan.hi ? std::min(plan.steps, t_lim - (uint32_t)plan.hi) : 0;  // extension steps of the first phase
   CK(ctx->fd_evals.reserve(n_evals * ent_bytes));
   CK(ctx->fd_p0.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_p1.reserve((size_t)h * ent_bytes));
@@ -165,6 +285,8 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   CK(ctx->fd_db.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_seedx.reserve((size_t)h * 4));
   CK(ctx->fd_dig.reserve((size_t)n_r * fd_dig_bytes(m)));
+  CK(ctx->fd_top.reserve((size_t)n_r * 4));
+  CK(ctx->fd_cols.reserve((size_t)n_r * 4));
   // per-share tables of the recombination: recipients are processed in chunks that fit the budget
   const size_t tab_per_recipient = (size_t)(m > 1 ? m - 1 : 0) * FD_TAB_SLOTS * 36 * n_pad * 4;
   const size_t tab_budget = (size_t)4 << 30;
@@ -172,74 +294,118 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   if (tab_per_recipient && tab_per_recipient * chunk_r > tab_budget) chunk_r = (uint32_t)(tab_budget / tab_per_recipient);
   if (chunk_r == 0) chunk_r = 1;
   CK(ctx->fd_tab.reserve(tab_per_recipient ? tab_per_recipient * chunk_r : 16));
-  // columns in ascending-id order: the extension produces f(x) in that order, so the recombination of a
-  // range of ids can start as soon as the wavefront has passed it
-  const bool pipelined = ctx->fd_overlap && ctx->fd_pipeline && m > 1 && chunk_r == n_r && !d_out48;
-  if (pipelined) {
-    ctx->fd_cols_host.resize(n_r);
-    for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
-    CK(ctx->fd_cols.reserve((size_t)n_r * 4));
-    CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
-    while (ctx->fd_chunk_ev.size() < (size_t)(FD_COMB_CHUNKS + 1) * FD_MAX_PARTS) {
-      cudaEvent_t ev;
-      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      ctx->fd_chunk_ev.push_back(ev);
-    }
-  }
-  auto launch_combine = [&](cudaStream_t cs, uint32_t r0, uint32_t nj, const uint32_t* cols, uint32_t tab_r0) {
-    if (d_out48) {  // evaluation output (cols == nullptr: this mode is never pipelined)
-      k_fd_combine_out<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
-                                                                     (const int32_t*)ctx->fd_top.p, d_ids, d_out48,
-                                                                     (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, tab_r0, d0);
-      ctx->launches++;
-      return;
-    }
-    k_fd_combine<<<dim3(n_pad / 32, nj), FD_NT, FD_SMEM, cs>>>(evals_c(ctx), plan.lo, m, (const int8_t*)ctx->fd_dig.p,
-                                                               (const int32_t*)ctx->fd_top.p, d_ids, d_shares, ctx->gtab,
-                                                               (const uint8_t*)ctx->dealer_bad.p, d_status, (uint32_t*)ctx->fd_tab.p,
-                                                               n_pad, n_d, n_r, r0, cols, tab_r0, d0);
-    ctx->launches++;
-  };
-  // recombination of the ids (x0, x1] on the comb stream once every part stream has produced them
-  uint32_t chunk_no = 0, next_chunk = 1;
-  auto chunk_end = [&](uint32_t c) { return (uint32_t)(((uint64_t)plan.steps * c + FD_COMB_CHUNKS - 1) / FD_COMB_CHUNKS); };
-  auto combine_after_parts = [&](uint32_t x0, uint32_t x1) -> int {
-    for (uint32_t p = 0; p < m; p++) {
-      cudaEvent_t ev = ctx->fd_chunk_ev[(size_t)chunk_no * FD_MAX_PARTS + p];
-      CK(cudaEventRecord(ev, ctx->fd_streams[p]));
-      CK(cudaStreamWaitEvent(ctx->fd_comb_stream, ev, 0));
-    }
-    chunk_no++;
-    if (x1 > x0) launch_combine(ctx->fd_comb_stream, x0, x1 - x0, (const uint32_t*)ctx->fd_cols.p, x0);
-    return 0;
-  };
-  CK(ctx->fd_top.reserve((size_t)n_r * 4));
   uint32_t* evals = (uint32_t*)ctx->fd_evals.p;
   uint32_t* pp[2] = {(uint32_t*)ctx->fd_p0.p, (uint32_t*)ctx->fd_p1.p};
   uint32_t* dd[2] = {(uint32_t*)ctx->fd_da.p, (uint32_t*)ctx->fd_db.p};
+  const uint32_t* cols = (const uint32_t*)ctx->fd_cols.p;
 
-  // seed points, most expensive first (blocks are dispatched in increasing blockIdx.y)
+  // seed points, most expensive first (blocks are dispatched in increasing blockIdx.y); columns in ascending-id order
   std::vector<int32_t> order(h);
   for (uint32_t i = 0; i < h; i++) order[i] = plan.lo + (int32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
     return fd_horner_cost(h, (uint32_t)(a < 0 ? -a : a)) > fd_horner_cost(h, (uint32_t)(b < 0 ? -b : b));
   });
-  ctx->fd_seed_host.assign(order.begin(), order.end());  // must outlive the async copy
+  ctx->fd_seed_host.assign(order.begin(), order.end());  // must outlive the async copies
+  ctx->fd_cols_host.resize(n_r);
+  for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
   CK(cudaMemcpyAsync(ctx->fd_seedx.p, ctx->fd_seed_host.data(), (size_t)h * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
 
-  const unsigned gx = n_pad / 32, gxv = n_padv / 32;
+  const unsigned gx = groups, gxv = n_padv / 32;
   const size_t e_hi = (size_t)(plan.hi - plan.lo);  // == h - 1
-  const uint32_t ticks = plan.steps + h - 2;
   const bool overlap = ctx->fd_overlap && m > 1;
   CK(cudaEventRecord(ctx->ev_fd[0], s));
   CK(cudaEventRecord(ctx->ev_hot0, s));
+  CK(cudaEventRecord(ctx->fd_fork, s));
+
+  // scalar side of the shortcut on its own stream, concurrent with the seeds
+  uint8_t* poly_ok = nullptr;
+  uint8_t* need_group = nullptr;
+  uint32_t* any_need = nullptr;
+  if (shortcut) {
+    CK(ctx->fd_sl.reserve((size_t)n_pad * n_r * 32));
+    CK(ctx->fd_flags.reserve((size_t)n_d + groups + 16));
+    if (ctx->fd_binom_t != t) {
+      CK(ctx->fd_binom.reserve((size_t)(t + 1) * 32));
+    }
+    poly_ok = (uint8_t*)ctx->fd_flags.p;
+    need_group = poly_ok + n_d;
+    any_need = (uint32_t*)(((uintptr_t)(need_group + groups) + 7) & ~(uintptr_t)7);
+    cudaStream_t cs = ctx->fd_comb_stream;
+    CK(cudaStreamWaitEvent(cs, ctx->fd_fork, 0));
+    if (ctx->fd_binom_t != t) {
+      k_fd_binom<<<(t + 128) / 128, 128, 0, cs>>>(t, (uint32_t*)ctx->fd_binom.p);
+      ctx->fd_binom_t = t;
+      ctx->launches++;
+    }
+    CK(cudaMemsetAsync(poly_ok + d0, 1, std::min(n_pad, n_d - d0), cs));
+    CK(cudaMemsetAsync(need_group, 0, groups + 16, cs));
+    k_fd_share_limbs<<<dim3((n_r + 127) / 128, std::min(n_pad, n_d - d0)), 128, 0, cs>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0,
+                                                                                       n_pad, n_d, n_r);
+    k_fd_polycheck<<<std::min(n_pad, n_d - d0), 256, 0, cs>>>((const uint32_t*)ctx->fd_sl.p, (const uint32_t*)ctx->fd_binom.p, poly_ok, d0, n_d,
+                                                             n_r, t);
+    ctx->launches += 2;
+    CK(cudaEventRecord(ctx->fd_comb_done, cs));
+  }
+
+  // one wavefront of `cnt` extension steps starting from the state in dd[] (both copies equal), ids hi+from+1 .. hi+from+cnt
+  auto run_extension = [&](uint32_t from, uint32_t cnt, const uint8_t* filter) -> int {
+    if (cnt == 0) return 0;
+    const uint32_t ticks = cnt + h - 2;
+    for (uint32_t tick = 1; tick <= ticks; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, cnt, tick, &k_lo, &k_hi);
+      if (k_lo > k_hi) continue;
+      uint32_t n_items = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, n_items);
+      if (!overlap) {
+        k_fd_ext<<<dim3(gxv, (n_items + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
+                                                                            (uint32_t)k_lo, (uint32_t)k_hi, e_hi + from, 0, ipb, filter, groups);
+        ctx->launches++;
+      } else {
+        for (uint32_t p = 0; p < m; p++) {
+          k_fd_ext<<<dim3(gx, (n_items + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv,
+                                                                                              h, tick, (uint32_t)k_lo, (uint32_t)k_hi,
+                                                                                              e_hi + from, p * n_pad, ipb, filter, groups);
+          ctx->launches++;
+        }
+      }
+    }
+    return 0;
+  };
+  auto fork_parts = [&]() -> int {
+    CK(cudaEventRecord(ctx->fd_fork, s));
+    for (uint32_t p = 0; p < m; p++) CK(cudaStreamWaitEvent(ctx->fd_streams[p], ctx->fd_fork, 0));
+    return 0;
+  };
+  auto join_parts = [&]() -> int {
+    for (uint32_t p = 0; p < m; p++) {
+      CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
+      CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
+    }
+    return 0;
+  };
+  // recombination + comparison (or evaluation output) of the ids x0+1 .. x1 in ascending-id order
+  auto run_combine = [&](uint32_t x0, uint32_t x1, const uint8_t* filter) {
+    for (uint32_t r0 = x0; r0 < x1; r0 += chunk_r) {
+      uint32_t nj = std::min(chunk_r, x1 - r0);
+      if (d_out48)
+        k_fd_combine_out<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p,
+                                                             d_ids, d_out48, (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, cols, 0, d0);
+      else
+        k_fd_combine<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
+                                                         d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status,
+                                                         (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, cols, 0, d0, filter);
+      ctx->launches++;
+    }
+  };
+
+  // ---- seeds, differences, first extension phase
   if (!overlap) {
     // one stream, phase after phase over all parts at once (also the mode that yields per-phase times)
     k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv, d0, n_pad);
     CK(cudaEventRecord(ctx->ev_hot1, s));
     CK(cudaEventRecord(ctx->ev_fd[1], s));
     ctx->launches++;
-    // backward differences of every part at hi
     CK(cudaMemcpyAsync(dd[0], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(dd[1], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
     const uint32_t* src = evals;
@@ -251,27 +417,11 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       src = dst;
     }
     CK(cudaEventRecord(ctx->ev_fd[2], s));
-    // wavefront extension hi+1 .. n_r
-    for (uint32_t tick = 1; tick <= ticks; tick++) {
-      int32_t k_lo, k_hi;
-      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
-      if (k_lo > k_hi) continue;
-      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
-      k_fd_ext<<<dim3(gxv, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
-                                                                      (uint32_t)k_lo, (uint32_t)k_hi, e_hi, 0, ipb);
-      ctx->launches++;
-    }
-    CK(cudaEventRecord(ctx->ev_fd[3], s));
+    if (int rc = run_extension(0, steps1, nullptr)) return rc;
   } else {
     // The parts are independent until the recombination: each runs its seed -> differences -> extension
     // chain on its own stream, so the tail of one part's kernel is filled by blocks of the others
     // (no grid-wide barrier per round / tick; matters when a rank holds few dealers).
-    CK(cudaEventRecord(ctx->fd_fork, s));
-    if (pipelined) {
-      CK(cudaStreamWaitEvent(ctx->fd_comb_stream, ctx->fd_fork, 0));
-      k_fd_digits<<<(n_r + 127) / 128, 128, 0, ctx->fd_comb_stream>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
-      ctx->launches++;
-    }
     for (uint32_t p = 0; p < m; p++) {
       cudaStream_t sp = ctx->fd_streams[p];
       CK(cudaStreamWaitEvent(sp, ctx->fd_fork, 0));
@@ -283,8 +433,6 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       CK(cudaMemcpy2DAsync(dd[0] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
       CK(cudaMemcpy2DAsync(dd[1] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
     }
-    if (pipelined)  // ids 1..hi are seed values
-      if (int rc = combine_after_parts(0, (uint32_t)plan.hi)) return rc;
     for (uint32_t r = 1; r < h; r++) {
       uint32_t ipb = items_per_block(gxv, h - r);
       for (uint32_t p = 0; p < m; p++) {
@@ -293,46 +441,47 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
         ctx->launches++;
       }
     }
-    for (uint32_t tick = 1; tick <= ticks; tick++) {
-      int32_t k_lo, k_hi;
-      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
-      if (k_lo > k_hi) continue;
-      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
-      for (uint32_t p = 0; p < m; p++) {
-        k_fd_ext<<<dim3(gx, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h,
-                                                                                         tick, (uint32_t)k_lo, (uint32_t)k_hi, e_hi,
-                                                                                         p * n_pad, ipb);
-        ctx->launches++;
-      }
-      if (pipelined && tick >= h - 1) {  // step tick - (h - 2) of every part is queued: ids up to hi + that step exist after it
-        uint32_t sdone = tick - (h - 2);
-        while (next_chunk <= FD_COMB_CHUNKS && chunk_end(next_chunk) <= sdone) {
-          uint32_t s_beg = chunk_end(next_chunk - 1), s_end = chunk_end(next_chunk);
-          next_chunk++;
-          if (s_end > s_beg)
-            if (int rc = combine_after_parts((uint32_t)plan.hi + s_beg, (uint32_t)plan.hi + s_end)) return rc;
-        }
-      }
-    }
-    for (uint32_t p = 0; p < m; p++) {
-      CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
-      CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
-    }
-    if (pipelined) {
-      CK(cudaEventRecord(ctx->fd_comb_done, ctx->fd_comb_stream));
-      CK(cudaStreamWaitEvent(s, ctx->fd_comb_done, 0));
-    }
+    if (int rc = run_extension(0, steps1, nullptr)) return rc;
+    if (int rc = join_parts()) return rc;
     CK(cudaEventRecord(ctx->ev_hot1, s));
-    for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
+    for (int i = 1; i <= 2; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
   }
   ctx->hot_recorded = true;
 
-  if (!pipelined) {
-    if (m > 1) {
-      k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
-      ctx->launches++;
+  // ---- recombination of the ids of the first phase
+  CK(cudaEventRecord(ctx->ev_fd[3], s));
+  if (m > 1) {
+    k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
+    ctx->launches++;
+  }
+  run_combine(0, t_lim, nullptr);
+
+  // ---- ids beyond t: only where the three conditions do not hold
+  if (shortcut) {
+    CK(cudaStreamWaitEvent(s, ctx->fd_comb_done, 0));
+    k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(d_status, cols, poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, n_r, t_lim,
+                                                  need_group, any_need);
+    ctx->launches++;
+    uint32_t h_any = 0;
+    CK(cudaMemcpyAsync(&h_any, any_need, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->fd_last_need = h_any != 0;
+    if (h_any) {
+      const uint32_t rest = plan.steps - steps1;
+      if (steps1 > 0 && rest > 0) {
+        size_t total = (size_t)36 * n_padv * (h - 1);
+        k_fd_sync_state<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(dd[0], dd[1], n_padv, h, steps1);
+        ctx->launches++;
+      }
+      if (overlap)
+        if (int rc = fork_parts()) return rc;
+      if (int rc = run_extension(steps1, rest, need_group)) return rc;
+      if (overlap)
+        if (int rc = join_parts()) return rc;
+      run_combine(t_lim, n_r, need_group);
     }
-    for (uint32_t j0 = 0; j0 < n_r; j0 += chunk_r) launch_combine(s, j0, n_r - j0 < chunk_r ? n_r - j0 : chunk_r, nullptr, 0);
+    k_fd_fill_ok<<<dim3((n_r - t_lim + 127) / 128, std::min(n_pad, n_d - d0)), 128, 0, s>>>(d_status, cols, need_group, d0, n_pad, n_d, n_r, t_lim);
+    ctx->launches++;
   }
   CK(cudaEventRecord(ctx->ev_fd[4], s));
   ctx->fd_recorded = true;

@@ -106,10 +106,19 @@ enum dkgv_share_path { DKGV_SHARE_PATH_AUTO = 0, DKGV_SHARE_PATH_HORNER = 1, DKG
 int dkgv_set_share_path(dkgv_ctx* ctx, int mode); /* FDIFF: use it whenever applicable, even if not cheaper */
 int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts); /* 0 = planner's choice (default), else 1..16 */
 /* 1 (default): the parts of the finite-difference path run on one internal stream each and join before the
- * recombination; 2: additionally the recombination of an id range starts as soon as the extension has passed
- * it (measured neutral to slightly slower on a full GPU, kept as an option for ranks with few dealers);
- * 0: everything on the caller's stream, phase after phase (gives per-phase device times)              */
+ * recombination; 0: everything on the caller's stream, phase after phase (gives per-phase device times).
+ * (Starting the recombination of an id range while the extension is still running was measured slower
+ * at N = 1 and N = 8 and removed.)                                                                     */
 int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
+/* Consistency shortcut of the finite-difference path (default on).  All n shares of a dealer are valid exactly when
+ * (1) each is < r, (2) they lie on a polynomial of degree <= t-1 over Fr - pure scalar arithmetic: the t-th forward
+ * differences of the share sequence vanish - and (3) G*s(x) == f(x) at t distinct ids x.  So only the ids 1..t go
+ * through the group arithmetic; a group of 32 dealers in which some dealer fails a condition continues with the full
+ * evaluation, which yields the exact per-share verdicts.  Deterministic and exact (no random linear combination).
+ * Costs one host synchronisation inside the call.  dkgv_last_share_continued: 1 when the last call had to continue
+ * beyond t for some dealer group, 0 when the shortcut settled everything.                                        */
+int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on);
+int dkgv_last_share_continued(const dkgv_ctx* ctx);
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
 /* the plan for ids 1..n_recipients (parts_force 0 = cheapest): parts, h = ceil(t / parts), Horner seed points
  * lo..hi (hi - lo + 1 == h), extension steps, field products per dealer by this plan and by per-share Horner
