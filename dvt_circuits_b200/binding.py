@@ -67,7 +67,7 @@ DECLARED_SYMBOLS = {
     "dkgv_set_share_overlap": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_set_share_shortcut": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_continued": (ctypes.c_int, [_vp]),
-    "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
+    "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
                                           ctypes.POINTER(ctypes.c_uint64)]),
     "dkgv_last_share_phases_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -367,12 +367,13 @@ def verdict_bits_to_matrix(words, n_dealers, n_recipients):
     return bits.reshape(n_dealers, n_recipients).astype(bool)
 
 
-def share_fd_plan(t, n_recipients, parts=0):
-    """dkgv_share_fd_plan -> dict(use, parts, h, lo, hi, steps, modmul_fd, modmul_horner) (per dealer, evaluation only)"""
+def share_fd_plan(t, n_recipients, parts=0, n_opt=0):
+    """dkgv_share_fd_plan -> dict(use, parts, h, lo, hi, steps, modmul_fd, modmul_horner) (per dealer, evaluation only);
+    n_opt = ids assumed evaluated in the group (0 = all; t = what the share matrix uses with the consistency shortcut on)"""
     lib = load_library()
     m, h, lo, hi, steps = _u32(), _u32(), ctypes.c_int32(), ctypes.c_int32(), _u32()
     cf, ch = ctypes.c_uint64(), ctypes.c_uint64()
-    use = lib.dkgv_share_fd_plan(t, n_recipients, parts, ctypes.byref(m), ctypes.byref(h), ctypes.byref(lo), ctypes.byref(hi),
+    use = lib.dkgv_share_fd_plan(t, n_recipients, parts, n_opt, ctypes.byref(m), ctypes.byref(h), ctypes.byref(lo), ctypes.byref(hi),
                                  ctypes.byref(steps), ctypes.byref(cf), ctypes.byref(ch))
     return {"use": use == 1, "exists": use >= 0, "parts": m.value, "h": h.value, "lo": lo.value, "hi": hi.value, "steps": steps.value,
             "modmul_fd": cf.value, "modmul_horner": ch.value}

@@ -392,9 +392,9 @@ extern "C" int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on) {
 }
 extern "C" int dkgv_last_share_continued(const dkgv_ctx* ctx) { return ctx ? (ctx->fd_last_need ? 1 : 0) : -1;
 }
-extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo, int32_t* hi,
-                                  uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner) {
-  FdPlan p = fd_make_plan(t, n_r, parts_force);
+extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t n_opt, uint32_t* parts, uint32_t* h, int32_t* lo,
+                                  int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner) {
+  FdPlan p = fd_make_plan(t, n_r, parts_force, n_opt);
   if (parts) *parts = p.m;
   if (h) *h = p.h;
   if (lo) *lo = p.lo;
@@ -439,7 +439,9 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
       h_ids = fetched.data();
     }
     if (dkgv_fd_ids_consecutive(h_ids, n_r)) {
-      plan = fd_make_plan(t, n_r, ctx->share_parts);
+      // planned for the full evaluation (n_opt = 0): measured within 0.5 % of the shortcut-optimal split on an honest ceremony
+      // (553 vs 551 ms at 1024 / 683) and 2 % better when the groups have to continue (734 vs 750 ms)
+      plan = fd_make_plan(t, n_r, ctx->share_parts, 0);
       use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
     }
   }

@@ -324,7 +324,8 @@ struct FdPlan {
   uint64_t cost_fd, cost_horner;  // field products per dealer, both ways (excluding G*s)
 };
 
-// cheapest window of h consecutive integers containing 1 for polynomials of h coefficients
+// cheapest window of h consecutive integers containing 1 for polynomials of h coefficients that are then
+// extended up to id n_r
 inline uint64_t fd_best_window(uint32_t h, uint32_t n_r, int32_t* lo_out) {
   uint64_t* pre = new uint64_t[h + 1];  // pre[a] = sum_{x=1..a} cost(x)
   pre[0] = 0;
@@ -333,7 +334,7 @@ inline uint64_t fd_best_window(uint32_t h, uint32_t n_r, int32_t* lo_out) {
   for (int32_t lo = 2 - (int32_t)h; lo <= 1; lo++) {
     int32_t hi = lo + (int32_t)h - 1;
     uint64_t c = pre[hi] + (lo < 0 ? pre[-lo] : 0);
-    c += (uint64_t)h * (h - 1) / 2 * 12 + (uint64_t)(n_r - (uint32_t)hi) * (h - 1) * 12;
+    c += (uint64_t)h * (h - 1) / 2 * 12 + (uint64_t)(n_r > (uint32_t)hi ? n_r - (uint32_t)hi : 0) * (h - 1) * 12;
     if (c < best) {
       best = c;
       *lo_out = lo;
@@ -343,8 +344,11 @@ inline uint64_t fd_best_window(uint32_t h, uint32_t n_r, int32_t* lo_out) {
   return best;
 }
 
-// ids must already be known to be a permutation of 1..n_r.  m_force != 0 fixes the number of parts.
-inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0) {
+// ids must already be known to be a permutation of 1..n_r.  m_force != 0 fixes the number of parts.  n_opt: the
+// number of ids the cost model assumes are evaluated in the group (0 = all n_r; t when the consistency shortcut of
+// share_fd.cu is expected to settle the ids beyond t) - it shapes the choice of m and of the seed window only.
+inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0, uint32_t n_opt = 0) {
+  if (n_opt == 0 || n_opt > n_r) n_opt = n_r;
   FdPlan p{};
   p.use = false;
   p.m = 1;
@@ -356,8 +360,8 @@ inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0) {
     uint32_t h = (t + m - 1) / m;
     if (h < 2 || n_r <= h || (m > 1 && (uint64_t)(m - 1) * h >= t)) continue;  // every part must hold a coefficient
     int32_t lo = 1;
-    uint64_t c = (uint64_t)m * fd_best_window(h, n_r, &lo);
-    if (m > 1) c += (uint64_t)n_r * fd_comb_cost(m);
+    uint64_t c = (uint64_t)m * fd_best_window(h, n_opt, &lo);
+    if (m > 1) c += (uint64_t)n_opt * fd_comb_cost(m);
     if (c < p.cost_fd) {
       p.cost_fd = c;
       p.m = m;

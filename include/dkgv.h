@@ -120,12 +120,13 @@ int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
 int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on);
 int dkgv_last_share_continued(const dkgv_ctx* ctx);
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
-/* the plan for ids 1..n_recipients (parts_force 0 = cheapest): parts, h = ceil(t / parts), Horner seed points
+/* the plan for ids 1..n_recipients (parts_force 0 = cheapest; n_opt = number of ids the cost model assumes are
+ * evaluated in the group, 0 = all, t when the consistency shortcut is on): parts, h = ceil(t / parts), Horner seed points
  * lo..hi (hi - lo + 1 == h), extension steps, field products per dealer by this plan and by per-share Horner
  * (evaluation only, G*s excluded).  Returns 1 when AUTO would take this plan, 0 when Horner per share is
  * cheaper, -1 when no plan exists for the shape.  Pure host function.                                */
-int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, uint32_t parts_force, uint32_t* parts, uint32_t* h, int32_t* lo,
-                       int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner);
+int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, uint32_t parts_force, uint32_t n_opt, uint32_t* parts, uint32_t* h,
+                       int32_t* lo, int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner);
 /* device times of the last finite-difference run: seed Horner, differences, extension, recombine + G*s compare;
  * with overlap on the first three run concurrently and only ms4[0] (their total) and ms4[3] are meaningful */
 int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4);
