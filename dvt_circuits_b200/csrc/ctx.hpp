@@ -43,7 +43,7 @@ struct dkgv_ctx {
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)
-  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom;
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef;
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
   bool fd_recorded = false;

@@ -303,7 +303,7 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
-                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols, &ctx->fd_sl, &ctx->fd_flags, &ctx->fd_binom, &ctx->bls_pk,
+                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols, &ctx->fd_sl, &ctx->fd_flags, &ctx->fd_binom, &ctx->fd_coef, &ctx->bls_pk,
                     &ctx->bls_sig, &ctx->bls_st})
     b->release();
   for (cudaEvent_t ev : ctx->ev_fd)

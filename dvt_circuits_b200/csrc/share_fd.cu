@@ -8,8 +8,8 @@
 //   k_fd_ext      steps + h - 2 wavefront ticks                (1 point addition per item)
 //   k_fd_digits   signed digits of the public recombination scalars x^(h i) mod r, one thread per id
 //   k_fd_combine  sum_i [y^i] f_i(x) by joint double-and-add, G * s, compare: one thread per share
-// plus the consistency shortcut (k_fd_binom / k_fd_share_limbs / k_fd_polycheck / k_fd_need / k_fd_fill_ok, see below):
-// only the ids 1..t go through the group arithmetic unless a dealer group fails the scalar-side conditions.
+// before them the consistency shortcut (k_fd_tables / k_fd_share_limbs / k_fd_polycheck / k_fd_interp / k_fd_coefcheck /
+// k_fd_need / k_fd_fill_ok, see below): a dealer group whose shares are provably all valid never enters the evaluation.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -25,8 +25,9 @@ constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_seed(VVView vv, const int32_t* __restrict__ seed_x, int32_t lo, uint32_t* __restrict__ evals, uint32_t n_d, uint32_t t,
-          uint32_t h, uint32_t part0, uint32_t n_padv, uint32_t d0, uint32_t n_cols) {
+          uint32_t h, uint32_t part0, uint32_t n_padv, uint32_t d0, uint32_t n_cols, const uint8_t* __restrict__ need_group) {
   extern __shared__ U4 opfile[];
+  if (need_group && !need_group[blockIdx.x]) return;  // only the dealer groups that need the evaluation
   uint32_t d = blockIdx.x * 32 + threadIdx.x;  // column of this dealer chunk; dealer d0 + d
   int32_t x = seed_x[blockIdx.y];              // most expensive points first
   uint32_t part = part0 + blockIdx.z;
@@ -38,8 +39,9 @@ k_fd_seed(VVView vv, const int32_t* __restrict__ seed_x, int32_t lo, uint32_t* _
 
 __global__ void __launch_bounds__(FD_NT)
 k_fd_init(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t* __restrict__ da, uint32_t* __restrict__ db,
-          uint32_t n_pad, uint32_t t, uint32_t r, uint32_t col0, uint32_t ipb) {
+          uint32_t n_pad, uint32_t t, uint32_t r, uint32_t col0, uint32_t ipb, const uint8_t* __restrict__ need_group, uint32_t groups) {
   extern __shared__ U4 opfile[];
+  if (need_group && !need_group[(col0 / 32 + blockIdx.x) % groups]) return;
   uint32_t d = col0 + blockIdx.x * 32 + threadIdx.x;
   OpFile f{opfile + threadIdx.x, FD_NT};
 #pragma unroll 1
@@ -92,19 +94,21 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 }
 
 // ---- consistency shortcut -------------------------------------------------------------------------------
-// All n shares of a dealer are valid  <=>  (1) every share is < r, (2) the shares s(1..n) lie on a polynomial of
-// degree <= t-1 over Fr, and (3) G*s(x) == f(x) at t distinct ids x.  (The commitments C_k = a_k G define
-// A(x) = sum a_k x^k of degree <= t-1 with f(x) = A(x) G; (3) makes A agree with the polynomial of (2) at t
-// points, hence everywhere.)  (2) is pure scalar arithmetic: the t-th forward differences of the share sequence,
-// sum_j (-1)^j C(t,j) s(x+j), must vanish for x = 1..n-t.  So only the ids 1..t go through the group arithmetic;
-// a dealer (group of 32) that fails any of the three conditions continues with the full path, which yields the
-// exact per-share verdicts.  Exact, deterministic - no random linear combination.
+// All n shares of a dealer are valid  <=>  (1) every share is < r, (2) the shares s(1..n) lie on a polynomial p of
+// degree <= t-1 over Fr, and (3) G * p_k == C_k for every coefficient k.  (The commitments C_k = a_k G define
+// A(x) = sum a_k x^k with f(x) = A(x) G; (3) says A = p, so s(x) = p(x) = A(x) for every id; the converse is
+// trivial.)  (1) and (2) are scalar arithmetic - (2): the t-th forward differences sum_j (-1)^j C(t,j) s(x+j) vanish
+// for x = 1..n-t - p is the Newton interpolant of s(1..t) converted to monomial coefficients, and (3) costs t
+// fixed-base multiplications per dealer instead of n evaluations in the exponent.  A group of 32 dealers in which
+// some dealer fails a condition (or has an undecodable commitment) goes through the full evaluation, which yields
+// the exact per-share verdicts.  Exact and deterministic - no random linear combination.
+constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient
 
-// c[j] = (-1)^j C(t, j) mod r in Montgomery form, j = 0..t  (one thread per j: products + one inversion)
-__global__ void __launch_bounds__(128) k_fd_binom(uint32_t t, uint32_t* __restrict__ c) {
+// c[j] = (-1)^j C(t, j) mod r (j = 0..t) and inv[j] = 1/j mod r (j = 1..t), Montgomery form; one thread per j
+__global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j > t) return;
-  Fr num = one<FrParams>(), den = one<FrParams>();
+  Fr num = one<FrParams>(), den = one<FrParams>(), jm = zero<FrParams>();
   for (uint32_t i = 1; i <= j; i++) {
     Fr a = zero<FrParams>(), b = zero<FrParams>();
     a.l[0] = t - i + 1;
@@ -112,18 +116,26 @@ __global__ void __launch_bounds__(128) k_fd_binom(uint32_t t, uint32_t* __restri
     num = mul(num, to_mont(a));
     den = mul(den, to_mont(b));
   }
-  // den^(r-2)
-  Fr inv = one<FrParams>();
+  jm.l[0] = j ? j : 1;
+  jm = to_mont(jm);
+  Fr iden = one<FrParams>(), ij = one<FrParams>();  // den^(r-2), j^(r-2)
   for (int l = 7; l >= 0; l--) {
     uint32_t w = consts::R_MINUS_2(l);
     for (int b = 31; b >= 0; b--) {
-      inv = mul(inv, inv);
-      if ((w >> b) & 1) inv = mul(inv, den);
+      iden = mul(iden, iden);
+      ij = mul(ij, ij);
+      if ((w >> b) & 1) {
+        iden = mul(iden, den);
+        ij = mul(ij, jm);
+      }
     }
   }
-  Fr v = mul(num, inv);
+  Fr v = mul(num, iden);
   if (j & 1) v = neg(v);
-  for (int l = 0; l < 8; l++) c[(size_t)j * 8 + l] = v.l[l];
+  for (int l = 0; l < 8; l++) {
+    c[(size_t)j * 8 + l] = v.l[l];
+    inv[(size_t)j * 8 + l] = ij.l[l];
+  }
 }
 
 // shares of one dealer chunk as little-endian limbs in ascending-id order: sl[d - d0][x - 1][8]; poly_ok[d] = 0 when a share is >= r
@@ -165,45 +177,104 @@ k_fd_polycheck(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ c, 
   if (bad) poly_ok[d0 + dl] = 0;
 }
 
-// need_group[g] = 1 when some dealer of the 32-dealer group g (of this chunk) fails a condition: undecodable
-// commitment, (1)/(2) failed, or a verdict other than OK among the ids 1..t_lim
+// p = the polynomial of degree <= t-1 through (x, s(x)), x = 1..t, as canonical monomial coefficients coef[dl][k][8]:
+// forward differences D_j = Delta^j s(1), then Horner in the Newton basis, P <- P (x - j) / j + D_{j-1}, on coefficient
+// vectors: new_c[i] = c[i-1] / j - c[i].  One block per dealer, thread i owns coefficient i; 3 x t Fr values in shared memory.
+__global__ void __launch_bounds__(1024)
+k_fd_interp(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ inv, uint32_t* __restrict__ coef, uint32_t d0, uint32_t n_d, uint32_t n_r,
+            uint32_t t) {
+  extern __shared__ uint32_t fr_sm[];  // [3][t][8]
+  uint32_t dl = blockIdx.x, i = threadIdx.x;
+  if (d0 + dl >= n_d) return;  // whole block
+  Fr* A = (Fr*)fr_sm;
+  Fr* B = A + t;
+  Fr* D = B + t;
+  if (i < t) {
+    Fr v;
+#pragma unroll
+    for (int l = 0; l < 8; l++) v.l[l] = sl[((size_t)dl * n_r + i) * 8 + l];
+    A[i] = to_mont(v);
+  }
+  __syncthreads();
+  Fr* cur = A;
+  Fr* nxt = B;
+  for (uint32_t r = 1; r < t; r++) {
+    if (i < t) nxt[i] = i >= r ? sub(cur[i], cur[i - 1]) : cur[i];
+    __syncthreads();
+    Fr* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  if (i < t) D[i] = cur[i];
+  __syncthreads();
+  if (i < t) cur[i] = i == 0 ? D[t - 1] : zero<FrParams>();
+  __syncthreads();
+  for (uint32_t j = t - 1; j >= 1; j--) {
+    if (i < t) {
+      Fr ij;
+#pragma unroll
+      for (int l = 0; l < 8; l++) ij.l[l] = inv[(size_t)j * 8 + l];
+      Fr v = i >= 1 ? sub(mul(cur[i - 1], ij), cur[i]) : neg(cur[0]);
+      if (i == 0) v = add(v, D[j - 1]);
+      nxt[i] = v;
+    }
+    __syncthreads();
+    Fr* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  if (i < t) {
+    Fr v = from_mont(cur[i]);
+#pragma unroll
+    for (int l = 0; l < 8; l++) coef[((size_t)dl * t + i) * 8 + l] = v.l[l];
+  }
+}
+
+// condition (3): G * p_k against the decoded commitment C_k; warp = 32 dealers x one k (the layout of the seeds)
+__global__ void __launch_bounds__(FD_NT)
+k_fd_coefcheck(VVView vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ poly_ok, uint32_t d0,
+               uint32_t n_d, uint32_t t) {
+  extern __shared__ U4 opfile[];
+  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
+  bool active = d0 + dl < n_d;
+  uint32_t dc = active ? dl : n_d - 1 - d0;
+  OpFile f{opfile + threadIdx.x, FD_NT};
+  uint32_t sc[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) sc[l] = coef[((size_t)dc * t + k) * 8 + l];
+  vm_fixed_base_mul(f, gtab, sc);  // B = G * p_k
+  G1Aff c = vv_load(vv, k, d0 + dc);
+  bool same;
+  if (c.inf) {
+    same = is_zero(of_load(f, BZ));
+  } else {
+    of_store(f, T0, c.x);
+    of_store(f, T1, c.y);
+    vm_mul(f, T2, T0, BZ);
+    vm_mul(f, T3, T1, BZ);
+    same = !is_zero(of_load(f, BZ)) && vm_eq(f, T2, BX) && vm_eq(f, T3, BY);
+  }
+  if (active && !same) poly_ok[d0 + dl] = 0;
+}
+
+// need_group[g] = 1 when some dealer of the 32-dealer group g (of this chunk) fails a condition or has an undecodable commitment
 __global__ void __launch_bounds__(128)
-k_fd_need(const uint8_t* __restrict__ status, const uint32_t* __restrict__ cols, const uint8_t* __restrict__ poly_ok,
-          const uint8_t* __restrict__ dealer_bad, uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r, uint32_t t_lim,
+k_fd_need(const uint8_t* __restrict__ poly_ok, const uint8_t* __restrict__ dealer_bad, uint32_t d0, uint32_t n_cols, uint32_t n_d,
           uint8_t* __restrict__ need_group, uint32_t* __restrict__ any_need) {
   uint32_t dl = blockIdx.x * blockDim.x + threadIdx.x;
   if (dl >= n_cols || d0 + dl >= n_d) return;
-  uint32_t d = d0 + dl;
-  bool need = dealer_bad[d] != 0 || poly_ok[d] == 0;
-  for (uint32_t xi = 0; xi < t_lim && !need; xi++) need = status[(size_t)d * n_r + cols[xi]] != DKGV_OK;
-  if (need) {
+  if (dealer_bad[d0 + dl] != 0 || poly_ok[d0 + dl] == 0) {
     need_group[dl / 32] = 1;
     atomicOr(any_need, 1u);
   }
 }
 
-// verdict OK for the ids beyond t_lim of every dealer group that met the three conditions
+// verdict OK for every share of the dealer groups that met the three conditions
 __global__ void __launch_bounds__(128)
-k_fd_fill_ok(uint8_t* __restrict__ status, const uint32_t* __restrict__ cols, const uint8_t* __restrict__ need_group, uint32_t d0,
-             uint32_t n_cols, uint32_t n_d, uint32_t n_r, uint32_t t_lim) {
-  uint32_t xi = t_lim + blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
-  if (xi >= n_r || d0 + dl >= n_d || need_group[dl / 32]) return;
-  status[(size_t)(d0 + dl) * n_r + cols[xi]] = DKGV_OK;
-}
-
-// both copies of the extension state <- the latest value of every item after a phase of `cnt` steps
-// (item k finished at tick cnt + h-2-k, whose parity says which copy holds it)
-__global__ void __launch_bounds__(128)
-k_fd_sync_state(uint32_t* __restrict__ da, uint32_t* __restrict__ db, uint32_t n_padv, uint32_t h, uint32_t cnt) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t per = (size_t)36 * n_padv;
-  if (i >= per * (h - 1)) return;
-  uint32_t k = (uint32_t)(i / per);
-  bool in_b = ((cnt + h - 2 - k) & 1) != 0;  // tick tau writes copy tau & 1: 1 = db
-  if (in_b)
-    da[i] = db[i];
-  else
-    db[i] = da[i];
+k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
+  if (j >= n_r || d0 + dl >= n_d || need_group[dl / 32]) return;
+  status[(size_t)(d0 + dl) * n_r + j] = DKGV_OK;
 }
 
 // evaluate_polynomial output instead of the share comparison: out[dealer][column j] = compress(f_d(ids[j]))
@@ -233,11 +304,12 @@ k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, con
 
 int dkgv_fd_setup(dkgv_ctx* ctx) {
   for (const void* k : {(const void*)k_fd_seed, (const void*)k_fd_init, (const void*)k_fd_ext, (const void*)k_fd_combine,
-                        (const void*)k_fd_combine_out}) {
+                        (const void*)k_fd_combine_out, (const void*)k_fd_coefcheck}) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   if (const char* e = getenv("DKGV_FD_IPB")) g_fd_ipb_force = (uint32_t)atoi(e);
+  CK(cudaFuncSetAttribute(k_fd_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * FD_SHORTCUT_MAX_T * 32)));
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
@@ -271,13 +343,61 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
                   uint8_t* d_out48, cudaStream_t s) {
   const uint32_t m = plan.m, h = plan.h;
   const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
-  const uint32_t groups = n_pad / 32;
+  const uint32_t groups = n_pad / 32, n_here = std::min(n_pad, n_d - d0);
   const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
-  // the consistency shortcut: ids 1..t through the group arithmetic, the rest only for dealer groups that need it
-  const bool shortcut = ctx->fd_polycheck && d_shares && !d_out48 && n_r > t;
-  const uint32_t t_lim = shortcut ? t : n_r;
-  const uint32_t steps1 = t_lim > (uint32_t)plan.hi ? std::min(plan.steps, t_lim - (uint32_t)plan.hi) : 0;  // extension steps of the first phase
+  CK(ctx->fd_cols.reserve((size_t)n_r * 4));
+  const uint32_t* cols = (const uint32_t*)ctx->fd_cols.p;
+  ctx->fd_cols_host.resize(n_r);  // columns in ascending-id order
+  for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
+  CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(ctx->ev_fd[0], s));
+  CK(cudaEventRecord(ctx->ev_hot0, s));
+
+  // ---- consistency shortcut: settle whole dealer groups by scalar arithmetic + t fixed-base multiplications
+  const uint8_t* filter = nullptr;  // dealer groups that go through the evaluation (nullptr: all)
+  ctx->fd_last_need = true;
+  if (ctx->fd_polycheck && d_shares && !d_out48 && n_r > t && t <= FD_SHORTCUT_MAX_T) {
+    CK(ctx->fd_sl.reserve((size_t)n_pad * n_r * 32));
+    CK(ctx->fd_coef.reserve((size_t)n_pad * t * 32));
+    CK(ctx->fd_flags.reserve((size_t)n_d + groups + 16));
+    uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
+    uint8_t* need_group = poly_ok + n_d;
+    uint32_t* any_need = (uint32_t*)(((uintptr_t)(need_group + groups) + 7) & ~(uintptr_t)7);
+    if (ctx->fd_binom_t != t) {
+      CK(ctx->fd_binom.reserve((size_t)(t + 1) * 64));
+      k_fd_tables<<<(t + 128) / 128, 128, 0, s>>>(t, (uint32_t*)ctx->fd_binom.p, (uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 8);
+      ctx->fd_binom_t = t;
+      ctx->launches++;
+    }
+    const uint32_t* binom = (const uint32_t*)ctx->fd_binom.p;
+    const uint32_t* invtab = binom + (size_t)(t + 1) * 8;
+    CK(cudaMemsetAsync(poly_ok + d0, 1, n_here, s));
+    CK(cudaMemsetAsync(need_group, 0, groups + 16, s));
+    k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_pad, n_d, n_r);
+    k_fd_polycheck<<<n_here, 256, 0, s>>>((const uint32_t*)ctx->fd_sl.p, binom, poly_ok, d0, n_d, n_r, t);
+    k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, d0, n_d,
+                                                                       n_r, t);
+    k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
+    k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, need_group, any_need);
+    k_fd_fill_ok<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_status, need_group, d0, n_pad, n_d, n_r);
+    ctx->launches += 6;
+    uint32_t h_any = 0;
+    CK(cudaMemcpyAsync(&h_any, any_need, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (!h_any) {  // an honest chunk: every verdict is OK and already written
+      ctx->fd_last_need = false;
+      CK(cudaEventRecord(ctx->ev_hot1, s));
+      for (int i = 1; i <= 4; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));
+      ctx->hot_recorded = true;
+      ctx->fd_recorded = true;
+      return 0;
+    }
+    filter = need_group;
+  }
+
+  // ---- evaluation of f_d at every id (for the dealer groups of `filter`)
   CK(ctx->fd_evals.reserve(n_evals * ent_bytes));
   CK(ctx->fd_p0.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_p1.reserve((size_t)h * ent_bytes));
@@ -286,7 +406,6 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   CK(ctx->fd_seedx.reserve((size_t)h * 4));
   CK(ctx->fd_dig.reserve((size_t)n_r * fd_dig_bytes(m)));
   CK(ctx->fd_top.reserve((size_t)n_r * 4));
-  CK(ctx->fd_cols.reserve((size_t)n_r * 4));
   // per-share tables of the recombination: recipients are processed in chunks that fit the budget
   const size_t tab_per_recipient = (size_t)(m > 1 ? m - 1 : 0) * FD_TAB_SLOTS * 36 * n_pad * 4;
   const size_t tab_budget = (size_t)4 << 30;
@@ -297,136 +416,60 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   uint32_t* evals = (uint32_t*)ctx->fd_evals.p;
   uint32_t* pp[2] = {(uint32_t*)ctx->fd_p0.p, (uint32_t*)ctx->fd_p1.p};
   uint32_t* dd[2] = {(uint32_t*)ctx->fd_da.p, (uint32_t*)ctx->fd_db.p};
-  const uint32_t* cols = (const uint32_t*)ctx->fd_cols.p;
 
-  // seed points, most expensive first (blocks are dispatched in increasing blockIdx.y); columns in ascending-id order
+  // seed points, most expensive first (blocks are dispatched in increasing blockIdx.y)
   std::vector<int32_t> order(h);
   for (uint32_t i = 0; i < h; i++) order[i] = plan.lo + (int32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
     return fd_horner_cost(h, (uint32_t)(a < 0 ? -a : a)) > fd_horner_cost(h, (uint32_t)(b < 0 ? -b : b));
   });
-  ctx->fd_seed_host.assign(order.begin(), order.end());  // must outlive the async copies
-  ctx->fd_cols_host.resize(n_r);
-  for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
+  ctx->fd_seed_host.assign(order.begin(), order.end());  // must outlive the async copy
   CK(cudaMemcpyAsync(ctx->fd_seedx.p, ctx->fd_seed_host.data(), (size_t)h * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
 
   const unsigned gx = groups, gxv = n_padv / 32;
   const size_t e_hi = (size_t)(plan.hi - plan.lo);  // == h - 1
+  const uint32_t ticks = plan.steps + h - 2;
   const bool overlap = ctx->fd_overlap && m > 1;
-  CK(cudaEventRecord(ctx->ev_fd[0], s));
-  CK(cudaEventRecord(ctx->ev_hot0, s));
-  CK(cudaEventRecord(ctx->fd_fork, s));
-
-  // scalar side of the shortcut on its own stream, concurrent with the seeds
-  uint8_t* poly_ok = nullptr;
-  uint8_t* need_group = nullptr;
-  uint32_t* any_need = nullptr;
-  if (shortcut) {
-    CK(ctx->fd_sl.reserve((size_t)n_pad * n_r * 32));
-    CK(ctx->fd_flags.reserve((size_t)n_d + groups + 16));
-    if (ctx->fd_binom_t != t) {
-      CK(ctx->fd_binom.reserve((size_t)(t + 1) * 32));
-    }
-    poly_ok = (uint8_t*)ctx->fd_flags.p;
-    need_group = poly_ok + n_d;
-    any_need = (uint32_t*)(((uintptr_t)(need_group + groups) + 7) & ~(uintptr_t)7);
-    cudaStream_t cs = ctx->fd_comb_stream;
-    CK(cudaStreamWaitEvent(cs, ctx->fd_fork, 0));
-    if (ctx->fd_binom_t != t) {
-      k_fd_binom<<<(t + 128) / 128, 128, 0, cs>>>(t, (uint32_t*)ctx->fd_binom.p);
-      ctx->fd_binom_t = t;
-      ctx->launches++;
-    }
-    CK(cudaMemsetAsync(poly_ok + d0, 1, std::min(n_pad, n_d - d0), cs));
-    CK(cudaMemsetAsync(need_group, 0, groups + 16, cs));
-    k_fd_share_limbs<<<dim3((n_r + 127) / 128, std::min(n_pad, n_d - d0)), 128, 0, cs>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0,
-                                                                                       n_pad, n_d, n_r);
-    k_fd_polycheck<<<std::min(n_pad, n_d - d0), 256, 0, cs>>>((const uint32_t*)ctx->fd_sl.p, (const uint32_t*)ctx->fd_binom.p, poly_ok, d0, n_d,
-                                                             n_r, t);
-    ctx->launches += 2;
-    CK(cudaEventRecord(ctx->fd_comb_done, cs));
-  }
-
-  // one wavefront of `cnt` extension steps starting from the state in dd[] (both copies equal), ids hi+from+1 .. hi+from+cnt
-  auto run_extension = [&](uint32_t from, uint32_t cnt, const uint8_t* filter) -> int {
-    if (cnt == 0) return 0;
-    const uint32_t ticks = cnt + h - 2;
-    for (uint32_t tick = 1; tick <= ticks; tick++) {
-      int32_t k_lo, k_hi;
-      fd_ext_band(h, cnt, tick, &k_lo, &k_hi);
-      if (k_lo > k_hi) continue;
-      uint32_t n_items = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, n_items);
-      if (!overlap) {
-        k_fd_ext<<<dim3(gxv, (n_items + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
-                                                                            (uint32_t)k_lo, (uint32_t)k_hi, e_hi + from, 0, ipb, filter, groups);
-        ctx->launches++;
-      } else {
-        for (uint32_t p = 0; p < m; p++) {
-          k_fd_ext<<<dim3(gx, (n_items + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv,
-                                                                                              h, tick, (uint32_t)k_lo, (uint32_t)k_hi,
-                                                                                              e_hi + from, p * n_pad, ipb, filter, groups);
-          ctx->launches++;
-        }
-      }
-    }
-    return 0;
-  };
-  auto fork_parts = [&]() -> int {
-    CK(cudaEventRecord(ctx->fd_fork, s));
-    for (uint32_t p = 0; p < m; p++) CK(cudaStreamWaitEvent(ctx->fd_streams[p], ctx->fd_fork, 0));
-    return 0;
-  };
-  auto join_parts = [&]() -> int {
-    for (uint32_t p = 0; p < m; p++) {
-      CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
-      CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
-    }
-    return 0;
-  };
-  // recombination + comparison (or evaluation output) of the ids x0+1 .. x1 in ascending-id order
-  auto run_combine = [&](uint32_t x0, uint32_t x1, const uint8_t* filter) {
-    for (uint32_t r0 = x0; r0 < x1; r0 += chunk_r) {
-      uint32_t nj = std::min(chunk_r, x1 - r0);
-      if (d_out48)
-        k_fd_combine_out<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p,
-                                                             d_ids, d_out48, (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, cols, 0, d0);
-      else
-        k_fd_combine<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
-                                                         d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status,
-                                                         (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, cols, 0, d0, filter);
-      ctx->launches++;
-    }
-  };
-
-  // ---- seeds, differences, first extension phase
   if (!overlap) {
     // one stream, phase after phase over all parts at once (also the mode that yields per-phase times)
-    k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv, d0, n_pad);
+    k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv, d0, n_pad,
+                                                     filter);
     CK(cudaEventRecord(ctx->ev_hot1, s));
     CK(cudaEventRecord(ctx->ev_fd[1], s));
     ctx->launches++;
+    // backward differences of every part at hi
     CK(cudaMemcpyAsync(dd[0], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(dd[1], evals + e_hi * ent_words, ent_bytes, cudaMemcpyDeviceToDevice, s));
     const uint32_t* src = evals;
     for (uint32_t r = 1; r < h; r++) {
       uint32_t* dst = pp[r & 1];
       uint32_t ipb = items_per_block(gxv, h - r);
-      k_fd_init<<<dim3(gxv, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0, ipb);
+      k_fd_init<<<dim3(gxv, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0, ipb, filter, groups);
       ctx->launches++;
       src = dst;
     }
     CK(cudaEventRecord(ctx->ev_fd[2], s));
-    if (int rc = run_extension(0, steps1, nullptr)) return rc;
+    // wavefront extension hi+1 .. n_r
+    for (uint32_t tick = 1; tick <= ticks; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
+      if (k_lo > k_hi) continue;
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
+      k_fd_ext<<<dim3(gxv, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
+                                                                      (uint32_t)k_lo, (uint32_t)k_hi, e_hi, 0, ipb, filter, groups);
+      ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev_fd[3], s));
   } else {
     // The parts are independent until the recombination: each runs its seed -> differences -> extension
     // chain on its own stream, so the tail of one part's kernel is filled by blocks of the others
     // (no grid-wide barrier per round / tick; matters when a rank holds few dealers).
+    CK(cudaEventRecord(ctx->fd_fork, s));
     for (uint32_t p = 0; p < m; p++) {
       cudaStream_t sp = ctx->fd_streams[p];
       CK(cudaStreamWaitEvent(sp, ctx->fd_fork, 0));
       k_fd_seed<<<dim3(gx, h, 1), FD_NT, FD_SMEM, sp>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, p, n_padv, d0,
-                                                        n_pad);
+                                                        n_pad, filter);
       ctx->launches++;
       const size_t w = (size_t)n_pad * 4, pitch = (size_t)n_padv * 4;
       const uint32_t* col = evals + e_hi * ent_words + (size_t)p * n_pad;
@@ -437,50 +480,45 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       uint32_t ipb = items_per_block(gxv, h - r);
       for (uint32_t p = 0; p < m; p++) {
         k_fd_init<<<dim3(gx, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0],
-                                                                                            dd[1], n_padv, h, r, p * n_pad, ipb);
+                                                                                            dd[1], n_padv, h, r, p * n_pad, ipb, filter, groups);
         ctx->launches++;
       }
     }
-    if (int rc = run_extension(0, steps1, nullptr)) return rc;
-    if (int rc = join_parts()) return rc;
+    for (uint32_t tick = 1; tick <= ticks; tick++) {
+      int32_t k_lo, k_hi;
+      fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
+      if (k_lo > k_hi) continue;
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
+      for (uint32_t p = 0; p < m; p++) {
+        k_fd_ext<<<dim3(gx, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h,
+                                                                                         tick, (uint32_t)k_lo, (uint32_t)k_hi, e_hi,
+                                                                                         p * n_pad, ipb, filter, groups);
+        ctx->launches++;
+      }
+    }
+    for (uint32_t p = 0; p < m; p++) {
+      CK(cudaEventRecord(ctx->fd_join[p], ctx->fd_streams[p]));
+      CK(cudaStreamWaitEvent(s, ctx->fd_join[p], 0));
+    }
     CK(cudaEventRecord(ctx->ev_hot1, s));
-    for (int i = 1; i <= 2; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
+    for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));  // phases overlap: only their sum is defined
   }
   ctx->hot_recorded = true;
 
-  // ---- recombination of the ids of the first phase
-  CK(cudaEventRecord(ctx->ev_fd[3], s));
+  // ---- recombination + comparison (or evaluation output), ids in ascending order, in chunks that fit the table budget
   if (m > 1) {
     k_fd_digits<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, h, m, (int8_t*)ctx->fd_dig.p, (int32_t*)ctx->fd_top.p);
     ctx->launches++;
   }
-  run_combine(0, t_lim, nullptr);
-
-  // ---- ids beyond t: only where the three conditions do not hold
-  if (shortcut) {
-    CK(cudaStreamWaitEvent(s, ctx->fd_comb_done, 0));
-    k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(d_status, cols, poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, n_r, t_lim,
-                                                  need_group, any_need);
-    ctx->launches++;
-    uint32_t h_any = 0;
-    CK(cudaMemcpyAsync(&h_any, any_need, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->fd_last_need = h_any != 0;
-    if (h_any) {
-      const uint32_t rest = plan.steps - steps1;
-      if (steps1 > 0 && rest > 0) {
-        size_t total = (size_t)36 * n_padv * (h - 1);
-        k_fd_sync_state<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(dd[0], dd[1], n_padv, h, steps1);
-        ctx->launches++;
-      }
-      if (overlap)
-        if (int rc = fork_parts()) return rc;
-      if (int rc = run_extension(steps1, rest, need_group)) return rc;
-      if (overlap)
-        if (int rc = join_parts()) return rc;
-      run_combine(t_lim, n_r, need_group);
-    }
-    k_fd_fill_ok<<<dim3((n_r - t_lim + 127) / 128, std::min(n_pad, n_d - d0)), 128, 0, s>>>(d_status, cols, need_group, d0, n_pad, n_d, n_r, t_lim);
+  for (uint32_t r0 = 0; r0 < n_r; r0 += chunk_r) {
+    uint32_t nj = std::min(chunk_r, n_r - r0);
+    if (d_out48)
+      k_fd_combine_out<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
+                                                           d_out48, (uint32_t*)ctx->fd_tab.p, n_pad, n_d, n_r, r0, cols, 0, d0);
+    else
+      k_fd_combine<<<dim3(gx, nj), FD_NT, FD_SMEM, s>>>(evals, plan.lo, m, (const int8_t*)ctx->fd_dig.p, (const int32_t*)ctx->fd_top.p, d_ids,
+                                                       d_shares, ctx->gtab, (const uint8_t*)ctx->dealer_bad.p, d_status, (uint32_t*)ctx->fd_tab.p,
+                                                       n_pad, n_d, n_r, r0, cols, 0, d0, filter);
     ctx->launches++;
   }
   CK(cudaEventRecord(ctx->ev_fd[4], s));
