@@ -40,6 +40,9 @@ struct dkgv_ctx {
   dkgv_host::DevBuf scratch_a, scratch_b, scratch_c;   // intermediates of the aggregation / pairing paths
   dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
+  bool vv_checked = true;            // the session's commitments were decoded with subgroup checks
+  const uint8_t* vv_src = nullptr;   // device pointer / shape of the session last decoded (for the lazy re-decode)
+  uint32_t vv_n_d = 0, vv_t = 0;
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)

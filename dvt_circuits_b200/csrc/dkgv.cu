@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab)
 //   (the reference panics on `.expect("Invalid pubkey")`, verification.rs:132-137).
 __global__ void __launch_bounds__(128)
 k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
-                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status) {
+                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status, bool check_subgroup) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= (size_t)n_pad * t) return;
   uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
@@ -51,7 +51,7 @@ k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32
   a.y = zero<FpParams>();
   a.inf = 1;
   if (d < n_d) {
-    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, true);
+    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, check_subgroup);
     if (st != G1_DEC_OK) dealer_bad[d] = 1;
     if (point_status) point_status[(size_t)d * t + k] = (uint8_t)st;
   }
@@ -341,8 +341,10 @@ extern "C" int dkgv_sync(dkgv_ctx* ctx) {
 }
 
 // decode vv into the ctx session buffers (asynchronous on s)
+// check_subgroup = false: flags, x < p and the curve equation only - for the consistency shortcut, where a commitment that
+// equals G * p_k is in the subgroup by construction; dkgv_session_redecode_checked redoes it in full before any evaluation
 static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, uint8_t* d_point_status, cudaStream_t s,
-                          VVView* view, uint32_t* n_pad_out, bool layout30 = false) {
+                          VVView* view, uint32_t* n_pad_out, bool layout30 = false, bool check_subgroup = true) {
   uint32_t n_pad = (n_d + 31) & ~31u;
   uint32_t tt = t ? t : 1;
   CK(ctx->vv_limbs.reserve((size_t)tt * (layout30 ? 26 : 24) * n_pad * 4));
@@ -357,15 +359,27 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
     else
       k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
                                                                     (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
-                                                                    d_point_status);
+                                                                    d_point_status, check_subgroup);
     ctx->launches++;
     CK(cudaGetLastError());
   }
+  ctx->vv_checked = check_subgroup;
+  ctx->vv_src = d_vv;
+  ctx->vv_n_d = n_d;
+  ctx->vv_t = t;
   view->limbs = (const uint32_t*)ctx->vv_limbs.p;
   view->inf = (const uint8_t*)ctx->vv_inf.p;
   view->n_pad = n_pad;
   *n_pad_out = n_pad;
   return 0;
+}
+
+// share_fd.cu calls this before the evaluation when the session was decoded without subgroup checks
+int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s) {
+  if (ctx->vv_checked) return 0;
+  VVView view;
+  uint32_t n_pad;
+  return session_decode(ctx, ctx->vv_n_d, ctx->vv_t, ctx->vv_src, nullptr, s, &view, &n_pad, false, true);
 }
 
 extern "C" int dkgv_set_share_path(dkgv_ctx* ctx, int mode) {
@@ -445,7 +459,9 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
       use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
     }
   }
-  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false);
+  // with the consistency shortcut ahead, the subgroup checks (2/3 of the decode) wait until a dealer group needs the evaluation
+  bool lazy_subgroup = use_fd && ctx->fd_polycheck && n_r > t && t <= 1024;
+  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false, !lazy_subgroup);
   if (rc) return rc;
   if (use_fd) {
     ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;

@@ -19,6 +19,8 @@
 
 using namespace dkgv;
 
+int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
+
 static uint32_t g_fd_ipb_force = 0;  // items per block of the difference / extension launches, DKGV_FD_IPB (experiments)
 constexpr int FD_NT = 32;  // one warp per block: 32 consecutive dealers, one entry (cf. SVM_NT in dkgv.cu)
 constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
@@ -102,7 +104,7 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // fixed-base multiplications per dealer instead of n evaluations in the exponent.  A group of 32 dealers in which
 // some dealer fails a condition (or has an undecodable commitment) goes through the full evaluation, which yields
 // the exact per-share verdicts.  Exact and deterministic - no random linear combination.
-constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient
+constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient (dkgv.cu's lazy_subgroup uses the same bound)
 
 // c[j] = (-1)^j C(t, j) mod r (j = 0..t) and inv[j] = 1/j mod r (j = 1..t), Montgomery form; one thread per j
 __global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv) {
@@ -396,6 +398,10 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     }
     filter = need_group;
   }
+  // the evaluation (and its PANIC_BAD_G1 verdicts) needs subgroup-checked commitments; only the share-matrix entry decodes
+  // lazily (the evaluation-output callers bring their own fully decoded view)
+  if (d_shares && !d_out48)
+    if (int rc = dkgv_session_redecode_checked(ctx, s)) return rc;
 
   // ---- evaluation of f_d at every id (for the dealer groups of `filter`)
   CK(ctx->fd_evals.reserve(n_evals * ent_bytes));
