@@ -305,7 +305,7 @@ def run_b200(args):
         if rank == 0:
             sampler.start()
         launches0 = v.launch_count
-        step_ms, hot_ms, phase_ms = [], [], []
+        step_ms, hot_ms, phase_ms, dec_ms = [], [], [], []
         barrier()
         wall0 = time.perf_counter()
         for _ in range(args.steps):
@@ -317,27 +317,37 @@ def run_b200(args):
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
             hot_ms.append(v.last_hot_kernel_ms())
+            dec_ms.append(v.last_decode_ms())
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
         clocks = sampler.stop() if rank == 0 else None
         continued = bool(v.last_share_continued) if v.last_share_path == v.PATH_FDIFF else False
+        full_ms, serial_ms = [], []
         if v.last_share_path == v.PATH_FDIFF:
-            # per-kernel times: the timed steps above run the parts on concurrent streams, where single
-            # phases have no duration of their own; repeat the same steps phase after phase on one stream
-            v.set_share_overlap(False)
-            serial_ms = []
-            for _ in range(args.steps):
-                flush.fill_(1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(ts)
-                step_device()
-                e1.record(ts)
-                e1.synchronize()
-                serial_ms.append(e0.elapsed_time(e1))
-                phase_ms.append(v.last_share_phases_ms())
+            # The evaluation kernels: the same steps with the consistency shortcut off (every share through the group
+            # arithmetic) - first as in production (parts on concurrent streams), then phase after phase on one stream,
+            # where single kernels have a duration of their own (roofline.kernels)
+            v.set_share_shortcut(False)
+            for mode, acc in ((args.overlap, full_ms), (0, serial_ms)):
+                v.set_share_overlap(mode)
+                for _ in range(args.steps):
+                    flush.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(ts)
+                    step_device()
+                    e1.record(ts)
+                    e1.synchronize()
+                    acc.append(e0.elapsed_time(e1))
+                    if mode == 0:
+                        phase_ms.append(v.last_share_phases_ms())
             v.set_share_overlap(args.overlap)
+            v.set_share_shortcut(args.shortcut)
             barrier()
+            full_total = torch.tensor([sum(full_ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(full_total, op=dist.ReduceOp.MAX)
+            full_ms_step = float(full_total.item()) / args.steps
 
         total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -450,7 +460,7 @@ def run_b200(args):
         fdiff = v.last_share_path == v.PATH_FDIFF
         step_mean = statistics.mean(step_ms)
         # whole path: canonical per-share work (84 314 modmul) of every verified share per second of step time
-        path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / (step_mean * 1e-3)
+        path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / ((statistics.mean(full_ms) if full_ms else step_mean) * 1e-3)
 
         def kernel_entry(name, units, unit_is, canon_unit, exec_unit, ms, ref_ms):
             a, e = units * canon_unit * MAC_PER_MODMUL / (ms * 1e-3), units * exec_unit * MAC_PER_MODMUL / (ms * 1e-3)
@@ -471,10 +481,8 @@ def run_b200(args):
             comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
             comb_exec = ((128 * EXEC_DBL + (m_parts - 1) * (EXEC_DBL + 3 * EXEC_ADD + 52 * EXEC_ADD + 26) + EXEC_ADD if m_parts > 1 else 0)
                          + 33 * EXEC_MADD + 4)
-            # consistency shortcut (honest ceremony): only the ids 1..t are evaluated in the group
-            short = args.shortcut and n > t and not continued
-            ids_eval = t if short else n
-            ext_steps = max(0, ids_eval - plan["hi"]) if short else plan["steps"]
+            short = bool(args.shortcut and n > t and not continued)  # the timed steps were settled by the consistency shortcut
+            ids_eval, ext_steps = n, plan["steps"]  # the kernel entries below come from the full-evaluation steps
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
@@ -486,11 +494,22 @@ def run_b200(args):
             ]
             top = max(kernels, key=lambda k_: k_["kernel_ms"])
             algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144
+            if short:
+                # dominant kernel of the shortcut path: the (lazy) decode of the commitments - flags, x < p, square root, curve equation
+                dms = statistics.mean(d_[0] for d_ in dec_ms)
+                dec_canon = 379 + 228 + 4  # a^((p+1)/4) by square-and-multiply + x^3 + 4, y^2 check
+                dec = kernel_entry("k_decompress_vv (no subgroup test)", rows * t, "one commitment: decompression without the subgroup test",
+                                   dec_canon, dec_canon, dms, step_mean)
+                dec["subgroup_checked"] = bool(dec_ms[-1][1])
         else:
             plan = None
             kernels = [kernel_entry("k_share_verify", rows * n, "one share", MODMUL_PER_SHARE, executed_modmul_per_share(n, t), hot, step_mean)]
             top = kernels[0]
             algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        if fdiff and short:
+            top_default = dec
+        else:
+            top_default = top
         roof = {"bound": "int_pipe", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak["imad_wide"] / 1e9,
                 "unit": "G wide-MAC/s (32x32->64)", "frac": top["frac"], "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
@@ -504,18 +523,24 @@ def run_b200(args):
                 "kernels": kernels,
                 "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
                                "modmul_per_share_canonical": MODMUL_PER_SHARE,
-                               "note": "canonical per-share Horner work of all verified shares / step time; finite differences "
-                                       "execute fewer products than that, so this exceeds the kernels' own utilisation"},
+                               "note": "canonical per-share Horner work of all verified shares / full-evaluation step time; finite "
+                                       "differences execute fewer products than that, so this exceeds the kernels' own utilisation"},
                 "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
         if fdiff:
-            roof["fdiff"] = {"consistency_shortcut": bool(short), "ids_evaluated_in_the_group": ids_eval, "extension_steps_run": ext_steps,
+            roof["note"] = ("`kernel`, `achieved`, `frac`, `kernels` describe the evaluation kernels (every share through the group arithmetic: "
+                            "the steps behind `full_evaluation`); the timed steps behind `value` were "
+                            + ("settled by the consistency shortcut, whose dominant kernel is `shortcut_path_top_kernel`" if short
+                               else "full evaluations as well"))
+            if short:
+                roof["shortcut_path_top_kernel"] = top_default
+            roof["fdiff"] = {"consistency_shortcut_settled_the_timed_steps": bool(short),
                              "parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
                              "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
                              "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "recombine_gs_compare": ph[3]},
-                             "serial_step_ms": ref, "overlapped_step_ms": step_mean,
-                             "note": "phase times from extra steps run phase-after-phase on one stream; the timed steps behind `value` "
-                                     "run the parts on concurrent streams",
+                             "serial_step_ms": ref, "overlapped_step_ms": full_ms_step,
+                             "note": "full evaluation (shortcut off): phase times from steps run phase-after-phase on one stream; "
+                                     "`overlapped_step_ms` with the parts on concurrent streams",
                              "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -523,8 +548,10 @@ def run_b200(args):
             "dtype": "u32 limbs (381-bit Montgomery Fp, 255-bit Fr)", "data": "synthetic",
             "config": {"workload": f"synthetic DKG n={n}, t={t}: full {n}x{n} share-matrix verification, dealer row blocks over {world} GPU(s)",
                        "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
-                       "share_path": (f"finite differences: {plan['parts']} parts x {plan['h']} coefficients per dealer, "
-                                      f"{plan['h']} Horner seeds per part, differences, recombination") if fdiff else "Horner per share",
+                       "share_path": (("consistency shortcut (range, t-th differences of the shares, G*p_k == C_k per coefficient) settled every dealer; "
+                                       if (fdiff and short) else "") +
+                                      (f"evaluation by finite differences: {plan['parts']} parts x {plan['h']} coefficients per dealer, "
+                                       f"{plan['h']} Horner seeds per part, differences, recombination") if fdiff else "Horner per share"),
                        "parallelism": f"row-block x{world}, NCCL all-gather of the verdict bitmask ({n * n // 8} B)" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",
@@ -535,6 +562,8 @@ def run_b200(args):
             "pairing": {"metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
                         "checks_per_step": m_total, "ms_per_step": pair_ms_step, "bad_verdicts": pair_bad,
                         "note": "e(pk,H(m)) == e(G1,sig) as 2 Miller loops + 1 final exponentiation per check, incl. G1/G2 decoding with subgroup checks"},
+            "full_evaluation": ({"metric": "verified shares/sec, every share evaluated in the group (consistency shortcut off)",
+                                 "value": shares / (full_ms_step * 1e-3), "unit": "shares/s", "ms_per_step": full_ms_step} if fdiff else None),
             "mixed_items": {"metric": "verified shares/sec, 50 % of the shares corrupted (BASELINE config 5)", "value": shares / (mixed_ms_step * 1e-3),
                             "unit": "shares/s", "ms_per_step": mixed_ms_step, "verdicts_flag_exactly_the_corrupted_shares": mixed_ok,
                             "note": "every dealer group fails the consistency conditions and takes the full evaluation"},

@@ -57,6 +57,7 @@ DECLARED_SYMBOLS = {
     "dkgv_launch_count": (ctypes.c_uint64, [_vp]),
     "dkgv_sync": (ctypes.c_int, [_vp]),
     "dkgv_last_hot_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "dkgv_last_decode_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_share_items_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
@@ -164,6 +165,12 @@ class Verifier:
         ms = ctypes.c_float()
         self._ck(self._lib.dkgv_last_hot_kernel_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def last_decode_ms(self):
+        """(device ms of the last verification-vector decode, whether it included the subgroup checks)"""
+        ms, chk = ctypes.c_float(), ctypes.c_int()
+        self._ck(self._lib.dkgv_last_decode_ms(self._h, ctypes.byref(ms), ctypes.byref(chk)))
+        return float(ms.value), bool(chk.value)
 
     def sync(self):
         self._ck(self._lib.dkgv_sync(self._h))

@@ -43,6 +43,8 @@ struct dkgv_ctx {
   bool vv_checked = true;            // the session's commitments were decoded with subgroup checks
   const uint8_t* vv_src = nullptr;   // device pointer / shape of the session last decoded (for the lazy re-decode)
   uint32_t vv_n_d = 0, vv_t = 0;
+  cudaEvent_t ev_dec0 = nullptr, ev_dec1 = nullptr;  // bracket the last verification-vector decode of the share path
+  bool dec_recorded = false;
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)

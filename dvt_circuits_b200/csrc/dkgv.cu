@@ -58,6 +58,25 @@ k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32
   vv_store(limbs, inf, n_pad, k, d, a);
 }
 
+// The subgroup tests a lazy decode (check_subgroup = false) left out, on the already decoded planes: a point outside G1
+// becomes the identity and marks its dealer, exactly as the full decode does.
+__global__ void __launch_bounds__(128)
+k_subgroup_check_vv(uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs, uint8_t* __restrict__ inf,
+                    uint8_t* __restrict__ dealer_bad) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)n_pad * t) return;
+  uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
+  if (d >= n_d) return;
+  VVView v{limbs, inf, n_pad};
+  G1Aff a = vv_load(v, k, d);
+  if (a.inf || g1_in_subgroup(a)) return;
+  dealer_bad[d] = 1;
+  a.x = zero<FpParams>();
+  a.y = zero<FpParams>();
+  a.inf = 1;
+  vv_store(limbs, inf, n_pad, k, d, a);
+}
+
 // Same decode, written in the 13 x 30-bit layout of vm30.cuh for the hot kernel.
 __global__ void __launch_bounds__(128)
 k_decompress_vv30(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
@@ -270,7 +289,8 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  if ((e = cudaEventCreate(&ctx->ev_hot0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_hot1)) != cudaSuccess)
+  if ((e = cudaEventCreate(&ctx->ev_hot0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_hot1)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_dec0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_dec1)) != cudaSuccess)
     return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
   if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
@@ -319,6 +339,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
+  if (ctx->ev_dec0) cudaEventDestroy(ctx->ev_dec0);
+  if (ctx->ev_dec1) cudaEventDestroy(ctx->ev_dec1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -331,6 +353,15 @@ extern "C" int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventSynchronize(ctx->ev_hot1));
   CK(cudaEventElapsedTime(ms, ctx->ev_hot0, ctx->ev_hot1));
+  return 0;
+}
+extern "C" int dkgv_last_decode_ms(dkgv_ctx* ctx, float* ms, int* subgroup_checked) {
+  if (!ctx || !ms) return -1;
+  if (!ctx->dec_recorded) return fail(ctx, "no verification-vector decode launched yet");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_dec1));
+  CK(cudaEventElapsedTime(ms, ctx->ev_dec0, ctx->ev_dec1));
+  if (subgroup_checked) *subgroup_checked = ctx->vv_checked ? 1 : 0;
   return 0;
 }
 extern "C" int dkgv_sync(dkgv_ctx* ctx) {
@@ -353,6 +384,7 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
   CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
   if (t) {
     size_t total = (size_t)n_pad * t;
+    if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
     if (layout30)
       k_decompress_vv30<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
                                                                       (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
@@ -360,6 +392,8 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
       k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
                                                                     (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
                                                                     d_point_status, check_subgroup);
+    if (ctx->ev_dec1) CK(cudaEventRecord(ctx->ev_dec1, s));
+    ctx->dec_recorded = true;
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -377,9 +411,16 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
 // share_fd.cu calls this before the evaluation when the session was decoded without subgroup checks
 int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s) {
   if (ctx->vv_checked) return 0;
-  VVView view;
-  uint32_t n_pad;
-  return session_decode(ctx, ctx->vv_n_d, ctx->vv_t, ctx->vv_src, nullptr, s, &view, &n_pad, false, true);
+  uint32_t n_pad = (ctx->vv_n_d + 31) & ~31u;
+  size_t total = (size_t)n_pad * ctx->vv_t;
+  if (total) {
+    k_subgroup_check_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ctx->vv_n_d, ctx->vv_t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                       (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  ctx->vv_checked = true;
+  return 0;
 }
 
 extern "C" int dkgv_set_share_path(dkgv_ctx* ctx, int mode) {

@@ -183,11 +183,11 @@ k_fd_polycheck(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ c, 
 // forward differences D_j = Delta^j s(1), then Horner in the Newton basis, P <- P (x - j) / j + D_{j-1}, on coefficient
 // vectors: new_c[i] = c[i-1] / j - c[i].  One block per dealer, thread i owns coefficient i; 3 x t Fr values in shared memory.
 __global__ void __launch_bounds__(1024)
-k_fd_interp(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ inv, uint32_t* __restrict__ coef, uint32_t d0, uint32_t n_d, uint32_t n_r,
-            uint32_t t) {
+k_fd_interp(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ inv, uint32_t* __restrict__ coef, const uint8_t* __restrict__ poly_ok,
+            uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
   extern __shared__ uint32_t fr_sm[];  // [3][t][8]
   uint32_t dl = blockIdx.x, i = threadIdx.x;
-  if (d0 + dl >= n_d) return;  // whole block
+  if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a dealer that already failed (1) or (2) needs no interpolation
   Fr* A = (Fr*)fr_sm;
   Fr* B = A + t;
   Fr* D = B + t;
@@ -240,6 +240,9 @@ k_fd_coefcheck(VVView vv, const uint32_t* __restrict__ coef, const uint32_t* __r
   uint32_t dl = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
   bool active = d0 + dl < n_d;
   uint32_t dc = active ? dl : n_d - 1 - d0;
+#if defined(__CUDA_ARCH__)
+  if (__ballot_sync(0xffffffffu, active && poly_ok[d0 + dl]) == 0) return;  // nobody in this group can still pass
+#endif
   OpFile f{opfile + threadIdx.x, FD_NT};
   uint32_t sc[8];
 #pragma unroll
@@ -378,8 +381,8 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     CK(cudaMemsetAsync(need_group, 0, groups + 16, s));
     k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_pad, n_d, n_r);
     k_fd_polycheck<<<n_here, 256, 0, s>>>((const uint32_t*)ctx->fd_sl.p, binom, poly_ok, d0, n_d, n_r, t);
-    k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, d0, n_d,
-                                                                       n_r, t);
+    k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, poly_ok, d0,
+                                                                       n_d, n_r, t);
     k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
     k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, need_group, any_need);
     k_fd_fill_ok<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_status, need_group, d0, n_pad, n_d, n_r);

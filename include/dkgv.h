@@ -72,6 +72,9 @@ int dkgv_sync(dkgv_ctx* ctx);
 /* device time (CUDA events on the launching stream) of the most recent hot-kernel launch
  * (k_share_verify) issued through this ctx; blocks until that launch has finished */
 int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms);
+/* device time of the most recent verification-vector decode of the share path (k_decompress_vv) and whether it included the
+ * subgroup checks (0: the lazy decode in front of the consistency shortcut)                                          */
+int dkgv_last_decode_ms(dkgv_ctx* ctx, float* ms, int* subgroup_checked);
 
 /* ---- Feldman share verification (replaces the loop body of verify_seed_exchange_commitment,
  *      crates/dkg/src/verification.rs:129-146, for a whole (dealer x recipient) matrix) ------- */
