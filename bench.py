@@ -84,7 +84,7 @@ METRIC = "verified shares/sec (n=1024,t=683)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PART, help="participants (default: the BASELINE config)")
@@ -113,7 +113,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -329,9 +329,10 @@ def run_b200(args):
             # arithmetic) - first as in production (parts on concurrent streams), then phase after phase on one stream,
             # where single kernels have a duration of their own (roofline.kernels)
             v.set_share_shortcut(False)
+            aux_steps = min(args.steps, 3)  # the evaluation legs take ~0.7 s per step
             for mode, acc in ((args.overlap, full_ms), (0, serial_ms)):
                 v.set_share_overlap(mode)
-                for _ in range(args.steps):
+                for _ in range(aux_steps):
                     flush.fill_(1)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(ts)
@@ -347,7 +348,7 @@ def run_b200(args):
             full_total = torch.tensor([sum(full_ms)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(full_total, op=dist.ReduceOp.MAX)
-            full_ms_step = float(full_total.item()) / args.steps
+            full_ms_step = float(full_total.item()) / aux_steps
 
         total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -379,7 +380,7 @@ def run_b200(args):
         sh_bad[mask, 31] ^= 1
         d_sh_bad = torch.from_numpy(sh_bad).to(dev)
         mixed_ms = []
-        for i in range(1 + max(1, args.steps - 1)):
+        for i in range(1 + max(1, min(args.steps, 3) - 1)):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
