@@ -33,3 +33,41 @@ def test_plan_headline_shape_and_degenerate_shapes():
     assert not dk.share_fd_plan(0, 8)["exists"]
     one = dk.share_fd_plan(683, 1024, 1)          # unsplit: t seeds, the window is roughly symmetric around 0
     assert one["parts"] == 1 and one["h"] == 683 and one["lo"] < 0 < one["hi"]
+
+
+def test_consistency_shortcut_recurrences():
+    """The scalar side of the consistency shortcut (share_fd.cu: k_fd_tables, k_fd_polycheck, k_fd_interp), restated with Python
+    integers: (2) the t-th forward differences sum_j (-1)^j C(t,j) s(x+j) vanish for every window iff the shares lie on a
+    polynomial of degree < t; the Newton interpolant of s(1..t), converted by new_c[i] = c[i-1] / j - c[i] (+ D_{j-1} at i = 0),
+    gives back the monomial coefficients."""
+    import random
+    from math import comb
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    rnd = random.Random(17)
+    for t, n in [(2, 5), (3, 9), (7, 12), (20, 33)]:
+        a = [rnd.randrange(R) for _ in range(t)]
+        s = [sum(c * pow(x, k, R) for k, c in enumerate(a)) % R for x in range(1, n + 1)]
+        binom = [(-1) ** j * comb(t, j) % R for j in range(t + 1)]
+        windows = lambda seq: [sum(binom[j] * seq[w + j] for j in range(t + 1)) % R for w in range(n - t)]  # noqa: E731
+        assert not any(windows(s))
+        # a deviation c * prod_{i<=t}(x - i) keeps s(1..t) (and hence the interpolant) intact but is caught by the differences
+        dev = list(s)
+        for x in range(1, n + 1):
+            d = 5
+            for i in range(1, t + 1):
+                d = d * (x - i) % R
+            dev[x - 1] = (dev[x - 1] + d) % R
+        assert dev[:t] == s[:t] and any(windows(dev))
+        one = list(s)
+        one[n - 1] ^= 1
+        assert any(windows(one))
+        # Newton forward differences of s(1..t), then Horner in the Newton basis on coefficient vectors
+        cur = s[:t]
+        for r in range(1, t):
+            cur = [(cur[i] - cur[i - 1]) % R if i >= r else cur[i] for i in range(t)]
+        D = cur
+        c = [D[t - 1]] + [0] * (t - 1)
+        for j in range(t - 1, 0, -1):
+            inv_j = pow(j, -1, R)
+            c = [(((c[i - 1] if i else 0) * inv_j - c[i]) + (D[j - 1] if i == 0 else 0)) % R for i in range(t)]
+        assert c == a
