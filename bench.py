@@ -4,17 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path (decode + subgroup-check the verification vectors, Feldman
-evaluation in the exponent for every (dealer, recipient), G*s, compare) over the whole share matrix.
-With N ranks the ONE ceremony is sharded by dealer row blocks (strong scaling, as BASELINE.json names
-it); the only exchange is an NCCL all-gather of the per-share verdict bitmask, inside the timed region.
+One "step" = one pass of the hot path over the whole share matrix through `dkgv_share_matrix_verify[_dev]` (decode of the
+verification vectors, verdict for every (dealer, recipient) share).  With N ranks the ONE ceremony is sharded by dealer row
+blocks (strong scaling, as BASELINE.json names it); the only exchange is an NCCL all-gather of the per-share verdict bitmask,
+inside the timed region.
 
-`value`     device-timed, inputs resident in HBM, max over ranks.
-`e2e`       same metric through the reference-facing C ABI with HOST (pinned) buffers:
+`value`     device-timed, inputs resident in HBM, max over ranks, the library's DEFAULT path on the synthetic (honest) ceremony:
+            the consistency shortcut proves every dealer's shares valid by scalar arithmetic + t fixed-base
+            multiplications, exactly (no randomness), so no share is evaluated in the exponent.
+`full_evaluation`  the same steps with the shortcut off - every share through the group arithmetic (finite differences);
+`mixed_items`      the same matrix with half of the shares corrupted (BASELINE config 5): the shortcut fails for every dealer
+            and the evaluation produces the per-share verdicts, which must flag exactly the corrupted shares.
+`e2e`       `value`'s metric through the reference-facing C ABI with HOST (pinned) buffers:
             H2D of vv + shares + ids and D2H of the verdicts inside the timed region.
-`roofline`  integer-pipe roofline of the dominant kernel (k_share_verify): canonical 32x32->64
-            multiply-accumulates per second (84 314 modmul/share x 300 MAC) against
-            the IMAD.WIDE peak measured live by bench/imad_peak on the same GPU.
+`roofline`  integer-pipe roofline of the evaluation kernels (`roofline.kernels`, from the full-evaluation steps run phase after
+            phase): canonical 32x32->64 multiply-accumulates per second (84 314 modmul/share x 300 MAC)
+            against the IMAD.WIDE peak measured live by bench/imad_peak on the same GPU.  The top-level fields describe the
+            dominant kernel of the timed (default-path) steps: the decode of the commitments.
 `cpu_baseline` the CPU oracle in reference-faithful mode (per-op affine round trips, constant-time
             255-step scalar multiplication - the reference's operation sequence) on a bounded sample
             of the same matrix, all host cores.  A restatement, not the Rust binary (no cargo here).
@@ -509,10 +515,9 @@ def run_b200(args):
             kernels = [kernel_entry("k_share_verify", rows * n, "one share", MODMUL_PER_SHARE, executed_modmul_per_share(n, t), hot, step_mean)]
             top = kernels[0]
             algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
+        eval_top = top
         if fdiff and short:
-            top_default = dec
-        else:
-            top_default = top
+            top = dec  # dominant kernel of the timed (default-path) steps, timed live inside them
         roof = {"bound": "int_pipe", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak["imad_wide"] / 1e9,
                 "unit": "G wide-MAC/s (32x32->64)", "frac": top["frac"], "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
@@ -528,15 +533,14 @@ def run_b200(args):
                                "modmul_per_share_canonical": MODMUL_PER_SHARE,
                                "note": "canonical per-share Horner work of all verified shares / full-evaluation step time; finite "
                                        "differences execute fewer products than that, so this exceeds the kernels' own utilisation"},
-                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (top["kernel_ms"] * 1e-3) / 1e9,
+                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (eval_top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
         if fdiff:
-            roof["note"] = ("`kernel`, `achieved`, `frac`, `kernels` describe the evaluation kernels (every share through the group arithmetic: "
-                            "the steps behind `full_evaluation`); the timed steps behind `value` were "
-                            + ("settled by the consistency shortcut, whose dominant kernel is `shortcut_path_top_kernel`" if short
-                               else "full evaluations as well"))
-            if short:
-                roof["shortcut_path_top_kernel"] = top_default
+            roof["note"] = (("the timed steps behind `value` were settled by the consistency shortcut: `kernel` ... `modmul_per_unit` describe their "
+                             "dominant kernel, the decode of the commitments (timed live inside them); " if short else "")
+                            + "`kernels` / `evaluation_top_kernel` describe the evaluation kernels (every share through the group arithmetic: "
+                              "the steps behind `full_evaluation`, run phase after phase)")
+            roof["evaluation_top_kernel"] = eval_top
             roof["fdiff"] = {"consistency_shortcut_settled_the_timed_steps": bool(short),
                              "parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
                              "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
