@@ -101,7 +101,7 @@ def parse():
                     help="evaluate every id in the group even when the scalar-side consistency conditions hold (dkgv_set_share_shortcut 0)")
     ap.add_argument("--no-finalization", action="store_true", help="skip the config-4 finalization leg")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
-    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2], help="dkgv_set_share_overlap mode of the timed steps")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1], help="dkgv_set_share_overlap mode of the evaluation steps")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
     ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
                     help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")

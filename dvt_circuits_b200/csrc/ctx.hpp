@@ -58,8 +58,6 @@ struct dkgv_ctx {
   bool fd_last_need = false; // the last finite-difference run had to continue beyond t for some dealer group
   cudaStream_t fd_streams[16] = {};
   cudaEvent_t fd_fork = nullptr, fd_join[16] = {};
-  cudaStream_t fd_comb_stream = nullptr;  // scalar-side checks of the shortcut, concurrent with the seeds
-  cudaEvent_t fd_comb_done = nullptr;
   std::vector<uint32_t> fd_cols_host;
   int share_path = 0;       // DKGV_SHARE_PATH_* requested
   uint32_t share_parts = 0; // 0: planner's choice of parts per dealer; else forced

@@ -333,8 +333,6 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
-  if (ctx->fd_comb_stream) cudaStreamSynchronize(ctx->fd_comb_stream), cudaStreamDestroy(ctx->fd_comb_stream);
-  if (ctx->fd_comb_done) cudaEventDestroy(ctx->fd_comb_done);
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);

@@ -321,8 +321,6 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
     CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->fd_join[i], cudaEventDisableTiming));
   }
-  CK(cudaStreamCreateWithFlags(&ctx->fd_comb_stream, cudaStreamNonBlocking));  // scalar-side checks, concurrent with the seeds
-  CK(cudaEventCreateWithFlags(&ctx->fd_comb_done, cudaEventDisableTiming));
   return 0;
 }
 
