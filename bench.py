@@ -530,6 +530,7 @@ def run_b200(args):
                 "units_per_launch": top["units_per_launch_total"], "unit_is": top["unit_is"],
                 "modmul_per_unit": top["modmul_per_unit"], "mac_per_modmul": MAC_PER_MODMUL,
                 "traffic": None, "traffic_ref": "profiles/ (ncu --set full captures: DRAM bytes per launch are negligible on this integer-bound path)",
+                "algorithmic_bytes": None,
                 "kernels": kernels,
                 "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
                                "modmul_per_share_canonical": MODMUL_PER_SHARE,
@@ -537,6 +538,13 @@ def run_b200(args):
                                        "differences execute fewer products than that, so this exceeds the kernels' own utilisation"},
                 "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (eval_top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
+        if fdiff and short:
+            # ncu --set full of k_decompress_vv at 699 392 commitments (profiles/r1_default_path.md): dram read 34 069 760 B +
+            # write 21 060 352 B per launch; algorithmic 48 B in + 100 B planar out per commitment (the planes mostly stay in L2)
+            roof["traffic"] = int(round((34069760 + 21060352) / 699392 * rows * t))
+            roof["algorithmic_bytes"] = rows * t * 148
+            roof["traffic_ref"] = ("profiles/r1_default_path.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress_vv launch "
+                                   "(78.8 B per commitment, scaled to this launch's commitments)")
         if fdiff:
             roof["note"] = (("the timed steps behind `value` were settled by the consistency shortcut: `kernel` ... `modmul_per_unit` describe their "
                              "dominant kernel, the decode of the commitments (timed live inside them); " if short else "")
