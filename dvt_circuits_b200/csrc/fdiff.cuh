@@ -376,4 +376,66 @@ inline FdPlan fd_make_plan(uint32_t t, uint32_t n_r, uint32_t m_force = 0, uint3
   return p;
 }
 
+// ---- difference table of the consistency shortcut (share_fd.cu k_fd_difftab) ------------------------------------
+// All values are CANONICAL residues mod r (no Montgomery form): the table needs subtractions and products by the small
+// integers j < 2^10 only.
+//
+// prev - j * a mod r for canonical prev, a < r and j < 2^10: v = prev + j * (r - a) < 2^10 r < 2^265, quotient estimate
+// q = floor(floor(v / 2^234) * floor(2^286 / r) / 2^52) in {floor(v / r) - 1, floor(v / r)} (both floors lose < 2^-20),
+// v - q r < 2r by one chain against 2^256 - r, one conditional subtraction.
+DKGV_HD Fr fr_submul_small(const Fr& prev, const Fr& a, uint32_t j) {
+  constexpr uint32_t NEGR[8] = {0xffffffffu, 0x00000000u, 0x0001a401u, 0xac425bfdu, 0xf65e27fau, 0xccc627f7u, 0xd66282b7u, 0x8c1258acu};  // 2^256 - r
+  constexpr uint32_t M = 0x8d54253bu;  // floor(2^286 / r)
+  uint32_t na[8], v[8];
+  uint64_t c = 0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {  // na = r - a in [1, r]
+    uint64_t d = (uint64_t)FrParams::mod(l) - a.l[l] - c;
+    na[l] = (uint32_t)d;
+    c = (d >> 32) & 1;
+  }
+  c = 0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    c += (uint64_t)na[l] * j + prev.l[l];
+    v[l] = (uint32_t)c;
+    c >>= 32;
+  }
+  uint32_t top = ((uint32_t)c << 22) | (v[7] >> 10);  // floor(v / 2^234) < 2^31
+  uint32_t q = (uint32_t)(((uint64_t)top * M) >> 52);
+  Fr w;
+  c = 0;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    c += (uint64_t)NEGR[l] * q + v[l];
+    w.l[l] = (uint32_t)c;
+    c >>= 32;
+  }
+  cond_sub_mod<FrParams>(w.l, 0);
+  return w;
+}
+
+// One thread of the table owns the adjacent entries a = e[2i], b = e[2i+1]; per round it publishes b, waits for the block,
+// and reads its left neighbour's b.
+struct DtPair {
+  Fr a, b;
+};
+// phase 1, round r = 1..t: e[k] <- e[k] - e[k-1] for k >= r.  After t rounds e[k] = Delta^k s(1) for k < t and
+// Delta^t s(k - t + 1) for k >= t (zero for every such k <=> the n shares lie on a polynomial of degree < t).
+DKGV_HD bool dt1_active(uint32_t i, uint32_t r) { return 2 * i + 1 >= r; }
+DKGV_HD bool dt1_publishes(uint32_t i, uint32_t r) { return 2 * i + 2 >= r; }  // the right neighbour still updates its a
+DKGV_HD void dt1_step(DtPair& p, uint32_t i, uint32_t r, const Fr* pub) {
+  Fr nb = sub(p.b, p.a);
+  if (2 * i >= r) p.a = i ? sub(p.a, pub[i - 1]) : p.a;  // (i = 0: e[0] never changes; 2i >= r >= 1 excludes it anyway)
+  p.b = nb;  // dt1_active(i, r) holds
+}
+// phase 2, round j = t-1 .. 1 on the coefficient vector of P <- P (x - j) + E_{j-1} (E_k = Delta^k s(1) / k!, deg P = t-1-j
+// before the round): c[k] <- c[k-1] - j c[k], c[-1] := E_{j-1}.  Entries k > t - j are still zero.
+DKGV_HD bool dt2_active(uint32_t i, uint32_t j, uint32_t t) { return 2 * i <= t - j; }
+DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, const Fr* pub, const Fr* E) {
+  Fr nb = fr_submul_small(p.a, p.b, j);
+  p.a = fr_submul_small(i ? pub[i - 1] : E[j - 1], p.a, j);
+  p.b = nb;
+}
+
 }  // namespace dkgv

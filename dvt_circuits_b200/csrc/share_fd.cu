@@ -21,6 +21,7 @@ using namespace dkgv;
 
 int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
 
+static bool g_fd_difftab = true;      // fused difference table (k_fd_difftab); DKGV_FD_DIFFTAB=0: k_fd_polycheck + k_fd_interp (A/B tests)
 static uint32_t g_fd_ipb_force = 0;  // items per block of the difference / extension launches, DKGV_FD_IPB (experiments)
 constexpr int FD_NT = 32;  // one warp per block: 32 consecutive dealers, one entry (cf. SVM_NT in dkgv.cu)
 constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
@@ -106,8 +107,8 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // the exact per-share verdicts.  Exact and deterministic - no random linear combination.
 constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient (dkgv.cu's lazy_subgroup uses the same bound)
 
-// c[j] = (-1)^j C(t, j) mod r (j = 0..t) and inv[j] = 1/j mod r (j = 1..t), Montgomery form; one thread per j
-__global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv) {
+// c[j] = (-1)^j C(t, j) mod r (j = 0..t), inv[j] = 1/j mod r (j = 1..t) and ifact[j] = 1/j! mod r, Montgomery form; one thread per j
+__global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv, uint32_t* __restrict__ ifact) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j > t) return;
   Fr num = one<FrParams>(), den = one<FrParams>(), jm = zero<FrParams>();
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restr
   for (int l = 0; l < 8; l++) {
     c[(size_t)j * 8 + l] = v.l[l];
     inv[(size_t)j * 8 + l] = ij.l[l];
+    ifact[(size_t)j * 8 + l] = iden.l[l];  // 1/j!
   }
 }
 
@@ -232,6 +234,75 @@ k_fd_interp(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ inv, u
   }
 }
 
+// Conditions (2) and the interpolation in ONE difference table per dealer (replaces k_fd_polycheck + k_fd_interp for
+// n_r <= 2048), canonical residues, no products except by small integers (fdiff.cuh, "difference table"):
+//   phase 1  t rounds e[k] <- e[k] - e[k-1] (k >= r) over all n_r shares: e[k] = Delta^k s(1) for k < t, and the entries
+//            k >= t are the t-th differences Delta^t s(k-t+1) - all zero <=> condition (2);
+//   phase 2  E_k = e[k] / k!, then P <- P (x - j) + E_{j-1} for j = t-1 .. 1 on monomial coefficients: c[k] <- c[k-1] - j c[k].
+// One block per dealer, thread i owns entries 2i and 2i+1 in registers and publishes only e[2i+1] per round (double-buffered,
+// one barrier per round); entries that are already final (phase 1: k < r) or still zero (phase 2: k > t - j) are skipped, so
+// whole warps drop out.  Work per dealer: t n - t^2/2 subtractions + t^2/2 small products, against (n - t)(t + 1) + t^2/2 full
+// Montgomery products before.
+__global__ void __launch_bounds__(1024)
+k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact, uint32_t* __restrict__ coef, uint8_t* __restrict__ poly_ok,
+             uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
+  extern __shared__ uint32_t fr_sm[];  // pub[2][blockDim.x], E[t]
+  const uint32_t dl = blockIdx.x, i = threadIdx.x, nt = blockDim.x;
+  if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a share >= r already failed condition (1)
+  Fr* pub = (Fr*)fr_sm;
+  Fr* E = pub + 2 * (size_t)nt;
+  const uint32_t k0 = 2 * i, k1 = 2 * i + 1;
+  DtPair p;
+  p.a = zero<FrParams>();
+  p.b = zero<FrParams>();
+  const uint32_t* row = sl + (size_t)dl * n_r * 8;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    if (k0 < n_r) p.a.l[l] = row[(size_t)k0 * 8 + l];
+    if (k1 < n_r) p.b.l[l] = row[(size_t)k1 * 8 + l];
+  }
+#pragma unroll 1
+  for (uint32_t r = 1; r <= t; r++) {
+    Fr* pr = pub + (size_t)(r & 1) * nt;
+    if (dt1_publishes(i, r)) pr[i] = p.b;
+    __syncthreads();
+    if (dt1_active(i, r)) dt1_step(p, i, r, pr);
+  }
+  bool bad = (k0 >= t && k0 < n_r && !is_zero(p.a)) || (k1 >= t && k1 < n_r && !is_zero(p.b));
+  if (__syncthreads_or(bad)) {  // some t-th difference is not zero: the shares are not on a polynomial of degree < t
+    if (i == 0) poly_ok[d0 + dl] = 0;
+    return;
+  }
+  Fr f;
+  if (k0 < t) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) f.l[l] = ifact[(size_t)k0 * 8 + l];
+    E[k0] = mul(p.a, f);  // canonical x Montgomery = canonical
+  }
+  if (k1 < t) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) f.l[l] = ifact[(size_t)k1 * 8 + l];
+    E[k1] = mul(p.b, f);
+  }
+  __syncthreads();
+  p.a = i == 0 ? E[t - 1] : zero<FrParams>();
+  p.b = zero<FrParams>();
+#pragma unroll 1
+  for (uint32_t j = t - 1; j >= 1; j--) {
+    Fr* pr = pub + (size_t)(j & 1) * nt;
+    const bool act = dt2_active(i, j, t);
+    if (act) pr[i] = p.b;
+    __syncthreads();
+    if (act) dt2_step(p, i, j, pr, E);
+  }
+  uint32_t* o = coef + (size_t)dl * t * 8;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    if (k0 < t) o[(size_t)k0 * 8 + l] = p.a.l[l];
+    if (k1 < t) o[(size_t)k1 * 8 + l] = p.b.l[l];
+  }
+}
+
 // condition (3): G * p_k against the decoded commitment C_k; warp = 32 dealers x one k (the layout of the seeds)
 __global__ void __launch_bounds__(FD_NT)
 k_fd_coefcheck(VVView vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ poly_ok, uint32_t d0,
@@ -315,6 +386,10 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   }
   if (const char* e = getenv("DKGV_FD_IPB")) g_fd_ipb_force = (uint32_t)atoi(e);
   CK(cudaFuncSetAttribute(k_fd_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * FD_SHORTCUT_MAX_T * 32)));
+  CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 1024 + FD_SHORTCUT_MAX_T) * 32)));
+  CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const char* dt = getenv("DKGV_FD_DIFFTAB");
+  g_fd_difftab = !dt || atoi(dt) != 0;
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
@@ -368,8 +443,9 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     uint8_t* need_group = poly_ok + n_d;
     uint32_t* any_need = (uint32_t*)(((uintptr_t)(need_group + groups) + 7) & ~(uintptr_t)7);
     if (ctx->fd_binom_t != t) {
-      CK(ctx->fd_binom.reserve((size_t)(t + 1) * 64));
-      k_fd_tables<<<(t + 128) / 128, 128, 0, s>>>(t, (uint32_t*)ctx->fd_binom.p, (uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 8);
+      CK(ctx->fd_binom.reserve((size_t)(t + 1) * 96));
+      k_fd_tables<<<(t + 128) / 128, 128, 0, s>>>(t, (uint32_t*)ctx->fd_binom.p, (uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 8,
+                                                   (uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16);
       ctx->fd_binom_t = t;
       ctx->launches++;
     }
@@ -378,13 +454,20 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     CK(cudaMemsetAsync(poly_ok + d0, 1, n_here, s));
     CK(cudaMemsetAsync(need_group, 0, groups + 16, s));
     k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_pad, n_d, n_r);
-    k_fd_polycheck<<<n_here, 256, 0, s>>>((const uint32_t*)ctx->fd_sl.p, binom, poly_ok, d0, n_d, n_r, t);
-    k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, poly_ok, d0,
-                                                                       n_d, n_r, t);
+    const bool fused = g_fd_difftab && n_r <= 2048 && t >= 1;
+    if (fused) {
+      const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
+      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab + (size_t)(t + 1) * 8,
+                                                               (uint32_t*)ctx->fd_coef.p, poly_ok, d0, n_d, n_r, t);
+    } else {
+      k_fd_polycheck<<<n_here, 256, 0, s>>>((const uint32_t*)ctx->fd_sl.p, binom, poly_ok, d0, n_d, n_r, t);
+      k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, poly_ok,
+                                                                         d0, n_d, n_r, t);
+    }
     k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
     k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, need_group, any_need);
     k_fd_fill_ok<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_status, need_group, d0, n_pad, n_d, n_r);
-    ctx->launches += 6;
+    ctx->launches += fused ? 5 : 6;
     uint32_t h_any = 0;
     CK(cudaMemcpyAsync(&h_any, any_need, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

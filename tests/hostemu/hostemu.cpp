@@ -287,4 +287,75 @@ void he_sha256(const uint8_t* msg, size_t len, uint8_t* out32) {
   sha_update(&s, msg, len);
   sha_finish(&s, out32);
 }
+
+// prev - j * a mod r through fr_submul_small (canonical 32-byte big-endian in / out)
+static void be32_to_fr(Fr& f, const uint8_t* b) { fr_raw_from_be32(f.l, b); }
+static void fr_to_be32(uint8_t* out32, const Fr& r) {
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = out32 + 28 - 4 * i;
+    q[0] = r.l[i] >> 24; q[1] = r.l[i] >> 16; q[2] = r.l[i] >> 8; q[3] = r.l[i];
+  }
+}
+void he_fr_submul_small(const uint8_t* prev32, const uint8_t* a32, uint32_t j, uint8_t* out32) {
+  Fr p, a;
+  be32_to_fr(p, prev32);
+  be32_to_fr(a, a32);
+  fr_to_be32(out32, fr_submul_small(p, a, j));
+}
+
+// One block of k_fd_difftab (share_fd.cu) with its threads run in lockstep: per round every thread publishes, then (the
+// barrier) every thread steps - the same dt1_* / dt2_* per-thread routines, predicates and double buffer as the kernel.
+// shares: n_r canonical values s(1..n_r) [n_r][32]; ifact: 1/k! canonical [t][32] (the kernel's table holds them in
+// Montgomery form).  Returns 0 and coef [t][32] when every t-th difference vanishes, 1 otherwise.
+int he_difftab(const uint8_t* shares, uint32_t n_r, uint32_t t, const uint8_t* ifact, uint8_t* coef) {
+  const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
+  std::vector<DtPair> th(nt);
+  std::vector<Fr> pub(2 * (size_t)nt), E(t);
+  for (uint32_t i = 0; i < nt; i++) {
+    th[i].a = zero<FrParams>();
+    th[i].b = zero<FrParams>();
+    if (2 * i < n_r) be32_to_fr(th[i].a, shares + (size_t)(2 * i) * 32);
+    if (2 * i + 1 < n_r) be32_to_fr(th[i].b, shares + (size_t)(2 * i + 1) * 32);
+  }
+  for (uint32_t r = 1; r <= t; r++) {
+    Fr* pr = pub.data() + (size_t)(r & 1) * nt;
+    for (uint32_t i = 0; i < nt; i++)
+      if (dt1_publishes(i, r)) pr[i] = th[i].b;
+    for (uint32_t i = 0; i < nt; i++)
+      if (dt1_active(i, r)) dt1_step(th[i], i, r, pr);
+  }
+  bool bad = false;
+  for (uint32_t i = 0; i < nt; i++) {
+    uint32_t k0 = 2 * i, k1 = 2 * i + 1;
+    bad |= (k0 >= t && k0 < n_r && !is_zero(th[i].a)) || (k1 >= t && k1 < n_r && !is_zero(th[i].b));
+  }
+  if (bad) return 1;
+  for (uint32_t i = 0; i < nt; i++) {
+    Fr f;
+    if (2 * i < t) {
+      be32_to_fr(f, ifact + (size_t)(2 * i) * 32);
+      E[2 * i] = mul(th[i].a, to_mont(f));
+    }
+    if (2 * i + 1 < t) {
+      be32_to_fr(f, ifact + (size_t)(2 * i + 1) * 32);
+      E[2 * i + 1] = mul(th[i].b, to_mont(f));
+    }
+  }
+  for (uint32_t i = 0; i < nt; i++) {
+    th[i].a = i == 0 ? E[t - 1] : zero<FrParams>();
+    th[i].b = zero<FrParams>();
+  }
+  for (uint32_t j = t - 1; j >= 1; j--) {
+    Fr* pr = pub.data() + (size_t)(j & 1) * nt;
+    for (uint32_t i = 0; i < nt; i++)
+      if (dt2_active(i, j, t)) pr[i] = th[i].b;
+    for (uint32_t i = 0; i < nt; i++)
+      if (dt2_active(i, j, t)) dt2_step(th[i], i, j, pr, E.data());
+  }
+  for (uint32_t i = 0; i < nt; i++) {
+    if (2 * i < t) fr_to_be32(coef + (size_t)(2 * i) * 32, th[i].a);
+    if (2 * i + 1 < t) fr_to_be32(coef + (size_t)(2 * i + 1) * 32, th[i].b);
+  }
+  return 0;
+}
 }

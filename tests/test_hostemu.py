@@ -175,3 +175,60 @@ def test_recombination_digits(L):
     p = B.g1_mul(B.G1, 12345)
     q = B.g1_mul(p, Z2 % B.R)
     assert q[1] == (-p[1]) % B.P and pow(q[0] * pow(p[0], -1, B.P) % B.P, 3, B.P) == 1
+
+
+def test_difference_table_shortcut(L):
+    """k_fd_difftab (share_fd.cu), the fused conditions-(2)-and-interpolation kernel of the consistency shortcut, run thread by
+    thread on the host (tests/hostemu he_difftab: the kernel's own per-thread routines, predicates and double buffer):
+    fr_submul_small against Python integers on random and extreme operands; the table returns the dealer's monomial
+    coefficients for consistent shares and flags every kind of inconsistency the t-th differences catch."""
+    from math import factorial
+    R = B.R
+    rnd = random.Random(23)
+    o = buf(32)
+    edge = [0, 1, 2, R - 1, R - 2, R >> 1, (1 << 224) - 1, 1 << 224, (1 << 234) - 1, 1 << 234]
+    cases = [(p_, a_, j_) for p_ in edge for a_ in edge for j_ in (0, 1, 2, 511, 682, 1022, 1023)]
+    cases += [(rnd.randrange(R), rnd.randrange(R), rnd.randrange(1024)) for _ in range(3000)]
+    for p_, a_, j_ in cases:
+        L.he_fr_submul_small(p_.to_bytes(32, "big"), a_.to_bytes(32, "big"), j_, o)
+        assert int.from_bytes(o.raw, "big") == (p_ - j_ * a_) % R, (hex(p_), hex(a_), j_)
+
+    def run(s, t):
+        n = len(s)
+        ifact = b"".join(pow(factorial(k), -1, R).to_bytes(32, "big") for k in range(t))
+        coef = buf(32 * t)
+        rc = L.he_difftab(b"".join(x.to_bytes(32, "big") for x in s), n, t, ifact, coef)
+        return rc, [int.from_bytes(coef.raw[32 * k:32 * k + 32], "big") for k in range(t)]
+
+    def horner(a, x):
+        v = 0
+        for c in reversed(a):
+            v = (v * x + c) % R
+        return v
+
+    for t, n in [(1, 2), (1, 5), (2, 3), (2, 5), (3, 9), (7, 12), (8, 9), (20, 33), (33, 64), (43, 64), (64, 65), (97, 200), (130, 131),
+                 (683, 1024), (1024, 1025), (1023, 2048)]:
+        a = [rnd.randrange(R) for _ in range(t)]
+        if t > 2:
+            a[t - 1] = 0 if n % 2 else a[t - 1]  # a polynomial of lower degree is fine too
+        s = [horner(a, x) for x in range(1, n + 1)]
+        rc, c = run(s, t)
+        assert rc == 0 and c == a, (t, n)
+        # one flipped bit anywhere (inside or beyond the first t shares)
+        for pos in {0, t - 1, t, n - 1, rnd.randrange(n)}:
+            bad = list(s)
+            bad[pos] ^= 1 << rnd.randrange(250)
+            bad[pos] %= R
+            assert run(bad, t)[0] == 1, (t, n, pos)
+        # a deviation c * prod_{i<=t}(x - i): s(1..t) intact, caught by the differences beyond t
+        dev = list(s)
+        for x in range(1, n + 1):
+            d = 5
+            for i in range(1, t + 1):
+                d = d * (x - i) % R
+            dev[x - 1] = (dev[x - 1] + d) % R
+        assert dev[:t] == s[:t] and run(dev, t)[0] == 1
+        # consistent shares of a polynomial of degree exactly t (one too many)
+        a2 = a + [rnd.randrange(1, R)]
+        s2 = [horner(a2, x) for x in range(1, n + 1)]
+        assert run(s2, t)[0] == 1
