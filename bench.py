@@ -313,7 +313,7 @@ def run_b200(args):
         if rank == 0:
             sampler.start()
         launches0 = v.launch_count
-        step_ms, hot_ms, phase_ms, dec_ms = [], [], [], []
+        step_ms, hot_ms, phase_ms, dec_ms, short_ms, decoded_steps = [], [], [], [], [], 0
         barrier()
         wall0 = time.perf_counter()
         for _ in range(args.steps):
@@ -325,7 +325,16 @@ def run_b200(args):
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
             hot_ms.append(v.last_hot_kernel_ms())
-            dec_ms.append(v.last_decode_ms())
+            # the default path settles an honest ceremony against the COMPRESSED commitments: no decode inside such a step
+            step_decoded = bool(getattr(v, "last_share_decoded", 1))
+            decoded_steps += step_decoded
+            if step_decoded:
+                dec_ms.append(v.last_decode_ms())
+            if v.last_share_path == v.PATH_FDIFF:
+                try:  # shortcut-settled step: [share limbs + difference table, x halves of G*p_k == C_k, sign halves, flags]
+                    short_ms.append(v.last_share_phases_ms())
+                except Exception:  # noqa: BLE001  (timing detail only)
+                    pass
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
@@ -505,13 +514,32 @@ def run_b200(args):
             ]
             top = max(kernels, key=lambda k_: k_["kernel_ms"])
             algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144
-            if short:
-                # dominant kernel of the shortcut path: the (lazy) decode of the commitments - flags, x < p, square root, curve equation
+            short_kernels = []
+            if short and decoded_steps == args.steps and dec_ms:
+                # (DKGV_FD_BYTES=0) dominant kernel of the shortcut path: the lazy decode of the commitments - flags, x < p, square root, curve equation
                 dms = statistics.mean(d_[0] for d_ in dec_ms)
                 dec_canon = 379 + 228 + 4  # a^((p+1)/4) by square-and-multiply + x^3 + 4, y^2 check
                 dec = kernel_entry("k_decompress_vv (no subgroup test)", rows * t, "one commitment: decompression without the subgroup test",
                                    dec_canon, dec_canon, dms, step_mean)
                 dec["subgroup_checked"] = bool(dec_ms[-1][1])
+            elif short and len(short_ms) == args.steps:
+                # default: no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base
+                # multiplication (33 mixed additions) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with
+                # one inversion (p - 2: 380 squarings + 227 products) - per point 607 / 8 + 3 products of the simultaneous
+                # inversion + Y / Z + the canonical form for the sign
+                sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
+                pt_canon, pt_exec = 33 * 11 + 2, 33 * EXEC_MADD + 2
+                sg = 607 / 8 + 3 + 2
+                dec = kernel_entry("k_fd_coefpoint", rows * t, "one coefficient: G * p_k by the fixed-base table, x_C * Z == X against the "
+                                   "compressed commitment", pt_canon, pt_exec, sp[1], step_mean)
+                short_kernels = [dec,
+                                 kernel_entry("k_fd_coefsign", rows * t, "one coefficient: sign of Y / Z (simultaneous inversion over 8)", sg, sg,
+                                              sp[2], step_mean),
+                                 {"kernel": "k_fd_share_limbs + k_fd_difftab", "kernel_ms": sp[0], "kernel_share_of_step": sp[0] / step_mean,
+                                  "unit_is": "one dealer: t rounds of subtractions over the n shares + basis conversion by small integers (Fr, no wide products to speak of)"},
+                                 {"kernel": "k_fd_need + k_fd_fill_ok + flag read-back", "kernel_ms": sp[3], "kernel_share_of_step": sp[3] / step_mean}]
+            else:
+                short = False
         else:
             plan = None
             kernels = [kernel_entry("k_share_verify", rows * n, "one share", MODMUL_PER_SHARE, executed_modmul_per_share(n, t), hot, step_mean)]
@@ -538,7 +566,11 @@ def run_b200(args):
                                        "differences execute fewer products than that, so this exceeds the kernels' own utilisation"},
                 "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (eval_top["kernel_ms"] * 1e-3) / 1e9,
                         "note": "integer-bound path: HBM use is a rounding error"}}
-        if fdiff and short:
+        if fdiff and short and short_kernels:
+            roof["shortcut_kernels"] = short_kernels
+            roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
+            roof["traffic_ref"] = "no ncu --set full capture of k_fd_coefpoint yet (integer-bound: 176 B per 365 field products)"
+        elif fdiff and short:
             # ncu --set full of k_decompress_vv at 699 392 commitments (profiles/r1_default_path.md): dram read 34 069 760 B +
             # write 21 060 352 B per launch; algorithmic 48 B in + 100 B planar out per commitment (the planes mostly stay in L2)
             roof["traffic"] = int(round((34069760 + 21060352) / 699392 * rows * t))
@@ -547,7 +579,7 @@ def run_b200(args):
                                    "(78.8 B per commitment, scaled to this launch's commitments)")
         if fdiff:
             roof["note"] = (("the timed steps behind `value` were settled by the consistency shortcut: `kernel` ... `modmul_per_unit` describe their "
-                             "dominant kernel, the decode of the commitments (timed live inside them); " if short else "")
+                             "dominant kernel (timed live inside them; all of them under `shortcut_kernels`); " if short else "")
                             + "`kernels` / `evaluation_top_kernel` describe the evaluation kernels (every share through the group arithmetic: "
                               "the steps behind `full_evaluation`, run phase after phase)")
             roof["evaluation_top_kernel"] = eval_top

@@ -68,6 +68,7 @@ DECLARED_SYMBOLS = {
     "dkgv_set_share_overlap": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_set_share_shortcut": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_continued": (ctypes.c_int, [_vp]),
+    "dkgv_last_share_decoded": (ctypes.c_int, [_vp]),
     "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
                                           ctypes.POINTER(ctypes.c_uint64)]),
@@ -192,6 +193,11 @@ class Verifier:
     @property
     def last_share_continued(self):
         return int(self._lib.dkgv_last_share_continued(self._h))
+
+    @property
+    def last_share_decoded(self):
+        """1: the last share-matrix call decoded the commitments; 0: settled against their compressed encodings"""
+        return int(self._lib.dkgv_last_share_decoded(self._h))
 
     def set_share_parts(self, parts):
         """parts per dealer polynomial on the finite-difference path (0 = planner's choice)"""

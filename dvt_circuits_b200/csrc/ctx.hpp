@@ -40,7 +40,8 @@ struct dkgv_ctx {
   dkgv_host::DevBuf scratch_a, scratch_b, scratch_c;   // intermediates of the aggregation / pairing paths
   dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
-  bool vv_checked = true;            // the session's commitments were decoded with subgroup checks
+  bool vv_decoded = true;            // the session's commitments are decoded (false: deferred by the consistency shortcut)
+  bool vv_checked = true;            // ... with subgroup checks
   const uint8_t* vv_src = nullptr;   // device pointer / shape of the session last decoded (for the lazy re-decode)
   uint32_t vv_n_d = 0, vv_t = 0;
   cudaEvent_t ev_dec0 = nullptr, ev_dec1 = nullptr;  // bracket the last verification-vector decode of the share path
@@ -48,7 +49,7 @@ struct dkgv_ctx {
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)
-  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef;
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef, fd_yz;
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
   bool fd_recorded = false;

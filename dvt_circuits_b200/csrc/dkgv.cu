@@ -22,6 +22,7 @@ int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
                          const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
 int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
                          const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s);
+bool dkgv_fd_defers_decode();
 
 // ============================================================================ kernels
 // Offset fixed-base table of the generator (layout in feldman.cuh).
@@ -373,14 +374,14 @@ extern "C" int dkgv_sync(dkgv_ctx* ctx) {
 // check_subgroup = false: flags, x < p and the curve equation only - for the consistency shortcut, where a commitment that
 // equals G * p_k is in the subgroup by construction; dkgv_session_redecode_checked redoes it in full before any evaluation
 static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, uint8_t* d_point_status, cudaStream_t s,
-                          VVView* view, uint32_t* n_pad_out, bool layout30 = false, bool check_subgroup = true) {
+                          VVView* view, uint32_t* n_pad_out, bool layout30 = false, bool check_subgroup = true, bool defer = false) {
   uint32_t n_pad = (n_d + 31) & ~31u;
   uint32_t tt = t ? t : 1;
   CK(ctx->vv_limbs.reserve((size_t)tt * (layout30 ? 26 : 24) * n_pad * 4));
   CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
   CK(ctx->dealer_bad.reserve(n_pad));
   CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
-  if (t) {
+  if (t && !defer) {
     size_t total = (size_t)n_pad * t;
     if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
     if (layout30)
@@ -395,7 +396,8 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
     ctx->launches++;
     CK(cudaGetLastError());
   }
-  ctx->vv_checked = check_subgroup;
+  ctx->vv_decoded = !defer;
+  ctx->vv_checked = check_subgroup && !defer;
   ctx->vv_src = d_vv;
   ctx->vv_n_d = n_d;
   ctx->vv_t = t;
@@ -411,12 +413,21 @@ int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s) {
   if (ctx->vv_checked) return 0;
   uint32_t n_pad = (ctx->vv_n_d + 31) & ~31u;
   size_t total = (size_t)n_pad * ctx->vv_t;
-  if (total) {
+  if (total && !ctx->vv_decoded) {  // deferred by the shortcut: the full decode, subgroup tests included
+    if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
+    k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ctx->vv_src, ctx->vv_n_d, ctx->vv_t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                  (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p, nullptr, true);
+    if (ctx->ev_dec1) CK(cudaEventRecord(ctx->ev_dec1, s));
+    ctx->dec_recorded = true;
+    ctx->launches++;
+    CK(cudaGetLastError());
+  } else if (total) {
     k_subgroup_check_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ctx->vv_n_d, ctx->vv_t, n_pad, (uint32_t*)ctx->vv_limbs.p,
                                                                        (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
     ctx->launches++;
     CK(cudaGetLastError());
   }
+  ctx->vv_decoded = true;
   ctx->vv_checked = true;
   return 0;
 }
@@ -443,6 +454,7 @@ extern "C" int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on) {
   ctx->fd_polycheck = on != 0;
   return 0;
 }
+extern "C" int dkgv_last_share_decoded(const dkgv_ctx* ctx) { return ctx ? (ctx->vv_decoded ? 1 : 0) : -1; }
 extern "C" int dkgv_last_share_continued(const dkgv_ctx* ctx) { return ctx ? (ctx->fd_last_need ? 1 : 0) : -1;
 }
 extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force, uint32_t n_opt, uint32_t* parts, uint32_t* h, int32_t* lo,
@@ -500,7 +512,8 @@ static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint
   }
   // with the consistency shortcut ahead, the subgroup checks (2/3 of the decode) wait until a dealer group needs the evaluation
   bool lazy_subgroup = use_fd && ctx->fd_polycheck && n_r > t && t <= 1024;
-  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false, !lazy_subgroup);
+  // ... and with condition (3) checked against the compressed commitments the whole decode waits (share_fd.cu k_fd_coefpoint)
+  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false, !lazy_subgroup, lazy_subgroup && dkgv_fd_defers_decode());
   if (rc) return rc;
   if (use_fd) {
     ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;

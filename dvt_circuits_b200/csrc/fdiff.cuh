@@ -438,4 +438,68 @@ DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, const Fr* pub, const Fr
   p.b = nb;
 }
 
+// ---- condition (3) against the COMPRESSED commitment (share_fd.cu k_fd_coefpoint / k_fd_coefsign) -----------------
+// compress(G * p_k) == C_k without decompressing C_k (no square root): the encoding of a non-identity point is its canonical
+// x plus the sign of y, so the bytes agree iff the flags are well-formed, x_C < p, x_C * Z == X and lex_largest(Y / Z) equals
+// the sign flag.  An encoding that is not a point of the subgroup can never equal the encoding of G * p_k, so an agreeing
+// commitment needs no curve or subgroup test either.  The x half runs right after the fixed-base multiplication (projectively);
+// the sign half needs 1/Z and is batched over FD_SIGN_K coefficients per thread (one inversion per batch).
+//
+// B <- G * sc; true when flags and x of c48 agree with B.  y_out / z_out: what the sign half consumes - (0, 1) for an agreeing
+// identity (its sign flag must be 0 = lex_largest(0)) and whenever the answer is already false (keeps the batch invertible).
+DKGV_HD bool fd_coef_point(const OpFile& f, const uint32_t* gtab, const uint32_t* sc, const uint8_t* c48, Fp* y_out, Fp* z_out) {
+  vm_fixed_base_mul(f, gtab, sc);
+  uint8_t b[48];
+#pragma unroll
+  for (int i = 0; i < 48; i++) b[i] = c48[i];
+  const bool fc = (b[0] >> 7) & 1, fi = (b[0] >> 6) & 1, fs = (b[0] >> 5) & 1;
+  b[0] &= 0x1f;
+  Fp xr;
+  fp_raw_from_be48(xr.l, b);
+  Fp bz = of_load(f, BZ);
+  const bool binf = is_zero(bz);
+  *y_out = zero<FpParams>();
+  *z_out = one<FpParams>();
+  if (!fc || !raw_lt_mod<FpParams>(xr.l)) return false;
+  if (fi) return !fs && is_zero(xr) && binf;
+  if (binf) return false;
+  Fp r2;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r2.l[i] = FpParams::r2(i);
+  of_store(f, T0, xr);
+  of_store(f, T1, r2);
+  vm_mul(f, T0, T0, T1);  // x_C in Montgomery form
+  vm_mul(f, T2, T0, BZ);
+  if (!vm_eq(f, T2, BX)) return false;
+  *y_out = of_load(f, BY);
+  *z_out = bz;
+  return true;
+}
+
+// sign halves of cnt <= K points: lex_largest(y[i] / z[i]) == fs[i] for every i; z[i] != 0 (Montgomery's simultaneous inversion)
+constexpr int FD_SIGN_K = 8;
+template <int K>
+DKGV_HD bool fd_coef_signs(const Fp* z, const Fp* y, const uint8_t* fs, int cnt) {
+  Fp pref[K];
+  Fp acc = z[0];
+  pref[0] = acc;
+#pragma unroll 1
+  for (int i = 1; i < cnt; i++) {
+    acc = mul(acc, z[i]);
+    pref[i] = acc;
+  }
+  Fp inv = fp_inv(acc);
+  bool ok = true;
+#pragma unroll 1
+  for (int i = cnt - 1; i >= 0; i--) {
+    Fp zi = inv;
+    if (i) {
+      zi = mul(inv, pref[i - 1]);
+      inv = mul(inv, z[i]);
+    }
+    ok &= fp_lex_largest(mul(y[i], zi)) == (fs[i] != 0);
+  }
+  return ok;
+}
+
 }  // namespace dkgv

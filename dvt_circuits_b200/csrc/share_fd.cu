@@ -21,6 +21,12 @@ using namespace dkgv;
 
 int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
 
+#ifndef DKGV_FD_BYTES_DEFAULT
+#define DKGV_FD_BYTES_DEFAULT 0  // flipped to 1 once the B200 parity run of the decode-free formulation is green
+#endif
+constexpr bool FD_BYTES_DEFAULT = DKGV_FD_BYTES_DEFAULT != 0;
+static bool g_fd_bytes = FD_BYTES_DEFAULT;         // condition (3) against the compressed commitments, decode deferred (k_fd_coefpoint + k_fd_coefsign);
+                                       // DKGV_FD_BYTES=0: lazy decode + k_fd_coefcheck (A/B tests)
 static bool g_fd_difftab = true;      // fused difference table (k_fd_difftab); DKGV_FD_DIFFTAB=0: k_fd_polycheck + k_fd_interp (A/B tests)
 static uint32_t g_fd_ipb_force = 0;  // items per block of the difference / extension launches, DKGV_FD_IPB (experiments)
 constexpr int FD_NT = 32;  // one warp per block: 32 consecutive dealers, one entry (cf. SVM_NT in dkgv.cu)
@@ -333,6 +339,56 @@ k_fd_coefcheck(VVView vv, const uint32_t* __restrict__ coef, const uint32_t* __r
   if (active && !same) poly_ok[d0 + dl] = 0;
 }
 
+// condition (3) WITHOUT decoding the commitments (fdiff.cuh, "against the COMPRESSED commitment"): x half.  Same launch shape
+// as k_fd_coefcheck; writes Z (limbs 0..11) and Y (12..23) of G * p_k to the chunk-local planes yz[(k*24 + w) * n_cols + dl].
+__global__ void __launch_bounds__(FD_NT)
+k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab,
+               uint8_t* __restrict__ poly_ok, uint32_t* __restrict__ yz, uint32_t d0, uint32_t n_d, uint32_t n_cols, uint32_t t) {
+  extern __shared__ U4 opfile[];
+  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
+  bool active = d0 + dl < n_d;
+  uint32_t dc = active ? dl : n_d - 1 - d0;
+#if defined(__CUDA_ARCH__)
+  if (__ballot_sync(0xffffffffu, active && poly_ok[d0 + dl]) == 0) return;  // nobody in this group can still pass
+#endif
+  OpFile f{opfile + threadIdx.x, FD_NT};
+  uint32_t sc[8];
+#pragma unroll
+  for (int l = 0; l < 8; l++) sc[l] = coef[((size_t)dc * t + k) * 8 + l];
+  Fp y, z;
+  bool same = fd_coef_point(f, gtab, sc, vv + ((size_t)(d0 + dc) * t + k) * 48, &y, &z);
+  uint32_t* o = yz + (size_t)k * 24 * n_cols + dl;
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    o[(size_t)w * n_cols] = z.l[w];
+    o[(size_t)(12 + w) * n_cols] = y.l[w];
+  }
+  if (active && !same) poly_ok[d0 + dl] = 0;
+}
+
+// sign half: thread = (dealer, batch of FD_SIGN_K consecutive coefficients), lanes = consecutive dealers (coalesced planes).
+// A dealer still marked ok here had every one of its points written by k_fd_coefpoint (poly_ok only ever drops).
+__global__ void __launch_bounds__(128)
+k_fd_coefsign(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ yz, uint8_t* __restrict__ poly_ok, uint32_t d0, uint32_t n_d,
+              uint32_t n_cols, uint32_t t) {
+  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k0 = (blockIdx.y * blockDim.y + threadIdx.y) * FD_SIGN_K;
+  if (d0 + dl >= n_d || k0 >= t || !poly_ok[d0 + dl]) return;
+  int cnt = (int)(t - k0 < (uint32_t)FD_SIGN_K ? t - k0 : (uint32_t)FD_SIGN_K);
+  Fp z[FD_SIGN_K], y[FD_SIGN_K];
+  uint8_t fs[FD_SIGN_K];
+#pragma unroll 1
+  for (int i = 0; i < cnt; i++) {
+    const uint32_t* e = yz + (size_t)(k0 + i) * 24 * n_cols + dl;
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      z[i].l[w] = e[(size_t)w * n_cols];
+      y[i].l[w] = e[(size_t)(12 + w) * n_cols];
+    }
+    fs[i] = (vv[((size_t)(d0 + dl) * t + k0 + i) * 48] >> 5) & 1;
+  }
+  if (!fd_coef_signs<FD_SIGN_K>(z, y, fs, cnt)) poly_ok[d0 + dl] = 0;
+}
+
 // need_group[g] = 1 when some dealer of the 32-dealer group g (of this chunk) fails a condition or has an undecodable commitment
 __global__ void __launch_bounds__(128)
 k_fd_need(const uint8_t* __restrict__ poly_ok, const uint8_t* __restrict__ dealer_bad, uint32_t d0, uint32_t n_cols, uint32_t n_d,
@@ -380,7 +436,7 @@ k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, con
 
 int dkgv_fd_setup(dkgv_ctx* ctx) {
   for (const void* k : {(const void*)k_fd_seed, (const void*)k_fd_init, (const void*)k_fd_ext, (const void*)k_fd_combine,
-                        (const void*)k_fd_combine_out, (const void*)k_fd_coefcheck}) {
+                        (const void*)k_fd_combine_out, (const void*)k_fd_coefcheck, (const void*)k_fd_coefpoint}) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
@@ -388,6 +444,11 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   CK(cudaFuncSetAttribute(k_fd_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * FD_SHORTCUT_MAX_T * 32)));
   CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 1024 + FD_SHORTCUT_MAX_T) * 32)));
   CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  size_t stack = 0;  // k_fd_coefsign keeps 3 x FD_SIGN_K field elements in local memory (1.2 KB frame); only ever raise the limit
+  CK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
+  if (stack < 2048) CK(cudaDeviceSetLimit(cudaLimitStackSize, 2048));
+  const char* by = getenv("DKGV_FD_BYTES");
+  g_fd_bytes = by ? atoi(by) != 0 : FD_BYTES_DEFAULT;
   const char* dt = getenv("DKGV_FD_DIFFTAB");
   g_fd_difftab = !dt || atoi(dt) != 0;
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
@@ -398,6 +459,9 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   }
   return 0;
 }
+
+// the share-matrix entry may skip the decode of the commitments until a dealer group needs the evaluation
+bool dkgv_fd_defers_decode() { return g_fd_bytes; }
 
 // ids (host copy) a permutation of 1..n_r ?
 bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
@@ -464,7 +528,22 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, poly_ok,
                                                                          d0, n_d, n_r, t);
     }
-    k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
+    CK(cudaEventRecord(ctx->ev_fd[1], s));  // shortcut phases: [limbs + difference table | x halves | sign halves | flags]
+    const bool bytes = !ctx->vv_decoded;  // the decode was deferred: compare against the compressed commitments
+    if (bytes) {
+      CK(ctx->fd_yz.reserve((size_t)t * 24 * n_pad * 4));
+      k_fd_coefpoint<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(ctx->vv_src, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok,
+                                                             (uint32_t*)ctx->fd_yz.p, d0, n_d, n_pad, t);
+      CK(cudaEventRecord(ctx->ev_fd[2], s));
+      const uint32_t batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
+      k_fd_coefsign<<<dim3(groups, (batches + 3) / 4), dim3(32, 4), 0, s>>>(ctx->vv_src, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d,
+                                                                         n_pad, t);
+      ctx->launches++;
+    } else {
+      k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
+      CK(cudaEventRecord(ctx->ev_fd[2], s));
+    }
+    CK(cudaEventRecord(ctx->ev_fd[3], s));
     k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, need_group, any_need);
     k_fd_fill_ok<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_status, need_group, d0, n_pad, n_d, n_r);
     ctx->launches += fused ? 5 : 6;
@@ -475,7 +554,7 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     if (!h_any) {  // an honest chunk: every verdict is OK and already written
       ctx->fd_last_need = false;
       CK(cudaEventRecord(ctx->ev_hot1, s));
-      for (int i = 1; i <= 4; i++) CK(cudaEventRecord(ctx->ev_fd[i], s));
+      CK(cudaEventRecord(ctx->ev_fd[4], s));
       ctx->hot_recorded = true;
       ctx->fd_recorded = true;
       return 0;

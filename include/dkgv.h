@@ -115,13 +115,17 @@ int dkgv_set_share_parts(dkgv_ctx* ctx, uint32_t parts); /* 0 = planner's choice
 int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
 /* Consistency shortcut of the finite-difference path (default on).  All n shares of a dealer are valid exactly when
  * (1) each is < r, (2) they lie on a polynomial of degree <= t-1 over Fr - pure scalar arithmetic: the t-th forward
- * differences of the share sequence vanish - and (3) G*s(x) == f(x) at t distinct ids x.  So only the ids 1..t go
- * through the group arithmetic; a group of 32 dealers in which some dealer fails a condition continues with the full
+ * differences of the share sequence vanish - and (3) G * p_k == C_k for each coefficient of the interpolated polynomial p.
+ * So no share goes through the group arithmetic; a group of 32 dealers in which some dealer fails a condition continues with the full
  * evaluation, which yields the exact per-share verdicts.  Deterministic and exact (no random linear combination).
  * Costs one host synchronisation inside the call.  dkgv_last_share_continued: 1 when the last call had to continue
  * beyond t for some dealer group, 0 when the shortcut settled everything.                                        */
 int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on);
 int dkgv_last_share_continued(const dkgv_ctx* ctx);
+/* 1 when the commitments of the last share-matrix call were decoded (square roots, subgroup tests), 0 when the shortcut
+ * settled the call against their compressed encodings: compress(G * p_k) == C_k needs no decompression, and an encoding
+ * that is not a subgroup point can never agree, so the decode waits until some dealer group needs the evaluation.   */
+int dkgv_last_share_decoded(const dkgv_ctx* ctx);
 int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the last share-matrix call ran */
 /* the plan for ids 1..n_recipients (parts_force 0 = cheapest; n_opt = number of ids the cost model assumes are
  * evaluated in the group, 0 = all, t when the consistency shortcut is on): parts, h = ceil(t / parts), Horner seed points

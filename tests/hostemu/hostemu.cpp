@@ -4,6 +4,7 @@
 // against the oracle on a machine without a GPU.  The only thing not covered here is the PTX
 // carry-chain Montgomery product, which the `-m gpu` tests pin on a real B200.
 // Nothing under dvt_circuits_b200/ links or loads this file.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -357,5 +358,46 @@ int he_difftab(const uint8_t* shares, uint32_t n_r, uint32_t t, const uint8_t* i
     if (2 * i + 1 < t) fr_to_be32(coef + (size_t)(2 * i + 1) * 32, th[i].b);
   }
   return 0;
+}
+
+// Condition (3) of the consistency shortcut against COMPRESSED commitments (fdiff.cuh fd_coef_point + fd_coef_signs, the
+// per-thread routines of k_fd_coefpoint / k_fd_coefsign): n (scalar, encoding) pairs of one dealer, sign halves in batches of
+// FD_SIGN_K as in the kernel.  out[i] = 1 when compress(G * scalar_i) == enc_i according to the two halves.
+void he_coef_bytes_check(const uint8_t* scalars32, const uint8_t* enc48, uint32_t n, uint8_t* out) {
+  const uint32_t NT = 4, me = 1;
+  std::vector<U4> file((size_t)VM_SLOTS * 3 * NT);
+  OpFile f{file.data() + me, NT};
+  std::vector<Fp> ys(n), zs(n);
+  std::vector<uint8_t> same(n);
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t sc[8];
+    fr_raw_from_be32(sc, scalars32 + (size_t)i * 32);
+    std::vector<uint32_t> gtab(GTAB_WORDS, 0);
+    for (int w = 0; w <= GTAB_WINDOWS; w++) {
+      uint32_t idx = gtab_index(sc, w);
+      G1Aff e = gtab_entry(idx);
+      for (int l = 0; l < 12; l++) {
+        gtab[(size_t)idx * 24 + l] = e.x.l[l];
+        gtab[(size_t)idx * 24 + 12 + l] = e.y.l[l];
+      }
+    }
+    same[i] = fd_coef_point(f, gtab.data(), sc, enc48 + (size_t)i * 48, &ys[i], &zs[i]);
+  }
+  for (uint32_t k0 = 0; k0 < n; k0 += FD_SIGN_K) {
+    int cnt = (int)std::min<uint32_t>(FD_SIGN_K, n - k0);
+    uint8_t fs[FD_SIGN_K];
+    for (int i = 0; i < cnt; i++) fs[i] = (enc48[(size_t)(k0 + i) * 48] >> 5) & 1;
+    // the kernel's verdict is per dealer (all batches); here each point separately as well: batch verdict with the other
+    // points' signs forced right, so that one wrong sign is attributed to its own point
+    for (int i = 0; i < cnt; i++) {
+      uint8_t g[FD_SIGN_K];
+      for (int j = 0; j < cnt; j++) {
+        Fp ya = mul(ys[k0 + j], fp_inv(zs[k0 + j]));
+        g[j] = j == i ? fs[j] : (uint8_t)fp_lex_largest(ya);
+      }
+      bool ok = fd_coef_signs<FD_SIGN_K>(zs.data() + k0, ys.data() + k0, g, cnt);
+      out[k0 + i] = same[k0 + i] && ok;
+    }
+  }
 }
 }

@@ -232,3 +232,47 @@ def test_difference_table_shortcut(L):
         a2 = a + [rnd.randrange(1, R)]
         s2 = [horner(a2, x) for x in range(1, n + 1)]
         assert run(s2, t)[0] == 1
+
+
+def test_compressed_commitment_check(L):
+    """fd_coef_point + fd_coef_signs (k_fd_coefpoint / k_fd_coefsign): compress(G * p_k) == C_k decided without decompressing C_k
+    (x_C * Z == X, batched 1/Z for the sign).  Against the Python oracle: the true encoding agrees; the other sign, another
+    point, x + p (non-canonical), missing compression flag, infinity flag on a point, the identity encoding against a non-zero
+    scalar and a non-identity encoding against the zero scalar do not; scalar 0 with the identity encoding agrees."""
+    rnd = random.Random(31)
+    G = B.G1
+    scal, encs, want = [], [], []
+
+    def add(k, e, w):
+        scal.append(k.to_bytes(32, "big"))
+        encs.append(bytes(e))
+        want.append(w)
+
+    ks = [1, 2, B.R - 1, rnd.randrange(B.R), rnd.randrange(B.R), rnd.randrange(1 << 64), rnd.randrange(B.R)]
+    for k in ks:
+        good = bytearray(B.g1_compress(B.g1_mul(G, k)))
+        add(k, good, 1)
+        e = bytearray(good)
+        e[0] ^= 0x20  # the other square root
+        add(k, e, 0)
+        add(k, B.g1_compress(B.g1_mul(G, (k + 1) % B.R or 2)), 0)
+        e = bytearray(good)
+        e[0] &= 0x7F  # compression flag missing
+        add(k, e, 0)
+        e = bytearray(good)
+        e[0] |= 0x40  # infinity flag on a point
+        add(k, e, 0)
+        x = int.from_bytes(bytes([good[0] & 0x1F]) + bytes(good[1:]), "big")
+        if x + B.P < 1 << 381:  # same residue, non-canonical encoding
+            e = bytearray((x + B.P).to_bytes(48, "big"))
+            e[0] |= good[0] & 0xE0
+            add(k, e, 0)
+        add(k, bytes([0xC0]) + bytes(47), 0)  # identity encoding, non-zero scalar
+    add(0, bytes([0xC0]) + bytes(47), 1)
+    add(0, bytes([0xE0]) + bytes(47), 0)  # identity with the sign flag
+    add(0, B.g1_compress(G), 0)
+    add(0, bytes([0xC0]) + bytes(46) + b"\x01", 0)
+    n = len(want)
+    out = buf(n)
+    L.he_coef_bytes_check(b"".join(scal), b"".join(encs), n, out)
+    assert list(out.raw) == want, [i for i in range(n) if out.raw[i] != want[i]]
