@@ -22,7 +22,7 @@ using namespace dkgv;
 int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
 
 #ifndef DKGV_FD_BYTES_DEFAULT
-#define DKGV_FD_BYTES_DEFAULT 0  // flipped to 1 once the B200 parity run of the decode-free formulation is green
+#define DKGV_FD_BYTES_DEFAULT 1  // B200 parity run green (tests/test_gpu_share.py test_shortcut_formulations_agree); 0: lazy decode + k_fd_coefcheck
 #endif
 constexpr bool FD_BYTES_DEFAULT = DKGV_FD_BYTES_DEFAULT != 0;
 static bool g_fd_bytes = FD_BYTES_DEFAULT;         // condition (3) against the compressed commitments, decode deferred (k_fd_coefpoint + k_fd_coefsign);
