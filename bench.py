@@ -11,7 +11,8 @@ inside the timed region.
 
 `value`     device-timed, inputs resident in HBM, max over ranks, the library's DEFAULT path on the synthetic (honest) ceremony:
             the consistency shortcut proves every dealer's shares valid by scalar arithmetic + t fixed-base
-            multiplications, exactly (no randomness), so no share is evaluated in the exponent.
+            multiplications compared with the COMPRESSED commitments, exactly (no randomness): no share is evaluated in the
+            exponent and no commitment is decompressed.
 `full_evaluation`  the same steps with the shortcut off - every share through the group arithmetic (finite differences);
 `mixed_items`      the same matrix with half of the shares corrupted (BASELINE config 5): the shortcut fails for every dealer
             and the evaluation produces the per-share verdicts, which must flag exactly the corrupted shares.
@@ -20,7 +21,8 @@ inside the timed region.
 `roofline`  integer-pipe roofline of the evaluation kernels (`roofline.kernels`, from the full-evaluation steps run phase after
             phase): canonical 32x32->64 multiply-accumulates per second (84 314 modmul/share x 300 MAC)
             against the IMAD.WIDE peak measured live by bench/imad_peak on the same GPU.  The top-level fields describe the
-            dominant kernel of the timed (default-path) steps: the decode of the commitments.
+            dominant kernel of the timed (default-path) steps - k_fd_coefpoint, G * p_k against the compressed commitment (the
+            default path decodes no commitment) - and `roofline.shortcut_kernels` all kernels of such a step, timed live.
 `cpu_baseline` the CPU oracle in reference-faithful mode (per-op affine round trips, constant-time
             255-step scalar multiplication - the reference's operation sequence) on a bounded sample
             of the same matrix, all host cores.  A restatement, not the Rust binary (no cargo here).
@@ -569,7 +571,11 @@ def run_b200(args):
         if fdiff and short and short_kernels:
             roof["shortcut_kernels"] = short_kernels
             roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
-            roof["traffic_ref"] = "no ncu --set full capture of k_fd_coefpoint yet (integer-bound: 176 B per 365 field products)"
+            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r1_default_path_v3.md): dram read 57 367 296 B +
+            # write 32 190 208 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
+            roof["traffic"] = int(round((57367296 + 32190208) / 699392 * rows * t))
+            roof["traffic_ref"] = ("profiles/r1_default_path_v3.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
+                                   "(128.1 B per coefficient, scaled to this launch's coefficients)")
         elif fdiff and short:
             # ncu --set full of k_decompress_vv at 699 392 commitments (profiles/r1_default_path.md): dram read 34 069 760 B +
             # write 21 060 352 B per launch; algorithmic 48 B in + 100 B planar out per commitment (the planes mostly stay in L2)
