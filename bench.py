@@ -117,7 +117,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.stamps, self.proc = gpu_index, [], [], None
 
     def start(self):
         try:
@@ -131,8 +131,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
+            self.stamps.append(time.perf_counter())
 
-    def stop(self):
+    def stop(self, since=None):
+        """summary of the samples taken after perf_counter() time `since` (None: all of them)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -140,6 +142,9 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        if since is not None:
+            n_rows = min(len(self.rows), len(self.stamps))
+            self.rows = [self.rows[i] for i in range(n_rows) if self.stamps[i] >= since]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -308,12 +313,12 @@ def run_b200(args):
                                                             "source": "paper peak 148 SM x 64 lanes x 1.965 GHz (--no-peak)"}
 
     with torch.cuda.stream(ts):
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()  # before the warm-up: nvidia-smi needs a moment before its first sample; only samples from wall0 on count
         for _ in range(args.warmup):
             step_device()
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         launches0 = v.launch_count
         step_ms, hot_ms, phase_ms, dec_ms, short_ms, decoded_steps = [], [], [], [], [], 0
         barrier()
@@ -340,7 +345,20 @@ def run_b200(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        # The timed region of the default path is short (10 steps of ~15 ms on one GPU, less on eight) against nvidia-smi's 50 ms
+        # sampling period: keep the same steps running, untimed, until the GPU has been under this load for ~0.6 s, so that the
+        # clocks line rests on several samples.  The count comes from the max-over-ranks step time: identical on every rank.
+        t_sum = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
+        per_step_s = max(float(t_sum.item()) / args.steps * 1e-3, 1e-4)
+        extra_steps = max(0, min(2000, int(0.6 / per_step_s) - args.steps))
+        for _ in range(extra_steps):
+            step_device()
+        barrier()
+        clocks = sampler.stop(since=wall0) if rank == 0 else None
+        if clocks is not None:
+            clocks["untimed_steps_under_the_same_load"] = extra_steps
         continued = bool(v.last_share_continued) if v.last_share_path == v.PATH_FDIFF else False
         full_ms, serial_ms = [], []
         if v.last_share_path == v.PATH_FDIFF:

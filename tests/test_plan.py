@@ -71,3 +71,39 @@ def test_consistency_shortcut_recurrences():
             inv_j = pow(j, -1, R)
             c = [(((c[i - 1] if i else 0) * inv_j - c[i]) + (D[j - 1] if i == 0 else 0)) % R for i in range(t)]
         assert c == a
+
+
+def test_bench_clock_sampler_window():
+    """bench.py's ClockSampler: only samples stamped at or after `since` (the start of the timed region) are summarised;
+    throttle reasons are collected; no sample -> None clocks (never a crash)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    def sampler(rows, stamps):
+        s = bench.ClockSampler(0)
+        s.proc, s.rows, s.stamps = FakeProc(), [list(r) for r in rows], list(stamps)
+        return s
+
+    na = "Not Active"
+    rows = [["0", "345", "1965", "200.0", "0x0", na, na, na, na],       # idle, before the timed region
+            ["0", "1965", "1965", "900.0", "0x0", na, na, na, na],
+            ["0", "1950", "1965", "950.0", "0x4", na, na, na, "Active"],
+            ["0", "1965", "1965", "940.0", "0x0", na, na, na, na]]
+    out = sampler(rows, [1.0, 2.0, 2.1, 2.2]).stop(since=1.5)
+    assert out == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    out = sampler(rows, [1.0, 2.0, 2.1, 2.2]).stop()
+    assert out["samples"] == 4 and out["sm_mhz"] == 1957.5
+    out = sampler(rows, [1.0, 2.0, 2.1, 2.2]).stop(since=5.0)
+    assert out["samples"] == 0 and out["sm_mhz"] is None and out["reasons"] == []
+    out = sampler(rows, [1.0, 2.0]).stop(since=1.5)  # a row whose stamp has not been appended yet is ignored
+    assert out["samples"] == 1
