@@ -8,8 +8,10 @@
 //   k_fd_ext      steps + h - 2 wavefront ticks                (1 point addition per item)
 //   k_fd_digits   signed digits of the public recombination scalars x^(h i) mod r, one thread per id
 //   k_fd_combine  sum_i [y^i] f_i(x) by joint double-and-add, G * s, compare: one thread per share
-// before them the consistency shortcut (k_fd_tables / k_fd_share_limbs / k_fd_polycheck / k_fd_interp / k_fd_coefcheck /
-// k_fd_need / k_fd_fill_ok, see below): a dealer group whose shares are provably all valid never enters the evaluation.
+// before them the consistency shortcut (k_fd_tables / k_fd_share_limbs / k_fd_difftab / k_fd_coefpoint / k_fd_coefsign /
+// k_fd_need / k_fd_fill_ok, see below; k_fd_polycheck / k_fd_interp / k_fd_coefcheck are the formulations they replaced, kept
+// behind DKGV_FD_DIFFTAB=0 / DKGV_FD_BYTES=0 for A/B tests): a dealer group whose shares are provably all valid never enters
+// the evaluation, and its commitments are never decompressed.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -111,7 +113,9 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // fixed-base multiplications per dealer instead of n evaluations in the exponent.  A group of 32 dealers in which
 // some dealer fails a condition (or has an undecodable commitment) goes through the full evaluation, which yields
 // the exact per-share verdicts.  Exact and deterministic - no random linear combination.
-constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient (dkgv.cu's lazy_subgroup uses the same bound)
+// Default formulation: (2) and the interpolation in one difference table per dealer (k_fd_difftab), (3) against the
+// compressed commitments (k_fd_coefpoint + k_fd_coefsign) with the decode deferred until a group needs the evaluation.
+constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient; fr_submul_small: factors j < 2^10 (dkgv.cu's lazy_subgroup uses the same bound)
 
 // c[j] = (-1)^j C(t, j) mod r (j = 0..t), inv[j] = 1/j mod r (j = 1..t) and ifact[j] = 1/j! mod r, Montgomery form; one thread per j
 __global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv, uint32_t* __restrict__ ifact) {
