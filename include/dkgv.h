@@ -73,7 +73,8 @@ int dkgv_sync(dkgv_ctx* ctx);
  * (k_share_verify) issued through this ctx; blocks until that launch has finished */
 int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms);
 /* device time of the most recent verification-vector decode of the share path (k_decompress_vv) and whether it included the
- * subgroup checks (0: the lazy decode in front of the consistency shortcut)                                          */
+ * subgroup checks.  A share-matrix call settled by the consistency shortcut decodes nothing (dkgv_last_share_decoded == 0):
+ * the value then belongs to an earlier call; fails when this ctx has not decoded yet.                                 */
 int dkgv_last_decode_ms(dkgv_ctx* ctx, float* ms, int* subgroup_checked);
 
 /* ---- Feldman share verification (replaces the loop body of verify_seed_exchange_commitment,
@@ -135,7 +136,9 @@ int dkgv_last_share_path(const dkgv_ctx* ctx);    /* HORNER or FDIFF: what the l
 int dkgv_share_fd_plan(uint32_t t, uint32_t n_recipients, uint32_t parts_force, uint32_t n_opt, uint32_t* parts, uint32_t* h,
                        int32_t* lo, int32_t* hi, uint32_t* steps, uint64_t* modmul_fd, uint64_t* modmul_horner);
 /* device times of the last finite-difference run: seed Horner, differences, extension, recombine + G*s compare;
- * with overlap on the first three run concurrently and only ms4[0] (their total) and ms4[3] are meaningful */
+ * with overlap on the first three run concurrently and only ms4[0] (their total) and ms4[3] are meaningful.
+ * When the consistency shortcut settled the call (dkgv_last_share_continued == 0) the four intervals are its own:
+ * share limbs + difference table, x halves of G*p_k == C_k, sign halves, flags + verdict fill.                */
 int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4);
 
 /* ---- evaluate_polynomial (crates/dkg/src/dkg_math.rs:160-174), batched ---------------------- */
