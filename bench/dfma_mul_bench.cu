@@ -2,7 +2,7 @@
 // the IMAD carry-chain product (csrc/field.cuh), alone and with the SM's warps split between the two.
 #include <cuda_runtime.h>
 #include <cstdio>
-#include "../dvt_circuits_b200/csrc/field_dfma.cuh"
+#include "experiments/field_dfma.cuh"
 using namespace dkgv;
 
 __device__ __forceinline__ uint32_t xs(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }

@@ -15,7 +15,7 @@
 // i.e. 4 FP64 instructions per 48x48-bit limb product and no integer work for the accumulation.
 // Reduction: 8 rounds q = (column * -p^-1) mod 2^48 (integer, 3 IMAD), then q * p through the same chains.
 #pragma once
-#include "field.cuh"
+#include "../../dvt_circuits_b200/csrc/field.cuh"
 
 namespace dkgv {
 

@@ -18,7 +18,7 @@
 // -DDKGV_BOUND_CHECK, see tests/hostemu).
 // Plain C on both host and device: nvcc maps `acc += (uint64_t)a * b` to IMAD.WIDE.U32.
 #pragma once
-#include "field.cuh"
+#include "../../dvt_circuits_b200/csrc/field.cuh"
 
 #if defined(DKGV_BOUND_CHECK) && !defined(__CUDA_ARCH__)
 #include <cassert>

@@ -3,7 +3,7 @@
 // carry chains, field.cuh), and fp30 with two independent chains interleaved (ILP 2).
 #include <cuda_runtime.h>
 #include <cstdio>
-#include "../dvt_circuits_b200/csrc/fp30.cuh"
+#include "fp30.cuh"
 using namespace dkgv;
 template <int MODE>
 __global__ void __launch_bounds__(128) k(uint32_t* out, uint32_t seed, int iters) {

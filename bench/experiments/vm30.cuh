@@ -13,7 +13,7 @@
 // every formula returns coordinates <= 16; each subtraction states the K it needs.
 #pragma once
 #include "fp30.cuh"
-#include "vm.cuh"
+#include "../../dvt_circuits_b200/csrc/vm.cuh"
 
 namespace dkgv {
 

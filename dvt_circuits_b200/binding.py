@@ -44,6 +44,12 @@ class Status(enum.IntEnum):
     PANIC_BAD_IDENTITY = 53
 
 
+class Report(ctypes.Structure):
+    """dkgh_report of include/dkgh.h"""
+    _fields_ = [("public_values", ctypes.c_void_p), ("public_cap", ctypes.c_size_t), ("public_len", ctypes.c_size_t),
+                ("n_public", ctypes.c_uint32), ("have_keys", ctypes.c_int), ("expected", ctypes.c_uint8 * 48), ("got", ctypes.c_uint8 * 48)]
+
+
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_u32p = ctypes.POINTER(ctypes.c_uint32)
 _vp = ctypes.c_void_p
@@ -60,6 +66,8 @@ DECLARED_SYMBOLS = {
     "dkgv_last_decode_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "dkgv_share_matrix_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_verify_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_submit_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_finish_dev": (ctypes.c_int, [_vp, _vp, _vp]),
     "dkgv_share_items_verify": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_pack_verdicts_dev": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "dkgv_set_share_path": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -85,11 +93,14 @@ DECLARED_SYMBOLS = {
     "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_bad_partial_key_verify_batch": (ctypes.c_int, [_vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_g2_mul_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_initial_commitment_hashes": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, ctypes.c_uint8, ctypes.c_uint8, _vp]),
     # include/dkgh.h
     "dkgh_execute": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                     ctypes.c_char_p, ctypes.c_size_t]),
+    "dkgh_execute_report": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                           ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(Report)]),
     "dkgh_initial_commitment_hash": (None, [_vp, ctypes.c_uint8, ctypes.c_uint8, _vp, _u32, _vp]),
 }
 
@@ -229,6 +240,17 @@ class Verifier:
         """device pointers (ints); asynchronous"""
         self._ck(self._lib.dkgv_share_matrix_verify_dev(self._h, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, stream))
 
+    def share_matrix_submit_dev(self, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, d_flags2=None, stream=None):
+        """queues the default path WITHOUT synchronising; d_flags2 (device, 2 x u32; None = ctx-owned) receives
+        [ids are no permutation of 1..n, dealers the consistency shortcut could not settle]"""
+        self._ck(self._lib.dkgv_share_matrix_submit_dev(self._h, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, d_flags2, stream))
+
+    def share_matrix_finish_dev(self, h_flags2=None, stream=None):
+        """h_flags2: the two flag words read back by the caller (numpy u32[2]) or None (read here: one synchronisation);
+        queues the evaluation of the unsettled dealer groups / the Horner route when the flags ask for it"""
+        fl = _host(h_flags2, np.uint32, (2,)) if h_flags2 is not None else None
+        self._ck(self._lib.dkgv_share_matrix_finish_dev(self._h, _p(fl) if fl is not None else None, stream))
+
     def share_items_verify(self, vv, ids, item_dealer, item_recipient, secrets):
         """sparse (dealer, recipient-column) items of one session -> status [m] u8"""
         vv = np.ascontiguousarray(vv, dtype=np.uint8)
@@ -345,6 +367,28 @@ class Verifier:
                                                  _p(idx) if idx is not None else None, _p(st)))
         return st
 
+    def bad_partial_key_verify_batch(self, vv, perp, pk, sig, msgs, msg_idx=None):
+        """vv [n,t,48] (base_hash-sorted generations), perp [m] u32, pk [m,48], sig [m,96], msgs = list of bytes, msg_idx [m] or None
+        -> (status [m] u8, expected keys [n,48], session status)"""
+        vv = np.ascontiguousarray(vv, dtype=np.uint8)
+        n, t = vv.shape[0], vv.shape[1]
+        perp = _host(perp, np.uint32)
+        m = perp.shape[0]
+        pk = _host(pk, np.uint8, (m, 48))
+        sig = _host(sig, np.uint8, (m, 96))
+        offs = np.zeros((len(msgs) + 1,), dtype=np.uint32)
+        for i, mm in enumerate(msgs):
+            offs[i + 1] = offs[i] + len(mm)
+        blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8).copy()
+        idx = _host(msg_idx, np.uint32, (m,)) if msg_idx is not None else None
+        st = np.empty((m,), dtype=np.uint8)
+        exp = np.zeros((n, 48), dtype=np.uint8)
+        sst = ctypes.c_uint8(0)
+        self._ck(self._lib.dkgv_bad_partial_key_verify_batch(self._h, n, t, _p(vv), m, _p(perp), _p(pk), _p(sig), len(msgs), _p(blob), _p(offs),
+                                                             _p(idx) if idx is not None else None, _p(st), _p(exp),
+                                                             ctypes.cast(ctypes.byref(sst), _vp)))
+        return st, exp, int(sst.value)
+
     def initial_commitment_hashes(self, vv, gen_id, n, k):
         """base hashes of all dealers at once: vv [n_d, t, 48] -> [n_d, 32]"""
         vv = np.ascontiguousarray(vv, dtype=np.uint8)
@@ -369,6 +413,27 @@ class Verifier:
             json_text = json_text.encode()
         code = self._lib.dkgh_execute(self._h, type_.encode(), json_text, int(auth), int(bls_identity), ctypes.byref(st), msg, 512)
         return int(code), int(st.value), msg.value.decode(errors="replace")
+
+
+    def execute_report(self, type_, json_text, auth=False, bls_identity=False):
+        """-> (exit_code, status, message, public values [bytes, in commit order], (expected48, got48) or None)"""
+        st = ctypes.c_int(0)
+        msg = ctypes.create_string_buffer(512)
+        pub = ctypes.create_string_buffer(1 << 20)
+        rep = Report()
+        rep.public_values = ctypes.cast(pub, ctypes.c_void_p)
+        rep.public_cap = len(pub)
+        if isinstance(json_text, str):
+            json_text = json_text.encode()
+        code = self._lib.dkgh_execute_report(self._h, type_.encode(), json_text, int(auth), int(bls_identity), ctypes.byref(st), msg, 512,
+                                             ctypes.byref(rep))
+        vals, raw, o = [], pub.raw, 0
+        for _ in range(rep.n_public):
+            ln = int.from_bytes(raw[o:o + 4], "little")
+            vals.append(raw[o + 4:o + 4 + ln])
+            o += 4 + ln
+        keys = (bytes(rep.expected), bytes(rep.got)) if rep.have_keys else None
+        return int(code), int(st.value), msg.value.decode(errors="replace"), vals, keys
 
 
 def verdict_bits_to_matrix(words, n_dealers, n_recipients):

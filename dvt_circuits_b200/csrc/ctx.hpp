@@ -25,6 +25,10 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
   }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }  // dkgv_ctx_destroy selects the device before the ctx (and with it every buffer) is deleted
 };
 }  // namespace dkgv_host
 
@@ -32,18 +36,14 @@ struct dkgv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   uint32_t* gtab = nullptr;
-  uint32_t* gtab30 = nullptr;
   uint64_t launches = 0;
   std::string err;
   dkgv_host::DevBuf vv_limbs, vv_inf, dealer_bad;      // session scratch (decoded verification vectors)
   dkgv_host::DevBuf in_a, in_b, in_c, out_a, out_b;    // staging for the host-pointer entry points
-  dkgv_host::DevBuf scratch_a, scratch_b, scratch_c;   // intermediates of the aggregation / pairing paths
+  dkgv_host::DevBuf scratch_a, scratch_b, scratch_c, scratch_d;   // intermediates of the aggregation / pairing paths
   dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
-  bool vv_decoded = true;            // the session's commitments are decoded (false: deferred by the consistency shortcut)
-  bool vv_checked = true;            // ... with subgroup checks
-  const uint8_t* vv_src = nullptr;   // device pointer / shape of the session last decoded (for the lazy re-decode)
-  uint32_t vv_n_d = 0, vv_t = 0;
+  bool vv_decoded = true;            // the last share-matrix call decoded its commitments (false: settled against their encodings)
   cudaEvent_t ev_dec0 = nullptr, ev_dec1 = nullptr;  // bracket the last verification-vector decode of the share path
   bool dec_recorded = false;
   bool hot_recorded = false;
@@ -51,8 +51,23 @@ struct dkgv_ctx {
   // finite-difference share path (share_fd.cu)
   dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef, fd_yz;
   std::vector<int32_t> fd_seed_host;
-  cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries
-  bool fd_recorded = false;
+  cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the evaluation
+  cudaEvent_t ev_sc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // ... of the consistency shortcut
+  bool fd_recorded = false, sc_recorded = false;
+  uint32_t fd_ipb_force = 0;  // items per block of the difference / extension launches (DKGV_FD_IPB, read once at create)
+  // share-matrix job between dkgv_share_matrix_submit_dev and dkgv_share_matrix_finish_dev
+  struct ShareJob {
+    bool open = false, fd = false, shortcut = false;
+    uint32_t n_d = 0, n_r = 0, t = 0;
+    const uint8_t* d_vv = nullptr;
+    const uint32_t* d_ids = nullptr;
+    const uint8_t* d_shares = nullptr;
+    uint8_t* d_status = nullptr;
+    uint32_t* d_flags = nullptr;
+    uint32_t parts = 0;
+  } job;
+  uint32_t* job_flags = nullptr;    // device: {ids are not a permutation of 1..n, dealers the shortcut could not settle}
+  uint32_t* h_job_flags = nullptr;  // pinned host copy
   bool fd_overlap = true;  // one stream per part (default) or everything on the caller's stream
   bool fd_polycheck = true;  // consistency shortcut: ids beyond t only for dealer groups that fail the scalar-side conditions
   uint32_t fd_binom_t = 0;   // t the cached binomial coefficients belong to

@@ -10,7 +10,6 @@
 #include <string>
 #include <vector>
 
-#include "vm30.cuh"
 #include "fdiff.cuh"
 
 using namespace dkgv;
@@ -18,11 +17,14 @@ using namespace dkgv;
 // share_fd.cu
 int dkgv_fd_setup(dkgv_ctx* ctx);
 bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r);
+bool dkgv_fd_shortcut_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t);
+int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
+                   uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s);
+const uint8_t* dkgv_fd_need_groups(const dkgv_ctx* ctx, uint32_t n_d);
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s);
+                         const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, const uint8_t* filter, cudaStream_t s);
 int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
                          const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s);
-bool dkgv_fd_defers_decode();
 
 // ============================================================================ kernels
 // Offset fixed-base table of the generator (layout in feldman.cuh).
@@ -43,45 +45,7 @@ __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab)
 //   (the reference panics on `.expect("Invalid pubkey")`, verification.rs:132-137).
 __global__ void __launch_bounds__(128)
 k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
-                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status, bool check_subgroup) {
-  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (size_t)n_pad * t) return;
-  uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
-  G1Aff a;
-  a.x = zero<FpParams>();
-  a.y = zero<FpParams>();
-  a.inf = 1;
-  if (d < n_d) {
-    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, check_subgroup);
-    if (st != G1_DEC_OK) dealer_bad[d] = 1;
-    if (point_status) point_status[(size_t)d * t + k] = (uint8_t)st;
-  }
-  vv_store(limbs, inf, n_pad, k, d, a);
-}
-
-// The subgroup tests a lazy decode (check_subgroup = false) left out, on the already decoded planes: a point outside G1
-// becomes the identity and marks its dealer, exactly as the full decode does.
-__global__ void __launch_bounds__(128)
-k_subgroup_check_vv(uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs, uint8_t* __restrict__ inf,
-                    uint8_t* __restrict__ dealer_bad) {
-  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (size_t)n_pad * t) return;
-  uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
-  if (d >= n_d) return;
-  VVView v{limbs, inf, n_pad};
-  G1Aff a = vv_load(v, k, d);
-  if (a.inf || g1_in_subgroup(a)) return;
-  dealer_bad[d] = 1;
-  a.x = zero<FpParams>();
-  a.y = zero<FpParams>();
-  a.inf = 1;
-  vv_store(limbs, inf, n_pad, k, d, a);
-}
-
-// Same decode, written in the 13 x 30-bit layout of vm30.cuh for the hot kernel.
-__global__ void __launch_bounds__(128)
-k_decompress_vv30(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
-                  uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad) {
+                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= (size_t)n_pad * t) return;
   uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
@@ -92,45 +56,22 @@ k_decompress_vv30(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint
   if (d < n_d) {
     uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, true);
     if (st != G1_DEC_OK) dealer_bad[d] = 1;
+    if (point_status) point_status[(size_t)d * t + k] = (uint8_t)st;
   }
-  vv30_store(limbs, inf, n_pad, k, d, fp30_from_fp(a.x), fp30_from_fp(a.y), a.inf != 0);
-}
-
-__global__ void __launch_bounds__(128) k_build_gtab30(const uint32_t* __restrict__ gtab, uint32_t* __restrict__ gtab30) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= GTAB_ENTRIES) return;
-  Fp x, y;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    x.l[i] = gtab[(size_t)tid * 24 + i];
-    y.l[i] = gtab[(size_t)tid * 24 + 12 + i];
-  }
-  Fp30 x30 = fp30_from_fp(x), y30 = fp30_from_fp(y);
-#pragma unroll
-  for (int i = 0; i < 13; i++) {
-    gtab30[(size_t)tid * 26 + i] = x30.l[i];
-    gtab30[(size_t)tid * 26 + 13 + i] = y30.l[i];
-  }
+  vv_store(limbs, inf, n_pad, k, d, a);
 }
 
 // The hot kernel.  Thread = one share (dealer d, recipient column j); the 32 lanes of a warp hold
 // 32 consecutive dealers and ONE recipient id, so the double-and-add over the id bits is
 // warp-uniform (no divergence) and every coefficient load is a fully coalesced 128 B line per limb.
 // Field operands live in the shared-memory operand file of vm.cuh (13 slots x 48 B per thread).
-// -DDKGV_HOT_FP30 selects the experimental carry-free 13 x 30-bit backend (vm30.cuh) instead; it is
-// slower on B200 (profiles/r1_fp30_experiment.md) and kept for reference only.
 constexpr int SV_WARPS = 4;   // k_feldman_eval (inlined formulas, cold path)
 #ifndef DKGV_SVM_NT
 #define DKGV_SVM_NT 32  // measured on B200: 32 -> 306k, 64 -> 286k, 128 -> 276k shares/s (n_r=1024,t=683,n_d=256)
 #endif
 constexpr int SVM_NT = DKGV_SVM_NT;  // threads per block of the hot kernel: one recipient id per warp
-#ifdef DKGV_HOT_FP30
-constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 4 * SVM_NT * sizeof(U4);
-typedef VV30View HotView;
-#else
 constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 3 * SVM_NT * sizeof(U4);
 typedef VVView HotView;
-#endif
 __global__ void __launch_bounds__(SVM_NT)
 k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
                const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status,
@@ -146,13 +87,8 @@ k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_
   j = n_r - 1 - j;
   bool active = d < n_d;
   uint32_t dd = active ? d : n_d - 1;
-#ifdef DKGV_HOT_FP30
-  OpFile30 f{opfile + threadIdx.x, SVM_NT};
-  uint8_t st = v30_share_check(f, vv, t, dd, ids[j], shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
-#else
   OpFile f{opfile + threadIdx.x, SVM_NT};
   uint8_t st = vm_share_check(f, vv, t, dd, ids[j], shares + ((size_t)dd * n_r + j) * 32, gtab, dealer_bad[dd] != 0);
-#endif
   if (active) status[(size_t)d * n_r + j] = st;
 }
 
@@ -301,6 +237,8 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
     return bail("cudaFuncSetAttribute carveout", e);
   if ((e = cudaFuncSetAttribute(k_share_items, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
     return bail("cudaFuncSetAttribute carveout", e);
+  if ((e = cudaMalloc(&ctx->job_flags, 16)) != cudaSuccess) return bail("cudaMalloc flags", e);
+  if ((e = cudaMallocHost(&ctx->h_job_flags, 16)) != cudaSuccess) return bail("cudaMallocHost flags", e);
   if (dkgv_fd_setup(ctx) != 0) {
     g_create_error = "finite-difference path setup: " + ctx->err;
     dkgv_ctx_destroy(ctx);
@@ -308,11 +246,6 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   }
   k_build_gtab<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
   ctx->launches++;
-#ifdef DKGV_HOT_FP30
-  if ((e = cudaMalloc(&ctx->gtab30, GTAB30_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab30", e);
-  k_build_gtab30<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab, ctx->gtab30);
-  ctx->launches++;
-#endif
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("k_build_gtab", e);
   *out = ctx;
   return 0;
@@ -322,11 +255,10 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->vv_limbs, &ctx->vv_inf, &ctx->dealer_bad, &ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->out_a, &ctx->out_b,
-                    &ctx->scratch_a, &ctx->scratch_b, &ctx->scratch_c, &ctx->fd_evals, &ctx->fd_p0, &ctx->fd_p1, &ctx->fd_da,
-                    &ctx->fd_db, &ctx->fd_seedx, &ctx->fd_dig, &ctx->fd_top, &ctx->fd_tab, &ctx->fd_cols, &ctx->fd_sl, &ctx->fd_flags, &ctx->fd_binom, &ctx->fd_coef, &ctx->bls_pk,
-                    &ctx->bls_sig, &ctx->bls_st})
-    b->release();
+  for (cudaEvent_t ev : ctx->ev_sc)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->job_flags) cudaFree(ctx->job_flags);
+  if (ctx->h_job_flags) cudaFreeHost(ctx->h_job_flags);
   for (cudaEvent_t ev : ctx->ev_fd)
     if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 16; i++) {
@@ -335,13 +267,12 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
   if (ctx->gtab) cudaFree(ctx->gtab);
-  if (ctx->gtab30) cudaFree(ctx->gtab30);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->ev_dec0) cudaEventDestroy(ctx->ev_dec0);
   if (ctx->ev_dec1) cudaEventDestroy(ctx->ev_dec1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  delete ctx;  // every DevBuf member frees its allocation (ctx.hpp)
 }
 
 extern "C" const char* dkgv_last_error(const dkgv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -360,7 +291,7 @@ extern "C" int dkgv_last_decode_ms(dkgv_ctx* ctx, float* ms, int* subgroup_check
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventSynchronize(ctx->ev_dec1));
   CK(cudaEventElapsedTime(ms, ctx->ev_dec0, ctx->ev_dec1));
-  if (subgroup_checked) *subgroup_checked = ctx->vv_checked ? 1 : 0;
+  if (subgroup_checked) *subgroup_checked = 1;
   return 0;
 }
 extern "C" int dkgv_sync(dkgv_ctx* ctx) {
@@ -370,65 +301,29 @@ extern "C" int dkgv_sync(dkgv_ctx* ctx) {
   return 0;
 }
 
-// decode vv into the ctx session buffers (asynchronous on s)
-// check_subgroup = false: flags, x < p and the curve equation only - for the consistency shortcut, where a commitment that
-// equals G * p_k is in the subgroup by construction; dkgv_session_redecode_checked redoes it in full before any evaluation
-static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, uint8_t* d_point_status, cudaStream_t s,
-                          VVView* view, uint32_t* n_pad_out, bool layout30 = false, bool check_subgroup = true, bool defer = false) {
+// decode + subgroup-check vv into the ctx session buffers (asynchronous on s)
+static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, cudaStream_t s, VVView* view, uint32_t* n_pad_out) {
   uint32_t n_pad = (n_d + 31) & ~31u;
   uint32_t tt = t ? t : 1;
-  CK(ctx->vv_limbs.reserve((size_t)tt * (layout30 ? 26 : 24) * n_pad * 4));
+  CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
   CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
   CK(ctx->dealer_bad.reserve(n_pad));
   CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
-  if (t && !defer) {
+  if (t) {
     size_t total = (size_t)n_pad * t;
     if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
-    if (layout30)
-      k_decompress_vv30<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                      (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
-    else
-      k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                    (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p,
-                                                                    d_point_status, check_subgroup);
+    k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p, (uint8_t*)ctx->vv_inf.p,
+                                                                  (uint8_t*)ctx->dealer_bad.p, nullptr);
     if (ctx->ev_dec1) CK(cudaEventRecord(ctx->ev_dec1, s));
     ctx->dec_recorded = true;
-    ctx->launches++;
-    CK(cudaGetLastError());
-  }
-  ctx->vv_decoded = !defer;
-  ctx->vv_checked = check_subgroup && !defer;
-  ctx->vv_src = d_vv;
-  ctx->vv_n_d = n_d;
-  ctx->vv_t = t;
-  view->limbs = (const uint32_t*)ctx->vv_limbs.p;
-  view->inf = (const uint8_t*)ctx->vv_inf.p;
-  view->n_pad = n_pad;
-  *n_pad_out = n_pad;
-  return 0;
-}
-
-// share_fd.cu calls this before the evaluation when the session was decoded without subgroup checks
-int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s) {
-  if (ctx->vv_checked) return 0;
-  uint32_t n_pad = (ctx->vv_n_d + 31) & ~31u;
-  size_t total = (size_t)n_pad * ctx->vv_t;
-  if (total && !ctx->vv_decoded) {  // deferred by the shortcut: the full decode, subgroup tests included
-    if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
-    k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ctx->vv_src, ctx->vv_n_d, ctx->vv_t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                  (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p, nullptr, true);
-    if (ctx->ev_dec1) CK(cudaEventRecord(ctx->ev_dec1, s));
-    ctx->dec_recorded = true;
-    ctx->launches++;
-    CK(cudaGetLastError());
-  } else if (total) {
-    k_subgroup_check_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ctx->vv_n_d, ctx->vv_t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                       (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
     ctx->launches++;
     CK(cudaGetLastError());
   }
   ctx->vv_decoded = true;
-  ctx->vv_checked = true;
+  view->limbs = (const uint32_t*)ctx->vv_limbs.p;
+  view->inf = (const uint8_t*)ctx->vv_inf.p;
+  view->n_pad = n_pad;
+  *n_pad_out = n_pad;
   return 0;
 }
 
@@ -472,66 +367,98 @@ extern "C" int dkgv_share_fd_plan(uint32_t t, uint32_t n_r, uint32_t parts_force
 extern "C" int dkgv_last_share_path(const dkgv_ctx* ctx) { return ctx ? ctx->last_share_path : -1; }
 extern "C" int dkgv_last_share_phases_ms(dkgv_ctx* ctx, float* ms4) {
   if (!ctx || !ms4) return -1;
-  if (!ctx->fd_recorded) return fail(ctx, "no finite-difference share verification launched yet");
+  const bool eval = ctx->fd_last_need;  // the last call continued into the evaluation: its phases; else the shortcut's
+  if (eval ? !ctx->fd_recorded : !ctx->sc_recorded) return fail(ctx, "no finite-difference share verification launched yet");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventSynchronize(ctx->ev_fd[4]));
-  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(ms4 + i, ctx->ev_fd[i], ctx->ev_fd[i + 1]));
+  cudaEvent_t* ev = eval ? ctx->ev_fd : ctx->ev_sc;
+  CK(cudaEventSynchronize(ev[4]));
+  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(ms4 + i, ev[i], ev[i + 1]));
   return 0;
 }
 
-// h_ids: host copy of the ids when the caller has one (else fetched from the device when the path
-// selection needs it)
-static int share_matrix_dev_impl(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
-                                 const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
+// Horner per share over the whole matrix (arbitrary ids, or shapes where finite differences do not pay); asynchronous
+static int share_matrix_horner(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
+                               const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
   VVView view;
   uint32_t n_pad;
-#ifdef DKGV_HOT_FP30
-  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, true);
-  if (rc) return rc;
-  HotView hv{view.limbs, view.inf, view.n_pad};
-  const uint32_t* hot_tab = ctx->gtab30;
-#else
-  // Recipient ids that are the consecutive ranks 1..n_r (always the case for a ceremony,
-  // verification.rs:50-66,129) allow t Horner evaluations + finite differences per dealer.
-  bool use_fd = false;
-  FdPlan plan{};
-  std::vector<uint32_t> fetched;  // must outlive the finite-difference call (it reads the ids again)
-  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r >= 3 && n_r <= 65535 && t <= 65535 * FD_MAX_PARTS) {
-    if (!h_ids) {  // device-pointer entry: fetch the (tiny) id list before any work is queued
-      fetched.resize(n_r);
-      CK(cudaMemcpyAsync(fetched.data(), d_ids, (size_t)n_r * 4, cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      h_ids = fetched.data();
-    }
-    if (dkgv_fd_ids_consecutive(h_ids, n_r)) {
-      // planned for the full evaluation (n_opt = 0): measured within 0.5 % of the shortcut-optimal split on an honest ceremony
-      // (553 vs 551 ms at 1024 / 683) and 2 % better when the groups have to continue (734 vs 750 ms)
-      plan = fd_make_plan(t, n_r, ctx->share_parts, 0);
-      use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
-    }
-  }
-  // with the consistency shortcut ahead, the subgroup checks (2/3 of the decode) wait until a dealer group needs the evaluation
-  bool lazy_subgroup = use_fd && ctx->fd_polycheck && n_r > t && t <= 1024;
-  // ... and with condition (3) checked against the compressed commitments the whole decode waits (share_fd.cu k_fd_coefpoint)
-  int rc = session_decode(ctx, n_d, t, d_vv, nullptr, s, &view, &n_pad, false, !lazy_subgroup, lazy_subgroup && dkgv_fd_defers_decode());
-  if (rc) return rc;
-  if (use_fd) {
-    ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;
-    return dkgv_share_matrix_fd(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, s);
-  }
-  HotView hv = view;
-  const uint32_t* hot_tab = ctx->gtab;
-#endif
+  if (int rc = session_decode(ctx, n_d, t, d_vv, s, &view, &n_pad)) return rc;
   ctx->last_share_path = DKGV_SHARE_PATH_HORNER;
   dim3 grid(n_pad / 32, (n_r + SVM_NT / 32 - 1) / (SVM_NT / 32));
   CK(cudaEventRecord(ctx->ev_hot0, s));
-  k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(hv, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, hot_tab, d_status,
-                                              n_d, n_r, t);
+  k_share_verify<<<grid, SVM_NT, SVM_SMEM, s>>>(view, (const uint8_t*)ctx->dealer_bad.p, d_ids, d_shares, ctx->gtab, d_status, n_d, n_r, t);
   CK(cudaEventRecord(ctx->ev_hot1, s));
   ctx->hot_recorded = true;
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+// Queue the default path without synchronising.  Recipient ids that are the consecutive ranks 1..n_r (always the case for a
+// ceremony, verification.rs:50-66,129) allow the consistency shortcut and, behind it, t Horner evaluations + finite differences
+// per dealer.  Whether the ids are such a permutation is decided ON THE DEVICE (flags[0]) while the shortcut already runs
+// speculatively; whether any dealer group still needs the evaluation is flags[1].  share_finish acts on the two words.
+static int share_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
+                        const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags, cudaStream_t s) {
+  dkgv_ctx::ShareJob& job = ctx->job;
+  job = dkgv_ctx::ShareJob();
+  job.n_d = n_d, job.n_r = n_r, job.t = t;
+  job.d_vv = d_vv, job.d_ids = d_ids, job.d_shares = d_shares, job.d_status = d_status;
+  job.d_flags = d_flags ? d_flags : ctx->job_flags;
+  job.parts = ctx->share_parts;
+  job.open = true;
+  ctx->fd_last_need = false;
+  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r >= 3 && n_r <= 65535 && t <= 65535 * FD_MAX_PARTS) {
+    // planned for the full evaluation (n_opt = 0): measured within 0.5 % of the shortcut-optimal split on an honest ceremony
+    // (553 vs 551 ms at 1024 / 683) and 2 % better when the groups have to continue (734 vs 750 ms)
+    FdPlan plan = fd_make_plan(t, n_r, ctx->share_parts, 0);
+    job.fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
+  }
+  if (!job.fd) {  // nothing to speculate on: the whole Horner route is queued now
+    CK(cudaMemsetAsync(job.d_flags, 0, 8, s));
+    return share_matrix_horner(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, s);
+  }
+  job.shortcut = dkgv_fd_shortcut_applies(ctx, n_r, t);
+  ctx->last_share_path = DKGV_SHARE_PATH_FDIFF;
+  ctx->vv_decoded = false;  // compress(G * p_k) == C_k needs no decompression; the decode waits until a group needs the evaluation
+  return dkgv_fd_submit(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, job.shortcut, job.d_flags, s);
+}
+
+// h_flags: the two flag words of the job as read back by the caller (after synchronising the stream), or nullptr: read them
+// here (one stream synchronisation).  Queues whatever the flags ask for: nothing (an honest ceremony), the evaluation of the
+// dealer groups the shortcut could not settle, or the Horner route when the ids were no permutation of 1..n_r.
+static int share_finish(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) {
+  dkgv_ctx::ShareJob job = ctx->job;
+  if (!job.open) return dkgv_fail(ctx, "no share-matrix job submitted");
+  ctx->job.open = false;
+  if (!job.fd) return 0;
+  if (!h_flags) {
+    CK(cudaMemcpyAsync(ctx->h_job_flags, job.d_flags, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h_flags = ctx->h_job_flags;
+  }
+  if (h_flags[0]) return share_matrix_horner(ctx, job.n_d, job.n_r, job.t, job.d_vv, job.d_ids, job.d_shares, job.d_status, s);
+  if (!h_flags[1]) return 0;  // every verdict is OK and already written
+  ctx->fd_last_need = true;
+  VVView view;
+  uint32_t n_pad;
+  if (int rc = session_decode(ctx, job.n_d, job.t, job.d_vv, s, &view, &n_pad)) return rc;
+  FdPlan plan = fd_make_plan(job.t, job.n_r, job.parts, 0);
+  return dkgv_share_matrix_fd(ctx, view, job.n_d, job.n_r, job.t, plan, job.d_ids, job.d_shares, job.d_status,
+                              job.shortcut ? dkgv_fd_need_groups(ctx, job.n_d) : nullptr, s);
+}
+
+extern "C" int dkgv_share_matrix_submit_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
+                                            const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags2,
+                                            void* stream) {
+  if (!ctx) return -1;
+  if (!d_ids || !d_shares || !d_status || (t && !d_vv) || n_d == 0 || n_r == 0) return fail(ctx, "null pointer or empty matrix");
+  CK(cudaSetDevice(ctx->device));
+  return share_submit(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, d_flags2, stream ? (cudaStream_t)stream : ctx->stream);
+}
+extern "C" int dkgv_share_matrix_finish_dev(dkgv_ctx* ctx, const uint32_t* h_flags2, void* stream) {
+  if (!ctx) return -1;
+  CK(cudaSetDevice(ctx->device));
+  return share_finish(ctx, h_flags2, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
 extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
@@ -541,7 +468,8 @@ extern "C" int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_
   if (!d_ids || !d_shares || !d_status || (t && !d_vv)) return fail(ctx, "null pointer argument");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-  return share_matrix_dev_impl(ctx, n_d, n_r, t, d_vv, d_ids, nullptr, d_shares, d_status, s);
+  if (int rc = share_submit(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, nullptr, s)) return rc;
+  return share_finish(ctx, nullptr, s);
 }
 
 extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* vv,
@@ -559,11 +487,19 @@ extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_
   if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->in_c.p, shares, shb, cudaMemcpyHostToDevice, s));
-  int rc = share_matrix_dev_impl(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, ids,
-                                 (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, s);
-  if (rc) return rc;
+  if (int rc = share_submit(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (const uint8_t*)ctx->in_c.p,
+                            (uint8_t*)ctx->out_a.p, nullptr, s))
+    return rc;
+  // the verdicts and the two flag words come back together: ONE synchronisation when the shortcut settled the ceremony
   CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->h_job_flags, ctx->job.d_flags, 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  const bool more = ctx->job.fd && (ctx->h_job_flags[0] || ctx->h_job_flags[1]);
+  if (int rc = share_finish(ctx, ctx->h_job_flags, s)) return rc;
+  if (more) {
+    CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   return 0;
 }
 
@@ -620,7 +556,7 @@ extern "C" int dkgv_share_items_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r
   CK(cudaMemcpyAsync(d_wf, wf.data(), (size_t)(n_warps + 1) * 4, cudaMemcpyHostToDevice, s));
   VVView view;
   uint32_t n_pad;
-  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, nullptr, s, &view, &n_pad, false);
+  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, s, &view, &n_pad);
   if (rc) return rc;
   k_share_items<<<n_warps, 32, (size_t)VM_SLOTS * 3 * 32 * sizeof(U4), s>>>(view, (const uint8_t*)ctx->dealer_bad.p,
                                                                            (const uint32_t*)ctx->in_b.p, d_sd, d_sc, d_so, d_wf,
@@ -647,7 +583,7 @@ extern "C" int dkgv_feldman_eval(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_ids, ui
   CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
   VVView view;
   uint32_t n_pad;
-  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, nullptr, s, &view, &n_pad);
+  int rc = session_decode(ctx, n_d, t, (const uint8_t*)ctx->in_a.p, s, &view, &n_pad);
   if (rc) return rc;
   FdPlan plan{};
   bool use_fd = false;

@@ -8,10 +8,11 @@
 //   k_fd_ext      steps + h - 2 wavefront ticks                (1 point addition per item)
 //   k_fd_digits   signed digits of the public recombination scalars x^(h i) mod r, one thread per id
 //   k_fd_combine  sum_i [y^i] f_i(x) by joint double-and-add, G * s, compare: one thread per share
-// before them the consistency shortcut (k_fd_tables / k_fd_share_limbs / k_fd_difftab / k_fd_coefpoint / k_fd_coefsign /
-// k_fd_need / k_fd_fill_ok, see below; k_fd_polycheck / k_fd_interp / k_fd_coefcheck are the formulations they replaced, kept
-// behind DKGV_FD_DIFFTAB=0 / DKGV_FD_BYTES=0 for A/B tests): a dealer group whose shares are provably all valid never enters
-// the evaluation, and its commitments are never decompressed.
+// before them the consistency shortcut (k_fd_cols / k_fd_tables / k_fd_share_limbs / k_fd_difftab / k_fd_coefpoint /
+// k_fd_coefsign / k_fd_need / k_fd_fill_ok, see below): a dealer group whose shares are provably all valid never enters
+// the evaluation, and its commitments are never decompressed.  The shortcut is queued WITHOUT any host synchronisation
+// (dkgv_share_submit); whether some dealer group still needs the evaluation is a device flag the caller reads together
+// with its results (dkgv_share_finish).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -21,16 +22,7 @@
 
 using namespace dkgv;
 
-int dkgv_session_redecode_checked(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
 
-#ifndef DKGV_FD_BYTES_DEFAULT
-#define DKGV_FD_BYTES_DEFAULT 1  // B200 parity run green (tests/test_gpu_share.py test_shortcut_formulations_agree); 0: lazy decode + k_fd_coefcheck
-#endif
-constexpr bool FD_BYTES_DEFAULT = DKGV_FD_BYTES_DEFAULT != 0;
-static bool g_fd_bytes = FD_BYTES_DEFAULT;         // condition (3) against the compressed commitments, decode deferred (k_fd_coefpoint + k_fd_coefsign);
-                                       // DKGV_FD_BYTES=0: lazy decode + k_fd_coefcheck (A/B tests)
-static bool g_fd_difftab = true;      // fused difference table (k_fd_difftab); DKGV_FD_DIFFTAB=0: k_fd_polycheck + k_fd_interp (A/B tests)
-static uint32_t g_fd_ipb_force = 0;  // items per block of the difference / extension launches, DKGV_FD_IPB (experiments)
 constexpr int FD_NT = 32;  // one warp per block: 32 consecutive dealers, one entry (cf. SVM_NT in dkgv.cu)
 constexpr size_t FD_SMEM = (size_t)VM_SLOTS * 3 * FD_NT * sizeof(U4);
 
@@ -115,7 +107,8 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // the exact per-share verdicts.  Exact and deterministic - no random linear combination.
 // Default formulation: (2) and the interpolation in one difference table per dealer (k_fd_difftab), (3) against the
 // compressed commitments (k_fd_coefpoint + k_fd_coefsign) with the decode deferred until a group needs the evaluation.
-constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // k_fd_interp: one thread per coefficient; fr_submul_small: factors j < 2^10 (dkgv.cu's lazy_subgroup uses the same bound)
+constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // fr_submul_small: factors j < 2^10
+constexpr uint32_t FD_SHORTCUT_MAX_N = 2048;  // k_fd_difftab: one block per dealer, two entries per thread
 
 // c[j] = (-1)^j C(t, j) mod r (j = 0..t), inv[j] = 1/j mod r (j = 1..t) and ifact[j] = 1/j! mod r, Montgomery form; one thread per j
 __global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restrict__ c, uint32_t* __restrict__ inv, uint32_t* __restrict__ ifact) {
@@ -159,93 +152,16 @@ k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict_
   uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
   if (xi >= n_r || d0 + dl >= n_d) return;
   uint32_t l[8];
-  bool ok = fr_raw_from_be32(l, shares + ((size_t)(d0 + dl) * n_r + cols[xi]) * 32);
+  uint32_t c = cols[xi];
+  if (c >= n_r) c = 0;  // ids that are not a permutation: the speculative run reads in bounds, its results are discarded
+  bool ok = fr_raw_from_be32(l, shares + ((size_t)(d0 + dl) * n_r + c) * 32);
   if (!ok) poly_ok[d0 + dl] = 0;
   uint32_t* o = sl + ((size_t)dl * n_r + xi) * 8;
 #pragma unroll
   for (int i = 0; i < 8; i++) o[i] = l[i];
 }
 
-// condition (2): one block per dealer, one thread per window x = w + 1; poly_ok[d] = 0 when a t-th difference is non-zero
-__global__ void __launch_bounds__(256)
-k_fd_polycheck(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ c, uint8_t* __restrict__ poly_ok, uint32_t d0, uint32_t n_d,
-               uint32_t n_r, uint32_t t) {
-  uint32_t dl = blockIdx.x;
-  if (d0 + dl >= n_d) return;
-  const uint32_t* row = sl + (size_t)dl * n_r * 8;
-  bool bad = false;
-  for (uint32_t w = threadIdx.x; w + t < n_r; w += blockDim.x) {
-    Fr acc = zero<FrParams>();
-#pragma unroll 1
-    for (uint32_t j = 0; j <= t; j++) {
-      Fr sv, cv;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        sv.l[i] = row[(size_t)(w + j) * 8 + i];
-        cv.l[i] = c[(size_t)j * 8 + i];
-      }
-      acc = add(acc, mul(sv, cv));  // canonical share x Montgomery coefficient = canonical product
-    }
-    bad |= !is_zero(acc);
-  }
-  if (bad) poly_ok[d0 + dl] = 0;
-}
-
-// p = the polynomial of degree <= t-1 through (x, s(x)), x = 1..t, as canonical monomial coefficients coef[dl][k][8]:
-// forward differences D_j = Delta^j s(1), then Horner in the Newton basis, P <- P (x - j) / j + D_{j-1}, on coefficient
-// vectors: new_c[i] = c[i-1] / j - c[i].  One block per dealer, thread i owns coefficient i; 3 x t Fr values in shared memory.
-__global__ void __launch_bounds__(1024)
-k_fd_interp(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ inv, uint32_t* __restrict__ coef, const uint8_t* __restrict__ poly_ok,
-            uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
-  extern __shared__ uint32_t fr_sm[];  // [3][t][8]
-  uint32_t dl = blockIdx.x, i = threadIdx.x;
-  if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a dealer that already failed (1) or (2) needs no interpolation
-  Fr* A = (Fr*)fr_sm;
-  Fr* B = A + t;
-  Fr* D = B + t;
-  if (i < t) {
-    Fr v;
-#pragma unroll
-    for (int l = 0; l < 8; l++) v.l[l] = sl[((size_t)dl * n_r + i) * 8 + l];
-    A[i] = to_mont(v);
-  }
-  __syncthreads();
-  Fr* cur = A;
-  Fr* nxt = B;
-  for (uint32_t r = 1; r < t; r++) {
-    if (i < t) nxt[i] = i >= r ? sub(cur[i], cur[i - 1]) : cur[i];
-    __syncthreads();
-    Fr* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
-  }
-  if (i < t) D[i] = cur[i];
-  __syncthreads();
-  if (i < t) cur[i] = i == 0 ? D[t - 1] : zero<FrParams>();
-  __syncthreads();
-  for (uint32_t j = t - 1; j >= 1; j--) {
-    if (i < t) {
-      Fr ij;
-#pragma unroll
-      for (int l = 0; l < 8; l++) ij.l[l] = inv[(size_t)j * 8 + l];
-      Fr v = i >= 1 ? sub(mul(cur[i - 1], ij), cur[i]) : neg(cur[0]);
-      if (i == 0) v = add(v, D[j - 1]);
-      nxt[i] = v;
-    }
-    __syncthreads();
-    Fr* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
-  }
-  if (i < t) {
-    Fr v = from_mont(cur[i]);
-#pragma unroll
-    for (int l = 0; l < 8; l++) coef[((size_t)dl * t + i) * 8 + l] = v.l[l];
-  }
-}
-
-// Conditions (2) and the interpolation in ONE difference table per dealer (replaces k_fd_polycheck + k_fd_interp for
-// n_r <= 2048), canonical residues, no products except by small integers (fdiff.cuh, "difference table"):
+// Condition (2) and the interpolation in ONE difference table per dealer (n_r <= 2048), canonical residues, no products except by small integers (fdiff.cuh, "difference table"):
 //   phase 1  t rounds e[k] <- e[k] - e[k-1] (k >= r) over all n_r shares: e[k] = Delta^k s(1) for k < t, and the entries
 //            k >= t are the t-th differences Delta^t s(k-t+1) - all zero <=> condition (2);
 //   phase 2  E_k = e[k] / k!, then P <- P (x - j) + E_{j-1} for j = t-1 .. 1 on monomial coefficients: c[k] <- c[k-1] - j c[k].
@@ -313,38 +229,8 @@ k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact
   }
 }
 
-// condition (3): G * p_k against the decoded commitment C_k; warp = 32 dealers x one k (the layout of the seeds)
-__global__ void __launch_bounds__(FD_NT)
-k_fd_coefcheck(VVView vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ poly_ok, uint32_t d0,
-               uint32_t n_d, uint32_t t) {
-  extern __shared__ U4 opfile[];
-  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
-  bool active = d0 + dl < n_d;
-  uint32_t dc = active ? dl : n_d - 1 - d0;
-#if defined(__CUDA_ARCH__)
-  if (__ballot_sync(0xffffffffu, active && poly_ok[d0 + dl]) == 0) return;  // nobody in this group can still pass
-#endif
-  OpFile f{opfile + threadIdx.x, FD_NT};
-  uint32_t sc[8];
-#pragma unroll
-  for (int l = 0; l < 8; l++) sc[l] = coef[((size_t)dc * t + k) * 8 + l];
-  vm_fixed_base_mul(f, gtab, sc);  // B = G * p_k
-  G1Aff c = vv_load(vv, k, d0 + dc);
-  bool same;
-  if (c.inf) {
-    same = is_zero(of_load(f, BZ));
-  } else {
-    of_store(f, T0, c.x);
-    of_store(f, T1, c.y);
-    vm_mul(f, T2, T0, BZ);
-    vm_mul(f, T3, T1, BZ);
-    same = !is_zero(of_load(f, BZ)) && vm_eq(f, T2, BX) && vm_eq(f, T3, BY);
-  }
-  if (active && !same) poly_ok[d0 + dl] = 0;
-}
-
 // condition (3) WITHOUT decoding the commitments (fdiff.cuh, "against the COMPRESSED commitment"): x half.  Same launch shape
-// as k_fd_coefcheck; writes Z (limbs 0..11) and Y (12..23) of G * p_k to the chunk-local planes yz[(k*24 + w) * n_cols + dl].
+// (warp = 32 dealers x one k, the layout of the seeds); writes Z (limbs 0..11) and Y (12..23) of G * p_k to the chunk-local planes yz[(k*24 + w) * n_cols + dl].
 __global__ void __launch_bounds__(FD_NT)
 k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab,
                uint8_t* __restrict__ poly_ok, uint32_t* __restrict__ yz, uint32_t d0, uint32_t n_d, uint32_t n_cols, uint32_t t) {
@@ -393,24 +279,49 @@ k_fd_coefsign(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ yz, u
   if (!fd_coef_signs<FD_SIGN_K>(z, y, fs, cnt)) poly_ok[d0 + dl] = 0;
 }
 
-// need_group[g] = 1 when some dealer of the 32-dealer group g (of this chunk) fails a condition or has an undecodable commitment
-__global__ void __launch_bounds__(128)
-k_fd_need(const uint8_t* __restrict__ poly_ok, const uint8_t* __restrict__ dealer_bad, uint32_t d0, uint32_t n_cols, uint32_t n_d,
-          uint8_t* __restrict__ need_group, uint32_t* __restrict__ any_need) {
-  uint32_t dl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (dl >= n_cols || d0 + dl >= n_d) return;
-  if (dealer_bad[d0 + dl] != 0 || poly_ok[d0 + dl] == 0) {
-    need_group[dl / 32] = 1;
-    atomicOr(any_need, 1u);
+// cols[x - 1] = the column j with ids[j] == x (columns in ascending-id order); flags[0] = 1 when the ids are not a permutation of
+// 1..n_r (then nothing the speculative shortcut wrote counts and dkgv_share_finish takes the Horner route).  cols starts at 0xffffffff.
+__global__ void __launch_bounds__(128) k_fd_cols(const uint32_t* __restrict__ ids, uint32_t n_r, uint32_t* __restrict__ cols, uint32_t* __restrict__ flags) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_r) return;
+  uint32_t x = ids[j];
+  if (x < 1 || x > n_r) {
+    atomicOr(&flags[0], 1u);
+    return;
+  }
+  if (atomicExch(&cols[x - 1], j) != 0xffffffffu) atomicOr(&flags[0], 1u);
+}
+
+// start of a submitted job: cols = 0xffffffff, poly_ok = 1, need_group = 0, flags = {0, pending0}
+__global__ void __launch_bounds__(256) k_fd_prep(uint32_t* __restrict__ cols, uint32_t n_r, uint8_t* __restrict__ poly_ok, uint32_t n_pad,
+                                                 uint8_t* __restrict__ need_group, uint32_t* __restrict__ flags, uint32_t pending0) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_r) cols[i] = 0xffffffffu;
+  if (i < n_pad) poly_ok[i] = 1;
+  if (i < n_pad / 32) need_group[i] = 0;
+  if (i == 0) {
+    flags[0] = 0;
+    flags[1] = pending0;
   }
 }
 
-// verdict OK for every share of the dealer groups that met the three conditions
+// need_group[g] = 1 when some dealer of the 32-dealer group g fails a condition; flags[1] counts the failing dealers
 __global__ void __launch_bounds__(128)
-k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
-  if (j >= n_r || d0 + dl >= n_d || need_group[dl / 32]) return;
-  status[(size_t)(d0 + dl) * n_r + j] = DKGV_OK;
+k_fd_need(const uint8_t* __restrict__ poly_ok, uint32_t n_d, uint8_t* __restrict__ need_group, uint32_t* __restrict__ flags) {
+  uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_d) return;
+  if (poly_ok[d] == 0) {
+    need_group[d / 32] = 1;
+    atomicAdd(&flags[1], 1u);
+  }
+}
+
+// verdict OK for every share of the dealer groups that met the three conditions (block = 128 columns of one dealer)
+__global__ void __launch_bounds__(128)
+k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, uint32_t n_d, uint32_t n_r) {
+  uint32_t j = blockIdx.y * blockDim.x + threadIdx.x, d = blockIdx.x;
+  if (j >= n_r || d >= n_d || need_group[d / 32]) return;
+  status[(size_t)d * n_r + j] = DKGV_OK;
 }
 
 // evaluate_polynomial output instead of the share comparison: out[dealer][column j] = compress(f_d(ids[j]))
@@ -438,24 +349,23 @@ k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, con
   }
 }
 
+
 int dkgv_fd_setup(dkgv_ctx* ctx) {
   for (const void* k : {(const void*)k_fd_seed, (const void*)k_fd_init, (const void*)k_fd_ext, (const void*)k_fd_combine,
-                        (const void*)k_fd_combine_out, (const void*)k_fd_coefcheck, (const void*)k_fd_coefpoint}) {
+                        (const void*)k_fd_combine_out, (const void*)k_fd_coefpoint}) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
-  if (const char* e = getenv("DKGV_FD_IPB")) g_fd_ipb_force = (uint32_t)atoi(e);
-  CK(cudaFuncSetAttribute(k_fd_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * FD_SHORTCUT_MAX_T * 32)));
+  if (const char* e = getenv("DKGV_FD_IPB")) ctx->fd_ipb_force = (uint32_t)atoi(e);  // experiments; read once per ctx
   CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 1024 + FD_SHORTCUT_MAX_T) * 32)));
   CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   size_t stack = 0;  // k_fd_coefsign keeps 3 x FD_SIGN_K field elements in local memory (1.2 KB frame); only ever raise the limit
   CK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
   if (stack < 2048) CK(cudaDeviceSetLimit(cudaLimitStackSize, 2048));
-  const char* by = getenv("DKGV_FD_BYTES");
-  g_fd_bytes = by ? atoi(by) != 0 : FD_BYTES_DEFAULT;
-  const char* dt = getenv("DKGV_FD_DIFFTAB");
-  g_fd_difftab = !dt || atoi(dt) != 0;
-  for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev_fd[i]));
+  for (int i = 0; i < 5; i++) {
+    CK(cudaEventCreate(&ctx->ev_fd[i]));
+    CK(cudaEventCreate(&ctx->ev_sc[i]));
+  }
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
     CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
@@ -463,9 +373,6 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
   }
   return 0;
 }
-
-// the share-matrix entry may skip the decode of the commitments until a dealer group needs the evaluation
-bool dkgv_fd_defers_decode() { return g_fd_bytes; }
 
 // ids (host copy) a permutation of 1..n_r ?
 bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
@@ -478,38 +385,29 @@ bool dkgv_fd_ids_consecutive(const uint32_t* h_ids, uint32_t n_r) {
   return true;
 }
 
-// Items (point additions) per block of the difference / extension launches.  One per block is the
-// measured optimum on B200 (n=1024, t=683, N=1: extension 336 ms with 1, 344 ms with 2, 367 ms with 4 items):
-// block scheduling is not what the one-addition blocks lose time on.  DKGV_FD_IPB overrides (experiments).
-static inline uint32_t items_per_block(uint32_t, uint32_t) { return g_fd_ipb_force ? g_fd_ipb_force : 1; }
+// the consistency shortcut can settle this shape (else every share goes through the evaluation)
+bool dkgv_fd_shortcut_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t) {
+  return ctx->fd_polycheck && t >= 1 && n_r > t && t <= FD_SHORTCUT_MAX_T && n_r <= FD_SHORTCUT_MAX_N;
+}
 
-// dealers d0 .. d0 + n_pad - 1 (n_pad a multiple of 32: the column count of this chunk's planes)
-static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad, uint32_t n_d, uint32_t n_r, uint32_t t,
-                  const FdPlan& plan, const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status,
-                  uint8_t* d_out48, cudaStream_t s) {
-  const uint32_t m = plan.m, h = plan.h;
-  const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
-  const uint32_t groups = n_pad / 32, n_here = std::min(n_pad, n_d - d0);
-  const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
-  const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
+// Queues, WITHOUT synchronising: cols from the device ids (flags[0] = ids are not a permutation of 1..n_r) and, when `shortcut`,
+// the consistency shortcut over all dealers - verdict OK written for every dealer group that met the three conditions,
+// need_group / flags[1] = the dealers that did not.  Without the shortcut flags[1] = 1: everything is still pending.
+int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
+                   uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s) {
+  const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
   CK(ctx->fd_cols.reserve((size_t)n_r * 4));
-  const uint32_t* cols = (const uint32_t*)ctx->fd_cols.p;
-  ctx->fd_cols_host.resize(n_r);  // columns in ascending-id order
-  for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
-  CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(ctx->ev_fd[0], s));
+  CK(ctx->fd_flags.reserve((size_t)n_pad + groups));
+  uint32_t* cols = (uint32_t*)ctx->fd_cols.p;
+  uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
+  uint8_t* need_group = poly_ok + n_pad;
+  CK(cudaEventRecord(ctx->ev_sc[0], s));
   CK(cudaEventRecord(ctx->ev_hot0, s));
-
-  // ---- consistency shortcut: settle whole dealer groups by scalar arithmetic + t fixed-base multiplications
-  const uint8_t* filter = nullptr;  // dealer groups that go through the evaluation (nullptr: all)
-  ctx->fd_last_need = true;
-  if (ctx->fd_polycheck && d_shares && !d_out48 && n_r > t && t <= FD_SHORTCUT_MAX_T) {
-    CK(ctx->fd_sl.reserve((size_t)n_pad * n_r * 32));
-    CK(ctx->fd_coef.reserve((size_t)n_pad * t * 32));
-    CK(ctx->fd_flags.reserve((size_t)n_d + groups + 16));
-    uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
-    uint8_t* need_group = poly_ok + n_d;
-    uint32_t* any_need = (uint32_t*)(((uintptr_t)(need_group + groups) + 7) & ~(uintptr_t)7);
+  const uint32_t prep_n = std::max(n_r, n_pad);
+  k_fd_prep<<<(prep_n + 255) / 256, 256, 0, s>>>(cols, n_r, poly_ok, n_pad, need_group, d_flags, shortcut ? 0u : 1u);
+  k_fd_cols<<<(n_r + 127) / 128, 128, 0, s>>>(d_ids, n_r, cols, d_flags);
+  ctx->launches += 2;
+  if (shortcut) {
     if (ctx->fd_binom_t != t) {
       CK(ctx->fd_binom.reserve((size_t)(t + 1) * 96));
       k_fd_tables<<<(t + 128) / 128, 128, 0, s>>>(t, (uint32_t*)ctx->fd_binom.p, (uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 8,
@@ -517,60 +415,60 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       ctx->fd_binom_t = t;
       ctx->launches++;
     }
-    const uint32_t* binom = (const uint32_t*)ctx->fd_binom.p;
-    const uint32_t* invtab = binom + (size_t)(t + 1) * 8;
-    CK(cudaMemsetAsync(poly_ok + d0, 1, n_here, s));
-    CK(cudaMemsetAsync(need_group, 0, groups + 16, s));
-    k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_pad, n_d, n_r);
-    const bool fused = g_fd_difftab && n_r <= 2048 && t >= 1;
-    if (fused) {
-      const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
-      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab + (size_t)(t + 1) * 8,
-                                                               (uint32_t*)ctx->fd_coef.p, poly_ok, d0, n_d, n_r, t);
-    } else {
-      k_fd_polycheck<<<n_here, 256, 0, s>>>((const uint32_t*)ctx->fd_sl.p, binom, poly_ok, d0, n_d, n_r, t);
-      k_fd_interp<<<n_here, ((t + 31) / 32) * 32, (size_t)3 * t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, invtab, (uint32_t*)ctx->fd_coef.p, poly_ok,
-                                                                         d0, n_d, n_r, t);
+    const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
+    // dealer chunks: share limbs + coefficients + Y/Z planes of a chunk stay within a 4 GB budget (123 MB at (1024, 683))
+    const size_t per_dealer = (size_t)n_r * 32 + (size_t)t * 128;
+    const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
+    CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
+    CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
+    CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
+    const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
+    const uint32_t batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
+    for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
+      const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
+      const bool first = d0 == 0, last = d0 + chunk >= n_d;
+      k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_cols, n_d, n_r);
+      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, d0, n_d, n_r, t);
+      if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
+      k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
+                                                             n_d, n_cols, t);
+      if (first) CK(cudaEventRecord(ctx->ev_sc[2], s));
+      k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d, n_cols, t);
+      if (last) CK(cudaEventRecord(ctx->ev_sc[3], s));
+      ctx->launches += 4;
     }
-    CK(cudaEventRecord(ctx->ev_fd[1], s));  // shortcut phases: [limbs + difference table | x halves | sign halves | flags]
-    const bool bytes = !ctx->vv_decoded;  // the decode was deferred: compare against the compressed commitments
-    if (bytes) {
-      CK(ctx->fd_yz.reserve((size_t)t * 24 * n_pad * 4));
-      k_fd_coefpoint<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(ctx->vv_src, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok,
-                                                             (uint32_t*)ctx->fd_yz.p, d0, n_d, n_pad, t);
-      CK(cudaEventRecord(ctx->ev_fd[2], s));
-      const uint32_t batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
-      k_fd_coefsign<<<dim3(groups, (batches + 3) / 4), dim3(32, 4), 0, s>>>(ctx->vv_src, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d,
-                                                                         n_pad, t);
-      ctx->launches++;
-    } else {
-      k_fd_coefcheck<<<dim3(groups, t), FD_NT, FD_SMEM, s>>>(view, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, d0, n_d, t);
-      CK(cudaEventRecord(ctx->ev_fd[2], s));
-    }
-    CK(cudaEventRecord(ctx->ev_fd[3], s));
-    k_fd_need<<<(n_pad + 127) / 128, 128, 0, s>>>(poly_ok, (const uint8_t*)ctx->dealer_bad.p, d0, n_pad, n_d, need_group, any_need);
-    k_fd_fill_ok<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_status, need_group, d0, n_pad, n_d, n_r);
-    ctx->launches += fused ? 5 : 6;
-    uint32_t h_any = 0;
-    CK(cudaMemcpyAsync(&h_any, any_need, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
-    if (!h_any) {  // an honest chunk: every verdict is OK and already written
-      ctx->fd_last_need = false;
-      CK(cudaEventRecord(ctx->ev_hot1, s));
-      CK(cudaEventRecord(ctx->ev_fd[4], s));
-      ctx->hot_recorded = true;
-      ctx->fd_recorded = true;
-      return 0;
-    }
-    filter = need_group;
+    k_fd_need<<<(n_d + 127) / 128, 128, 0, s>>>(poly_ok, n_d, need_group, d_flags);
+    k_fd_fill_ok<<<dim3(n_d, (n_r + 127) / 128), 128, 0, s>>>(d_status, need_group, n_d, n_r);
+    ctx->launches += 2;
+  } else {
+    for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_sc[i], s));
   }
-  // the evaluation (and its PANIC_BAD_G1 verdicts) needs subgroup-checked commitments; only the share-matrix entry decodes
-  // lazily (the evaluation-output callers bring their own fully decoded view)
-  if (d_shares && !d_out48)
-    if (int rc = dkgv_session_redecode_checked(ctx, s)) return rc;
+  CK(cudaEventRecord(ctx->ev_sc[4], s));
+  CK(cudaEventRecord(ctx->ev_hot1, s));
+  ctx->hot_recorded = true;
+  ctx->sc_recorded = true;
+  CK(cudaGetLastError());
+  return 0;
+}
+const uint8_t* dkgv_fd_need_groups(const dkgv_ctx* ctx, uint32_t n_d) { return (const uint8_t*)ctx->fd_flags.p + ((n_d + 31) & ~31u); }
 
-  // ---- evaluation of f_d at every id (for the dealer groups of `filter`)
+// Items (point additions) per block of the difference / extension launches.  One per block is the
+// measured optimum on B200 (n=1024, t=683, N=1: extension 336 ms with 1, 344 ms with 2, 367 ms with 4 items):
+// block scheduling is not what the one-addition blocks lose time on.  DKGV_FD_IPB overrides (experiments).
+static inline uint32_t items_per_block(const dkgv_ctx* ctx) { return ctx->fd_ipb_force ? ctx->fd_ipb_force : 1; }
+
+// Evaluation of dealers d0 .. d0 + n_pad - 1 (n_pad a multiple of 32: the column count of this chunk's planes) at every id;
+// cols (device) = columns in ascending-id order; filter (per 32-dealer group of this chunk, or nullptr = all): the groups to evaluate
+static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad, uint32_t n_d, uint32_t n_r, uint32_t t,
+                  const FdPlan& plan, const uint32_t* d_ids, const uint32_t* cols, const uint8_t* d_shares, uint8_t* d_status,
+                  uint8_t* d_out48, const uint8_t* filter, cudaStream_t s) {
+  const uint32_t m = plan.m, h = plan.h;
+  const uint32_t n_padv = n_pad * m;  // plane width: one column per virtual dealer
+  const uint32_t groups = n_pad / 32;
+  const size_t ent_words = (size_t)36 * n_padv, ent_bytes = ent_words * 4;
+  const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
+  CK(cudaEventRecord(ctx->ev_fd[0], s));
+  CK(cudaEventRecord(ctx->ev_hot0, s));
   CK(ctx->fd_evals.reserve(n_evals * ent_bytes));
   CK(ctx->fd_p0.reserve((size_t)h * ent_bytes));
   CK(ctx->fd_p1.reserve((size_t)h * ent_bytes));
@@ -603,6 +501,7 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
   const size_t e_hi = (size_t)(plan.hi - plan.lo);  // == h - 1
   const uint32_t ticks = plan.steps + h - 2;
   const bool overlap = ctx->fd_overlap && m > 1;
+  const uint32_t ipb = items_per_block(ctx);
   if (!overlap) {
     // one stream, phase after phase over all parts at once (also the mode that yields per-phase times)
     k_fd_seed<<<dim3(gx, h, m), FD_NT, FD_SMEM, s>>>(view, (const int32_t*)ctx->fd_seedx.p, plan.lo, evals, n_d, t, h, 0, n_padv, d0, n_pad,
@@ -616,7 +515,6 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
     const uint32_t* src = evals;
     for (uint32_t r = 1; r < h; r++) {
       uint32_t* dst = pp[r & 1];
-      uint32_t ipb = items_per_block(gxv, h - r);
       k_fd_init<<<dim3(gxv, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(src, dst, dd[0], dd[1], n_padv, h, r, 0, ipb, filter, groups);
       ctx->launches++;
       src = dst;
@@ -627,7 +525,7 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       int32_t k_lo, k_hi;
       fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
       if (k_lo > k_hi) continue;
-      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1);
       k_fd_ext<<<dim3(gxv, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, s>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h, tick,
                                                                       (uint32_t)k_lo, (uint32_t)k_hi, e_hi, 0, ipb, filter, groups);
       ctx->launches++;
@@ -650,7 +548,6 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       CK(cudaMemcpy2DAsync(dd[1] + (size_t)p * n_pad, pitch, col, pitch, w, 36, cudaMemcpyDeviceToDevice, sp));
     }
     for (uint32_t r = 1; r < h; r++) {
-      uint32_t ipb = items_per_block(gxv, h - r);
       for (uint32_t p = 0; p < m; p++) {
         k_fd_init<<<dim3(gx, (h - r + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(r == 1 ? evals : pp[(r - 1) & 1], pp[r & 1], dd[0],
                                                                                             dd[1], n_padv, h, r, p * n_pad, ipb, filter, groups);
@@ -661,7 +558,7 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
       int32_t k_lo, k_hi;
       fd_ext_band(h, plan.steps, tick, &k_lo, &k_hi);
       if (k_lo > k_hi) continue;
-      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1), ipb = items_per_block(gxv, cnt);
+      uint32_t cnt = (uint32_t)(k_hi - k_lo + 1);
       for (uint32_t p = 0; p < m; p++) {
         k_fd_ext<<<dim3(gx, (cnt + ipb - 1) / ipb), FD_NT, FD_SMEM, ctx->fd_streams[p]>>>(dd[(tick & 1) ^ 1], dd[tick & 1], evals, n_padv, h,
                                                                                          tick, (uint32_t)k_lo, (uint32_t)k_hi, e_hi,
@@ -702,30 +599,37 @@ static int fd_run(dkgv_ctx* ctx, const VVView& view, uint32_t d0, uint32_t n_pad
 
 // Dealers are independent, so a ceremony whose planes would not fit the memory budget is processed in
 // dealer chunks (multiples of 32 columns).  (1024, 683) on one GPU needs 1.5 GB of planes + 3.6 GB of tables.
+// filter: need flags per 32-dealer group of the whole session (nullptr = every group)
 static int fd_run_chunks(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, uint8_t* d_out48,
-                         cudaStream_t s) {
+                         const uint32_t* d_ids, const uint32_t* cols, const uint8_t* d_shares, uint8_t* d_status, uint8_t* d_out48,
+                         const uint8_t* filter, cudaStream_t s) {
   const size_t n_evals = (size_t)((int64_t)n_r - plan.lo + 1);
   const size_t bytes_per_col = (n_evals + 4 * (size_t)plan.h) * 36 * plan.m * 4;
   size_t budget = (size_t)12 << 30;
   if (const char* e = getenv("DKGV_FD_PLANE_BUDGET_MB")) budget = (size_t)atoll(e) << 20;  // tests force several chunks
   uint32_t chunk = (uint32_t)std::min<size_t>(view.n_pad, std::max<size_t>(32, (budget / bytes_per_col) & ~(size_t)31));
   for (uint32_t d0 = 0; d0 < view.n_pad && d0 < n_d; d0 += chunk) {
-    uint32_t cols = std::min(chunk, view.n_pad - d0);
-    if (int rc = fd_run(ctx, view, d0, cols, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, d_out48, s)) return rc;
+    uint32_t ncols = std::min(chunk, view.n_pad - d0);
+    if (int rc = fd_run(ctx, view, d0, ncols, n_d, n_r, t, plan, d_ids, cols, d_shares, d_status, d_out48, filter ? filter + d0 / 32 : nullptr, s))
+      return rc;
   }
   return 0;
 }
 
+// share verdicts by evaluation for the dealer groups of `filter` (nullptr: all); cols were computed by dkgv_fd_submit
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
-                         const uint32_t* d_ids, const uint32_t* h_ids, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s) {
-  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, d_shares, d_status, nullptr, s);
+                         const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, const uint8_t* filter, cudaStream_t s) {
+  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, (const uint32_t*)ctx->fd_cols.p, d_shares, d_status, nullptr, filter, s);
 }
 
-// evaluate_polynomial (dkg_math.rs:160-174) of every dealer at every id, ids a permutation of 1..n_r:
-// d_out48[d][j] = compress(f_d(ids[j])).  Used for the final keys K_j of agg_coefficients (one "dealer": the
+// evaluate_polynomial (dkg_math.rs:160-174) of every dealer at every id, ids a permutation of 1..n_r (h_ids: the caller's host
+// copy): d_out48[d][j] = compress(f_d(ids[j])).  Used for the final keys K_j of agg_coefficients (one "dealer": the
 // column sums) and the batched dkgv_feldman_eval.
 int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
                          const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s) {
-  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, h_ids, nullptr, nullptr, d_out48, s);
+  CK(ctx->fd_cols.reserve((size_t)n_r * 4));
+  ctx->fd_cols_host.resize(n_r);  // columns in ascending-id order; must outlive the async copy
+  for (uint32_t j = 0; j < n_r; j++) ctx->fd_cols_host[h_ids[j] - 1] = j;
+  CK(cudaMemcpyAsync(ctx->fd_cols.p, ctx->fd_cols_host.data(), (size_t)n_r * 4, cudaMemcpyHostToDevice, s));
+  return fd_run_chunks(ctx, view, n_d, n_r, t, plan, d_ids, (const uint32_t*)ctx->fd_cols.p, nullptr, nullptr, d_out48, nullptr, s);
 }

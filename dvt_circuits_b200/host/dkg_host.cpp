@@ -14,7 +14,7 @@
 #include <fstream>
 #include <sstream>
 
-#include "../../include/dkgv.h"
+#include "../../include/dkgh.h"
 #include "util.hpp"
 
 namespace dkgh {
@@ -75,7 +75,10 @@ struct Host {
   dkgv_ctx* ctx;
   Setup su;
   Secp256k1 secp;
-  std::string detail;  // expected / got keys for messages
+  std::string detail;  // unused by the flows; kept for callers that want a free-form note
+  // what the guests hand back besides the outcome:
+  std::vector<Bytes> commits;  // sp1_zkvm::io::commit values in commit order (the guests' public outputs)
+  Bytes expected, got;         // the two keys of the reference's error message (verification.rs:141-145,304-307,323-326,414-417)
 
   void ck(int rc) {
     if (rc != 0) throw std::runtime_error(std::string("dkgv: ") + dkgv_last_error(ctx));
@@ -135,6 +138,12 @@ struct Host {
     uint8_t st = 0;
     ck(dkgv_share_matrix_verify(ctx, 1, 1, (uint32_t)base_pubkeys.size(), vv.data(), &id, secret.data(), &st));
     if (st == DKGV_PANIC_BAD_G1) throw Panic{DKGV_PANIC_BAD_G1};
+    if (st == DKGV_SLASHABLE_SHARE_MISMATCH) {  // "Expected secret with public key: {eval_result}, got public key: {G*s}"
+      uint8_t ev[48], rst = 0;
+      ck(dkgv_feldman_eval(ctx, 1, 1, (uint32_t)base_pubkeys.size(), vv.data(), &id, ev, &rst));
+      expected.assign(ev, ev + 48);
+      got.assign(pk, pk + 48);
+    }
     return st;
   }
 
@@ -155,7 +164,12 @@ struct Host {
     if (st.n < st.k) throw Panic{DKGV_PANIC_PRECHECK};
     if (std::find(hashes.begin(), hashes.end(), ihash) == hashes.end()) throw Panic{DKGV_PANIC_PRECHECK};
     if (compute_initial_commitment_hash(st, base_pubkeys) != ihash) throw Panic{DKGV_PANIC_PRECHECK};
-    return verify_seed_exchange_commitment(hashes, se, base_pubkeys);
+    int rc = verify_seed_exchange_commitment(hashes, se, base_pubkeys);
+    if (rc >= 1 && rc < 16) {  // Slashable: commit every verification hash, then the perpetrator's identity key (guest :57-71)
+      commits = hashes;
+      commits.push_back(parse_commitment(se.at("commitment"), su).pubkey);
+    }
+    return rc;
   }
 
   struct Generation {
@@ -240,13 +254,21 @@ struct Host {
     uint8_t lst = 0, computed[48];
     ck(dkgv_lagrange_at_zero(ctx, (uint32_t)ids.size(), keys.data(), ids.data(), computed, &lst));
     if (lst != DKGV_OK) return lst;
-    if (memcmp(computed, agg_key.data(), 48) != 0) return DKGV_ERR_AGG_MISMATCH_VV;
+    if (memcmp(computed, agg_key.data(), 48) != 0) {  // "Computed key {} does not match aggregate public key {}"
+      expected = agg_key;
+      got.assign(computed, computed + 48);
+      return DKGV_ERR_AGG_MISMATCH_VV;
+    }
     Bytes ppk;
     for (auto* g : sorted) ppk.insert(ppk.end(), g->partial_pubkey.begin(), g->partial_pubkey.end());
     ck(dkgv_lagrange_at_zero(ctx, (uint32_t)ids.size(), ppk.data(), ids.data(), computed, &lst));
     if (lst == DKGV_PANIC_BAD_G1) throw Panic{lst};
     if (lst != DKGV_OK) return lst;
-    if (memcmp(computed, agg_key.data(), 48) != 0) return DKGV_ERR_AGG_MISMATCH_PK;
+    if (memcmp(computed, agg_key.data(), 48) != 0) {
+      expected = agg_key;
+      got.assign(computed, computed + 48);
+      return DKGV_ERR_AGG_MISMATCH_PK;
+    }
     return DKGV_OK;
   }
 
@@ -261,7 +283,12 @@ struct Host {
     uint8_t dst = 0;
     ck(dkgv_g1_decompress_check(ctx, 1, agg_key.data(), &dst));
     if (dst) throw Panic{DKGV_PANIC_BAD_G1};
-    return verify_generations(gens, st, agg_key);
+    int rc = verify_generations(gens, st, agg_key);
+    if (rc == DKGV_OK) {  // guest :26-32: every base_hash in input order, then the aggregate key
+      for (auto& g : gens) commits.push_back(g.base_hash);
+      commits.push_back(agg_key);
+    }
+    return rc;
   }
 
   // ---- prove_wrong_final_key_generation (verification.rs:422-466)
@@ -299,29 +326,53 @@ struct Host {
     for (size_t i = 0; i < sorted.size(); i++)
       if (sorted[i]->base_hash == bp.base_hash) perp = (int)i;
     if (perp < 0) return DKGV_UNSLASHABLE_PERP_NOT_FOUND;
-    uint8_t dst = 0;
-    ck(dkgv_g1_decompress_check(ctx, 1, bp.partial_pubkey.data(), &dst));
-    if (dst) return DKGV_SLASHABLE_BAD_PK;
-    ck(dkgv_g2_decompress_check(ctx, 1, bp.message_signature.data(), &dst));
-    if (dst) return DKGV_SLASHABLE_BAD_SIG;
-    uint32_t offs[2] = {0, (uint32_t)bp.message.size()};
-    uint8_t hm[96], vst = 0;
-    ck(dkgv_hash_to_g2(ctx, 1, (const uint8_t*)bp.message.data(), offs, hm));
-    ck(dkgv_bls_verify_batch(ctx, 1, bp.partial_pubkey.data(), bp.message_signature.data(), 1, hm, nullptr, &vst));
-    if (vst != DKGV_OK) return DKGV_SLASHABLE_SIG_INVALID;
-    // verify_expected_key -> compute_pubkey_share (:399-420, :523-551), quirk Q1 kept: Horner over the K_j
+    // everything on the curve - key / signature decoding, hash-to-G2, the pairing check, agg_coefficients and the expected
+    // key of verify_expected_key (quirk Q1 kept: Horner over the final keys K_j) - is ONE batch call with m = 1
     if (sorted.empty()) throw Panic{DKGV_PANIC_INDEX};
-    expect_all_points(sorted);
-    std::vector<uint32_t> ids;
-    for (size_t i = 0; i < sorted.size(); i++) ids.push_back((uint32_t)i + 1);
-    Bytes coeffs, keys;
-    agg(sorted, ids, &coeffs, &keys);
-    uint32_t pid = (uint32_t)perp + 1;
-    uint8_t expected[48], est = 0;
-    ck(dkgv_eval_points(ctx, (uint32_t)ids.size(), keys.data(), &pid, 1, expected, &est));
-    if (est != DKGV_OK) throw Panic{est};
-    if (memcmp(expected, bp.partial_pubkey.data(), 48) != 0) return DKGV_SLASHABLE_KEY_MISMATCH;
-    return DKGV_OK;
+    size_t t = sorted[0]->vv.size();
+    Bytes flat;
+    bool ragged = false;
+    for (auto* g : sorted) {
+      if (g->vv.size() < t) {
+        ragged = true;  // dkg_math.rs:235-239 indexes vv[i][k] for k < vv[0].len(): panics once the flow gets there
+        break;
+      }
+      for (size_t k = 0; k < t; k++) flat.insert(flat.end(), g->vv[k].begin(), g->vv[k].end());
+    }
+    uint32_t pidx = (uint32_t)perp, offs[2] = {0, (uint32_t)bp.message.size()};
+    uint8_t ist = 0, sst = 0;
+    Bytes exp_keys(sorted.size() * 48);
+    if (ragged) {  // decide the pre-aggregation exits on a one-generation session, then panic as the reference does
+      Bytes one;
+      for (auto& p : sorted[0]->vv) one.insert(one.end(), p.begin(), p.end());
+      uint32_t zero = 0;
+      ck(dkgv_bad_partial_key_verify_batch(ctx, 1, (uint32_t)t, one.data(), 1, &zero, bp.partial_pubkey.data(), bp.message_signature.data(), 1,
+                                           (const uint8_t*)bp.message.data(), offs, nullptr, &ist, nullptr, &sst));
+      if (ist == DKGV_SLASHABLE_BAD_PK || ist == DKGV_SLASHABLE_BAD_SIG || ist == DKGV_SLASHABLE_SIG_INVALID) return ist;
+      expect_all_points(sorted);
+      throw Panic{DKGV_PANIC_INDEX};
+    }
+    ck(dkgv_bad_partial_key_verify_batch(ctx, (uint32_t)sorted.size(), (uint32_t)t, flat.data(), 1, &pidx, bp.partial_pubkey.data(),
+                                         bp.message_signature.data(), 1, (const uint8_t*)bp.message.data(), offs, nullptr, &ist, exp_keys.data(),
+                                         &sst));
+    if (ist == DKGV_SLASHABLE_BAD_PK || ist == DKGV_SLASHABLE_BAD_SIG || ist == DKGV_SLASHABLE_SIG_INVALID) return ist;
+    expect_all_points(sorted);  // every coefficient must decode - also the tail the aggregation ignores (verification.rs:529-538)
+    if (ist >= DKGV_PANIC_BAD_G1) throw Panic{ist};
+    if (ist == DKGV_SLASHABLE_KEY_MISMATCH) {  // "Computed key {expected} does not match expected key {key}"
+      expected.assign(exp_keys.begin() + (size_t)perp * 48, exp_keys.begin() + (size_t)(perp + 1) * 48);
+      got = bp.partial_pubkey;
+    }
+    return ist;
+  }
+
+  // ---- guest 2 (crates/bad_parial_key_prove/src/main.rs:16-51)
+  int guest_bad_partial_key(const Json& data) {
+    int rc = prove_wrong_final_key_generation(data);
+    if (rc >= 1 && rc < 16) {  // Slashable: every generation's base_hash in input order, then the perpetrator's identity key
+      for (auto& g : data.at("generations").arr) commits.push_back(hex_fixed(g.at("base_hash"), 32, "base_hash"));
+      commits.push_back(parse_commitment(data.at("bad_partial").at("commitment"), su).pubkey);
+    }
+    return rc;
   }
 };
 
@@ -399,15 +450,17 @@ static int guest_bad_encrypted_share(Host& h, const Json& data, int* exit_code) 
   }
   chacha20_xor(digest.data(), digest.data(), msg);
   size_t want = 16 + 1 + 32 + (su.auth ? 32 + su.id_pk() + su.id_sig() : su.id_pk());
-  if (msg.size() < want) {  // ReadError -> commit + return
+  auto commit_parse_failure = [&]() {  // guest :359-369: every base hash, the receiver's key G * sk, the sender's key, the ciphertext string
+    h.commits = hashes;
+    h.commits.emplace_back(rpk, rpk + 48);
+    h.commits.push_back(sender_encr_pubkey);
+    h.commits.emplace_back(hexs.begin(), hexs.end());
     *exit_code = 0;
-    return DKGV_SLASHABLE_BAD_ENCRYPTED_MSG;
-  }
+    return (int)DKGV_SLASHABLE_BAD_ENCRYPTED_MSG;
+  };
+  if (msg.size() < want) return commit_parse_failure();  // ReadError -> commit + return
   if (msg.size() > want) throw Panic{DKGV_PANIC_PRECHECK};  // stream.finalize() assert
-  if (!std::equal(st.gen_id.begin(), st.gen_id.end(), msg.begin()) || msg[16] != 3) {
-    *exit_code = 0;
-    return DKGV_SLASHABLE_BAD_ENCRYPTED_MSG;
-  }
+  if (!std::equal(st.gen_id.begin(), st.gen_id.end(), msg.begin()) || msg[16] != 3) return commit_parse_failure();
   // rebuild the SharedData the guest hands to verify_seed_exchange_commitment
   auto hexs_of = [](const uint8_t* p, size_t n) {
     static const char* d = "0123456789abcdef";
@@ -452,15 +505,24 @@ static bool is_slashable(int s) { return s >= 1 && s < 16; }
 
 extern "C" {
 // `dkg_prover_host execute --type <type> --input-file <json>` semantics on the GPU.
-//   type: "bad-share" | "finalization" | "bad-partial-key";  auth: feature auth_commitment;
+//   type: "bad-share" | "finalization" | "bad-partial-key" | "bad-encrypted-share";  auth: feature auth_commitment;
 //   bls_identity: 1 = BlsDkgWithBlsCommitment (always used by finalization, as the reference does)
 // returns the process exit code of the reference (0 = misbehaviour proven / ceremony valid, 1 = anything
-// else), *status = the dkgv_status reached (255 = input rejected by the JSON / hex layer, as serde would)
-int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg, size_t msg_cap) {
+// else), *status = the dkgv_status reached (255 = input rejected by the JSON / hex layer, as serde would).
+// rep (may be NULL): the guests' committed public values and the (expected, got) keys of the reference's message.
+int dkgh_execute_report(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg,
+                        size_t msg_cap, dkgh_report* rep) {
   using namespace dkgh;
   int st = 255;
   std::string m;
   int code = 1;
+  if (rep) {
+    rep->n_public = 0;
+    rep->public_len = 0;
+    rep->have_keys = 0;
+    memset(rep->expected, 0, 48);
+    memset(rep->got, 0, 48);
+  }
   try {
     std::string text(json_text);
     Json data = JsonParser(text).parse();
@@ -474,12 +536,34 @@ int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int aut
       st = h.guest_finalization(data);
       code = st == DKGV_OK ? 0 : 1;
     } else if (ty == "bad-partial-key") {
-      st = h.prove_wrong_final_key_generation(data);
+      st = h.guest_bad_partial_key(data);
       code = is_slashable(st) ? 0 : 1;
     } else if (ty == "bad-encrypted-share") {
       st = guest_bad_encrypted_share(h, data, &code);
     } else {
       m = "unknown type";
+    }
+    if (rep) {
+      if (h.expected.size() == 48 && h.got.size() == 48) {
+        rep->have_keys = 1;
+        memcpy(rep->expected, h.expected.data(), 48);
+        memcpy(rep->got, h.got.data(), 48);
+      }
+      if (code == 0) {  // a run that ends in a panic commits nothing a verifier would ever see
+        size_t need = 0;
+        for (auto& c : h.commits) need += 4 + c.size();
+        rep->n_public = (uint32_t)h.commits.size();
+        rep->public_len = need;
+        if (rep->public_values && need <= rep->public_cap) {
+          uint8_t* o = rep->public_values;
+          for (auto& c : h.commits) {
+            uint32_t l = (uint32_t)c.size();
+            for (int b = 0; b < 4; b++) *o++ = (uint8_t)(l >> (8 * b));
+            memcpy(o, c.data(), c.size());
+            o += c.size();
+          }
+        }
+      }
     }
   } catch (const dkgh::Panic& p) {
     st = p.code;
@@ -493,6 +577,9 @@ int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int aut
     snprintf(msg, msg_cap, "%s", m.c_str());
   }
   return code;
+}
+int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg, size_t msg_cap) {
+  return dkgh_execute_report(ctx, type, json_text, auth, bls_identity, status, msg, msg_cap, nullptr);
 }
 // compute_initial_commitment_hash (verification.rs:151-175) for callers that build inputs
 void dkgh_initial_commitment_hash(const uint8_t* gen_id16, uint8_t n, uint8_t k, const uint8_t* base_pubkeys, uint32_t count, uint8_t* out32) {
@@ -535,8 +622,30 @@ int main(int argc, char** argv) {
   }
   int status = 0;
   char msg[512];
-  int code = dkgh_execute(ctx, type.c_str(), ss.str().c_str(), auth, bls, &status, msg, sizeof msg);
+  std::vector<uint8_t> pub(1 << 20);
+  dkgh_report rep{};
+  rep.public_values = pub.data();
+  rep.public_cap = pub.size();
+  int code = dkgh_execute_report(ctx, type.c_str(), ss.str().c_str(), auth, bls, &status, msg, sizeof msg, &rep);
   printf("status=%d exit=%d %s\n", status, code, msg);
+  auto hex = [](const uint8_t* p, size_t n) {
+    for (size_t i = 0; i < n; i++) printf("%02x", p[i]);
+  };
+  if (rep.have_keys) {
+    printf("expected key: ");
+    hex(rep.expected, 48);
+    printf("\ngot key:      ");
+    hex(rep.got, 48);
+    printf("\n");
+  }
+  const uint8_t* o = pub.data();
+  for (uint32_t i = 0; i < rep.n_public && rep.public_len <= pub.size(); i++) {  // the guest's sp1_zkvm::io::commit values, in order
+    uint32_t l = o[0] | o[1] << 8 | o[2] << 16 | (uint32_t)o[3] << 24;
+    printf("public[%u]: ", i);
+    hex(o + 4, l);
+    printf("\n");
+    o += 4 + l;
+  }
   dkgv_ctx_destroy(ctx);
   return code;
 }

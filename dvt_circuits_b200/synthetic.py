@@ -75,3 +75,51 @@ def make_finalization(verifier, n, t, seed=DEFAULT_SEED, message=b"Sign with new
     sigs = verifier.g2_mul_batch(hm.tobytes(), sk)
     s.update({"partial_pubkeys": pks, "signatures": sigs, "hm": hm, "message": message, "partial_secrets": sk})
     return s
+
+
+def make_bad_partial_items(verifier, fin, m, p_bad=0.5, seed=DEFAULT_SEED):
+    """BASELINE config 5, second half: m bad-partial-key items over the finalization session `fin` (make_finalization), cycling
+    the perpetrator index, a Bernoulli(p_bad) half of them corrupted with the reference's own mutation taxonomy
+    (test_vectors/*/wrong_final_key_generation: -bad- = one flipped bit, -wrong- = another valid value).
+    A VALID item is one prove_wrong_final_key_generation cannot slash: the accused key is the "expected key" of
+    compute_pubkey_share (quirk Q1: Horner over the final keys K_j at the perpetrator's id, verification.rs:548-549) and the
+    signature verifies under it - built here from the partial secrets.  kinds of corruption -> expected status:
+      0 one bit of the key flipped            -> SLASHABLE_BAD_PK (5)      1 one bit of the signature flipped -> SLASHABLE_BAD_SIG (6)
+      2 another perpetrator's signature       -> SLASHABLE_SIG_INVALID (7) 3 the honest partial key K_p + its honest signature
+      4 another perpetrator's expected key    -> SLASHABLE_SIG_INVALID (7)   -> SLASHABLE_KEY_MISMATCH (8)
+    -> dict(perp [m] u32, pk [m,48], sig [m,96], expected [m] u8, q1_keys [n,48])"""
+    n = fin["ids"].shape[0]
+    S = [int.from_bytes(fin["partial_secrets"][j].tobytes(), "big") for j in range(n)]
+    q = []
+    for p in range(n):
+        acc = 0
+        for s_j in reversed(S):  # evaluate_polynomial(K, id = p + 1) in the exponent
+            acc = (acc * (p + 1) + s_j) % R_INT
+        q.append(acc.to_bytes(32, "big"))
+    qsk = np.frombuffer(b"".join(q), dtype=np.uint8).reshape(n, 32)
+    qpk, st = verifier.g1_fixed_base_mul(qsk)
+    assert not st.any()
+    qsig = verifier.g2_mul_batch(fin["hm"].tobytes(), qsk)
+    rng = np.random.Generator(np.random.PCG64([seed, 0xB9C]))
+    perp = (np.arange(m, dtype=np.uint32) % n).astype(np.uint32)
+    bad = rng.random(m) < p_bad
+    kind = rng.integers(0, 5, size=m)
+    other = ((perp + 1 + rng.integers(0, max(n - 1, 1), size=m)) % n).astype(np.uint32) if n > 1 else perp
+    pk, sig = qpk[perp].copy(), qsig[perp].copy()
+    expected = np.zeros((m,), dtype=np.uint8)
+    k0 = np.nonzero(bad & (kind == 0))[0]
+    pk[k0, 1 + rng.integers(0, 47, size=k0.size)] ^= (1 << rng.integers(0, 8, size=k0.size)).astype(np.uint8)
+    expected[k0] = 5
+    k1 = np.nonzero(bad & (kind == 1))[0]
+    sig[k1, 1 + rng.integers(0, 95, size=k1.size)] ^= (1 << rng.integers(0, 8, size=k1.size)).astype(np.uint8)
+    expected[k1] = 6
+    k2 = np.nonzero(bad & (kind == 2))[0]
+    sig[k2] = qsig[other[k2]]
+    expected[k2] = 7 if n > 1 else 0
+    k3 = np.nonzero(bad & (kind == 3))[0]
+    pk[k3], sig[k3] = fin["partial_pubkeys"][perp[k3]], fin["signatures"][perp[k3]]
+    expected[k3] = 8
+    k4 = np.nonzero(bad & (kind == 4))[0]
+    pk[k4] = qpk[other[k4]]
+    expected[k4] = 7 if n > 1 else 0
+    return {"perp": perp, "pk": pk, "sig": sig, "expected": expected, "q1_keys": qpk, "kind": np.where(bad, kind, -1)}

@@ -23,6 +23,25 @@ extern "C" {
 int dkgh_execute(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg,
                  size_t msg_cap);
 
+/* The same run, also returning what the reference's guest hands to the outside world:
+ *  - the public values it commits with sp1_zkvm::io::commit, in commit order (bad_share_exchange_prove/src/main.rs:57-71: every
+ *    verification hash, then the perpetrator's identity key; finalization_prove/src/main.rs:26-32: every generation's base_hash
+ *    in input order, then the aggregate key; bad_parial_key_prove/src/main.rs:31-41; bad_encrypted_share_prove/src/main.rs:359-369).
+ *    Only runs that exit 0 commit anything.  public_values (caller-allocated, public_cap bytes) receives n_public entries of
+ *    [u32 little-endian length][bytes]; public_len is the size needed (nothing is written when it exceeds public_cap).
+ *  - the two keys the reference prints in its message for a share mismatch (verification.rs:141-145: expected = the Feldman
+ *    evaluation, got = G * s), an aggregate-key mismatch (:304-307, :323-326: expected = the claimed aggregate key, got = the
+ *    computed one) and a partial-key mismatch (:414-417: expected = compute_pubkey_share, got = the accused key).            */
+typedef struct dkgh_report {
+  uint8_t* public_values;
+  size_t public_cap, public_len;
+  uint32_t n_public;
+  int have_keys;
+  uint8_t expected[48], got[48];
+} dkgh_report;
+int dkgh_execute_report(dkgv_ctx* ctx, const char* type, const char* json_text, int auth, int bls_identity, int* status, char* msg,
+                        size_t msg_cap, dkgh_report* report);
+
 /* compute_initial_commitment_hash (crates/dkg/src/verification.rs:151-175) */
 void dkgh_initial_commitment_hash(const uint8_t* gen_id16, uint8_t n, uint8_t k, const uint8_t* base_pubkeys, uint32_t count,
                                   uint8_t* out32);

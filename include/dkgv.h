@@ -11,9 +11,14 @@
  *    the dkgv_status codes below: one code per distinct exit of the reference
  *    (Ok / SlashableError / UnslashableError / io::Error / panic!).
  *  - Pointers named `h_*`/unprefixed are HOST pointers; functions ending in `_dev` take DEVICE
- *    pointers (current device of the ctx) and a stream handle and do not synchronise.
- *  - A ctx is single-owner (Send, not Sync), bound to one GPU.  Multi-GPU = one ctx per
- *    process/GPU; shard rows (dealers / items) across ranks, gather the status bytes.
+ *    pointers (current device of the ctx) and a stream handle.  They queue their work on that stream
+ *    and do not synchronise it, with ONE documented exception: dkgv_share_matrix_verify_dev reads a
+ *    two-word flag back (one stream synchronisation) to decide whether anything is left to evaluate;
+ *    its split form dkgv_share_matrix_submit_dev / dkgv_share_matrix_finish_dev leaves that read-back
+ *    to the caller and is fully asynchronous (CUDA-graph capturable once its buffers exist).
+ *  - A ctx is single-owner (Send, not Sync), bound to one GPU.  Multi-GPU: one ctx per process/GPU with
+ *    a dkgv_comm (NCCL inside the library: dkgv_comm_*, *_sharded entry points), or one dkgv_multi
+ *    driving several GPUs from one host thread (dkgv_multi_*).
  *  - There is no CPU fallback: without a CUDA device dkgv_ctx_create fails.
  */
 #ifndef DKGV_H
@@ -86,10 +91,24 @@ int dkgv_last_decode_ms(dkgv_ctx* ctx, float* ms, int* subgroup_checked);
  * t == 0 evaluates to the identity, t == 1 to C_0 (dkg_math.rs:161-166).                        */
 int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t,
                              const uint8_t* vv, const uint32_t* ids, const uint8_t* shares, uint8_t* status);
-/* same with device-resident buffers, asynchronous on `stream` (a cudaStream_t, may be NULL) */
+/* same with device-resident buffers on `stream` (a cudaStream_t, may be NULL = the ctx stream): submit + finish below, i.e.
+ * everything is queued asynchronously except ONE stream synchronisation that reads the two flag words.                   */
 int dkgv_share_matrix_verify_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t,
                                  const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
                                  uint8_t* d_status, void* stream);
+/* The same call in two halves, for callers that overlap it with other work or capture it into a CUDA graph.
+ * submit: queues the default path on `stream` and returns WITHOUT synchronising.  When the ids look like ceremony ranks the
+ *   consistency shortcut (below) runs speculatively while a kernel checks that they really are a permutation of 1..n;
+ *   d_status receives OK for every dealer group the shortcut settles.  d_flags2 (device, 2 x u32; NULL = a ctx-owned pair):
+ *     [0] != 0  the ids are not a permutation of 1..n_recipients: nothing written so far counts;
+ *     [1]       number of dealers the shortcut could not settle (their 32-dealer groups still hold no verdicts).
+ * finish: h_flags2 = those two words as the caller read them back after synchronising (typically in the same copy as its
+ *   results), or NULL to let the library read them (one synchronisation).  {0, 0}: returns at once - every verdict is OK
+ *   and already in d_status.  Otherwise queues the evaluation of the pending dealer groups (or the Horner route over the
+ *   whole matrix) on `stream`, asynchronously.  The buffers of submit must stay valid until finish's work has run.     */
+int dkgv_share_matrix_submit_dev(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv,
+                                 const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags2, void* stream);
+int dkgv_share_matrix_finish_dev(dkgv_ctx* ctx, const uint32_t* h_flags2, void* stream);
 
 /* Sparse item list over one session (e.g. only the complained-about shares): item i is the pair
  * (item_dealer[i] < n_dealers, item_recipient[i] < n_recipients = column into ids) with secret secrets[i][32];
@@ -119,8 +138,9 @@ int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
  * differences of the share sequence vanish - and (3) G * p_k == C_k for each coefficient of the interpolated polynomial p.
  * So no share goes through the group arithmetic; a group of 32 dealers in which some dealer fails a condition continues with the full
  * evaluation, which yields the exact per-share verdicts.  Deterministic and exact (no random linear combination).
- * Costs one host synchronisation inside the call.  dkgv_last_share_continued: 1 when the last call had to continue
- * beyond t for some dealer group, 0 when the shortcut settled everything.                                        */
+ * Applies for t <= 1024 and t < n_recipients <= 2048 (other shapes: every share through the evaluation).
+ * dkgv_last_share_continued: 1 when the last call had to continue into the evaluation for some dealer group, 0 when the
+ * shortcut settled everything.                                                                                   */
 int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on);
 int dkgv_last_share_continued(const dkgv_ctx* ctx);
 /* 1 when the commitments of the last share-matrix call were decoded (square roots, subgroup tests), 0 when the shortcut
@@ -187,6 +207,26 @@ int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pk, const ui
                           const uint32_t* hm_idx, uint8_t* status);
 int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
                               const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status, void* stream);
+
+/* ---- prove_wrong_final_key_generation (crates/dkg/src/verification.rs:422-466) for m items over ONE session -------------
+ * The curve part of the flow, batched: one hash-to-G2 launch over all messages, one decode + pairing batch over all items, one
+ * aggregation per session and the "expected key" of every perpetrator index at once (verify_expected_key :399-420 ->
+ * compute_pubkey_share :523-551, including its quirk: evaluate_polynomial over the n FINAL KEYS K_j at the perpetrator's id).
+ * The caller has done the per-item hash / identity-signature checks and the sort by base_hash (:428-438).
+ *   vv [n][t][48]  verification vectors of the n generations in base_hash-sorted order (ids 1..n; t = len of vv[0])
+ *   perp [m]       index of the accused generation in that order (find_perpetrator_index :498-521)
+ *   pk [m][48], sig [m][96], msgs/msg_offsets [n_msg + 1]/msg_idx [m] (NULL: message 0)   partial_pubkey, message_signature,
+ *                  message_cleartext of bad_partial.data
+ *   status [m]     SLASHABLE_BAD_PK / SLASHABLE_BAD_SIG / SLASHABLE_SIG_INVALID / SLASHABLE_KEY_MISMATCH / OK in the reference's
+ *                  order of checks; PANIC_BAD_G1 for an item that reaches verify_expected_key of a session with an undecodable
+ *                  commitment (the reference's .expect, verification.rs:534)
+ *   expected_out [n][48] (may be NULL)  the expected key per perpetrator index - with pk[i] the (expected, got) pair of the
+ *                  reference's message (verification.rs:414-417)
+ *   *session_status  OK / PANIC_BAD_G1                                                                                  */
+int dkgv_bad_partial_key_verify_batch(dkgv_ctx* ctx, uint32_t n, uint32_t t, const uint8_t* vv, uint32_t m, const uint32_t* perp,
+                                      const uint8_t* pk, const uint8_t* sig, uint32_t n_msg, const uint8_t* msgs,
+                                      const uint32_t* msg_offsets, const uint32_t* msg_idx, uint8_t* status, uint8_t* expected_out,
+                                      uint8_t* session_status);
 
 /* ---- initial-commitment hashes (crates/dkg/src/verification.rs:151-175) on the GPU ------------- */
 /* out[d] = SHA-256(gen_id(16) || n || k || (t as u8) || vv[d][0..t)), one per dealer, out [n_dealers][32] */

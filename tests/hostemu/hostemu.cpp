@@ -8,8 +8,7 @@
 #include <cstring>
 #include <vector>
 
-#define DKGV_BOUND_CHECK 1
-#include "../../dvt_circuits_b200/csrc/vm30.cuh"
+#include "../../dvt_circuits_b200/csrc/vm.cuh"
 #include "../../dvt_circuits_b200/csrc/fdiff.cuh"
 
 using namespace dkgv;
@@ -101,58 +100,9 @@ uint32_t he_share_check(const uint8_t* vv, uint32_t t, uint32_t id, const uint8_
   vm_fixed_base_mul(f, gtab.data(), s);
   g1_compress(g1_to_affine(vm_get_point(f, BX)), ev2);
   if (memcmp(ev2, pk48, 48)) return 0x300;
-  // v2: the 13 x 30-bit carry-free backend (vm30.cuh) with static bound tracking switched on
-  {
-    std::vector<uint32_t> l30((size_t)tt * 26 * n_pad, 0);
-    std::vector<uint8_t> inf30((size_t)tt * n_pad, 1);
-    for (uint32_t k = 0; k < t; k++) {
-      G1Aff a = vv_load(view, k, 0);
-      vv30_store(l30.data(), inf30.data(), n_pad, k, 0, fp30_from_fp(a.x), fp30_from_fp(a.y), a.inf != 0);
-    }
-    VV30View v30{l30.data(), inf30.data(), n_pad};
-    std::vector<uint32_t> g30(GTAB30_WORDS, 0);
-    for (int w = 0; w <= GTAB_WINDOWS; w++) {
-      uint32_t idx = gtab_index(s, w);
-      Fp x, y;
-      for (int i = 0; i < 12; i++) {
-        x.l[i] = gtab[(size_t)idx * 24 + i];
-        y.l[i] = gtab[(size_t)idx * 24 + 12 + i];
-      }
-      Fp30 x30 = fp30_from_fp(x), y30 = fp30_from_fp(y);
-      for (int i = 0; i < 13; i++) {
-        g30[(size_t)idx * 26 + i] = x30.l[i];
-        g30[(size_t)idx * 26 + 13 + i] = y30.l[i];
-      }
-    }
-    std::vector<U4> file30((size_t)VM_SLOTS * 4 * NT);
-    OpFile30 f30{file30.data() + me, NT};
-    uint32_t st30 = v30_share_check(f30, v30, t, 0, id, secret32, g30.data(), bad);
-    if (st30 != st) return 0x400 | st30;
-    // the evaluation point itself must match too (compare after full reduction)
-    v30_feldman_eval(f30, v30, t, 0, id);
-    G1Proj pe;
-    fp30_to_canonical(o30_load(f30, AX), pe.x.l);
-    fp30_to_canonical(o30_load(f30, AY), pe.y.l);
-    fp30_to_canonical(o30_load(f30, AZ), pe.z.l);
-    pe.x = to_mont(pe.x); pe.y = to_mont(pe.y); pe.z = to_mont(pe.z);
-    g1_compress(g1_to_affine(pe), ev2);
-    if (memcmp(ev2, eval48, 48)) return 0x500;
-  }
   return st;
 }
 
-// canonical 48-byte a, b -> a*b mod p through the 30-bit backend (+ add, sub, small multiples)
-void he_fp30_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t* add48, uint8_t* sub48, uint8_t* m12_48) {
-  Fp a, b;
-  fp_raw_from_be48(a.l, a48);
-  fp_raw_from_be48(b.l, b48);
-  Fp30 x = fp30_from_canonical(a.l), y = fp30_from_canonical(b.l);
-  Fp o;
-  fp30_to_canonical(fp30_mul(x, y), o.l); fp_raw_to_be48(mul48, o.l);
-  fp30_to_canonical(fp30_add(x, y), o.l); fp_raw_to_be48(add48, o.l);
-  fp30_to_canonical(fp30_sub<8>(x, y), o.l); fp_raw_to_be48(sub48, o.l);
-  fp30_to_canonical(fp30_mul_small<12>(fp30_add(fp30_add(x, y), fp30_sub<32>(y, x))), o.l); fp_raw_to_be48(m12_48, o.l);
-}
 }
 
 // ---- finite-difference share path (fdiff.cuh): the exact sequence of k_fd_seed / k_fd_init /

@@ -9,6 +9,27 @@ _L = None
 FAITHFUL, FAST = 0, 1
 
 
+def use_native_build():
+    """bench.py's CPU-baseline legs: build the oracle with -march=native ON this machine (oracle/Makefile `native`) and use it from
+    now on; silently keeps the portable build when that fails.  Call before the first oracle function."""
+    global _L
+    import subprocess
+    try:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _L = None
+        return _load(os.path.join(ROOT, "oracle", "liboracle_native.so"))
+    except Exception:  # noqa: BLE001
+        return lib()
+
+
+def _load(path):
+    global _L
+    _L = ctypes.CDLL(path)
+    _L.orc_fp_mul_count.restype = ctypes.c_uint64
+    _L.orc_init()
+    return _L
+
+
 def lib():
     global _L
     if _L is None:

@@ -1,6 +1,8 @@
 """-m gpu parity tests of the finalization path through the C ABI: key aggregation, Lagrange at 0,
 hash-to-G2, G2 decoding and the batched BLS pairing checks - against the reference's own KATs
 (crates/dkg/src/dkg_math.rs:259-375) and the CPU oracle on seeded random inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,87 @@ def test_initial_commitment_hashes(verifier):
             exp = hashlib.sha256(gen_id + bytes([n & 0xFF, t & 0xFF, t & 0xFF]) + vv[d].tobytes()).digest()
             assert bytes(out[d]) == exp
             assert dk.initial_commitment_hash(gen_id, n, t, vv[d]) == exp
+
+
+def test_q1_expected_key_on_gpu(verifier):
+    """quirk Q1 on the GPU, pinned on SURVEY App. C3: a valid-signature item built from the reference's finalization/report-1.json
+    reaches verify_expected_key (verification.rs:399-420, 523-551) through the dkg_prover_host front end: status 8, exit 0, the
+    (expected, got) keys of the reference's message and the guest's committed public values."""
+    import json
+    import q1_fixture as Q
+    st, out = verifier.eval_points(np.array([list(bytes.fromhex(h)) for h in Q.FINAL_KEYS], dtype=np.uint8), [1, 2, 3])
+    assert st == 0 and [bytes(o).hex() for o in out] == Q.Q1_EXPECTED
+    for perp in range(3):
+        item = Q.q1_item(perp)
+        code, status, msg, public, keys = verifier.execute_report("bad-partial-key", json.dumps(item), auth=False)
+        assert (code, status) == (0, 8), msg
+        assert keys is not None and keys[0].hex() == Q.Q1_EXPECTED[perp] and keys[1].hex() == Q.FINAL_KEYS[perp]
+        # bad_parial_key_prove/src/main.rs:31-41: every generation's base_hash in INPUT order, then the perpetrator's identity key
+        assert [p.hex() for p in public] == [g["base_hash"] for g in item["generations"]] + [item["bad_partial"]["commitment"]["pubkey"]]
+    # the same items through the batch entry: one call, three perpetrators, + an item accusing the expected key itself
+    gens = Q.sorted_generations()
+    vv = np.array([[list(bytes.fromhex(p)) for p in g["base_pubkeys"]] for g in gens], dtype=np.uint8)
+    pk = np.array([list(bytes.fromhex(g["partial_pubkey"])) for g in gens], dtype=np.uint8)
+    sig = np.array([list(bytes.fromhex(g["message_signature"])) for g in gens], dtype=np.uint8)
+    stt, exp, sst = verifier.bad_partial_key_verify_batch(vv, [0, 1, 2], pk, sig, [gens[0]["message_cleartext"].encode()])
+    assert sst == 0 and stt.tolist() == [8, 8, 8] and [bytes(e).hex() for e in exp] == Q.Q1_EXPECTED
+    # accused key == expected key but the signature is for another key: the pairing check fires first (7)
+    stt, _, _ = verifier.bad_partial_key_verify_batch(vv, [0], exp[:1], sig[:1], [gens[0]["message_cleartext"].encode()])
+    assert stt.tolist() == [7]
+
+
+def test_guest_public_values(verifier):
+    """the public values each guest commits, in commit order (bad_share_exchange_prove/src/main.rs:57-71,
+    finalization_prove/src/main.rs:26-32), and the (expected, got) pair of a share mismatch (verification.rs:141-145)"""
+    import json
+    vec = os.path.join(O.ROOT, "tests", "golden", "reference_vectors", "no_auth")
+    j = json.load(open(os.path.join(vec, "share", "seeds-commitment-from-2-to-1-bad-secret-key.json")))["scenario"]
+    code, status, msg, public, keys = verifier.execute_report("bad-share", json.dumps(j), auth=False)
+    assert (code, status) == (0, 4), msg
+    assert [p.hex() for p in public] == j["base_hashes"] + [j["seeds_exchange_commitment"]["commitment"]["pubkey"]]
+    assert keys[0].hex() == "b29c8acec16b2193a36e635e65727bbbad73bbbbc933295863b92fe1dee26fe3581d0ecb22cdfc09a714ad1ffa0e8ccb"  # C1
+    assert keys[1].hex() == "8d13ea70941e0ac58adeecc4bd4105d213de0113369e69c7d1b9d0222e31b163015ed08bc95f458dba3599504ce3d401"  # C2
+    j = json.load(open(os.path.join(vec, "finalization", "report-1.json")))["scenario"]
+    code, status, msg, public, keys = verifier.execute_report("finalization", json.dumps(j))
+    assert (code, status) == (0, 0) and keys is None
+    assert [p.hex() for p in public] == [g["base_hash"] for g in j["generations"]] + [j["aggregate_pubkey"]]
+    # a valid share proves nothing: exit 1, nothing committed
+    j = json.load(open(os.path.join(vec, "share", "seeds-commitment-from-2-to-1.json")))["scenario"]
+    code, status, msg, public, keys = verifier.execute_report("bad-share", json.dumps(j), auth=False)
+    assert (code, status, public, keys) == (1, 0, [], None)
+
+
+@pytest.mark.parametrize("n,t,m", [(8, 5, 96), (3, 2, 40)])
+def test_bad_partial_key_batch_against_oracle(verifier, n, t, m):
+    """dkgv_bad_partial_key_verify_batch on a synthetic session with every kind of item (valid under quirk Q1, flipped key /
+    signature bits, wrong-but-valid key / signature, the honest partial key) against the C++ oracle composed per item in the
+    reference's order of checks (verification.rs:440-463)."""
+    from dvt_circuits_b200 import synthetic
+    fin = synthetic.make_finalization(verifier, n, t)
+    it = synthetic.make_bad_partial_items(verifier, fin, m, p_bad=0.7)
+    st, exp, sst = verifier.bad_partial_key_verify_batch(fin["vv"], it["perp"], it["pk"], it["sig"], [fin["message"]])
+    assert sst == 0
+    assert (st == it["expected"]).all(), np.argwhere(st != it["expected"])[:10]
+    assert set(st.tolist()) == {0, 5, 6, 7, 8}
+    ast, co, keys = O.agg_coefficients(fin["vv"], fin["ids"])
+    assert ast == 0
+    for p in range(n):
+        est, q1 = O.evaluate_polynomial(keys.tobytes(), n, p + 1)
+        assert est == 0 and q1 == bytes(exp[p]) == bytes(it["q1_keys"][p])
+    for i in range(m):
+        pk, sg = bytes(it["pk"][i]), bytes(it["sig"][i])
+        if O.g1_decompress(pk)[0]:
+            want = 5
+        elif O.g2_decompress(sg)[0]:
+            want = 6
+        elif O.bls_verify(pk, sg, fin["message"]) != 1:
+            want = 7
+        else:
+            want = 0 if pk == bytes(exp[it["perp"][i]]) else 8
+        assert st[i] == want, (i, int(it["kind"][i]), st[i], want)
+    # an undecodable commitment in the session: items that reach verify_expected_key panic (48), earlier exits are unchanged
+    vv2 = fin["vv"].copy()
+    vv2[1, 0, 0] &= 0x7F
+    st2, _, sst2 = verifier.bad_partial_key_verify_batch(vv2, it["perp"], it["pk"], it["sig"], [fin["message"]])
+    assert sst2 == 48
+    assert (st2 == np.where((st == 0) | (st == 8), 48, st)).all()

@@ -1,6 +1,6 @@
 """CPU-only: the per-thread logic of the CUDA kernels (dvt_circuits_b200/csrc/*.cuh compiled for the
 host by tests/hostemu) against the oracles - field arithmetic, G1 formulas and codecs, the operand-file
-(vm.cuh) and 30-bit (vm30.cuh, with static bound checking) formulations of the share check, the tower,
+(vm.cuh) formulation of the share check, the tower,
 pairing and hash-to-G2.  The PTX carry-chain product itself is pinned by the -m gpu tests."""
 import ctypes
 import hashlib
@@ -44,12 +44,6 @@ def test_field_ops(L):
         assert int.from_bytes(ad.raw, "big") == (a + b) % B.P
         assert int.from_bytes(sb.raw, "big") == (a - b) % B.P
         assert int.from_bytes(iv.raw, "big") == pow(a, B.P - 2, B.P)
-        o = [buf(48) for _ in range(4)]
-        L.he_fp30_ops(a.to_bytes(48, "big"), b.to_bytes(48, "big"), *o)
-        assert int.from_bytes(o[0].raw, "big") == a * b % B.P
-        assert int.from_bytes(o[1].raw, "big") == (a + b) % B.P
-        assert int.from_bytes(o[2].raw, "big") == (a - b) % B.P
-        assert int.from_bytes(o[3].raw, "big") == 12 * ((a + b) + (b - a)) % B.P
         x, y, r = rnd.randrange(B.R), rnd.randrange(B.R), buf(32)
         L.he_fr_mul(x.to_bytes(32, "big"), y.to_bytes(32, "big"), r)
         assert int.from_bytes(r.raw, "big") == x * y % B.R
@@ -83,7 +77,7 @@ def test_g1_formulas_and_codec(L):
 
 
 def test_share_check_all_formulations(L):
-    """he_share_check runs the inlined, operand-file and 30-bit variants and returns >= 0x100 on any
+    """he_share_check runs the inlined and operand-file variants and returns >= 0x100 on any
     disagreement between them"""
     ev, pk = buf(48), buf(48)
     vv = b"".join(H(h) for h in EVAL_PKS)
