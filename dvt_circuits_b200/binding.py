@@ -93,6 +93,9 @@ DECLARED_SYMBOLS = {
     "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_set_bls_path": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dkgv_last_bls_path": (ctypes.c_int, [_vp]),
+    "dkgv_last_bls_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dkgv_bad_partial_key_verify_batch": (ctypes.c_int, [_vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_g2_mul_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_initial_commitment_hashes": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, ctypes.c_uint8, ctypes.c_uint8, _vp]),
@@ -388,6 +391,21 @@ class Verifier:
                                                              _p(idx) if idx is not None else None, _p(st), _p(exp),
                                                              ctypes.cast(ctypes.byref(sst), _vp)))
         return st, exp, int(sst.value)
+
+    BLS_AUTO, BLS_VM, BLS_THREAD = 0, 1, 2
+
+    def set_bls_path(self, mode):
+        """enum dkgv_bls_path: AUTO / VM (pairing VM, several warps per 32 checks) / THREAD (one thread per check)"""
+        self._ck(self._lib.dkgv_set_bls_path(self._h, int(mode)))
+
+    @property
+    def last_bls_path(self):
+        return int(self._lib.dkgv_last_bls_path(self._h))
+
+    def last_bls_kernel_ms(self):
+        ms = ctypes.c_float()
+        self._ck(self._lib.dkgv_last_bls_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def initial_commitment_hashes(self, vv, gen_id, n, k):
         """base hashes of all dealers at once: vv [n_d, t, 48] -> [n_d, 32]"""

@@ -42,6 +42,10 @@ struct dkgv_ctx {
   dkgv_host::DevBuf in_a, in_b, in_c, out_a, out_b;    // staging for the host-pointer entry points
   dkgv_host::DevBuf scratch_a, scratch_b, scratch_c, scratch_d;   // intermediates of the aggregation / pairing paths
   dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
+  dkgv_host::DevBuf bls_scratch;                       // Fp12 values the pairing VM parks in global memory
+  cudaEvent_t ev_bls0 = nullptr, ev_bls1 = nullptr;    // bracket the pairing kernel
+  bool bls_recorded = false, pvm_attr_set = false;
+  int bls_path = 0, last_bls_path = 0;                 // enum dkgv_bls_path
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
   bool vv_decoded = true;            // the last share-matrix call decoded its commitments (false: settled against their encodings)
   cudaEvent_t ev_dec0 = nullptr, ev_dec1 = nullptr;  // bracket the last verification-vector decode of the share path

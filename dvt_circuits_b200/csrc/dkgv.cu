@@ -227,7 +227,8 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_hot0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_hot1)) != cudaSuccess ||
-      (e = cudaEventCreate(&ctx->ev_dec0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_dec1)) != cudaSuccess)
+      (e = cudaEventCreate(&ctx->ev_dec0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_dec1)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_bls0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_bls1)) != cudaSuccess)
     return bail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
   if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
@@ -271,6 +272,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->ev_dec0) cudaEventDestroy(ctx->ev_dec0);
   if (ctx->ev_dec1) cudaEventDestroy(ctx->ev_dec1);
+  if (ctx->ev_bls0) cudaEventDestroy(ctx->ev_bls0);
+  if (ctx->ev_bls1) cudaEventDestroy(ctx->ev_bls1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;  // every DevBuf member frees its allocation (ctx.hpp)
 }

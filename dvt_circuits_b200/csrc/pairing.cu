@@ -6,6 +6,7 @@
 
 #include "ctx.hpp"
 #include "h2c.cuh"
+#include "pairing_vm.cuh"
 
 using namespace dkgv;
 
@@ -92,6 +93,62 @@ k_bls_verify(const G1Aff* __restrict__ pk, const uint8_t* __restrict__ pk_st, co
                                                                                                        : DKGV_SLASHABLE_SIG_INVALID;
   }
   status[i] = st;
+}
+
+// The pairing VM (pairing_vm.cuh): PVM_R warps x 32 checks per block, every Fp2 of a check in shared memory.  status as
+// k_bls_verify.  scratch: two Fp12 per check that the final exponentiation parks in global memory (f and t2 / t3 of
+// tower.cuh final_exponentiation), chunk-planar: U4 index ((g * 6 + k) * 6 + chunk) * m_pad + check - coalesced.
+constexpr size_t PVM_SMEM = (size_t)PVM_SLOTS * 6 * PVM_LANES * sizeof(U4);
+__global__ void __launch_bounds__(PVM_LANES * PVM_R, 2)
+k_pairing_vm(const G1Aff* __restrict__ pk, const uint8_t* __restrict__ pk_st, const G2Aff* __restrict__ sig, const uint8_t* __restrict__ sig_st,
+             const G2Aff* __restrict__ hm, const G2Line* __restrict__ hm_lines, const uint32_t* __restrict__ hm_idx, uint8_t* __restrict__ status,
+             uint32_t m, U4* __restrict__ scratch, uint32_t m_pad) {
+  extern __shared__ U4 pvm_file[];
+  const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * PVM_LANES + lane, ii = i < m ? i : m - 1;
+  const uint32_t hi = hm_idx ? hm_idx[ii] : 0;
+  const PvmCtx c{pvm_file + lane, (const uint32_t*)(hm_lines + (size_t)hi * G2_PREP_LINES), (const uint32_t*)&pk[ii], (const uint32_t*)&sig[ii]};
+  if (role == 0) pvm_init_point(c);
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t ci = 0; ci < PVM_N_CALLS; ci++) {
+    const PvmCall k = pvm_call(ci);
+    if (k.kind == 0) {
+      uint32_t pc = pvm_seg_start[k.a][role];
+#pragma unroll 1
+      for (;;) {
+        pc = pvm_exec(c, pc, k.b);
+        if (pc & PVM_END_FLAG) break;
+        __syncthreads();
+      }
+    } else {
+#pragma unroll 1
+      for (uint32_t s = role; s < 6; s += PVM_R) {
+#pragma unroll
+        for (uint32_t ch = 0; ch < 6; ch++) {
+          if (k.kind == 1) {
+            c.file[(size_t)((pvm_reg_slot(k.a) + s) * 6 + ch) * PVM_LANES] = c.file[(size_t)((pvm_reg_slot(k.b) + s) * 6 + ch) * PVM_LANES];
+          } else if (k.kind == 2) {
+            scratch[(size_t)((k.a * 6 + s) * 6 + ch) * m_pad + i] = c.file[(size_t)((pvm_reg_slot(k.b) + s) * 6 + ch) * PVM_LANES];
+          } else {
+            c.file[(size_t)((pvm_reg_slot(k.a) + s) * 6 + ch) * PVM_LANES] = scratch[(size_t)((k.b * 6 + s) * 6 + ch) * m_pad + i];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (role == 0 && i < m) {
+    uint8_t st;
+    if (sig_st[i] != G1_DEC_OK) {  // decode order of the reference: signature first, then key (verification.rs:238-241)
+      st = DKGV_PANIC_BAD_G2;
+    } else if (pk_st[i] != G1_DEC_OK) {
+      st = DKGV_PANIC_BAD_G1;
+    } else {
+      st = pvm_status(pk[i].inf != 0, sig[i].inf != 0, hm[hi].inf != 0, pvm_result_is_one(c));
+    }
+    status[i] = st;
+  }
 }
 
 // signer-side helper for synthetic ceremonies (not a verification step): out[i] = [scalars[i]] * base
@@ -202,7 +259,8 @@ extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_
   CK(cudaGetLastError());
   // messages shared by several checks: their lines are computed once (19.6 KB per message)
   const G2Line* lines = nullptr;
-  if ((size_t)n_hm * 4 <= m && (size_t)n_hm * G2_PREP_LINES * sizeof(G2Line) <= ((size_t)256 << 20)) {
+  const bool want_vm = ctx->bls_path != DKGV_BLS_PATH_THREAD;
+  if (((size_t)n_hm * 4 <= m || want_vm) && (size_t)n_hm * G2_PREP_LINES * sizeof(G2Line) <= ((size_t)1 << 30)) {
     CK(ctx->scratch_c.reserve((size_t)n_hm * G2_PREP_LINES * sizeof(G2Line)));
     k_g2_prepare<<<(n_hm + 31) / 32, 32, 0, s>>>((const G2Aff*)ctx->scratch_a.p, (const uint8_t*)ctx->scratch_b.p, (G2Line*)ctx->scratch_c.p,
                                                  n_hm);
@@ -220,14 +278,32 @@ extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_
   k_g1_decode<<<(m + 63) / 64, 64, 0, s>>>(d_pk, (G1Aff*)ctx->bls_pk.p, pk_st, m);
   ctx->launches += 2;
   CK(cudaGetLastError());
-  static int cap_kb = -1;  // experiment: DKGV_BLS_SMEM_KB of unused dynamic shared memory per block caps the resident checks per SM
-  if (cap_kb < 0) {
-    const char* e = getenv("DKGV_BLS_SMEM_KB");
-    cap_kb = e ? atoi(e) : 0;
-    if (cap_kb > 48) CK(cudaFuncSetAttribute(k_bls_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_kb * 1024));
+  if (lines && ctx->bls_path != DKGV_BLS_PATH_THREAD) {
+    // the VM needs the prepared lines of every hashed message (19.6 KB each); batches with more distinct messages than
+    // that budget allows take the one-thread-per-check kernel below
+    if (!ctx->pvm_attr_set) {
+      CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PVM_SMEM));
+      CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      ctx->pvm_attr_set = true;
+    }
+    const uint32_t blocks = (m + PVM_LANES - 1) / PVM_LANES, m_pad = blocks * PVM_LANES;
+    CK(ctx->bls_scratch.reserve((size_t)2 * 6 * 6 * m_pad * sizeof(U4)));
+    CK(cudaEventRecord(ctx->ev_bls0, s));
+    k_pairing_vm<<<blocks, PVM_LANES * PVM_R, PVM_SMEM, s>>>((const G1Aff*)ctx->bls_pk.p, pk_st, (const G2Aff*)ctx->bls_sig.p, sig_st,
+                                                            (const G2Aff*)ctx->scratch_a.p, lines, d_hm_idx, d_status, m, (U4*)ctx->bls_scratch.p, m_pad);
+    CK(cudaEventRecord(ctx->ev_bls1, s));
+    ctx->bls_recorded = true;
+    ctx->last_bls_path = DKGV_BLS_PATH_VM;
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
   }
-  k_bls_verify<<<(m + 31) / 32, 32, (size_t)cap_kb * 1024, s>>>((const G1Aff*)ctx->bls_pk.p, pk_st, (const G2Aff*)ctx->bls_sig.p, sig_st,
+  ctx->last_bls_path = DKGV_BLS_PATH_THREAD;
+  CK(cudaEventRecord(ctx->ev_bls0, s));
+  k_bls_verify<<<(m + 31) / 32, 32, 0, s>>>((const G1Aff*)ctx->bls_pk.p, pk_st, (const G2Aff*)ctx->bls_sig.p, sig_st,
                                             (const G2Aff*)ctx->scratch_a.p, lines, d_hm_idx, d_status, m);
+  CK(cudaEventRecord(ctx->ev_bls1, s));
+  ctx->bls_recorded = true;
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -311,5 +387,21 @@ extern "C" int dkgv_initial_commitment_hashes(dkgv_ctx* ctx, uint32_t n_dealers,
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, ctx->out_a.p, (size_t)n_dealers * 32, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dkgv_set_bls_path(dkgv_ctx* ctx, int mode) {
+  if (!ctx) return -1;
+  if (mode < DKGV_BLS_PATH_AUTO || mode > DKGV_BLS_PATH_THREAD) return dkgv_fail(ctx, "unknown pairing path");
+  ctx->bls_path = mode;
+  return 0;
+}
+extern "C" int dkgv_last_bls_path(const dkgv_ctx* ctx) { return ctx ? ctx->last_bls_path : -1; }
+extern "C" int dkgv_last_bls_kernel_ms(dkgv_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return -1;
+  if (!ctx->bls_recorded) return dkgv_fail(ctx, "no pairing batch launched yet");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_bls1));
+  CK(cudaEventElapsedTime(ms, ctx->ev_bls0, ctx->ev_bls1));
   return 0;
 }

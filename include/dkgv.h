@@ -208,6 +208,15 @@ int dkgv_bls_verify_batch(dkgv_ctx* ctx, uint32_t m, const uint8_t* pk, const ui
 int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
                               const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status, void* stream);
 
+/* Execution of the pairing batch.  AUTO (default): the pairing VM - several warps cooperate on each group of 32 checks with
+ * every Fp2 of a check in shared memory (csrc/pairing_vm.cuh) - whenever the prepared Miller-loop lines of all hashed messages fit
+ * a 1 GB budget (19.6 KB per distinct message), else one thread per check.  THREAD forces the latter (parity tests: two independent
+ * implementations of the same check).  dkgv_last_bls_kernel_ms: device time of the last pairing kernel alone (without decoding). */
+enum dkgv_bls_path { DKGV_BLS_PATH_AUTO = 0, DKGV_BLS_PATH_VM = 1, DKGV_BLS_PATH_THREAD = 2 };
+int dkgv_set_bls_path(dkgv_ctx* ctx, int mode);
+int dkgv_last_bls_path(const dkgv_ctx* ctx);
+int dkgv_last_bls_kernel_ms(dkgv_ctx* ctx, float* ms);
+
 /* ---- prove_wrong_final_key_generation (crates/dkg/src/verification.rs:422-466) for m items over ONE session -------------
  * The curve part of the flow, batched: one hash-to-G2 launch over all messages, one decode + pairing batch over all items, one
  * aggregation per session and the "expected key" of every perpetrator index at once (verify_expected_key :399-420 ->

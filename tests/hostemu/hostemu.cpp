@@ -232,6 +232,57 @@ int he_pairing_bytes(const uint8_t* p48, const uint8_t* q96, uint8_t* out576) {
   }
   return 0;
 }
+}
+// ---- the pairing VM (pairing_vm.cuh): the interpreter and the generated program, all PVM_R roles of ONE check run level by level
+#include "../../dvt_circuits_b200/csrc/pairing_vm.cuh"
+extern "C" {
+// status as k_pairing_vm (0 ok, 7 invalid, 48 bad pk, 49 bad sig); out576: the final value of RA, canonical big-endian, or nullptr
+int he_pairing_vm(const uint8_t* pk48, const uint8_t* sig96, const uint8_t* hm96, uint8_t* out576) {
+  G1Aff pk;
+  G2Aff sig, hm;
+  if (g2_decompress(hm96, &hm, true) != G1_DEC_OK) return -1;
+  uint32_t sst = g2_decompress(sig96, &sig, true), pst = g1_decompress(pk48, &pk, true);
+  std::vector<G2Line> lines(G2_PREP_LINES);
+  if (!hm.inf) g2_prepare(lines.data(), &hm);
+  const int lane = 5;  // any lane of the 32-wide file
+  std::vector<U4> file((size_t)PVM_SLOTS * 6 * PVM_LANES);
+  std::vector<U4> scratch((size_t)2 * 6 * 6);
+  PvmCtx c{file.data() + lane, (const uint32_t*)lines.data(), (const uint32_t*)&pk, (const uint32_t*)&sig};
+  pvm_init_point(c);
+  for (uint32_t ci = 0; ci < PVM_N_CALLS; ci++) {
+    PvmCall k = pvm_call(ci);
+    if (k.kind == 0) {
+      uint32_t pc[PVM_R];
+      for (uint32_t r = 0; r < PVM_R; r++) pc[r] = pvm_seg_start[k.a][r];
+      for (;;) {  // one level: every role up to its barrier
+        uint32_t ended = 0;
+        for (uint32_t r = 0; r < PVM_R; r++) {
+          pc[r] = pvm_exec(c, pc[r], k.b);
+          ended += (pc[r] & PVM_END_FLAG) ? 1 : 0;
+        }
+        if (ended == PVM_R) break;
+        if (ended != 0) return -2;  // the roles of a segment must agree on the number of levels
+      }
+    } else {
+      for (uint32_t s2 = 0; s2 < 6; s2++)
+        for (uint32_t ch = 0; ch < 6; ch++) {
+          if (k.kind == 1) c.file[(size_t)((pvm_reg_slot(k.a) + s2) * 6 + ch) * PVM_LANES] = c.file[(size_t)((pvm_reg_slot(k.b) + s2) * 6 + ch) * PVM_LANES];
+          else if (k.kind == 2) scratch[(k.a * 6 + s2) * 6 + ch] = c.file[(size_t)((pvm_reg_slot(k.b) + s2) * 6 + ch) * PVM_LANES];
+          else c.file[(size_t)((pvm_reg_slot(k.a) + s2) * 6 + ch) * PVM_LANES] = scratch[(k.b * 6 + s2) * 6 + ch];
+        }
+    }
+  }
+  if (out576)
+    for (uint32_t k = 0; k < 6; k++) {
+      Fp a, b;
+      pvm_ld_slot(c, SLOT_A0 + k, a, b);
+      fp_raw_to_be48(out576 + 96 * k, from_mont(a).l);
+      fp_raw_to_be48(out576 + 96 * k + 48, from_mont(b).l);
+    }
+  if (sst != G1_DEC_OK) return DKGV_PANIC_BAD_G2;
+  if (pst != G1_DEC_OK) return DKGV_PANIC_BAD_G1;
+  return pvm_status(pk.inf != 0, sig.inf != 0, hm.inf != 0, pvm_result_is_one(c));
+}
 void he_sha256(const uint8_t* msg, size_t len, uint8_t* out32) {
   Sha256 s;
   sha_init(&s);

@@ -239,3 +239,51 @@ def test_bad_partial_key_batch_against_oracle(verifier, n, t, m):
     st2, _, sst2 = verifier.bad_partial_key_verify_batch(vv2, it["perp"], it["pk"], it["sig"], [fin["message"]])
     assert sst2 == 48
     assert (st2 == np.where((st == 0) | (st == 8), 48, st)).all()
+
+
+@pytest.mark.parametrize("m", [1, 31, 33, 200])
+def test_pairing_vm_against_thread_kernel_and_oracle(verifier, m):
+    """the pairing VM (several warps per 32 checks, csrc/pairing_vm.cuh) and the one-thread-per-check kernel are two independent
+    implementations of bls_verify_precomputed_hash: same statuses on valid, wrong, undecodable and identity arguments, with
+    several hashed messages - and both equal the C++ oracle's."""
+    from dvt_circuits_b200 import synthetic
+    fin = synthetic.make_finalization(verifier, 8, 3)
+    msgs = [b"Sign with new partial key", b"another message", b""]
+    hms = verifier.hash_to_g2(msgs)
+    sk = fin["partial_secrets"]
+    sigs = [verifier.g2_mul_batch(hms[k].tobytes(), sk) for k in range(3)]
+    rng = np.random.Generator(np.random.PCG64(m))
+    who = rng.integers(0, 8, size=m)
+    idx = rng.integers(0, 3, size=m).astype(np.uint32)
+    pk = fin["partial_pubkeys"][who].copy()
+    sg = np.stack([sigs[idx[i]][who[i]] for i in range(m)])
+    kind = rng.integers(0, 8, size=m)
+    for i in range(m):
+        if kind[i] == 0:
+            sg[i] = sigs[idx[i]][(who[i] + 1) % 8]      # wrong signer
+        elif kind[i] == 1:
+            sg[i] = sigs[(idx[i] + 1) % 3][who[i]]      # wrong message
+        elif kind[i] == 2:
+            pk[i, 17] ^= 4                              # undecodable key
+        elif kind[i] == 3:
+            sg[i, 60] ^= 1                              # undecodable signature
+        elif kind[i] == 4:
+            pk[i], sg[i] = np.frombuffer(INF1, dtype=np.uint8), np.frombuffer(INF2, dtype=np.uint8)  # identity = identity
+        elif kind[i] == 5:
+            pk[i] = np.frombuffer(INF1, dtype=np.uint8)  # e(O, H) = 1 != e(G, sig)
+    try:
+        verifier.set_bls_path(verifier.BLS_VM)
+        st_vm = verifier.bls_verify_batch(pk, sg, hms, idx)
+        assert verifier.last_bls_path == verifier.BLS_VM
+        verifier.set_bls_path(verifier.BLS_THREAD)
+        st_th = verifier.bls_verify_batch(pk, sg, hms, idx)
+        assert verifier.last_bls_path == verifier.BLS_THREAD
+    finally:
+        verifier.set_bls_path(verifier.BLS_AUTO)
+    assert (st_vm == st_th).all(), np.argwhere(st_vm != st_th)[:10]
+    for i in range(m):
+        r = O.bls_verify_hm(bytes(pk[i]), bytes(sg[i]), bytes(hms[idx[i]]))
+        want = {1: 0, 0: 7, -48: 48, -49: 49}[r]
+        if kind[i] == 3 and r == -48:
+            want = 49
+        assert st_vm[i] == want, (i, int(kind[i]), int(st_vm[i]), r)
