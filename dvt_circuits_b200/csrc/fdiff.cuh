@@ -488,7 +488,7 @@ DKGV_HD bool fd_coef_signs(const Fp* z, const Fp* y, const uint8_t* fs, int cnt)
     acc = mul(acc, z[i]);
     pref[i] = acc;
   }
-  Fp inv = fp_inv(acc);
+  Fp inv = fp_inv_bgcd(acc);
   bool ok = true;
 #pragma unroll 1
   for (int i = cnt - 1; i >= 0; i--) {

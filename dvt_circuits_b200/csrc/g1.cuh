@@ -184,7 +184,7 @@ DKGV_HD bool g1_in_subgroup(const G1Aff& a) {
 
 DKGV_HD G1Aff g1_to_affine(const G1Proj& p) {
   G1Aff r;
-  Fp zi = fp_inv(p.z);
+  Fp zi = fp_inv_bgcd(p.z);
   r.x = mul(p.x, zi);
   r.y = mul(p.y, zi);
   r.inf = is_zero(p.z) ? 1u : 0u;

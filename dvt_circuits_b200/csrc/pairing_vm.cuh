@@ -26,7 +26,10 @@
 #else
 #define PVM_CONST static const
 #endif
-#include "pairing_prog.inc"
+#ifndef PVM_PROG_FILE
+#define PVM_PROG_FILE "pairing_prog.inc"
+#endif
+#include PVM_PROG_FILE
 
 namespace dkgv {
 
@@ -111,16 +114,17 @@ DKGV_HD uint32_t pvm_exec(const PvmCtx& c, uint32_t pc, uint32_t line_idx) {
       }
       case PVM_MUL: {  // (x0 y0 - x1 y1, x0 y1 + x1 y0): two fused sum-of-two-products routines
         t0 = neg(y1);
-        t1 = mul2add(x0, y1, x1, y0);
-        x0 = mul2add(x0, y0, x1, t0);
+        mul2add_pair(t0, t1, x0, y0, x1, t0, x0, y1, x1, y0);  // the two sums interleaved: four carry chains in flight
+        x0 = t0;
         x1 = t1;
         break;
       }
       case PVM_SQR: {  // ((x0 + x1)(x0 - x1), 2 x0 x1)
         t0 = add(x0, x1);
         t1 = sub(x0, x1);
-        x1 = dbl(mul(x0, x1));
-        x0 = mul(t0, t1);
+        mul_pair(t0, t1, t0, t1, x0, x1);  // the two products interleaved
+        x0 = t0;
+        x1 = dbl(t1);
         break;
       }
       case PVM_XI: t0 = sub(x0, x1); x1 = add(x0, x1); x0 = t0; break;
@@ -130,7 +134,7 @@ DKGV_HD uint32_t pvm_exec(const PvmCtx& c, uint32_t pc, uint32_t line_idx) {
       case PVM_CONJX: x1 = neg(x1); break;
       case PVM_INVX: {  // 1 / (x0 + x1 u) = (x0 - x1 u) / (x0^2 + x1^2); 0 -> 0
         t0 = add(mul(x0, x0), mul(x1, x1));
-        t0 = fp_inv(t0);
+        t0 = fp_inv_bgcd(t0);
         x0 = mul(x0, t0);
         x1 = neg(mul(x1, t0));
         break;

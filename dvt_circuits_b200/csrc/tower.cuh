@@ -46,7 +46,7 @@ DKGV_NI2 void fp_pow_ni(Fp* r, const Fp* a, int which) {
   }
   *r = acc;
 }
-DKGV_NI2 void fp_inv_ni(Fp* r, const Fp* a) { fp_pow_ni(r, a, 0); }
+DKGV_NI2 void fp_inv_ni(Fp* r, const Fp* a) { *r = fp_inv_bgcd(*a); }  // binary extended Euclid (field.cuh): ~8x fewer instructions than a^(p-2)
 DKGV_NI2 void fp_sqrt_ni(Fp* r, const Fp* a) { fp_pow_ni(r, a, 1); }
 DKGV_NI2 bool fp_is_square(const Fp* a) {
   if (is_zero(*a)) return true;

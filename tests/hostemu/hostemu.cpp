@@ -27,6 +27,12 @@ void he_fp_ops(const uint8_t* a48, const uint8_t* b48, uint8_t* mul48, uint8_t* 
   fp_raw_to_be48(sub48, from_mont(sub(a, b)).l);
   fp_raw_to_be48(inv48, from_mont(fp_inv(a)).l);
 }
+// canonical a -> a^-1 by the binary extended Euclid routine (field.cuh fp_inv_bgcd)
+void he_fp_inv_bgcd(const uint8_t* a48, uint8_t* inv48) {
+  Fp a;
+  fp_raw_from_be48(a.l, a48);
+  fp_raw_to_be48(inv48, from_mont(fp_inv_bgcd(to_mont(a))).l);
+}
 
 void he_fr_mul(const uint8_t* a32, const uint8_t* b32, uint8_t* out32) {
   Fr a, b;

@@ -49,6 +49,17 @@ def test_field_ops(L):
         assert int.from_bytes(r.raw, "big") == x * y % B.R
 
 
+def test_inversion_by_binary_gcd(L):
+    """fp_inv_bgcd (binary extended Euclid with count-trailing-zeros strips) == a^(p-2) on random and extreme operands"""
+    rnd = random.Random(21)
+    cases = [0, 1, 2, 3, B.P - 1, B.P - 2, (B.P - 1) // 2, (B.P + 1) // 2, 1 << 32, 1 << 64, (1 << 380) + 1, 1 << 380, 3 << 200]
+    cases += [pow(2, k, B.P) for k in (31, 32, 33, 95, 96, 383, 384)] + [rnd.randrange(B.P) for _ in range(400)]
+    for a in cases:
+        o = buf(48)
+        L.he_fp_inv_bgcd(a.to_bytes(48, "big"), o)
+        assert int.from_bytes(o.raw, "big") == pow(a, B.P - 2, B.P), hex(a)
+
+
 def test_g1_formulas_and_codec(L):
     rnd = random.Random(3)
     for it in range(6):

@@ -148,8 +148,13 @@ class Node:
         return s
 
     def cost(self):
-        n_add = sum(abs(c) for c in self.x.t.values()) + (sum(abs(c) for c in self.y.t.values()) if self.y is not None else 0)
-        return COST[self.kind] + ADD_COST * (n_add + 2)
+        def adds(l):
+            g = max(abs(c) for c in l.t.values())
+            if g in (2, 3) and len(l.t) > 1 and all(k == 0 for (_v, k), c in l.t.items() if abs(c) != g):
+                return sum(1 if abs(c) == g else abs(c) for c in l.t.values()) + 1
+            return sum(abs(c) for c in l.t.values())
+        n_add = adds(self.x) + (adds(self.y) if self.y is not None else 0)
+        return COST[self.kind] + ADD_COST * (n_add + 2) + (COST["mul"] if getattr(self, "then_const", None) is not None else 0)
 
 
 def factor_chain(m):
@@ -191,6 +196,10 @@ class Prog:
     @staticmethod
     def inp(k): return Lin.of(Var(f"IN{k}", ("IN", k)))
 
+    def at_least(self, level):
+        """nodes created from now on sit at dependency level >= `level` (hand-placed pipelining inside a segment)"""
+        self.floor = level
+
     def _node(self, kind, x, y, dst, post):
         if dst is None:
             self.n_tmp += 1
@@ -199,6 +208,7 @@ class Prog:
             assert dst in self.state_slots, dst
             out = Var(f"{dst}@{len(self.nodes)}", ("S", dst))
         n = Node(kind, x, y, out, post)
+        n.min_level = getattr(self, "floor", 1)
         out.node = n
         for v in n.inputs():
             self.readers[v].append(n)
@@ -215,8 +225,11 @@ class Prog:
         a, b = Lin.of(a), Lin.of(b)
         return self._node("mul", a, b, dst, post)
 
-    def sqr(self, a, dst=None, post=(0, 1)):
-        return self._node("sqr", Lin.of(a), None, dst, post)
+    def sqr(self, a, dst=None, post=(0, 1), then_const=None):
+        """xi^post[0] * post[1] * a^2 [* constant then_const]"""
+        r = self._node("sqr", Lin.of(a), None, dst, post)
+        self.nodes[-1].then_const = then_const
+        return r
 
     def lin(self, a, dst=None):
         return self._node("lin", Lin.of(a), None, dst, (0, 1))
@@ -225,7 +238,7 @@ class Prog:
         return self._node("inv", Lin.of(a), None, dst, (0, 1))
 
     # ---- scheduling
-    def schedule(self, R):
+    def schedule(self, R, balance=True):
         nodes = self.nodes
         changed = True
         while changed:
@@ -246,6 +259,8 @@ class Prog:
                     changed = True
         self.n_levels = max(n.level for n in nodes)
         self.R = R
+        if balance:
+            self._balance(R)
         for lv in range(1, self.n_levels + 1):
             load = [0] * R
             for n in sorted([n for n in nodes if n.level == lv], key=lambda n: -n.cost()):
@@ -255,13 +270,72 @@ class Prog:
         # a role executes its nodes of a level in program order; a node writing a fixed slot must not run before a node of the SAME
         # role and level that still reads the old value - program order guarantees that (the reader was created first)
 
+    def _makespan(self, R, lv):
+        load = [0] * R
+        for n in sorted([n for n in self.nodes if n.level == lv], key=lambda n: -n.cost()):
+            r = min(range(R), key=lambda i: load[i])
+            load[r] += n.cost()
+        return max(load)
+
+    def _latest(self, n):
+        """latest level node n may move to with every other node where it is"""
+        hi = self.n_levels
+        for c in self.readers.get(n.out, []):
+            hi = min(hi, c.level - 1)
+        for m in self.nodes:
+            if m is n or m.overwrites is None:
+                continue
+            if m.overwrites is n.out:                      # a later write to the same fixed slot
+                hi = min(hi, m.level - 1)
+            if m.overwrites in n.inputs():                 # n still reads the value m overwrites
+                hi = min(hi, m.level - 1)
+        return hi
+
+    def _balance(self, R):
+        """nodes with slack move to a later level when that shortens the sum over levels of the busiest role's load"""
+        improved = True
+        while improved:
+            improved = False
+            for n in sorted(self.nodes, key=lambda n: -n.cost()):
+                lo, hi = n.level, self._latest(n)
+                if hi <= lo:
+                    continue
+                base = {lv: self._makespan(R, lv) for lv in range(lo, hi + 1)}
+                best, best_gain = None, 0
+                for lv in range(lo + 1, hi + 1):
+                    n.level = lv
+                    gain = (base[lo] + base[lv]) - (self._makespan(R, lo) + self._makespan(R, lv))
+                    if gain > best_gain:
+                        best, best_gain = lv, gain
+                n.level = best if best is not None else lo
+                improved |= best is not None
+
     def allocate(self, fixed_index, n_fixed):
-        """temporaries -> slots >= n_fixed by liveness over levels; returns number of slots used"""
+        """temporaries -> slots by liveness over levels: first the dead windows of the fixed state slots (between the last read of a
+        value and the level that writes the next one - e.g. the merged line's slots while the step is still computing it), then
+        slots >= n_fixed; returns number of slots used"""
         last = {}
         for n in self.nodes:
             for v in n.inputs():
-                if v.loc is None:
-                    last[v] = max(last.get(v, 0), n.level)
+                last[v] = max(last.get(v, 0), n.level)
+        # dead windows [lo, hi] of fixed slots
+        versions = defaultdict(list)  # slot name -> [(def level, var)] in program order
+        for n in self.nodes:
+            for v in n.inputs():
+                if v.loc is not None and v.loc[0] == "S" and v.node is None and not versions[v.loc[1]]:
+                    versions[v.loc[1]].append((0, v))
+        for n in self.nodes:
+            if n.out.loc is not None:
+                name = n.out.loc[1]
+                if not versions[name]:
+                    versions[name].append((0, None))  # the incoming value is never read in this segment: dead on entry
+                versions[name].append((n.level, n.out))
+        windows = []  # (slot index, lo, hi)
+        for name, vs in versions.items():
+            for (d0, v0), (d1, _v1) in zip(vs, vs[1:]):
+                lo = (max(last.get(v0, d0), d0) if v0 is not None else 0) + 1
+                if lo <= d1 - 1:
+                    windows.append([fixed_index[name], lo, d1 - 1])
         free_at = []  # (slot, free from level)
         used = n_fixed
         for n in sorted(self.nodes, key=lambda n: n.level):
@@ -271,6 +345,14 @@ class Prog:
                 continue
             end = last.get(v, n.level)
             pick = None
+            for w in windows:  # a fixed slot that is dead for the whole life of this temporary
+                if w[1] <= n.level and end <= w[2]:
+                    v.slot = w[0]
+                    w[1] = end + 1
+                    pick = -1
+                    break
+            if pick == -1:
+                continue
             for i, (s, fr) in enumerate(free_at):
                 if fr <= n.level:
                     pick = i
@@ -294,6 +376,22 @@ class Prog:
         ins = []
         if lin.conj:
             assert reg == "X"
+        # 3 (a + xi b) - 2 z  /  2 (a + b - c): sum the terms that share the largest coefficient once, scale, then add the rest
+        if reg == "X" and not lin.conj and len(lin.t) > 1:
+            g = max(abs(c) for c in lin.t.values())
+            rest = {k: c for k, c in lin.t.items() if abs(c) != g}
+            if g in (2, 3) and all(k == 0 for (_v, k) in rest) and \
+                    any(c > 0 and (v.loc is None or v.loc[0] == "S") for (v, _k), c in lin.t.items() if abs(c) == g):
+                head = Lin({k: (1 if c > 0 else -1) for k, c in lin.t.items() if abs(c) == g})
+                ins = self._emit_operand(head, "X") + [("TPLX" if g == 3 else "DBLX", 0)]
+                for (v, _k), c in sorted(rest.items(), key=lambda kv: kv[1] < 0):
+                    assert v.loc is None or v.loc[0] == "S"
+                    ins += [(("ADDX" if c > 0 else "SUBX"), v.slot)] * abs(c)
+                for _ in range(lin.pk):
+                    ins.append(("XI", 0))
+                if lin.mult != 1:
+                    ins += [(o, 0) for o in factor_chain(lin.mult)]
+                return ins
         by_k = defaultdict(list)
         for (v, k), c in lin.t.items():
             by_k[k].append((v, c))
@@ -368,6 +466,8 @@ class Prog:
                     s += self._emit_operand(x, "X") + yi + [("MUL", 0)]
                 elif n.kind == "sqr":
                     s += self._emit_operand(x, "X") + [("SQR", 0)]
+                    if getattr(n, "then_const", None) is not None:
+                        s += [("LDYK", n.then_const), ("MUL", 0)]
                 elif n.kind == "inv":
                     s += self._emit_operand(x, "X") + [("INVX", 0)]
                 else:
@@ -499,20 +599,17 @@ def f_state(p, pre="A"):
     return [p.state(pre + str(i)) for i in range(6)]
 
 
-def f_part_sqr_mul(p):
-    """f <- f^2 * L: complex squaring over Fp6 (2 x 6 products), then the 17-product multiplication by the merged line"""
+def f_part_sqr(p):
+    """f <- f^2: complex squaring over Fp6 (2 x 6 products), back into f's own slots"""
     a = f_state(p)
     f0, f1 = a[:3], a[3:]
-    L = [p.state(n) for n in ["L00", "L01", "L02", "L11", "L12"]]
     ab = fp6_mul(p, f1, f0)
     vb = mul_v(f1)
     t = fp6_mul(p, [f0[i] + vb[i] for i in range(3)], [f0[i] + f1[i] for i in range(3)])
     vab = mul_v(ab)
-    s0 = [p.lin(t[i] - ab[i] - vab[i], dst=f"A{i}") for i in range(3)]  # f^2 goes back into f's own slots
-    s1 = [p.lin(2 * ab[i], dst=f"A{3 + i}") for i in range(3)]
-    out = f_times_line(p, s0, s1, L)
-    for i, e in enumerate(out):
-        p.lin(e, dst=f"A{i}")
+    for i in range(3):
+        p.lin(t[i] - ab[i] - vab[i], dst=f"A{i}")
+        p.lin(2 * ab[i], dst=f"A{3 + i}")
 
 
 def f_part_mul(p):
@@ -551,6 +648,8 @@ def seg_fe_cyc(p):
     def fp4(x, y):
         s0, s1, s2 = p.sqr(x), p.sqr(y), p.sqr(x + y)
         return s0 + s1.xi(), s2 - s0 - s1
+    # (placing the third Fp4 squaring one level down, next to the sums of the first, balances the roles better on paper - 9
+    # squarings on 6 roles - but costs a third barrier: measured 246.8 ms against 239.1 ms for 262 144 checks on B200)
     t0, t1 = fp4(z0, z1)
     u0, u1 = fp4(z2, z3)
     w0, w1 = fp4(z4, z5)
@@ -610,11 +709,11 @@ def build_segments(R):
             part(p)
         p.schedule(R)
         segs[name] = p
-    seg("T_D", STATE_MILLER, t_part_dbl)        # point step (doubling) + merged line of the step
-    seg("T_A", STATE_MILLER, t_part_add)        # point step (addition)
-    seg("F_C", STATE_MILLER, f_part_copy)       # f <- L_0
-    seg("F_D", STATE_MILLER, f_part_sqr_mul)    # f <- f^2 L
-    seg("F_A", STATE_MILLER, f_part_mul)        # f <- f L
+    # one segment per Miller step.  Doubling step: f^2 (which does not need the line) runs next to the point step that produces the
+    # merged line, then f takes the line in: 6 dependency levels instead of 4 + 4 for the two halves run one after the other.
+    seg("S_0", STATE_MILLER, t_part_dbl, f_part_copy)           # first step: f <- L_0
+    seg("S_D", STATE_MILLER, f_part_sqr, t_part_dbl, f_part_mul)
+    seg("S_A", STATE_MILLER, t_part_add, f_part_mul)
     seg("FE_MUL", STATE_FE, seg_fe_mul)
     seg("FE_CYC", STATE_FE, seg_fe_cyc)
     seg("FE_INV", STATE_FE, seg_fe_inv)
@@ -627,7 +726,7 @@ def build_segments(R):
     return segs, n_slots
 
 
-SEG_ORDER = ["T_D", "T_A", "F_C", "F_D", "F_A", "FE_MUL", "FE_CYC", "FE_INV", "FE_CONJA", "FE_CONJB", "FE_FROBB"]
+SEG_ORDER = ["S_0", "S_D", "S_A", "FE_MUL", "FE_CYC", "FE_INV", "FE_CONJA", "FE_CONJB", "FE_FROBB"]
 
 
 def miller_steps():
@@ -645,9 +744,8 @@ def driver_sequence():
     itself, as tuples ('COPY', dst, src) / ('SPILL', k, reg) / ('FILL', reg, k) with reg in 'A', 'B'"""
     steps = miller_steps()
     seq = []
-    for j, k in enumerate(steps):  # point step j (it also merges the two lines of the step), then f takes the merged line in
-        seq.append(("T_" + k, j))
-        seq.append((("F_C" if j == 0 else "F_" + k), None))
+    for j, k in enumerate(steps):
+        seq.append((("S_0" if j == 0 else "S_" + k), j))
     # f = conj(f) (x < 0), then the final exponentiation of tower.cuh final_exponentiation()
     seq.append(("FE_CONJA", None))
     seq += [("FE_INV", None), ("FE_CONJA", None), ("FE_MUL", None)]                 # f^(p^6 - 1)
@@ -915,9 +1013,10 @@ if __name__ == "__main__":
     ap.add_argument("--roles", type=int, default=6)
     ap.add_argument("--check", action="store_true", help="simulate the program against oracle/pyref and print the schedule")
     ap.add_argument("--write", action="store_true", help="write dvt_circuits_b200/csrc/pairing_prog.inc")
+    ap.add_argument("--out", default=None, help="other output path (experiments with another number of roles)")
     a = ap.parse_args()
     if a.check or not a.write:
         self_check(a.roles)
     if a.write:
-        nw, ns = write_inc(os.path.join(ROOT, "dvt_circuits_b200", "csrc", "pairing_prog.inc"), a.roles)
+        nw, ns = write_inc(a.out or os.path.join(ROOT, "dvt_circuits_b200", "csrc", "pairing_prog.inc"), a.roles)
         print(f"wrote pairing_prog.inc: {nw} words, {ns} slots")
