@@ -1,31 +1,31 @@
 #!/usr/bin/env python
-"""bench.py - verified shares/s on the synthetic DKG ceremony n=1024, t=683 (BASELINE.json metric).
+"""bench.py - verified shares/s on the synthetic DKG ceremony n=1024, t=683 and BLS pairing checks/s (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over the whole share matrix through `dkgv_share_matrix_verify[_dev]` (decode of the
-verification vectors, verdict for every (dealer, recipient) share).  With N ranks the ONE ceremony is sharded by dealer row
-blocks (strong scaling, as BASELINE.json names it); the only exchange is an NCCL all-gather of the per-share verdict bitmask,
-inside the timed region.
+One "step" = one pass of the hot path over the whole share matrix.  With N ranks the ONE ceremony is sharded by dealer row blocks
+(strong scaling, as BASELINE.json names it) through the LIBRARY's own multi-GPU entry point `dkgv_share_matrix_verify_sharded_dev`:
+local rows, verdict bitmask packed, one NCCL all-gather inside the library (dkgv_comm_*), all inside the timed region.
+torch.distributed is only the plumbing that hands the 128-byte communicator id round and takes the max over ranks of the timings.
 
-`value`     device-timed, inputs resident in HBM, max over ranks, the library's DEFAULT path on the synthetic (honest) ceremony:
-            the consistency shortcut proves every dealer's shares valid by scalar arithmetic + t fixed-base
-            multiplications compared with the COMPRESSED commitments, exactly (no randomness): no share is evaluated in the
-            exponent and no commitment is decompressed.
-`full_evaluation`  the same steps with the shortcut off - every share through the group arithmetic (finite differences);
-`mixed_items`      the same matrix with half of the shares corrupted (BASELINE config 5): the shortcut fails for every dealer
-            and the evaluation produces the per-share verdicts, which must flag exactly the corrupted shares.
-`e2e`       `value`'s metric through the reference-facing C ABI with HOST (pinned) buffers:
-            H2D of vv + shares + ids and D2H of the verdicts inside the timed region.
-`roofline`  integer-pipe roofline of the evaluation kernels (`roofline.kernels`, from the full-evaluation steps run phase after
-            phase): canonical 32x32->64 multiply-accumulates per second (84 314 modmul/share x 300 MAC)
-            against the IMAD.WIDE peak measured live by bench/imad_peak on the same GPU.  The top-level fields describe the
-            dominant kernel of the timed (default-path) steps - k_fd_coefpoint, G * p_k against the compressed commitment (the
-            default path decodes no commitment) - and `roofline.shortcut_kernels` all kernels of such a step, timed live.
-`cpu_baseline` the CPU oracle in reference-faithful mode (per-op affine round trips, constant-time
-            255-step scalar multiplication - the reference's operation sequence) on a bounded sample
-            of the same matrix, all host cores.  A restatement, not the Rust binary (no cargo here).
+`value`      device-timed, inputs resident in HBM, max over ranks: the library's DEFAULT path on the synthetic (honest) ceremony - the
+             exact consistency shortcut: no share is evaluated in the exponent, no commitment decompressed.
+`e2e`        the same metric with HOST (pinned) buffers: H2D of vv + shares + ids and D2H of the verdicts inside the timed region.
+`roofline`   integer-pipe roofline of the dominant kernel of the timed steps (k_fd_coefpoint), all shortcut kernels and the
+             evaluation kernels, against the IMAD.WIDE peak measured live by bench/imad_peak.
+`corruption` the same matrix with 1 share / 1 dealer / 1 % / 10 % / 50 % (BASELINE config 5) of the shares corrupted: verdicts must
+             flag exactly the corrupted shares; `full_evaluation`: shortcut switched off.
+`pairing`    second BASELINE metric: 262 144 bls_verify_precomputed_hash checks (every 7th with a wrong signature), sharded over the
+             ranks; device-timed value, kernel-only roofline (executed products from the pairing VM program), e2e from host buffers,
+             cpu_baseline (oracle, two full pairings per check as the reference does).
+`bad_partial_key`  BASELINE config 5, second half: 1 M bad-partial-key items over a (64, 43) session, half of them corrupted.
+`config_a`   BASELINE config 2: n=64, t=43 full matrix on one GPU, with the CPU full-matrix baseline.
+`finalization`  BASELINE config 4 at (n, t): sharded aggregation + Lagrange + the n partial-signature checks; CPU baseline on a
+             bounded (64, 43) ceremony.
+`cpu_baseline`  the CPU oracle in reference-faithful mode (per-op affine round trips, constant-time 255-step scalar multiplication - the
+             reference's operation sequence) on a bounded sample of the same matrix, all host cores; `same_algorithm`: the GPU
+             library's own shortcut run on the CPU (oracle shortcut leg), so algorithmic and hardware gain separate.
 """
 import argparse
 import json
@@ -42,6 +42,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_PART, THRESH = 1024, 683
 MAC_PER_MODMUL = 300          # 2*12^2 + 12 wide multiply-accumulates per 12-limb Montgomery product
+PAPER_PEAK_MAC = 148 * 64 * 1.965e9
+METRIC = "verified shares/sec (n=1024,t=683)"
 
 
 def canonical_modmul_per_share(n, t):
@@ -49,15 +51,6 @@ def canonical_modmul_per_share(n, t):
     G*s and the comparison; averaged over ids 1..n.  (n=1024, t=683) -> 84 314."""
     tot = sum(8 * (j.bit_length() - 1) + 12 * (bin(j).count("1") - 1) + 11 for j in range(1, n + 1))
     return (t - 1) * tot / n + 356
-
-
-def executed_modmul_per_share(n, t):
-    """what k_share_verify really executes: signed-digit chain (vm.cuh make_small_chain), full add (12)
-    for the coefficient, 33 mixed adds (11) + 4 for G*s and the comparison."""
-    def cost(pos, neg):
-        m = pos | neg
-        return 8 * (m.bit_length() - 1) + 12 * (bin(m).count("1") - 1)
-    return sum(executed_horner_modmul(t, j) for j in range(1, n + 1)) / n + 33 * EXEC_MADD + 4
 
 
 def canonical_horner_modmul(t, x):
@@ -77,16 +70,13 @@ def executed_horner_modmul(t, x):
     x = abs(x)
     if x == 0:
         return 0
+
     def shape(pos, neg):
         m = pos | neg
         return m.bit_length() - 1, bin(m).count("1") - 1
     k3 = 3 * x
     dbl, adds = min((shape(x, 0), shape((k3 & ~x) >> 1, (~k3 & x) >> 1)), key=lambda s_: 8 * s_[0] + 12 * s_[1])
     return (t - 1) * (EXEC_DBL * dbl + EXEC_ADD * adds + EXEC_ADD)
-
-
-PAPER_PEAK_MAC = 148 * 64 * 1.965e9
-METRIC = "verified shares/sec (n=1024,t=683)"
 
 
 def parse():
@@ -98,15 +88,14 @@ def parse():
     ap.add_argument("--n", type=int, default=N_PART, help="participants (default: the BASELINE config)")
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-shortcut", dest="shortcut", action="store_false",
-                    help="evaluate every id in the group even when the scalar-side consistency conditions hold (dkgv_set_share_shortcut 0)")
-    ap.add_argument("--no-finalization", action="store_true", help="skip the config-4 finalization leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip every CPU-baseline leg")
+    ap.add_argument("--quick", action="store_true", help="main leg only (value, e2e, roofline of the default path): for profiling runs")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="single GPU: process only the row block one rank of a W-rank job would hold (no collective) - the per-kernel view "
+                         "of the N = W step for ncu; the printed value is NOT a whole-ceremony number")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1], help="dkgv_set_share_overlap mode of the evaluation steps")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
-    ap.add_argument("--share-path", default="auto", choices=["auto", "horner", "fdiff"],
-                    help="evaluation strategy (enum dkgv_share_path); auto = finite differences for ids 1..n, n > t")
     return ap.parse_args()
 
 
@@ -171,32 +160,38 @@ def measured_int_peak():
                 "source": f"fallback paper peak 148 SM x 64 lanes x 1.965 GHz ({type(e).__name__})"}
 
 
-def cpu_baseline(n, t, cols, threads):
-    """oracle in reference-faithful mode on a bounded sample of the same matrix (threads x cols shares:
-    one dealer row per host thread, `cols` recipient ids spread over 1..n).  The sample rows reuse one
-    dealer's polynomial - the faithful cost per share depends on t only - and the verification vector is
-    decoded once per row, which under-counts the reference (it decodes all t points per share,
-    verification.rs:132-137): the baseline is favoured, not the GPU."""
+# ------------------------------------------------------------------------------------------ CPU legs (the only users of oracle/)
+def cpu_share_session(n, t, rows, ids):
+    """`rows` copies of one dealer of the synthetic ceremony at the recipient ids `ids` (built with the oracle itself)"""
     import numpy as np
     import oracle_lib as O
     from dvt_circuits_b200 import synthetic
-    rows = max(1, threads)
     coeffs = synthetic.make_coefficients(1, t)
-    ids = np.unique(np.linspace(1, n, cols).astype(np.uint32))
-    cols = len(ids)
     vv1 = np.zeros((t, 48), dtype=np.uint8)
     cs = [int.from_bytes(coeffs[0, k].tobytes(), "big") for k in range(t)]
     for k in range(t):
         st, pk = O.g1_fixed_base(coeffs[0, k].tobytes(), O.FAST)
         vv1[k] = np.frombuffer(pk, dtype=np.uint8)
-    sh1 = np.zeros((cols, 32), dtype=np.uint8)
+    sh1 = np.zeros((len(ids), 32), dtype=np.uint8)
     for j, i in enumerate(ids.tolist()):
         acc = 0
         for c in reversed(cs):
             acc = (acc * i + c) % synthetic.R_INT
         sh1[j] = np.frombuffer(acc.to_bytes(32, "big"), dtype=np.uint8)
-    vv = np.broadcast_to(vv1, (rows, t, 48)).copy()
-    shares = np.broadcast_to(sh1, (rows, cols, 32)).copy()
+    return np.broadcast_to(vv1, (rows, t, 48)).copy(), np.broadcast_to(sh1, (rows, len(ids), 32)).copy()
+
+
+def cpu_baseline(n, t, cols, threads):
+    """oracle in reference-faithful mode on a bounded sample of the same matrix (threads x cols shares: one dealer row per host
+    thread, `cols` recipient ids spread over 1..n).  The sample rows reuse one dealer's polynomial - the faithful cost per share
+    depends on t only - and the verification vector is decoded once per row, which under-counts the reference (it decodes all t
+    points per share, verification.rs:132-137): the baseline is favoured, not the GPU."""
+    import numpy as np
+    import oracle_lib as O
+    rows = max(1, threads)
+    ids = np.unique(np.linspace(1, n, cols).astype(np.uint32))
+    cols = len(ids)
+    vv, shares = cpu_share_session(n, t, rows, ids)
     t0 = time.perf_counter()
     st = O.share_matrix(vv, ids, shares, O.FAITHFUL, threads=threads)
     dt = time.perf_counter() - t0
@@ -209,6 +204,80 @@ def cpu_baseline(n, t, cols, threads):
             "fast_mode_value": rows * cols / dt_fast, "n_shares": rows * cols}
 
 
+def cpu_same_algorithm(n, t, threads):
+    """the GPU library's own exact shortcut (range, t-th differences, compress(G p_k) == C_k) on the host cores: `threads` dealers
+    of the ceremony with all n shares each, oracle shortcut leg.  Separates the algorithmic gain from the hardware gain."""
+    import numpy as np
+    import oracle_lib as O
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    vv, shares = cpu_share_session(n, t, threads, ids)
+    O.share_matrix_shortcut(vv[:1], shares[:1], threads=1)  # builds the fixed-base table (untimed, as the GPU's)
+    t0 = time.perf_counter()
+    st, fb = O.share_matrix_shortcut(vv, shares, threads=threads)
+    dt = time.perf_counter() - t0
+    assert fb == 0 and not st.any()
+    return {"value": threads * n / dt, "unit": "shares/s", "cores": threads, "kind": "port",
+            "sample": f"{threads} dealers x {n} shares, the consistency shortcut of the GPU path run by the CPU oracle, {dt:.2f}s wall"}
+
+
+def cpu_pairing(threads, per_thread=12):
+    """oracle bls_verify_precomputed_hash exactly as the reference computes it (two full pairings + Gt equality, decoding included)"""
+    import numpy as np
+    import oracle_lib as O
+    from oracle.pyref import bls12_381 as B
+    hmp = B.hash_to_g2(b"Sign with new partial key")
+    hm = B.g2_compress(hmp)
+    pks, sigs = [], []
+    for i in range(4):
+        sk = 0x1234567 + i
+        pks.append(list(B.g1_compress(B.g1_mul(B.G1, sk))))
+        sigs.append(list(B.g2_compress(B.g2_mul(hmp, sk))))
+    m = threads * per_thread
+    pk = np.array([pks[i % 4] for i in range(m)], dtype=np.uint8)
+    sg = np.array([sigs[i % 4] for i in range(m)], dtype=np.uint8)
+    O.fp_mul_count(reset=True)
+    O.bls_verify_hm(bytes(pk[0]), bytes(sg[0]), hm)
+    modmul = O.fp_mul_count(reset=True)
+    t0 = time.perf_counter()
+    out = O.bls_verify_batch(pk, sg, hm, threads=threads)
+    dt = time.perf_counter() - t0
+    assert (out == 1).all()
+    return {"value": m / dt, "unit": "checks/s", "cores": threads, "kind": "port",
+            "sample": f"{m} checks (decode + 2 full pairings each, as bls_common.rs:26-35), {dt:.1f}s wall",
+            "modmul_per_check_reference_sequence": modmul}
+
+
+def cpu_config_a(threads):
+    """BASELINE config 2 on the CPU: the FULL 64 x 64 matrix at t = 43, oracle faithful mode, all cores"""
+    import numpy as np
+    import oracle_lib as O
+    n, t = 64, 43
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    vv, shares = cpu_share_session(n, t, n, ids)
+    t0 = time.perf_counter()
+    st = O.share_matrix(vv, ids, shares, O.FAITHFUL, threads=threads)
+    dt = time.perf_counter() - t0
+    assert not st.any()
+    return {"value": n * n / dt, "unit": "shares/s", "cores": threads, "kind": "port",
+            "sample": f"full {n}x{n} matrix, t={t}, oracle faithful mode, {dt:.1f}s wall"}
+
+
+def cpu_finalization(fin, threads):
+    """config 4 on the CPU at a bounded size (the (64, 43) ceremony `fin`): agg_coefficients + keys, two Lagrange interpolations and
+    the n partial-signature checks, oracle faithful mode (the aggregation and Lagrange are single-threaded, as in the reference)"""
+    import oracle_lib as O
+    n = fin["ids"].shape[0]
+    t0 = time.perf_counter()
+    ast, co, keys = O.agg_coefficients(fin["vv"], fin["ids"], O.FAITHFUL)
+    l1 = O.lagrange(keys, fin["ids"], O.FAITHFUL)
+    l2 = O.lagrange(fin["partial_pubkeys"], fin["ids"], O.FAITHFUL)
+    out = O.bls_verify_batch(fin["partial_pubkeys"], fin["signatures"], bytes(fin["hm"]), threads=threads)
+    dt = time.perf_counter() - t0
+    assert ast == 0 and l1 == l2 and l1[1] == bytes(co[0]) and (out == 1).all()
+    return {"total_ms": dt * 1e3, "n": n, "t": int(fin["vv"].shape[1]), "cores": threads, "kind": "port",
+            "sample": f"whole finalization of a ({n}, {fin['vv'].shape[1]}) ceremony, oracle faithful mode"}
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """--impl reference: the reference's CPU path for the same metric.  The Rust crate cannot be built
@@ -217,6 +286,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import oracle_lib as O
+    O.use_native_build()
     threads = os.cpu_count() or 1
     cols = args.cpu_sample or 24
     vals, cb = [], None
@@ -260,46 +331,29 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     n, t = args.n, args.t
-    if n % world:
+    split = args.emulate_world if (args.emulate_world and world == 1) else world
+    if n % split:
         raise SystemExit("participants must divide by the number of ranks")
-    rows = n // world
+    rows = n // split
 
     v = dk.Verifier(local)
+    if world > 1:  # the library owns the collectives; torch.distributed only carries the 128-byte id to the other ranks
+        box = [dk.Verifier.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        v.comm_init(box[0], rank, world)
     v.set_share_parts(args.parts)
     v.set_share_overlap(args.overlap)
-    v.set_share_shortcut(args.shortcut)
-    v.set_share_path({"auto": v.PATH_AUTO, "horner": v.PATH_HORNER, "fdiff": v.PATH_FDIFF}[args.share_path])
     sess = synthetic.make_session(v, rows, n, t, dealer_offset=rank * rows)  # set-up, untimed
     ts = torch.cuda.Stream(device=dev)
     stream = ts.cuda_stream
-    with torch.cuda.stream(ts):
-        d_vv = torch.from_numpy(sess["vv"]).to(dev)
-        d_ids = torch.from_numpy(sess["ids"].view(np.int32)).to(dev)
-        d_sh = torch.from_numpy(sess["shares"]).to(dev)
-        d_st = torch.empty((rows, n), dtype=torch.uint8, device=dev)
-        # ranks exchange the verdict BITMASK (1 bit per share), not the status bytes
-        d_bits = torch.zeros(((rows * n + 31) // 32,), dtype=torch.int32, device=dev)
-        d_all = torch.zeros((world * d_bits.numel(),), dtype=torch.int32, device=dev) if world > 1 else d_st
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    # pinned host copies for the end-to-end leg
-    h_vv = torch.from_numpy(sess["vv"]).pin_memory()
-    h_ids = torch.from_numpy(sess["ids"].view(np.int32)).pin_memory()
-    h_sh = torch.from_numpy(sess["shares"]).pin_memory()
-    h_st = torch.empty((rows, n), dtype=torch.uint8).pin_memory()
+    chunk = v.share_gather_words(rows, n)
+    words = (rows * n + 31) // 32
 
-    def step_device():
-        v.share_matrix_verify_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh.data_ptr(), d_st.data_ptr(), stream)
+    def dmax(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
-            v.pack_verdicts_dev(rows * n, d_st.data_ptr(), d_bits.data_ptr(), stream)
-            dist.all_gather_into_tensor(d_all, d_bits)
-
-    def step_e2e():
-        rc = v._lib.dkgv_share_matrix_verify(v._h, rows, n, t, h_vv.data_ptr(), h_ids.data_ptr(), h_sh.data_ptr(), h_st.data_ptr())
-        v._ck(rc)
-        if world > 1:
-            d_st.copy_(h_st, non_blocking=True)
-            v.pack_verdicts_dev(rows * n, d_st.data_ptr(), d_bits.data_ptr(), stream)
-            dist.all_gather_into_tensor(d_all, d_bits)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
     def barrier():
         torch.cuda.synchronize()
@@ -307,11 +361,58 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    with torch.cuda.stream(ts):
+        d_vv = torch.from_numpy(sess["vv"]).to(dev)
+        d_ids = torch.from_numpy(sess["ids"].view(np.int32)).to(dev)
+        d_sh = torch.from_numpy(sess["shares"]).to(dev)
+        d_st = torch.empty((rows, n), dtype=torch.uint8, device=dev)
+        d_gather = torch.zeros((world, chunk), dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # pinned host copies for the end-to-end leg
+    h_vv = torch.from_numpy(sess["vv"]).pin_memory()
+    h_ids = torch.from_numpy(sess["ids"].view(np.int32)).pin_memory()
+    h_sh = torch.from_numpy(sess["shares"]).pin_memory()
+    h_st = torch.empty((rows, n), dtype=torch.uint8).pin_memory()
+    h_gather = torch.empty((world, chunk), dtype=torch.int32).pin_memory()
+
+    def step_device(shares=None):
+        v.share_matrix_verify_sharded_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), (d_sh if shares is None else shares).data_ptr(),
+                                          d_st.data_ptr(), d_gather.data_ptr(), stream)
+
+    def step_e2e():
+        if world == 1:
+            v._ck(v._lib.dkgv_share_matrix_verify(v._h, rows, n, t, h_vv.data_ptr(), h_ids.data_ptr(), h_sh.data_ptr(), h_st.data_ptr()))
+        else:  # host rows in, gathered verdict bitmask of the WHOLE ceremony out
+            d_vv.copy_(h_vv, non_blocking=True)
+            d_ids.copy_(h_ids, non_blocking=True)
+            d_sh.copy_(h_sh, non_blocking=True)
+            step_device()
+            h_gather.copy_(d_gather, non_blocking=True)
+            h_st.copy_(d_st, non_blocking=True)
+            ts.synchronize()
+
+    def timed_steps(fn, count, do_flush=True):
+        out = []
+        for _ in range(count):
+            if do_flush:
+                flush.fill_(1)  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            fn()
+            e1.record(ts)
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return out
+
+    def bad_bits():
+        g = d_gather[:, :words]
+        return int(torch.count_nonzero(g).item())
+
     peak = None
     if rank == 0:
         peak = measured_int_peak() if not args.no_peak else {"imad_wide": PAPER_PEAK_MAC, "imad_wide_x": None, "fp_mul_per_s": None,
                                                             "source": "paper peak 148 SM x 64 lanes x 1.965 GHz (--no-peak)"}
-
+    line = {}
     with torch.cuda.stream(ts):
         sampler = ClockSampler(local)
         if rank == 0:
@@ -320,82 +421,32 @@ def run_b200(args):
             step_device()
         barrier()
         launches0 = v.launch_count
-        step_ms, hot_ms, phase_ms, dec_ms, short_ms, decoded_steps = [], [], [], [], [], 0
         barrier()
         wall0 = time.perf_counter()
+        step_ms, short_ms = [], []
         for _ in range(args.steps):
-            flush.fill_(1)  # L2 flush between timed iterations (not timed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ts)
-            step_device()
-            e1.record(ts)
-            e1.synchronize()
-            step_ms.append(e0.elapsed_time(e1))
-            hot_ms.append(v.last_hot_kernel_ms())
-            # the default path settles an honest ceremony against the COMPRESSED commitments: no decode inside such a step
-            step_decoded = bool(getattr(v, "last_share_decoded", 1))
-            decoded_steps += step_decoded
-            if step_decoded:
-                dec_ms.append(v.last_decode_ms())
-            if v.last_share_path == v.PATH_FDIFF:
-                try:  # shortcut-settled step: [share limbs + difference table, x halves of G*p_k == C_k, sign halves, flags]
-                    short_ms.append(v.last_share_phases_ms())
-                except Exception:  # noqa: BLE001  (timing detail only)
-                    pass
+            step_ms += timed_steps(step_device, 1)
+            if v.last_share_path == v.PATH_FDIFF and not v.last_share_continued:
+                short_ms.append(v.last_share_phases_ms())  # [share limbs + difference table, x halves of G*p_k == C_k, sign halves, flags]
         barrier()
         wall = time.perf_counter() - wall0
         launches = v.launch_count - launches0
-        # The timed region of the default path is short (10 steps of ~15 ms on one GPU, less on eight) against nvidia-smi's 50 ms
+        # The timed region of the default path is short (10 steps of ~13 ms on one GPU, less on eight) against nvidia-smi's 50 ms
         # sampling period: keep the same steps running, untimed, until the GPU has been under this load for ~0.6 s, so that the
         # clocks line rests on several samples.  The count comes from the max-over-ranks step time: identical on every rank.
-        t_sum = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
-        per_step_s = max(float(t_sum.item()) / args.steps * 1e-3, 1e-4)
-        extra_steps = max(0, min(2000, int(0.6 / per_step_s) - args.steps))
+        ms_per_step = dmax(sum(step_ms)) / args.steps
+        extra_steps = max(0, min(2000, int(0.6 / max(ms_per_step * 1e-3, 1e-4)) - args.steps))
         for _ in range(extra_steps):
             step_device()
         barrier()
         clocks = sampler.stop(since=wall0) if rank == 0 else None
         if clocks is not None:
             clocks["untimed_steps_under_the_same_load"] = extra_steps
-        continued = bool(v.last_share_continued) if v.last_share_path == v.PATH_FDIFF else False
-        full_ms, serial_ms = [], []
-        if v.last_share_path == v.PATH_FDIFF:
-            # The evaluation kernels: the same steps with the consistency shortcut off (every share through the group
-            # arithmetic) - first as in production (parts on concurrent streams), then phase after phase on one stream,
-            # where single kernels have a duration of their own (roofline.kernels)
-            v.set_share_shortcut(False)
-            aux_steps = min(args.steps, 3)  # the evaluation legs take ~0.7 s per step
-            step_device()  # untimed: the evaluation buffers are allocated on first use
-            torch.cuda.synchronize()
-            for mode, acc in ((args.overlap, full_ms), (0, serial_ms)):
-                v.set_share_overlap(mode)
-                for _ in range(aux_steps):
-                    flush.fill_(1)
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(ts)
-                    step_device()
-                    e1.record(ts)
-                    e1.synchronize()
-                    acc.append(e0.elapsed_time(e1))
-                    if mode == 0:
-                        phase_ms.append(v.last_share_phases_ms())
-            v.set_share_overlap(args.overlap)
-            v.set_share_shortcut(args.shortcut)
-            barrier()
-            full_total = torch.tensor([sum(full_ms)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(full_total, op=dist.ReduceOp.MAX)
-            full_ms_step = float(full_total.item()) / aux_steps
+        bad = bad_bits()
+        settled_by_shortcut = v.last_share_path == v.PATH_FDIFF and not v.last_share_continued
+        shares_total = rows * n * world
 
-        total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        ms_per_step = float(total_ms.item()) / args.steps
-        bad = int(d_all.count_nonzero().item())
-
-        # end-to-end through the host-pointer C ABI
+        # end-to-end with host buffers
         step_e2e()
         barrier()
         e2e_t = []
@@ -405,113 +456,228 @@ def run_b200(args):
             step_e2e()
             torch.cuda.synchronize()
             e2e_t.append(time.perf_counter() - t0)
-        e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-        e2e_s_per_step = float(e2e_total.item()) / args.steps
+        e2e_s_per_step = dmax(sum(e2e_t)) / args.steps
         bad_e2e = int(h_st.count_nonzero().item())
 
-        # BASELINE config 5: the same matrix with half of the shares corrupted (one flipped bit each): every dealer group
-        # takes the full evaluation; verdicts must flag exactly the corrupted shares
-        rng = np.random.Generator(np.random.PCG64([0xBAD, rank]))
-        mask = rng.random((rows, n)) < 0.5
-        sh_bad = sess["shares"].copy()
-        sh_bad[mask, 31] ^= 1
-        d_sh_bad = torch.from_numpy(sh_bad).to(dev)
-        mixed_ms = []
-        for i in range(1 + max(1, min(args.steps, 3) - 1)):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ts)
-            v.share_matrix_verify_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), d_sh_bad.data_ptr(), d_st.data_ptr(), stream)
-            e1.record(ts)
-            e1.synchronize()
-            if i:
-                mixed_ms.append(e0.elapsed_time(e1))
-        mixed_ok = bool(((d_st != 0) == torch.from_numpy(mask).to(dev)).all().item())
-        mixed_total = torch.tensor([sum(mixed_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(mixed_total, op=dist.ReduceOp.MAX)
-        mixed_ms_step = float(mixed_total.item()) / len(mixed_ms)
-        del d_sh_bad
+        legs = {}
+        if not args.quick:
+            # ---- the evaluation route: shortcut off (every share through the group arithmetic), production mode then phase by phase
+            aux = min(args.steps, 3)
+            v.set_share_shortcut(False)
+            step_device()  # untimed: the evaluation buffers are allocated on first use
+            full_ms = timed_steps(step_device, aux)
+            v.set_share_overlap(0)
+            phase_ms, serial_ms = [], []
+            for _ in range(aux):
+                serial_ms += timed_steps(step_device, 1)
+                phase_ms.append(v.last_share_phases_ms())
+            v.set_share_overlap(args.overlap)
+            v.set_share_shortcut(True)
+            barrier()
+            full_ms_step = dmax(sum(full_ms)) / aux
+            legs["full_evaluation"] = {"metric": "verified shares/sec, every share evaluated in the group (consistency shortcut off)",
+                                       "value": shares_total / (full_ms_step * 1e-3), "unit": "shares/s", "ms_per_step": full_ms_step}
 
-        # second BASELINE metric: BLS pairing checks/s (bls_verify_precomputed_hash, one common message),
-        # 262144 checks (a batch that saturates the GPU) sharded over the ranks, inputs resident in HBM, verdict bytes all-gathered
-        m_total = 262144
-        m_loc = m_total // world
-        fin = synthetic.make_finalization(v, 64, 8)
-        reps = (m_loc + 63) // 64
-        d_pk = torch.from_numpy(np.tile(fin["partial_pubkeys"], (reps, 1))[:m_loc].copy()).to(dev)
-        d_sg = torch.from_numpy(np.tile(fin["signatures"], (reps, 1))[:m_loc].copy()).to(dev)
-        d_hm = torch.from_numpy(fin["hm"].copy()).to(dev)
-        d_ps = torch.empty((m_loc,), dtype=torch.uint8, device=dev)
-        d_pall = torch.empty((m_total,), dtype=torch.uint8, device=dev) if world > 1 else d_ps
+            # ---- corrupted shares: the reference exists to PROVE misbehaviour; how the default path degrades with the corruption rate
+            rng = np.random.Generator(np.random.PCG64([0xBAD, rank]))
+            corr = {}
+            for name, kind in (("one_share", 1), ("one_dealer", 2), ("p_1pct", 0.01), ("p_10pct", 0.10), ("p_50pct_config5", 0.50)):
+                mask = np.zeros((rows, n), dtype=bool)
+                if kind == 1:
+                    if rank == 0:
+                        mask[rows // 2, n // 3] = True
+                elif kind == 2:
+                    if rank == 0:
+                        mask[rows // 2, :] = True
+                else:
+                    mask = rng.random((rows, n)) < kind
+                sh_bad = sess["shares"].copy()
+                sh_bad[mask, 31] ^= 1
+                d_bad = torch.from_numpy(sh_bad).to(dev)
+                step_device(d_bad)
+                ms = timed_steps(lambda: step_device(d_bad), 2)
+                ok = bool(((d_st != 0) == torch.from_numpy(mask).to(dev)).all().item())
+                ok_all = dmax(0.0 if ok else 1.0) == 0.0
+                ms_step = dmax(sum(ms)) / len(ms)
+                corr[name] = {"corrupted_shares_this_rank0": int(mask.sum()), "ms_per_step": ms_step,
+                              "value": shares_total / (ms_step * 1e-3), "unit": "shares/s",
+                              "verdicts_flag_exactly_the_corrupted_shares": ok_all, "took_the_evaluation": bool(v.last_share_continued)}
+                del d_bad
+            legs["corruption"] = corr
+            legs["mixed_items"] = dict(corr["p_50pct_config5"], metric="verified shares/sec, 50 % of the shares corrupted (BASELINE config 5)")
 
-        def step_pairing():
-            v._ck(v._lib.dkgv_bls_verify_batch_dev(v._h, m_loc, d_pk.data_ptr(), d_sg.data_ptr(), 1, d_hm.data_ptr(), None,
-                                                   d_ps.data_ptr(), stream))
-            if world > 1:
-                dist.all_gather_into_tensor(d_pall, d_ps)
+            # ---- second BASELINE metric: BLS pairing checks/s (bls_verify_precomputed_hash, one common message), 262 144 checks sharded
+            # over the ranks, every 7th with another signer's (valid, wrong) signature; status bytes all-gathered inside the library
+            m_total = 262144
+            m_loc = m_total // world
+            fin = synthetic.make_finalization(v, 64, 8)
+            reps = (m_loc + 63) // 64
+            pk_np = np.tile(fin["partial_pubkeys"], (reps, 1))[:m_loc].copy()
+            sg_np = np.tile(fin["signatures"], (reps, 1))[:m_loc].copy()
+            wrong = np.arange(m_loc) % 7 == 3
+            sg_np[wrong] = np.roll(sg_np, 1, axis=0)[wrong]
+            d_pk, d_sg = torch.from_numpy(pk_np).to(dev), torch.from_numpy(sg_np).to(dev)
+            d_hm = torch.from_numpy(fin["hm"].copy()).to(dev)
+            d_pall = torch.empty((world, m_loc), dtype=torch.uint8, device=dev)
 
-        step_pairing()
-        barrier()
-        pair_ms = []
-        for _ in range(max(2, args.steps)):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ts)
+            def step_pairing():
+                v.bls_verify_batch_sharded_dev(m_loc, d_pk.data_ptr(), d_sg.data_ptr(), 1, d_hm.data_ptr(), None, d_pall.data_ptr(), stream)
+
             step_pairing()
-            e1.record(ts)
-            e1.synchronize()
-            pair_ms.append(e0.elapsed_time(e1))
-        pair_total = torch.tensor([sum(pair_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(pair_total, op=dist.ReduceOp.MAX)
-        pair_ms_step = float(pair_total.item()) / len(pair_ms)
-        pair_bad = int(d_pall.count_nonzero().item())
+            barrier()
+            pair_ms, pair_kernel_ms = [], []
+            for _ in range(max(2, min(args.steps, 5))):
+                pair_ms += timed_steps(step_pairing, 1, do_flush=False)
+                pair_kernel_ms.append(v.last_bls_kernel_ms())
+            pair_ms_step = dmax(sum(pair_ms)) / len(pair_ms)
+            want = torch.from_numpy(np.where(wrong, 7, 0).astype(np.uint8)).to(dev)
+            pair_ok = bool((d_pall == want.unsqueeze(0)).all().item())
+            # e2e: host buffers through dkgv_bls_verify_batch (H2D of keys + signatures, D2H of the statuses inside)
+            t0 = time.perf_counter()
+            st_h = v.bls_verify_batch(pk_np, sg_np, fin["hm"])
+            pair_e2e_s = dmax(time.perf_counter() - t0)
+            prog = json.load(open(os.path.join(ROOT, "dvt_circuits_b200", "csrc", "pairing_prog.json")))
+            kms = statistics.mean(pair_kernel_ms)
+            legs["pairing"] = {
+                "metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
+                "checks_per_step": m_total, "ms_per_step": pair_ms_step, "wrong_signatures_per_step": int(wrong.sum()) * world,
+                "verdicts_flag_exactly_the_wrong_signatures": pair_ok and bool((st_h == np.where(wrong, 7, 0)).all()),
+                "path": {1: "pairing VM (6 warps per 32 checks, operands in shared memory)", 2: "one thread per check"}[v.last_bls_path],
+                "e2e": {"value": m_total / pair_e2e_s, "unit": "checks/s", "h2d_bytes_per_step": int(m_total * 144 + 96), "d2h_bytes_per_step": m_total,
+                        "timing": "host wall clock around dkgv_bls_verify_batch (host buffers), max over ranks"},
+                "note": "e(pk,H(m)) == e(G1,sig) as ONE product of two Miller loops + one final exponentiation per check, incl. G1/G2 decoding "
+                        "with subgroup checks and the preparation of the hashed message's lines",
+            }
+            if rank == 0:
+                macs = prog["wide_macs_per_check"]
+                ach = m_loc * macs / (kms * 1e-3)
+                legs["pairing"]["roofline"] = {
+                    "bound": "int_pipe", "kernel": "k_pairing_vm", "kernel_ms": kms, "kernel_share_of_step": kms / statistics.mean(pair_ms),
+                    "achieved": ach / 1e9, "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "frac": ach / peak["imad_wide"],
+                    "frac_of_carry_chain_peak": (ach / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                    "executed_wide_macs_per_check": macs, "executed_fp_mul_equivalents_per_check": prog["fp_mul_equivalents_per_check"],
+                    "fp2_products_per_check": prog["fp2_mul_per_check"], "fp2_squarings_per_check": prog["fp2_sqr_per_check"],
+                    "barriers_per_check": prog["barriers_per_check"], "units_per_launch": m_loc, "unit_is": "one pairing check (Miller loops + final exponentiation; decoding is in other kernels)",
+                    "traffic": 327 * m_loc, "traffic_ref": "profiles/r2_pairing_vm.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_pairing_vm launch = 327 B per check (no local memory)",
+                    "algorithmic_bytes": 145 * m_loc,
+                    "note": "executed products counted from the VM program (csrc/pairing_prog.json); an Fp2 product = 2 fused sums of two products (888 MACs), a squaring = 2 products (600)"}
+            del d_pk, d_sg, d_pall
 
-        # BASELINE config 4: finalization of the whole ceremony through the host-pointer C ABI (rank 0, one GPU):
-        # agg_coefficients + the n final keys, two Lagrange interpolations at 0, n partial-signature checks
-        fin_line = None
-        if rank == 0 and not args.no_finalization:
-            ff = synthetic.make_finalization(v, n, t)
+            # ---- BASELINE config 5, second half: 1 M bad-partial-key items over a (64, 43) session, half of them corrupted
+            m_bp = (1 << 20) // world
+            fin_a = synthetic.make_finalization(v, 64, 43)
+            items = synthetic.make_bad_partial_items(v, fin_a, m_bp, p_bad=0.5, seed=synthetic.DEFAULT_SEED + rank)
+            st_bp, exp_keys, sst = v.bad_partial_key_verify_batch(fin_a["vv"], items["perp"], items["pk"], items["sig"], [fin_a["message"]])
+            barrier()
+            t0 = time.perf_counter()
+            st_bp, exp_keys, sst = v.bad_partial_key_verify_batch(fin_a["vv"], items["perp"], items["pk"], items["sig"], [fin_a["message"]])
+            # verdict = 1 bit per item, gathered over NVLink by the library's communicator
+            d_bst = torch.from_numpy(st_bp).to(dev)
+            d_bbits = torch.zeros((world, (m_bp + 31) // 32), dtype=torch.int32, device=dev)
+            v.pack_verdicts_dev(m_bp, d_bst.data_ptr(), d_bbits[rank].data_ptr(), stream)
+            v.all_gather_dev(d_bbits[rank].data_ptr(), d_bbits.data_ptr(), d_bbits[rank].numel() * 4, stream)
+            ts.synchronize()
+            bp_s = dmax(time.perf_counter() - t0)
+            bp_ok = dmax(0.0 if (sst == 0 and (st_bp == items["expected"]).all()) else 1.0) == 0.0
+            legs["bad_partial_key"] = {
+                "metric": "bad-partial-key items/sec (prove_wrong_final_key_generation, 1 M items over a (64, 43) session, 50 % corrupted)",
+                "value": m_bp * world / bp_s, "unit": "items/s", "items_per_step": m_bp * world, "s_per_step": bp_s,
+                "statuses_equal_the_expected_ones": bp_ok, "status_histogram_rank0": {int(k): int(c) for k, c in zip(*np.unique(st_bp, return_counts=True))},
+                "slashable_bits_gathered": int(torch.count_nonzero(d_bbits).item() > 0),
+                "timing": "host wall clock around dkgv_bad_partial_key_verify_batch (host buffers: H2D of keys, signatures, perpetrator "
+                          "indices; aggregation + expected keys of the session; hash-to-G2; decode + pairing of every item; D2H of the statuses) "
+                          "+ bitmask all-gather, max over ranks"}
+            del d_bst, d_bbits
+
+            # ---- BASELINE config 4: finalization of the whole ceremony.  Aggregation sharded by generations (each rank decodes and
+            # sums its rows, one all-gather of the t partial sums), the n partial-signature checks sharded by items; the Lagrange
+            # interpolations and the evaluation of the n final keys are latency-bound one-thread-per-term kernels and run replicated.
+            ff = synthetic.make_finalization(v, n, t) if rank == 0 or world > 1 else None
+            fr = slice(rank * (n // world), (rank + 1) * (n // world))
             best = None
             for _ in range(2):
+                barrier()
                 t0 = time.perf_counter()
-                ast, co, keys = v.agg_final_keys(ff["vv"], ff["ids"])
+                ast, co, keys = v.agg_final_keys_sharded(ff["vv"][fr], ff["ids"])
                 t1 = time.perf_counter()
                 l1 = v.lagrange_at_zero(keys, ff["ids"])
                 l2 = v.lagrange_at_zero(ff["partial_pubkeys"], ff["ids"])
                 t2 = time.perf_counter()
-                st_f = v.bls_verify_batch(ff["partial_pubkeys"], ff["signatures"], ff["hm"])
+                st_f = v.bls_verify_batch(ff["partial_pubkeys"][fr], ff["signatures"][fr], ff["hm"])
                 t3 = time.perf_counter()
                 ok = bool(ast == 0 and (keys == ff["partial_pubkeys"]).all() and l1 == (0, bytes(co[0])) and l2 == l1 and not st_f.any())
-                cur = {"metric": "finalization of one ceremony (host buffers, wall clock)", "n": n, "t": t, "total_ms": (t3 - t0) * 1e3,
-                       "agg_final_keys_ms": (t1 - t0) * 1e3, "lagrange_x2_ms": (t2 - t1) * 1e3, "partial_signature_checks_ms": (t3 - t2) * 1e3,
-                       "final_keys_per_s": n / (t1 - t0), "all_checks_hold": ok}
+                cur = {"metric": "finalization of one ceremony (host buffers, wall clock, max over ranks)", "n": n, "t": t,
+                       "total_ms": dmax(t3 - t0) * 1e3, "agg_final_keys_ms": dmax(t1 - t0) * 1e3, "lagrange_x2_ms": dmax(t2 - t1) * 1e3,
+                       "partial_signature_checks_ms": dmax(t3 - t2) * 1e3, "all_checks_hold": dmax(0.0 if ok else 1.0) == 0.0,
+                       "sharding": f"aggregation: {n // world} generations per rank + all-gather of {t} x 144 B partial sums; signature checks: "
+                                   f"{n // world} per rank; final keys + Lagrange replicated"}
                 if best is None or cur["total_ms"] < best["total_ms"]:
                     best = cur
-            fin_line = best
+            legs["finalization"] = best
+
+            # ---- BASELINE config 2 (rank 0, one GPU): n = 64, t = 43, the full 64 x 64 matrix
+            if rank == 0:
+                sa = synthetic.make_session(v, 64, 64, 43)
+                da_vv, da_ids = torch.from_numpy(sa["vv"]).to(dev), torch.from_numpy(sa["ids"].view(np.int32)).to(dev)
+                da_sh, da_st = torch.from_numpy(sa["shares"]).to(dev), torch.empty((64, 64), dtype=torch.uint8, device=dev)
+
+                def step_a():
+                    v.share_matrix_verify_dev(64, 64, 43, da_vv.data_ptr(), da_ids.data_ptr(), da_sh.data_ptr(), da_st.data_ptr(), stream)
+                step_a()
+                a_ms = statistics.mean(timed_steps(step_a, 5, do_flush=False))
+                v.set_share_shortcut(False)
+                step_a()
+                a_full_ms = statistics.mean(timed_steps(step_a, 3, do_flush=False))
+                v.set_share_shortcut(True)
+                legs["config_a"] = {"metric": "verified shares/sec (n=64,t=43), full 64x64 matrix on one GPU", "value": 4096 / (a_ms * 1e-3),
+                                    "unit": "shares/s", "ms_per_step": a_ms, "bad_verdicts": int(da_st.count_nonzero().item()),
+                                    "every_share_evaluated": {"value": 4096 / (a_full_ms * 1e-3), "ms_per_step": a_full_ms},
+                                    "note": "latency-bound: 4 096 shares are a fraction of one wave"}
 
     if rank == 0:
-        shares = n * n
-        value = shares / (ms_per_step * 1e-3)
-        hot = statistics.mean(hot_ms)
+        value = shares_total / (ms_per_step * 1e-3)
         MODMUL_PER_SHARE = canonical_modmul_per_share(n, t)
-        fdiff = v.last_share_path == v.PATH_FDIFF
         step_mean = statistics.mean(step_ms)
-        # whole path: canonical per-share work (84 314 modmul) of every verified share per second of step time
-        path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / ((statistics.mean(full_ms) if full_ms else step_mean) * 1e-3)
 
         def kernel_entry(name, units, unit_is, canon_unit, exec_unit, ms, ref_ms):
             a, e = units * canon_unit * MAC_PER_MODMUL / (ms * 1e-3), units * exec_unit * MAC_PER_MODMUL / (ms * 1e-3)
             return {"kernel": name, "achieved": a / 1e9, "frac": a / peak["imad_wide"],
                     "frac_of_carry_chain_peak": (a / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                    "executed_gmac_per_s": e / 1e9,
+                    "executed_gmac_per_s": e / 1e9, "executed_frac": e / peak["imad_wide"],
                     "executed_frac_of_carry_chain_peak": (e / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
                     "kernel_ms": ms, "kernel_share_of_step": ms / ref_ms, "units_per_launch_total": units, "unit_is": unit_is,
                     "modmul_per_unit": canon_unit, "executed_modmul_per_unit": exec_unit}
 
-        if fdiff:
+        roof = {"bound": "int_pipe", "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "peak_source": peak["source"],
+                "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9, "mac_per_modmul": MAC_PER_MODMUL, "traffic": None, "algorithmic_bytes": None}
+        if settled_by_shortcut and len(short_ms) == args.steps:
+            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (33 mixed
+            # additions) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
+            # ALU work + 2 products) - per point 3 products of the simultaneous inversion + Y / Z + the canonical form for the sign
+            sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
+            pt_canon, pt_exec = 33 * 11 + 2, 33 * EXEC_MADD + 2
+            sg = 2 / 8 + 3 + 2
+            top = kernel_entry("k_fd_coefpoint", rows * t, "one coefficient: G * p_k by the fixed-base table, x_C * Z == X against the "
+                               "compressed commitment", pt_canon, pt_exec, sp[1], step_mean)
+            roof.update({k_: top[k_] for k_ in ("kernel", "achieved", "frac", "frac_of_carry_chain_peak", "executed_gmac_per_s", "executed_frac",
+                                                "executed_frac_of_carry_chain_peak", "kernel_ms", "kernel_share_of_step", "unit_is", "modmul_per_unit")})
+            roof["units_per_launch"] = top["units_per_launch_total"]
+            roof["shortcut_kernels"] = [
+                top,
+                kernel_entry("k_fd_coefsign", rows * t, "one coefficient: sign of Y / Z (simultaneous inversion over 8, inversion by binary extended Euclid)",
+                             sg, sg, sp[2], step_mean),
+                {"kernel": "k_fd_prep + k_fd_cols + k_fd_share_limbs + k_fd_difftab", "kernel_ms": sp[0], "kernel_share_of_step": sp[0] / step_mean,
+                 "unit_is": "one dealer: t rounds of subtractions over the n shares + basis conversion by small integers (Fr, no wide products to speak of)"},
+                {"kernel": "k_fd_need + k_fd_fill_ok", "kernel_ms": sp[3], "kernel_share_of_step": sp[3] / step_mean},
+                {"kernel": "pack + all-gather + flag read-back (the rest of the step)", "kernel_ms": step_mean - sum(sp),
+                 "kernel_share_of_step": (step_mean - sum(sp)) / step_mean}]
+            roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
+            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r1_default_path_v3.md): dram read 57 367 296 B +
+            # write 32 190 208 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
+            roof["traffic"] = int(round((57367296 + 32190208) / 699392 * rows * t))
+            roof["traffic_ref"] = ("profiles/r1_default_path_v3.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
+                                   "(128.1 B per coefficient, scaled to this launch's coefficients)")
+        if "full_evaluation" in legs:
             plan = dk.share_fd_plan(t, n, args.parts)
             m_parts, h_part = plan["parts"], plan["h"]
             seeds = range(plan["lo"], plan["hi"] + 1)
@@ -521,140 +687,74 @@ def run_b200(args):
             comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
             comb_exec = ((128 * EXEC_DBL + (m_parts - 1) * (EXEC_DBL + 3 * EXEC_ADD + 52 * EXEC_ADD + 26) + EXEC_ADD if m_parts > 1 else 0)
                          + 33 * EXEC_MADD + 4)
-            short = bool(args.shortcut and n > t and not continued)  # the timed steps were settled by the consistency shortcut
-            ids_eval, ext_steps = n, plan["steps"]  # the kernel entries below come from the full-evaluation steps
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,
                              sum(executed_horner_modmul(h_part, x) for x in seeds) / h_part, ph[0], ref),
                 kernel_entry("k_fd_init", rows * m_parts * h_part * (h_part - 1) // 2, "one point subtraction (all rounds)", 12, EXEC_ADD, ph[1], ref),
-                kernel_entry("k_fd_ext", rows * m_parts * ext_steps * (h_part - 1), "one point addition (all ticks)", 12, EXEC_ADD, ph[2], ref),
-                kernel_entry("k_fd_combine", rows * ids_eval, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare",
+                kernel_entry("k_fd_ext", rows * m_parts * plan["steps"] * (h_part - 1), "one point addition (all ticks)", 12, EXEC_ADD, ph[2], ref),
+                kernel_entry("k_fd_combine", rows * n, "one share: joint GLV / width-4 double-and-add over the parts, G*s, compare",
                              comb_canon, comb_exec, ph[3], ref),
             ]
-            top = max(kernels, key=lambda k_: k_["kernel_ms"])
-            algo_bytes = rows * t * 100 + rows * m_parts * h_part * 144
-            short_kernels = []
-            if short and decoded_steps == args.steps and dec_ms:
-                # (DKGV_FD_BYTES=0) dominant kernel of the shortcut path: the lazy decode of the commitments - flags, x < p, square root, curve equation
-                dms = statistics.mean(d_[0] for d_ in dec_ms)
-                dec_canon = 379 + 228 + 4  # a^((p+1)/4) by square-and-multiply + x^3 + 4, y^2 check
-                dec = kernel_entry("k_decompress_vv (no subgroup test)", rows * t, "one commitment: decompression without the subgroup test",
-                                   dec_canon, dec_canon, dms, step_mean)
-                dec["subgroup_checked"] = bool(dec_ms[-1][1])
-            elif short and len(short_ms) == args.steps:
-                # default: no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base
-                # multiplication (33 mixed additions) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with
-                # one inversion (p - 2: 380 squarings + 227 products) - per point 607 / 8 + 3 products of the simultaneous
-                # inversion + Y / Z + the canonical form for the sign
-                sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
-                pt_canon, pt_exec = 33 * 11 + 2, 33 * EXEC_MADD + 2
-                sg = 607 / 8 + 3 + 2
-                dec = kernel_entry("k_fd_coefpoint", rows * t, "one coefficient: G * p_k by the fixed-base table, x_C * Z == X against the "
-                                   "compressed commitment", pt_canon, pt_exec, sp[1], step_mean)
-                short_kernels = [dec,
-                                 kernel_entry("k_fd_coefsign", rows * t, "one coefficient: sign of Y / Z (simultaneous inversion over 8)", sg, sg,
-                                              sp[2], step_mean),
-                                 {"kernel": "k_fd_share_limbs + k_fd_difftab", "kernel_ms": sp[0], "kernel_share_of_step": sp[0] / step_mean,
-                                  "unit_is": "one dealer: t rounds of subtractions over the n shares + basis conversion by small integers (Fr, no wide products to speak of)"},
-                                 {"kernel": "k_fd_need + k_fd_fill_ok + flag read-back", "kernel_ms": sp[3], "kernel_share_of_step": sp[3] / step_mean}]
-            else:
-                short = False
-        else:
-            plan = None
-            kernels = [kernel_entry("k_share_verify", rows * n, "one share", MODMUL_PER_SHARE, executed_modmul_per_share(n, t), hot, step_mean)]
-            top = kernels[0]
-            algo_bytes = rows * n * (32 + 1) + rows * t * 100 + n * 4  # shares + verdicts + decoded vv + ids
-        eval_top = top
-        if fdiff and short:
-            top = dec  # dominant kernel of the timed (default-path) steps, timed live inside them
-        roof = {"bound": "int_pipe", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak["imad_wide"] / 1e9,
-                "unit": "G wide-MAC/s (32x32->64)", "frac": top["frac"], "peak_source": peak["source"],
-                "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9,
-                "frac_of_carry_chain_peak": top["frac_of_carry_chain_peak"],
-                "executed_gmac_per_s": top["executed_gmac_per_s"],
-                "executed_frac_of_carry_chain_peak": top["executed_frac_of_carry_chain_peak"],
-                "kernel_ms": top["kernel_ms"], "kernel_share_of_step": top["kernel_share_of_step"],
-                "units_per_launch": top["units_per_launch_total"], "unit_is": top["unit_is"],
-                "modmul_per_unit": top["modmul_per_unit"], "mac_per_modmul": MAC_PER_MODMUL,
-                "traffic": None, "traffic_ref": "profiles/ (ncu --set full captures: DRAM bytes per launch are negligible on this integer-bound path)",
-                "algorithmic_bytes": None,
-                "kernels": kernels,
-                "whole_path": {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
-                               "modmul_per_share_canonical": MODMUL_PER_SHARE,
-                               "note": "canonical per-share Horner work of all verified shares / full-evaluation step time; finite "
-                                       "differences execute fewer products than that, so this exceeds the kernels' own utilisation"},
-                "hbm": {"algorithmic_bytes_per_launch": algo_bytes, "achieved_gbs": algo_bytes / (eval_top["kernel_ms"] * 1e-3) / 1e9,
-                        "note": "integer-bound path: HBM use is a rounding error"}}
-        if fdiff and short and short_kernels:
-            roof["shortcut_kernels"] = short_kernels
-            roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
-            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r1_default_path_v3.md): dram read 57 367 296 B +
-            # write 32 190 208 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
-            roof["traffic"] = int(round((57367296 + 32190208) / 699392 * rows * t))
-            roof["traffic_ref"] = ("profiles/r1_default_path_v3.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
-                                   "(128.1 B per coefficient, scaled to this launch's coefficients)")
-        elif fdiff and short:
-            # ncu --set full of k_decompress_vv at 699 392 commitments (profiles/r1_default_path.md): dram read 34 069 760 B +
-            # write 21 060 352 B per launch; algorithmic 48 B in + 100 B planar out per commitment (the planes mostly stay in L2)
-            roof["traffic"] = int(round((34069760 + 21060352) / 699392 * rows * t))
-            roof["algorithmic_bytes"] = rows * t * 148
-            roof["traffic_ref"] = ("profiles/r1_default_path.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_decompress_vv launch "
-                                   "(78.8 B per commitment, scaled to this launch's commitments)")
-        if fdiff:
-            roof["note"] = (("the timed steps behind `value` were settled by the consistency shortcut: `kernel` ... `modmul_per_unit` describe their "
-                             "dominant kernel (timed live inside them; all of them under `shortcut_kernels`); " if short else "")
-                            + "`kernels` / `evaluation_top_kernel` describe the evaluation kernels (every share through the group arithmetic: "
-                              "the steps behind `full_evaluation`, run phase after phase)")
-            roof["evaluation_top_kernel"] = eval_top
-            roof["fdiff"] = {"consistency_shortcut_settled_the_timed_steps": bool(short),
-                             "parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"],
-                             "seed_points": [plan["lo"], plan["hi"]], "extension_steps": plan["steps"],
+            path_canon = rows * n * MODMUL_PER_SHARE * MAC_PER_MODMUL / (statistics.mean(full_ms) * 1e-3)
+            roof["kernels"] = kernels
+            roof["evaluation_top_kernel"] = max(kernels, key=lambda k_: k_["kernel_ms"])
+            if "kernel" not in roof:
+                roof.update({k_: roof["evaluation_top_kernel"][k_] for k_ in ("kernel", "achieved", "frac", "kernel_ms", "kernel_share_of_step", "unit_is")})
+            roof["whole_path"] = {"canonical_gmac_per_s": path_canon / 1e9, "frac_of_peak": path_canon / peak["imad_wide"],
+                                  "modmul_per_share_canonical": MODMUL_PER_SHARE,
+                                  "note": "canonical per-share Horner work of all verified shares / full-evaluation step time; finite "
+                                          "differences execute fewer products than that, so this exceeds the kernels' own utilisation"}
+            roof["fdiff"] = {"parts_per_dealer": plan["parts"], "coefficients_per_part": plan["h"], "seed_points": [plan["lo"], plan["hi"]],
+                             "extension_steps": plan["steps"],
                              "phase_ms": {"seed_horner": ph[0], "differences": ph[1], "extension": ph[2], "recombine_gs_compare": ph[3]},
                              "serial_step_ms": ref, "overlapped_step_ms": full_ms_step,
-                             "note": "full evaluation (shortcut off): phase times from steps run phase-after-phase on one stream; "
-                                     "`overlapped_step_ms` with the parts on concurrent streams",
                              "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
+        roof["note"] = ("`kernel` ... `modmul_per_unit`: the dominant kernel of the timed (default-path) steps, timed live inside them, all of them under "
+                        "`shortcut_kernels`; `kernels` / `evaluation_top_kernel`: the evaluation kernels (the steps behind `full_evaluation`, run "
+                        "phase after phase).  `frac` = canonical wide MACs / measured IMAD.WIDE.U32 peak; `executed_frac` counts the fused products as executed")
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs (381-bit Montgomery Fp, 255-bit Fr)", "data": "synthetic",
             "config": {"workload": f"synthetic DKG n={n}, t={t}: full {n}x{n} share-matrix verification, dealer row blocks over {world} GPU(s)",
-                       "n": n, "t": t, "shares_per_step": shares, "l2": "flushed (256 MB fill) between timed iterations",
-                       "share_path": (("consistency shortcut (range, t-th differences of the shares, G*p_k == C_k per coefficient) settled every dealer; "
-                                       if (fdiff and short) else "") +
-                                      (f"evaluation by finite differences: {plan['parts']} parts x {plan['h']} coefficients per dealer, "
-                                       f"{plan['h']} Horner seeds per part, differences, recombination") if fdiff else "Horner per share"),
-                       "parallelism": f"row-block x{world}, NCCL all-gather of the verdict bitmask ({n * n // 8} B)" if world > 1 else "single GPU"},
+                       "n": n, "t": t, "shares_per_step": shares_total, "l2": "flushed (256 MB fill) between timed iterations",
+                       "share_path": ("consistency shortcut (range, t-th differences of the shares, compress(G*p_k) == C_k per coefficient) settled every "
+                                      "dealer: no evaluation in the exponent, no commitment decoded" if settled_by_shortcut else "evaluation"),
+                       "parallelism": (f"row-block x{world}; inside dkgv_share_matrix_verify_sharded_dev: one NCCL all-gather of the verdict bitmask + job flags "
+                                       f"({chunk * 4} B per rank), one host synchronisation") if world > 1 else "single GPU"},
             "clocks": clocks,
-            "e2e": {"value": shares / e2e_s_per_step, "unit": "shares/s",
+            "e2e": {"value": shares_total / e2e_s_per_step, "unit": "shares/s",
                     "h2d_bytes_per_step": int(h_vv.numel() + h_sh.numel() + h_ids.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(h_st.numel()) * world, "timing": "host wall clock around dkgv_share_matrix_verify, max over ranks"},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": int(h_st.numel() + (h_gather.numel() * 4 if world > 1 else 0)) * world,
+                    "timing": "host wall clock, max over ranks: pinned host buffers in, verdicts (and the gathered bitmask) back on the host"},
+            "gpu_launches": int(launches), "collectives_in_library": world > 1,
             "roofline": roof,
-            "pairing": {"metric": "BLS pairing checks/sec", "value": m_total / (pair_ms_step * 1e-3), "unit": "checks/s",
-                        "checks_per_step": m_total, "ms_per_step": pair_ms_step, "bad_verdicts": pair_bad,
-                        "note": "e(pk,H(m)) == e(G1,sig) as 2 Miller loops + 1 final exponentiation per check, incl. G1/G2 decoding with subgroup checks"},
-            "full_evaluation": ({"metric": "verified shares/sec, every share evaluated in the group (consistency shortcut off)",
-                                 "value": shares / (full_ms_step * 1e-3), "unit": "shares/s", "ms_per_step": full_ms_step} if fdiff else None),
-            "mixed_items": {"metric": "verified shares/sec, 50 % of the shares corrupted (BASELINE config 5)", "value": shares / (mixed_ms_step * 1e-3),
-                            "unit": "shares/s", "ms_per_step": mixed_ms_step, "verdicts_flag_exactly_the_corrupted_shares": mixed_ok,
-                            "note": "every dealer group fails the consistency conditions and takes the full evaluation"},
-            "finalization": fin_line,
-            "parity": {"bad_verdicts_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
+            "parity": {"bad_verdict_bits_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
             "wall_s_timed_region": wall,
         }
-        if not args.no_cpu:
+        if args.emulate_world and world == 1:
+            line["emulated"] = (f"ONE rank's row block of a {split}-rank job ({rows} dealers) on one GPU, no collective: value is NOT a whole-ceremony "
+                                f"number; ms_per_step is the per-rank step time to expect at N = {split}")
+        line.update(legs)
+        if not args.no_cpu and not args.quick:
+            import oracle_lib as O
+            O.use_native_build()
             threads = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_baseline(n, t, args.cpu_sample or 24, threads)
+            line["cpu_baseline"]["same_algorithm"] = cpu_same_algorithm(n, t, threads)
+            line["pairing"]["cpu_baseline"] = cpu_pairing(threads)
+            line["config_a"]["cpu_baseline"] = cpu_config_a(threads)
+            line["finalization"]["cpu_baseline"] = cpu_finalization(fin_a, threads)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)  # anything printed during teardown stays out of stdout as well
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     v.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

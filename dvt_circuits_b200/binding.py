@@ -93,6 +93,16 @@ DECLARED_SYMBOLS = {
     "dkgv_hash_to_g2": (ctypes.c_int, [_vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_bls_verify_batch_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_comm_unique_id": (ctypes.c_int, [_vp]),
+    "dkgv_comm_init": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "dkgv_comm_destroy": (ctypes.c_int, [_vp]),
+    "dkgv_comm_world": (ctypes.c_int, [_vp]),
+    "dkgv_comm_rank": (ctypes.c_int, [_vp]),
+    "dkgv_all_gather_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "dkgv_share_gather_words": (_u32, [_u32, _u32]),
+    "dkgv_share_matrix_verify_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_bls_verify_batch_sharded_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "dkgv_agg_final_keys_sharded": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_set_bls_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_bls_path": (ctypes.c_int, [_vp]),
     "dkgv_last_bls_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -391,6 +401,56 @@ class Verifier:
                                                              _p(idx) if idx is not None else None, _p(st), _p(exp),
                                                              ctypes.cast(ctypes.byref(sst), _vp)))
         return st, exp, int(sst.value)
+
+    # ---- multi-GPU (include/dkgv.h dkgv_comm_*): one Verifier per process / GPU
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: 128 bytes to hand to every rank"""
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        if lib.dkgv_comm_unique_id(ctypes.cast(buf, _vp)) != 0:
+            raise DkgvError("dkgv_comm_unique_id failed (NCCL not loadable)")
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self._lib.dkgv_comm_init(self._h, ctypes.cast(buf, _vp), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._ck(self._lib.dkgv_comm_destroy(self._h))
+
+    @property
+    def comm_world(self):
+        return int(self._lib.dkgv_comm_world(self._h))
+
+    @property
+    def comm_rank(self):
+        return int(self._lib.dkgv_comm_rank(self._h))
+
+    def all_gather_dev(self, d_send, d_recv, nbytes, stream=None):
+        self._ck(self._lib.dkgv_all_gather_dev(self._h, d_send, d_recv, int(nbytes), stream))
+
+    def share_gather_words(self, n_local, n_r):
+        return int(self._lib.dkgv_share_gather_words(n_local, n_r))
+
+    def share_matrix_verify_sharded_dev(self, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, stream=None):
+        """this rank's dealer row block; d_gather [world, share_gather_words(n_local, n_r)] u32 on the device"""
+        self._ck(self._lib.dkgv_share_matrix_verify_sharded_dev(self._h, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, stream))
+
+    def bls_verify_batch_sharded_dev(self, m_local, d_pk, d_sig, n_hm, d_hm, d_hm_idx, d_status_all, stream=None):
+        self._ck(self._lib.dkgv_bls_verify_batch_sharded_dev(self._h, m_local, d_pk, d_sig, n_hm, d_hm, d_hm_idx, d_status_all, stream))
+
+    def agg_final_keys_sharded(self, vv_local, ids):
+        """this rank's generations [n_local, t, 48] -> (status, coeffs [t,48], keys [m,48]) on every rank"""
+        vv = np.ascontiguousarray(vv_local, dtype=np.uint8)
+        n, t = vv.shape[0], vv.shape[1]
+        ids = _host(ids, np.uint32)
+        co = np.zeros((t, 48), dtype=np.uint8)
+        keys = np.zeros((ids.shape[0], 48), dtype=np.uint8)
+        st = ctypes.c_uint8(0)
+        self._ck(self._lib.dkgv_agg_final_keys_sharded(self._h, n, t, _p(vv), _p(ids), ids.shape[0], _p(co), _p(keys),
+                                                       ctypes.cast(ctypes.byref(st), _vp)))
+        return int(st.value), co, keys
 
     BLS_AUTO, BLS_VM, BLS_THREAD = 0, 1, 2
 

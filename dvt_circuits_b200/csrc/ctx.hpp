@@ -7,6 +7,9 @@
 
 #include "../../include/dkgv.h"
 
+struct ncclUniqueIdBytes {
+  char internal[128];
+};
 namespace dkgv_host {
 struct DevBuf {
   void* p = nullptr;
@@ -46,6 +49,13 @@ struct dkgv_ctx {
   cudaEvent_t ev_bls0 = nullptr, ev_bls1 = nullptr;    // bracket the pairing kernel
   bool bls_recorded = false, pvm_attr_set = false;
   int bls_path = 0, last_bls_path = 0;                 // enum dkgv_bls_path
+  // communicator (comm.cu): NCCL, one process per GPU
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  uint64_t collectives = 0;
+  dkgv_host::DevBuf comm_flags, comm_buf;
+  uint32_t* h_comm_flags = nullptr;
+  size_t h_comm_flags_cap = 0;
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)
   bool vv_decoded = true;            // the last share-matrix call decoded its commitments (false: settled against their encodings)
   cudaEvent_t ev_dec0 = nullptr, ev_dec1 = nullptr;  // bracket the last verification-vector decode of the share path

@@ -258,6 +258,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (cudaEvent_t ev : ctx->ev_sc)
     if (ev) cudaEventDestroy(ev);
+  dkgv_comm_destroy(ctx);
+  if (ctx->h_comm_flags) cudaFreeHost(ctx->h_comm_flags);
   if (ctx->job_flags) cudaFree(ctx->job_flags);
   if (ctx->h_job_flags) cudaFreeHost(ctx->h_job_flags);
   for (cudaEvent_t ev : ctx->ev_fd)
@@ -449,6 +451,12 @@ static int share_finish(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) 
   return dkgv_share_matrix_fd(ctx, view, job.n_d, job.n_r, job.t, plan, job.d_ids, job.d_shares, job.d_status,
                               job.shortcut ? dkgv_fd_need_groups(ctx, job.n_d) : nullptr, s);
 }
+
+int dkgv_share_submit_internal(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
+                               const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags, cudaStream_t s) {
+  return share_submit(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, d_flags, s);
+}
+int dkgv_share_finish_internal(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) { return share_finish(ctx, h_flags, s); }
 
 extern "C" int dkgv_share_matrix_submit_dev(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv,
                                             const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags2,

@@ -245,7 +245,99 @@ __global__ void __launch_bounds__(32) k_sum_points(const uint32_t* __restrict__ 
   }
 }
 
+// projective column sums of a row block, for the sharded aggregation (comm.cu): part36[k] = sum over this block's dealers of vv[d][k]
+// (X, Y, Z Montgomery limbs), and after the t points a 4-word tail whose first word is 1 when some commitment failed to decode
+__global__ void __launch_bounds__(128)
+k_column_partials(VVView vv, uint32_t t, const uint8_t* __restrict__ dealer_bad, uint32_t n_d, uint32_t* __restrict__ part36) {
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= t) return;
+  G1Proj acc = g1_identity();
+#pragma unroll 1
+  for (uint32_t d = lane; d < vv.n_pad; d += 32) acc = g1_add_mixed(acc, vv_load(vv, warp, d));
+  acc = warp_reduce_points(acc);
+  if (lane == 0) {
+    uint32_t* o = part36 + (size_t)warp * 36;
+#pragma unroll
+    for (int l = 0; l < 12; l++) {
+      o[l] = acc.x.l[l];
+      o[12 + l] = acc.y.l[l];
+      o[24 + l] = acc.z.l[l];
+    }
+  }
+  if (warp == 0) {
+    uint32_t bad = 0;
+    for (uint32_t d = lane; d < n_d; d += 32) bad |= dealer_bad[d];
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      uint32_t* tail = part36 + (size_t)t * 36;
+      tail[0] = bad ? 1u : 0u;
+      tail[1] = tail[2] = tail[3] = 0;
+    }
+  }
+}
+
 // ============================================================================ C ABI
+// decode + subgroup-check the rows vv [n][t][48] (host) into the session planes; asynchronous on s
+static int decode_rows(dkgv_ctx* ctx, uint32_t n, uint32_t t, const uint8_t* vv, cudaStream_t s, VVView* view) {
+  uint32_t n_pad = (n + 31) & ~31u, tt = t ? t : 1;
+  size_t vvb = (size_t)n * t * 48;
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
+  CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
+  CK(ctx->dealer_bad.reserve(n_pad));
+  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
+  if (t) {
+    size_t total = (size_t)n_pad * t;
+    k_decompress_vv_f<<<(unsigned)((total + 127) / 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
+                                                                    (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  *view = VVView{(const uint32_t*)ctx->vv_limbs.p, (const uint8_t*)ctx->vv_inf.p, n_pad};
+  return 0;
+}
+
+int dkgv_column_partials_internal(dkgv_ctx* ctx, uint32_t n_local, uint32_t t, const uint8_t* h_vv, uint32_t* d_partial36, cudaStream_t s) {
+  VVView view;
+  if (int rc = decode_rows(ctx, n_local, t, h_vv, s, &view)) return rc;
+  k_column_partials<<<(t * 32 + 127) / 128, 128, 0, s>>>(view, t, (const uint8_t*)ctx->dealer_bad.p, n_local, d_partial36);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// K_j = evaluate_polynomial(C, ids[j]) from the column sums in ctx->scratch_a (25-word affine records); keys_out: host
+int dkgv_keys_from_coeffs_internal(dkgv_ctx* ctx, uint32_t t, const uint32_t* ids, uint32_t n_ids, uint8_t* keys_out, cudaStream_t s) {
+  CK(ctx->in_b.reserve((size_t)n_ids * 4));
+  CK(ctx->out_b.reserve((size_t)n_ids * 48));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
+  // ids 1..n_ids (the ranks of a ceremony): the n final keys come from t-ish Horner seeds + finite differences
+  // (csrc/fdiff.cuh) instead of n Horner chains of t-1 steps; same points, same encodings
+  FdPlan plan{};
+  bool use_fd = false;
+  if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_ids >= 3 && n_ids <= 65535 && dkgv_fd_ids_consecutive(ids, n_ids)) {
+    plan = fd_make_plan(t, n_ids, ctx->share_parts);
+    use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
+  }
+  if (use_fd) {
+    CK(ctx->scratch_b.reserve((size_t)t * 24 * 32 * 4));
+    CK(ctx->scratch_c.reserve((size_t)t * 32));
+    k_coeffs_to_planar<<<(t * 32 + 127) / 128, 128, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (uint32_t*)ctx->scratch_b.p,
+                                                            (uint8_t*)ctx->scratch_c.p);
+    ctx->launches++;
+    VVView one{(const uint32_t*)ctx->scratch_b.p, (const uint8_t*)ctx->scratch_c.p, 32};
+    if (int rc = dkgv_feldman_eval_fd(ctx, one, 1, n_ids, t, plan, (const uint32_t*)ctx->in_b.p, ids, (uint8_t*)ctx->out_b.p, s)) return rc;
+  } else {
+    k_eval_points_at_ids<<<(n_ids + 63) / 64, 64, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (const uint32_t*)ctx->in_b.p, n_ids,
+                                                         (uint8_t*)ctx->out_b.p);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(keys_out, ctx->out_b.p, (size_t)n_ids * 48, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
 extern "C" int dkgv_agg_final_keys(dkgv_ctx* ctx, uint32_t n, uint32_t t, const uint8_t* vv, const uint32_t* ids, uint32_t n_ids,
                                    uint8_t* coeff_out, uint8_t* keys_out, uint8_t* status) {
   if (!ctx || !status) return -1;
@@ -255,53 +347,17 @@ extern "C" int dkgv_agg_final_keys(dkgv_ctx* ctx, uint32_t n, uint32_t t, const 
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   uint32_t n_pad = (n + 31) & ~31u, tt = t ? t : 1;
-  size_t vvb = (size_t)n * t * 48;
-  CK(ctx->in_a.reserve(vvb ? vvb : 1));
-  CK(ctx->in_b.reserve(n_ids ? (size_t)n_ids * 4 : 4));
-  CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
-  CK(ctx->vv_inf.reserve((size_t)tt * n_pad));
-  CK(ctx->dealer_bad.reserve(n_pad));
   CK(ctx->scratch_a.reserve((size_t)tt * 25 * 4));
   CK(ctx->out_a.reserve((size_t)tt * 48));
-  CK(ctx->out_b.reserve(n_ids ? (size_t)n_ids * 48 : 1));
-  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
-  if (n_ids) CK(cudaMemcpyAsync(ctx->in_b.p, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(ctx->dealer_bad.p, 0, n_pad, s));
+  VVView view;
+  if (int rc = decode_rows(ctx, n, t, vv, s, &view)) return rc;
   if (t) {
-    size_t total = (size_t)n_pad * t;
-    k_decompress_vv_f<<<(unsigned)((total + 127) / 128), 128, 0, s>>>((const uint8_t*)ctx->in_a.p, n, t, n_pad, (uint32_t*)ctx->vv_limbs.p,
-                                                                    (uint8_t*)ctx->vv_inf.p, (uint8_t*)ctx->dealer_bad.p);
-    ctx->launches++;
-    VVView view{(const uint32_t*)ctx->vv_limbs.p, (const uint8_t*)ctx->vv_inf.p, n_pad};
     k_column_sums<<<(t * 32 + 127) / 128, 128, 0, s>>>(view, t, (uint32_t*)ctx->scratch_a.p, (uint8_t*)ctx->out_a.p);
     ctx->launches++;
     CK(cudaGetLastError());
   }
-  if (n_ids) {
-    // ids 1..n_ids (the ranks of a ceremony): the n final keys come from t-ish Horner seeds + finite differences
-    // (csrc/fdiff.cuh) instead of n Horner chains of t-1 steps; same points, same encodings
-    FdPlan plan{};
-    bool use_fd = false;
-    if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_ids >= 3 && n_ids <= 65535 && dkgv_fd_ids_consecutive(ids, n_ids)) {
-      plan = fd_make_plan(t, n_ids, ctx->share_parts);
-      use_fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
-    }
-    if (use_fd) {
-      CK(ctx->scratch_b.reserve((size_t)t * 24 * 32 * 4));
-      CK(ctx->scratch_c.reserve((size_t)t * 32));
-      k_coeffs_to_planar<<<(t * 32 + 127) / 128, 128, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (uint32_t*)ctx->scratch_b.p,
-                                                              (uint8_t*)ctx->scratch_c.p);
-      ctx->launches++;
-      VVView one{(const uint32_t*)ctx->scratch_b.p, (const uint8_t*)ctx->scratch_c.p, 32};
-      if (int rc = dkgv_feldman_eval_fd(ctx, one, 1, n_ids, t, plan, (const uint32_t*)ctx->in_b.p, ids, (uint8_t*)ctx->out_b.p, s)) return rc;
-    } else {
-      k_eval_points_at_ids<<<(n_ids + 63) / 64, 64, 0, s>>>((const uint32_t*)ctx->scratch_a.p, t, (const uint32_t*)ctx->in_b.p, n_ids,
-                                                           (uint8_t*)ctx->out_b.p);
-      ctx->launches++;
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(keys_out, ctx->out_b.p, (size_t)n_ids * 48, cudaMemcpyDeviceToHost, s));
-  }
+  if (n_ids)
+    if (int rc = dkgv_keys_from_coeffs_internal(ctx, t, ids, n_ids, keys_out, s)) return rc;
   if (coeff_out && t) CK(cudaMemcpyAsync(coeff_out, ctx->out_a.p, (size_t)t * 48, cudaMemcpyDeviceToHost, s));
   std::string bad(n_pad, 0);
   CK(cudaMemcpyAsync(&bad[0], ctx->dealer_bad.p, n, cudaMemcpyDeviceToHost, s));

@@ -237,6 +237,36 @@ int dkgv_bad_partial_key_verify_batch(dkgv_ctx* ctx, uint32_t n, uint32_t t, con
                                       const uint32_t* msg_offsets, const uint32_t* msg_idx, uint8_t* status, uint8_t* expected_out,
                                       uint8_t* session_status);
 
+/* ---- multi-GPU: one process (and one ctx) per GPU, the collectives INSIDE the library (NCCL over NVLink / NVSwitch) -----------
+ * Rank 0 asks for a 128-byte unique id and hands it to the other ranks (any transport); every rank then calls dkgv_comm_init on
+ * its ctx.  NCCL is bound at run time (libnccl.so.2; DKGV_NCCL_LIB overrides), the library links against nothing but the CUDA
+ * runtime.  A ctx without a communicator behaves as world = 1 in every *_sharded call.  dkgv_ctx_destroy releases the comm.   */
+int dkgv_comm_unique_id(uint8_t id_out[128]);
+int dkgv_comm_init(dkgv_ctx* ctx, const uint8_t id[128], int rank, int world);
+int dkgv_comm_destroy(dkgv_ctx* ctx);
+int dkgv_comm_world(const dkgv_ctx* ctx);
+int dkgv_comm_rank(const dkgv_ctx* ctx);
+/* rank r's `bytes` land at d_recv + r * bytes on every rank (world 1: a copy); asynchronous on `stream` */
+int dkgv_all_gather_dev(dkgv_ctx* ctx, const void* d_send, void* d_recv, size_t bytes, void* stream);
+/* Share matrix of one ceremony, sharded by dealer row blocks: every rank passes ITS n_local dealers' verification
+ * vectors and shares (the same n_local on every rank) and the full id list; no exchange during compute.  d_gather [world][chunk]
+ * u32, chunk = dkgv_share_gather_words(n_local, n_recipients): after the call, on EVERY rank, rank r's chunk holds the verdict
+ * bitmask of its row block (bit i % 32 of word i / 32 set = share i of the block is NOT ok) and, behind the bitmask, its two job
+ * flags.  Honest ceremony: asynchronous submit + pack + ONE all-gather + one synchronisation; otherwise the ranks that have
+ * unsettled dealers evaluate them and a second all-gather follows (every rank sees every flag, so all agree on that).
+ * d_status_local [n_local][n_recipients] keeps the status bytes (outcome classes) of the own rows.                          */
+uint32_t dkgv_share_gather_words(uint32_t n_local, uint32_t n_recipients);
+int dkgv_share_matrix_verify_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv_local,
+                                         const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local, uint32_t* d_gather,
+                                         void* stream);
+/* Pairing checks sharded by items: every rank its m_local pairs; d_status_all [world][m_local] on every rank.  Asynchronous. */
+int dkgv_bls_verify_batch_sharded_dev(dkgv_ctx* ctx, uint32_t m_local, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
+                                      const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status_all, void* stream);
+/* agg_coefficients sharded by generations (dkg_math.rs:230-248): every rank decodes and sums ITS n_local rows, one all-gather of
+ * the t projective partial sums (144 B each), every rank adds the partials and evaluates the keys.  Outputs on every rank.    */
+int dkgv_agg_final_keys_sharded(dkgv_ctx* ctx, uint32_t n_local, uint32_t t, const uint8_t* vv_local, const uint32_t* ids, uint32_t n_ids,
+                                uint8_t* coeff_out, uint8_t* keys_out, uint8_t* status);
+
 /* ---- initial-commitment hashes (crates/dkg/src/verification.rs:151-175) on the GPU ------------- */
 /* out[d] = SHA-256(gen_id(16) || n || k || (t as u8) || vv[d][0..t)), one per dealer, out [n_dealers][32] */
 int dkgv_initial_commitment_hashes(dkgv_ctx* ctx, uint32_t n_dealers, uint32_t t, const uint8_t* vv, const uint8_t* gen_id16,

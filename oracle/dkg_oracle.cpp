@@ -80,6 +80,92 @@ uint8_t share_status(const std::vector<G1Aff>& cfs, bool vv_ok, uint32_t id, con
 }
 }  // namespace
 
+// The SAME exact shortcut the GPU library's default share path takes (dvt_circuits_b200/csrc/share_fd.cu), on the CPU, so that a
+// bench can separate what the algorithm buys from what the hardware buys: all n shares of a dealer are valid iff each is < r, their
+// t-th forward differences vanish, and compress(G * p_k) == C_k for every coefficient of the interpolated polynomial p.  ids must be
+// 1..n_r in order.  status[d][j] = OK for a dealer that meets the conditions; dealers that do not are evaluated share by share (fast
+// mode).  Test infrastructure (the CPU leg of bench.py), never part of the product.  fixed-base G * s: 8-bit windows, built once.
+static std::vector<G1Aff> g_gwin;  // [32][256]: (b * 2^(8w)) * G, b = 0..255 (b = 0: identity)
+static void build_gwin() {
+  if (!g_gwin.empty()) return;
+  std::vector<G1Aff> tab(32 * 256);
+  G1 base = G1::from_affine(g1_generator());
+  for (int w = 0; w < 32; w++) {
+    G1 acc = G1::identity();
+    for (int b = 0; b < 256; b++) {
+      tab[w * 256 + b] = acc.to_affine();
+      acc = acc.add(base);
+    }
+    base = acc;  // 256 * previous base
+  }
+  g_gwin.swap(tab);
+}
+static G1Aff g_times_windowed(const u64* s4) {
+  G1 acc = G1::identity();
+  for (int w = 0; w < 32; w++) {
+    unsigned b = (unsigned)(s4[w / 8] >> (8 * (w % 8))) & 0xff;
+    if (b) acc = acc.add_mixed(g_gwin[w * 256 + b]);
+  }
+  return acc.to_affine();
+}
+extern "C" void orc_share_matrix_shortcut(uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* vv, const uint8_t* shares, uint8_t* status,
+                                          int threads, uint32_t* n_fallback) {
+  init();
+  build_gwin();
+  if (threads < 1) threads = 1;
+  std::vector<uint32_t> fb(threads, 0);
+  auto work = [&](int tid) {
+    std::vector<Fr> d(n_r), c(t);
+    for (uint32_t dl = tid; dl < n_d; dl += threads) {
+      bool ok = n_r > t && t >= 1;
+      for (uint32_t j = 0; ok && j < n_r; j++) ok = Fr::from_be(&d[j], shares + ((size_t)dl * n_r + j) * 32, 32);
+      if (ok) {  // t rounds of differences: d[k] = Delta^k s(1) for k < t, the t-th differences beyond
+        for (uint32_t r = 1; r <= t; r++)
+          for (uint32_t k = n_r - 1; k >= r; k--) d[k] = d[k] - d[k - 1];
+        for (uint32_t k = t; ok && k < n_r; k++) ok = d[k].is_zero();
+      }
+      if (ok) {  // Newton basis at the nodes 1, 2, ... -> monomial coefficients:  P <- P (x - j) + Delta^(j-1) s(1) / (j-1)!
+        Fr fact = Fr::one();
+        std::vector<Fr> E(t);
+        for (uint32_t k = 0; k < t; k++) {
+          if (k) fact = fact * Fr::from_u64(k);
+          E[k] = d[k] * fact.inv();
+        }
+        for (uint32_t k = 0; k < t; k++) c[k] = Fr::zero();
+        c[0] = E[t - 1];
+        for (uint32_t j = t - 1; j >= 1; j--) {
+          Fr fj = Fr::from_u64(j);
+          for (uint32_t k = t - j; k >= 1; k--) c[k] = c[k - 1] - fj * c[k];
+          c[0] = E[j - 1] - fj * c[0];
+        }
+        for (uint32_t k = 0; ok && k < t; k++) {  // compress(G * p_k) == C_k, the commitment never decoded
+          u64 raw[4];
+          c[k].to_raw(raw);
+          uint8_t enc[48];
+          g1_compress(g_times_windowed(raw), enc);
+          ok = memcmp(enc, vv + ((size_t)dl * t + k) * 48, 48) == 0;
+        }
+      }
+      if (ok) {
+        memset(status + (size_t)dl * n_r, DKGV_OK, n_r);
+      } else {
+        fb[tid]++;
+        std::vector<G1Aff> cfs;
+        bool vok = decode_vv(vv + (size_t)dl * t * 48, t, &cfs);
+        for (uint32_t j = 0; j < n_r; j++) status[(size_t)dl * n_r + j] = share_status(cfs, vok, j + 1, shares + ((size_t)dl * n_r + j) * 32, 1);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < threads; i++) th.emplace_back(work, i);
+  work(0);
+  for (auto& x : th) x.join();
+  if (n_fallback) {
+    *n_fallback = 0;
+    for (uint32_t f : fb) *n_fallback += f;
+  }
+}
+
 extern "C" {
 int orc_init() {
   init();

@@ -142,3 +142,16 @@ def pairing_bytes(p48, q96):
 
 def fp_mul_count(reset=False):
     return int(lib().orc_fp_mul_count(1 if reset else 0))
+
+
+def share_matrix_shortcut(vv, shares, threads=1):
+    """the GPU library's exact consistency shortcut on the CPU (ids 1..n_r in order) -> (status [n_d, n_r], dealers that fell back)"""
+    vv = np.ascontiguousarray(vv, dtype=np.uint8)
+    shares = np.ascontiguousarray(shares, dtype=np.uint8)
+    n_d, t = vv.shape[0], vv.shape[1]
+    n_r = shares.shape[1]
+    st = np.empty((n_d, n_r), dtype=np.uint8)
+    fb = ctypes.c_uint32(0)
+    lib().orc_share_matrix_shortcut(n_d, n_r, t, vv.ctypes.data_as(ctypes.c_void_p), shares.ctypes.data_as(ctypes.c_void_p),
+                                    st.ctypes.data_as(ctypes.c_void_p), threads, ctypes.byref(fb))
+    return st, int(fb.value)

@@ -1005,6 +1005,29 @@ def write_inc(path, R):
     out.append("};")
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")
+    # executed work of one whole check, for the roofline of bench.py: Fp2 products / squarings / barriers over the driver's call list
+    import json
+    cnt = defaultdict(int)
+    for item in driver_sequence():
+        if item[0] in ("COPY", "SPILL", "FILL"):
+            cnt["copies"] += 1
+            continue
+        st = streams[item[0]]
+        for r in range(R):
+            for op, _arg in st[r]:
+                if op in ("MUL", "SQR", "INVX"):
+                    cnt[op] += 1
+        cnt["BAR"] += sum(1 for op, _ in st[0] if op == "BAR")
+        cnt["segments"] += 1
+    # wide multiply-accumulates (32x32->64): an Fp2 product = two fused sums of two products (2 x 444), an Fp2 squaring = two
+    # products (2 x 300); the inversion (binary extended Euclid) runs on the ALU pipe + 6 products
+    macs = cnt["MUL"] * 888 + cnt["SQR"] * 600 + cnt["INVX"] * 6 * 300
+    meta = {"roles": R, "slots": n_slots, "words": len(words), "fp2_mul_per_check": cnt["MUL"], "fp2_sqr_per_check": cnt["SQR"],
+            "fp2_inv_per_check": cnt["INVX"], "barriers_per_check": cnt["BAR"], "segments_per_check": cnt["segments"],
+            "wide_macs_per_check": macs, "fp_mul_equivalents_per_check": macs / 300}
+    with open(os.path.splitext(path)[0] + ".json", "w") as f:
+        json.dump(meta, f, indent=1)
+        f.write("\n")
     return len(words), n_slots
 
 
