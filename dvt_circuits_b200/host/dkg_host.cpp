@@ -540,6 +540,22 @@ int dkgh_execute_report(dkgv_ctx* ctx, const char* type, const char* json_text, 
       code = is_slashable(st) ? 0 : 1;
     } else if (ty == "bad-encrypted-share") {
       st = guest_bad_encrypted_share(h, data, &code);
+    } else if (ty == "fn:verify_seed_exchange_commitment") {
+      // the crate function alone (crates/dkg/src/lib.rs:6-9), without the guest's pre-checks: data = SharedData
+      const Json& ic = data.at("initial_commitment");
+      st = h.verify_seed_exchange_commitment(parse_hex_list(data.at("base_hashes"), 32, "base_hashes"), data.at("seeds_exchange_commitment"),
+                                             parse_hex_list(ic.at("base_pubkeys"), 48, "base_pubkeys"));
+      code = st == DKGV_OK ? 0 : 1;
+    } else if (ty == "fn:verify_generations") {  // data = FinalizationData; the aggregate key arrives as an already decoded key object
+      const Json& gj = data.at("generations");
+      if (gj.kind != Json::Arr) throw std::runtime_error("generations: expected an array");
+      std::vector<Host::Generation> gens;
+      for (auto& g : gj.arr) gens.push_back(Host::parse_generation(g, true));
+      st = h.verify_generations(gens, parse_settings(data.at("settings")), hex_fixed(data.at("aggregate_pubkey"), 48, "aggregate_pubkey"));
+      code = st == DKGV_OK ? 0 : 1;
+    } else if (ty == "fn:prove_wrong_final_key_generation") {  // data = BadPartialShareData
+      st = h.prove_wrong_final_key_generation(data);
+      code = st == DKGV_OK ? 0 : 1;
     } else {
       m = "unknown type";
     }

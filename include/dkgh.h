@@ -17,6 +17,9 @@ extern "C" {
  *        | "finalization"     crates/finalization_prove/src/main.rs:7-33   (BLS identity setup, as the reference)
  *        | "bad-partial-key"  crates/bad_parial_key_prove/src/main.rs:16-51
  *        | "bad-encrypted-share" crates/bad_encrypted_share_prove/src/main.rs:281-405 (incl. quirk Q2)
+ *        | "fn:verify_seed_exchange_commitment" | "fn:verify_generations" | "fn:prove_wrong_final_key_generation"
+ *                             the crate functions of crates/dkg/src/lib.rs:6-9 ALONE, without a guest's pre-checks and outcome
+ *                             mapping (inputs: SharedData / FinalizationData / BadPartialShareData); return value 0 = Ok(()), 1 = Err
  *   auth = cargo feature auth_commitment; bls_identity = BlsDkgWithBlsCommitment instead of secp256k1.
  * Returns the reference's process exit code (0 = misbehaviour proven / ceremony valid, 1 otherwise);
  * *status = dkgv_status reached, or 255 when the input is rejected while parsing (serde error).   */

@@ -52,3 +52,22 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert "oracle/" not in text.replace("never the oracle/", "") and "liboracle" not in text and "oracle_lib" not in text, f
+
+
+def test_rust_sys_crate_matches_the_headers():
+    """rust/dkg-cuda-sys/src/lib.rs is generated from include/*.h (tools/gen_rust_sys.py): committed file == generator output, and
+    every declared C function has its `pub fn`; the wrapper crate only calls functions the sys crate declares"""
+    import subprocess
+    import sys
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py")], capture_output=True, text=True, check=True).stdout
+    committed = open(os.path.join(ROOT, "rust", "dkg-cuda-sys", "src", "lib.rs")).read()
+    assert gen == committed, "run: python tools/gen_rust_sys.py > rust/dkg-cuda-sys/src/lib.rs"
+    for name in declared_functions():
+        assert f"pub fn {name}(" in committed, name
+    wrapper = open(os.path.join(ROOT, "rust", "dkg-gpu", "src", "lib.rs")).read()
+    for name in set(re.findall(r"sys::(dkg[vh]_\w+)\(", wrapper)):
+        assert f"pub fn {name}(" in committed, name
+    # the wrapper keeps the names of crates/dkg/src/lib.rs:6-12
+    for fn in ("verify_seed_exchange_commitment", "verify_generations", "prove_wrong_final_key_generation",
+               "compute_initial_commitment_hash", "verify_initial_commitment_hash"):
+        assert re.search(rf"pub fn {fn}<Setup>\(", wrapper), fn
