@@ -76,6 +76,8 @@ DECLARED_SYMBOLS = {
     "dkgv_set_share_overlap": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_set_share_shortcut": (ctypes.c_int, [_vp, ctypes.c_int]),
     "dkgv_last_share_continued": (ctypes.c_int, [_vp]),
+    "dkgv_set_share_repair": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dkgv_last_share_repaired": (ctypes.c_int, [_vp]),
     "dkgv_last_share_decoded": (ctypes.c_int, [_vp]),
     "dkgv_share_fd_plan": (ctypes.c_int, [_u32, _u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_uint64),
@@ -213,6 +215,14 @@ class Verifier:
     def set_share_shortcut(self, on):
         """True (default): ids beyond t only for dealer groups that fail the scalar-side consistency conditions"""
         self._ck(self._lib.dkgv_set_share_shortcut(self._h, int(bool(on))))
+
+    def set_share_repair(self, on):
+        """True (default): inconsistent dealers are first decoded as Reed-Solomon words (scalar arithmetic), evaluation only for the rest"""
+        self._ck(self._lib.dkgv_set_share_repair(self._h, int(bool(on))))
+
+    @property
+    def last_share_repaired(self):
+        return int(self._lib.dkgv_last_share_repaired(self._h))
 
     @property
     def last_share_continued(self):

@@ -83,6 +83,10 @@ struct dkgv_ctx {
   uint32_t* job_flags = nullptr;    // device: {ids are not a permutation of 1..n, dealers the shortcut could not settle}
   uint32_t* h_job_flags = nullptr;  // pinned host copy
   bool fd_overlap = true;  // one stream per part (default) or everything on the caller's stream
+  bool fd_repair = true;     // repair route: Reed-Solomon decoding of the share sequence of an inconsistent dealer (share_rs.cuh)
+  dkgv_host::DevBuf rs_tab, rs_work;
+  uint32_t rs_n = 0, rs_t = 0;    // shape the cached tables belong to
+  uint32_t last_repaired = 0;     // dealers the repair route settled in the last share-matrix call
   bool fd_polycheck = true;  // consistency shortcut: ids beyond t only for dealer groups that fail the scalar-side conditions
   uint32_t fd_binom_t = 0;   // t the cached binomial coefficients belong to
   bool fd_last_need = false; // the last finite-difference run had to continue beyond t for some dealer group

@@ -21,6 +21,9 @@ bool dkgv_fd_shortcut_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t);
 int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
                    uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s);
 const uint8_t* dkgv_fd_need_groups(const dkgv_ctx* ctx, uint32_t n_d);
+bool dkgv_fd_repair_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t);
+int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint8_t* d_shares, uint8_t* d_status,
+                   uint32_t* d_flags, cudaStream_t s);
 int dkgv_share_matrix_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
                          const uint32_t* d_ids, const uint8_t* d_shares, uint8_t* d_status, const uint8_t* filter, cudaStream_t s);
 int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32_t n_r, uint32_t t, const FdPlan& plan,
@@ -354,6 +357,12 @@ extern "C" int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on) {
   ctx->fd_polycheck = on != 0;
   return 0;
 }
+extern "C" int dkgv_set_share_repair(dkgv_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->fd_repair = on != 0;
+  return 0;
+}
+extern "C" int dkgv_last_share_repaired(const dkgv_ctx* ctx) { return ctx ? (int)ctx->last_repaired : -1; }
 extern "C" int dkgv_last_share_decoded(const dkgv_ctx* ctx) { return ctx ? (ctx->vv_decoded ? 1 : 0) : -1; }
 extern "C" int dkgv_last_share_continued(const dkgv_ctx* ctx) { return ctx ? (ctx->fd_last_need ? 1 : 0) : -1;
 }
@@ -412,6 +421,7 @@ static int share_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, c
   job.parts = ctx->share_parts;
   job.open = true;
   ctx->fd_last_need = false;
+  ctx->last_repaired = 0;
   if (ctx->share_path != DKGV_SHARE_PATH_HORNER && t >= 2 && n_r >= 3 && n_r <= 65535 && t <= 65535 * FD_MAX_PARTS) {
     // planned for the full evaluation (n_opt = 0): measured within 0.5 % of the shortcut-optimal split on an honest ceremony
     // (553 vs 551 ms at 1024 / 683) and 2 % better when the groups have to continue (734 vs 750 ms)
@@ -443,6 +453,15 @@ static int share_finish(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) 
   }
   if (h_flags[0]) return share_matrix_horner(ctx, job.n_d, job.n_r, job.t, job.d_vv, job.d_ids, job.d_shares, job.d_status, s);
   if (!h_flags[1]) return 0;  // every verdict is OK and already written
+  if (job.shortcut && dkgv_fd_repair_applies(ctx, job.n_r, job.t)) {
+    // some dealers' shares are not on one polynomial: decode them as Reed-Solomon words with errors before anything is evaluated
+    // in the exponent; what the decoder settles (exactly - share_rs.cuh) needs no evaluation.  One more read-back of the flags.
+    if (int rc = dkgv_fd_repair(ctx, job.n_d, job.n_r, job.t, job.d_vv, job.d_shares, job.d_status, job.d_flags, s)) return rc;
+    CK(cudaMemcpyAsync(ctx->h_job_flags, job.d_flags, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->last_repaired = ctx->h_job_flags[2];
+    if (!ctx->h_job_flags[1]) return 0;
+  }
   ctx->fd_last_need = true;
   VVView view;
   uint32_t n_pad;

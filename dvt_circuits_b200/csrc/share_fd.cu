@@ -19,6 +19,7 @@
 
 #include "ctx.hpp"
 #include "fdiff.cuh"
+#include "share_rs.cuh"
 
 using namespace dkgv;
 
@@ -145,20 +146,26 @@ __global__ void __launch_bounds__(128) k_fd_tables(uint32_t t, uint32_t* __restr
   }
 }
 
-// shares of one dealer chunk as little-endian limbs in ascending-id order: sl[d - d0][x - 1][8]; poly_ok[d] = 0 when a share is >= r
+// shares of one dealer chunk as little-endian limbs in ascending-id order: sl[d - d0][x - 1][8].  A share >= r fails condition (1):
+// poly_ok[d] = 0, the dealer is marked for the repair route (share_rs.cuh), which treats the share as a wrong value (0 in the table,
+// oor[d - d0][x - 1] = 1 so that its verdict stays SECRET_RANGE whatever the decoder finds)
 __global__ void __launch_bounds__(128)
 k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict__ cols, uint32_t* __restrict__ sl, uint8_t* __restrict__ poly_ok,
-                 uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r) {
+                 uint8_t* __restrict__ state, uint8_t* __restrict__ oor, uint32_t d0, uint32_t n_cols, uint32_t n_d, uint32_t n_r) {
   uint32_t xi = blockIdx.x * blockDim.x + threadIdx.x, dl = blockIdx.y;
   if (xi >= n_r || d0 + dl >= n_d) return;
   uint32_t l[8];
   uint32_t c = cols[xi];
   if (c >= n_r) c = 0;  // ids that are not a permutation: the speculative run reads in bounds, its results are discarded
   bool ok = fr_raw_from_be32(l, shares + ((size_t)(d0 + dl) * n_r + c) * 32);
-  if (!ok) poly_ok[d0 + dl] = 0;
+  if (!ok) {
+    poly_ok[d0 + dl] = 0;
+    state[d0 + dl] = RS_REPAIR;
+  }
+  if (oor) oor[(size_t)dl * n_r + xi] = ok ? 0 : 1;
   uint32_t* o = sl + ((size_t)dl * n_r + xi) * 8;
 #pragma unroll
-  for (int i = 0; i < 8; i++) o[i] = l[i];
+  for (int i = 0; i < 8; i++) o[i] = ok ? l[i] : 0u;
 }
 
 // Condition (2) and the interpolation in ONE difference table per dealer (n_r <= 2048), canonical residues, no products except by small integers (fdiff.cuh, "difference table"):
@@ -171,7 +178,7 @@ k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict_
 // Montgomery products before.
 __global__ void __launch_bounds__(1024)
 k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact, uint32_t* __restrict__ coef, uint8_t* __restrict__ poly_ok,
-             uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
+             uint8_t* __restrict__ state, uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
   extern __shared__ uint32_t fr_sm[];  // pub[2][blockDim.x], E[t]
   const uint32_t dl = blockIdx.x, i = threadIdx.x, nt = blockDim.x;
   if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a share >= r already failed condition (1)
@@ -196,7 +203,10 @@ k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact
   }
   bool bad = (k0 >= t && k0 < n_r && !is_zero(p.a)) || (k1 >= t && k1 < n_r && !is_zero(p.b));
   if (__syncthreads_or(bad)) {  // some t-th difference is not zero: the shares are not on a polynomial of degree < t
-    if (i == 0) poly_ok[d0 + dl] = 0;
+    if (i == 0) {
+      poly_ok[d0 + dl] = 0;
+      if (state) state[d0 + dl] = RS_REPAIR;  // the shares are not on one polynomial: the repair route may still find it
+    }
     return;
   }
   Fr f;
@@ -294,10 +304,14 @@ __global__ void __launch_bounds__(128) k_fd_cols(const uint32_t* __restrict__ id
 
 // start of a submitted job: cols = 0xffffffff, poly_ok = 1, need_group = 0, flags = {0, pending0}
 __global__ void __launch_bounds__(256) k_fd_prep(uint32_t* __restrict__ cols, uint32_t n_r, uint8_t* __restrict__ poly_ok, uint32_t n_pad,
-                                                 uint8_t* __restrict__ need_group, uint32_t* __restrict__ flags, uint32_t pending0) {
+                                                 uint8_t* __restrict__ need_group, uint32_t* __restrict__ flags, uint32_t pending0,
+                                                 uint8_t* __restrict__ state) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_r) cols[i] = 0xffffffffu;
-  if (i < n_pad) poly_ok[i] = 1;
+  if (i < n_pad) {
+    poly_ok[i] = 1;
+    state[i] = RS_IDLE;
+  }
   if (i < n_pad / 32) need_group[i] = 0;
   if (i == 0) {
     flags[0] = 0;
@@ -318,9 +332,9 @@ k_fd_need(const uint8_t* __restrict__ poly_ok, uint32_t n_d, uint8_t* __restrict
 
 // verdict OK for every share of the dealer groups that met the three conditions (block = 128 columns of one dealer)
 __global__ void __launch_bounds__(128)
-k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, uint32_t n_d, uint32_t n_r) {
+k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, const uint8_t* __restrict__ state, uint32_t n_d, uint32_t n_r) {
   uint32_t j = blockIdx.y * blockDim.x + threadIdx.x, d = blockIdx.x;
-  if (j >= n_r || d >= n_d || need_group[d / 32]) return;
+  if (j >= n_r || d >= n_d || need_group[d / 32] || state[d] == RS_CANDIDATE) return;  // a repaired dealer keeps its own verdicts
   status[(size_t)d * n_r + j] = DKGV_OK;
 }
 
@@ -397,14 +411,15 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
                    uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s) {
   const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
   CK(ctx->fd_cols.reserve((size_t)n_r * 4));
-  CK(ctx->fd_flags.reserve((size_t)n_pad + groups));
+  CK(ctx->fd_flags.reserve((size_t)n_pad * 3 + groups + (size_t)n_pad * 8 + 64));
   uint32_t* cols = (uint32_t*)ctx->fd_cols.p;
   uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
   uint8_t* need_group = poly_ok + n_pad;
+  uint8_t* state = need_group + groups;  // [n_pad] dealer states of the repair route; behind it ok2 [n_pad], deg / cnt [n_pad] u32, counter
   CK(cudaEventRecord(ctx->ev_sc[0], s));
   CK(cudaEventRecord(ctx->ev_hot0, s));
   const uint32_t prep_n = std::max(n_r, n_pad);
-  k_fd_prep<<<(prep_n + 255) / 256, 256, 0, s>>>(cols, n_r, poly_ok, n_pad, need_group, d_flags, shortcut ? 0u : 1u);
+  k_fd_prep<<<(prep_n + 255) / 256, 256, 0, s>>>(cols, n_r, poly_ok, n_pad, need_group, d_flags, shortcut ? 0u : 1u, state);
   k_fd_cols<<<(n_r + 127) / 128, 128, 0, s>>>(d_ids, n_r, cols, d_flags);
   ctx->launches += 2;
   if (shortcut) {
@@ -427,8 +442,10 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
       const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
       const bool first = d0 == 0, last = d0 + chunk >= n_d;
-      k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, d0, n_cols, n_d, n_r);
-      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, d0, n_d, n_r, t);
+      k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, nullptr, d0, n_cols, n_d,
+                                                                       n_r);
+      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
+                                                               n_r, t);
       if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
       k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
                                                              n_d, n_cols, t);
@@ -438,7 +455,7 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
       ctx->launches += 4;
     }
     k_fd_need<<<(n_d + 127) / 128, 128, 0, s>>>(poly_ok, n_d, need_group, d_flags);
-    k_fd_fill_ok<<<dim3(n_d, (n_r + 127) / 128), 128, 0, s>>>(d_status, need_group, n_d, n_r);
+    k_fd_fill_ok<<<dim3(n_d, (n_r + 127) / 128), 128, 0, s>>>(d_status, need_group, state, n_d, n_r);
     ctx->launches += 2;
   } else {
     for (int i = 1; i <= 3; i++) CK(cudaEventRecord(ctx->ev_sc[i], s));
@@ -451,6 +468,89 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   return 0;
 }
 const uint8_t* dkgv_fd_need_groups(const dkgv_ctx* ctx, uint32_t n_d) { return (const uint8_t*)ctx->fd_flags.p + ((n_d + 31) & ~31u); }
+
+// the repair route applies: the shortcut's shapes, at least one correctable error, blocks that fit (k_rs_bm: tau + 2 threads)
+bool dkgv_fd_repair_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t) {
+  return ctx->fd_repair && dkgv_fd_shortcut_applies(ctx, n_r, t) && (n_r - t) / 2 >= 1 && (n_r - t) / 2 + 2 <= 1024 && t >= 2;
+}
+
+// Repair route (share_rs.cuh) for the dealers a submitted job marked RS_REPAIR, then the need flags again: asynchronous on s; d_flags[1]
+// ends as the number of dealers STILL unsettled.  Called by share_finish after it has seen flags[1] != 0.
+int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint8_t* d_shares, uint8_t* d_status,
+                   uint32_t* d_flags, cudaStream_t s) {
+  const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
+  const uint32_t nsyn = n_r - t, tau = nsyn / 2;
+  uint32_t* cols = (uint32_t*)ctx->fd_cols.p;
+  uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
+  uint8_t* need_group = poly_ok + n_pad;
+  uint8_t* state = need_group + groups;
+  uint8_t* ok2 = state + n_pad;
+  uint32_t* deg = (uint32_t*)(((uintptr_t)(ok2 + n_pad) + 15) & ~(uintptr_t)15);
+  uint32_t* cnt = deg + n_pad;
+  uint32_t* repaired = cnt + n_pad;
+  if (ctx->rs_n != n_r || ctx->rs_t != t) {  // tables of the shape: dual weights, 1 / d, powers (11 MB at (1024, 683))
+    CK(ctx->rs_tab.reserve(((size_t)2 * n_r + (size_t)n_r * nsyn) * 32));
+    k_rs_tables<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, nsyn, (uint32_t*)ctx->rs_tab.p, (uint32_t*)ctx->rs_tab.p + (size_t)n_r * 8,
+                                                 (uint32_t*)ctx->rs_tab.p + (size_t)2 * n_r * 8);
+    ctx->rs_n = n_r;
+    ctx->rs_t = t;
+    ctx->launches++;
+  }
+  const uint32_t* tab_u = (const uint32_t*)ctx->rs_tab.p;
+  const uint32_t* tab_inv = tab_u + (size_t)n_r * 8;
+  const uint32_t* tab_pw = tab_u + (size_t)2 * n_r * 8;
+  const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
+  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 164 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32;
+  const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
+  CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
+  CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
+  CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)t * 36 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32) + 256));
+  uint8_t* w = (uint8_t*)ctx->rs_work.p;
+  uint32_t* syn = (uint32_t*)w;
+  uint32_t* lam = syn + (size_t)chunk * nsyn * 8;
+  uint32_t* newt = lam + (size_t)chunk * (tau + 1) * 8;
+  uint32_t* nodes = newt + (size_t)chunk * t * 8;
+  uint8_t* err = (uint8_t*)(nodes + (size_t)chunk * t);
+  uint8_t* oor = err + (size_t)chunk * n_r;
+  CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
+  CK(cudaMemsetAsync(ok2, 0, n_pad, s));
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(k_rs_syndromes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
+    CK(cudaFuncSetAttribute(k_rs_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (2048 + 1024 + 40) * 32));
+    CK(cudaFuncSetAttribute(k_rs_divdiff, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 68));
+    attr = true;
+  }
+  const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32, batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
+  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u), dd_threads = (t + 31) & ~31u;
+  const unsigned gy = (n_r + 127) / 128;
+  for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
+    const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
+    // the share table of this chunk again (chunks of a large session share the buffers), now with the out-of-range marks
+    k_fd_share_limbs<<<dim3(gy, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, oor, d0, n_cols, n_d, n_r);
+    k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)n_r * 32, s>>>((const uint32_t*)ctx->fd_sl.p, state, tab_u, tab_pw, syn, d0, n_r, nsyn);
+    k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, d0, nsyn, tau);
+    k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
+    k_rs_divdiff<<<n_here, dd_threads, (size_t)t * 68, s>>>((const uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, tab_inv, nodes, newt, d0, n_r, t);
+    k_rs_correct<<<dim3(n_here, gy), 128, 0, s>>>((uint32_t*)ctx->fd_sl.p, err, state, nodes, newt, d0, n_r, t);
+    k_rs_stage<<<(n_here + 127) / 128, 128, 0, s>>>(state, ok2, d0, n_here);
+    // second pass of the exact conditions on the corrected table: t-th differences + coefficients, compress(G * p_k) == C_k
+    k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, ok2, nullptr, d0, n_d, n_r, t);
+    k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, ok2, (uint32_t*)ctx->fd_yz.p, d0, n_d, n_cols, t);
+    k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, ok2, d0, n_d, n_cols, t);
+    k_rs_verdicts<<<dim3(n_here, gy), 128, 0, s>>>(d_status, err, oor, ok2, poly_ok, state, cols, repaired, d0, n_r);
+    ctx->launches += 11;
+  }
+  CK(cudaMemsetAsync(need_group, 0, groups, s));
+  CK(cudaMemsetAsync(d_flags + 1, 0, 4, s));
+  k_fd_need<<<(n_d + 127) / 128, 128, 0, s>>>(poly_ok, n_d, need_group, d_flags);
+  k_fd_fill_ok<<<dim3(n_d, gy), 128, 0, s>>>(d_status, need_group, state, n_d, n_r);
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(&ctx->h_job_flags[2], repaired, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaGetLastError());
+  return 0;
+}
 
 // Items (point additions) per block of the difference / extension launches.  One per block is the
 // measured optimum on B200 (n=1024, t=683, N=1: extension 336 ms with 1, 344 ms with 2, 367 ms with 4 items):

@@ -143,6 +143,15 @@ int dkgv_set_share_overlap(dkgv_ctx* ctx, int on);
  * shortcut settled everything.                                                                                   */
 int dkgv_set_share_shortcut(dkgv_ctx* ctx, int on);
 int dkgv_last_share_continued(const dkgv_ctx* ctx);
+/* Repair route behind the shortcut (default on).  A dealer whose shares are NOT on one polynomial of degree < t is first decoded as
+ * a Reed-Solomon word with errors over Fr (syndromes, Berlekamp-Massey, root search, Newton interpolation through the shares not
+ * located as wrong - scalar arithmetic only): with at most floor((n - t) / 2) wrong shares this recovers the dealer's polynomial p,
+ * which is then put through the SAME exact conditions as an honest dealer's (t-th differences of the corrected sequence,
+ * compress(G * p_k) == C_k).  Only a confirmed p yields verdicts - share != p(id) -> SLASHABLE_SHARE_MISMATCH, >= r ->
+ * SLASHABLE_SECRET_RANGE, else OK - so they are exact and no randomness is involved; anything the decoder cannot settle goes to the
+ * evaluation as before.  dkgv_last_share_repaired: dealers the route settled in the last share-matrix call.                       */
+int dkgv_set_share_repair(dkgv_ctx* ctx, int on);
+int dkgv_last_share_repaired(const dkgv_ctx* ctx);
 /* 1 when the commitments of the last share-matrix call were decoded (square roots, subgroup tests), 0 when the shortcut
  * settled the call against their compressed encodings: compress(G * p_k) == C_k needs no decompression, and an encoding
  * that is not a subgroup point can never agree, so the decode waits until some dealer group needs the evaluation.   */
