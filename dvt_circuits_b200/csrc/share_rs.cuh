@@ -124,7 +124,7 @@ __device__ __forceinline__ Fr rs_block_sum(Fr v, Fr* red) {
 // Inversion-free Berlekamp-Massey, one block per dealer under repair, thread k owns Lambda_k (k <= tau + 1).
 //   d = sum_{k <= L} Lambda_k S_{r-k};  d != 0:  Lambda <- b Lambda - d z^m B  (and, when 2 L <= r: B <- old Lambda, L <- r + 1 - L, b <- d, m <- 1)
 // out: lam[dl][0..tau] (Montgomery), deg[d] = L, or state -> RS_FAILED when L > tau (more wrong shares than the code corrects)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t* __restrict__ lam, uint32_t* __restrict__ deg, uint32_t d0,
         uint32_t nsyn, uint32_t tau) {
   extern __shared__ uint32_t rs_sm[];  // S[nsyn], B[blockDim.x], red[blockDim.x / 32 + 1]
