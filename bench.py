@@ -62,6 +62,9 @@ def canonical_horner_modmul(t, x):
 # executed product-equivalents (300 wide MACs each) of the vm.cuh formulas: the fused sum-of-two-products routine
 # (mul2add, 444 MACs) replaces three pairs in the additions and one in the doubling
 EXEC_ADD, EXEC_DBL, EXEC_MADD = 6 + 3 * 444 / 300, 6 + 444 / 300, 5 + 3 * 444 / 300
+# fixed-base multiplication G * s: the canonical algorithm of SURVEY 8(d) is 8-bit windows (32 + 1 mixed additions); the library's table
+# has 13-bit windows (csrc/feldman.cuh GTAB_BITS): 20 + 1 mixed additions
+CANON_FIX_MADDS, EXEC_FIX_MADDS = 33, 21
 
 
 def executed_horner_modmul(t, x):
@@ -651,11 +654,11 @@ def run_b200(args):
         roof = {"bound": "int_pipe", "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9, "mac_per_modmul": MAC_PER_MODMUL, "traffic": None, "algorithmic_bytes": None}
         if settled_by_shortcut and len(short_ms) == args.steps:
-            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (33 mixed
-            # additions) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
+            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (21 mixed
+            # additions over the 13-bit-window table; canonical: 33 over byte windows) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
             # ALU work + 2 products) - per point 3 products of the simultaneous inversion + Y / Z + the canonical form for the sign
             sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
-            pt_canon, pt_exec = 33 * 11 + 2, 33 * EXEC_MADD + 2
+            pt_canon, pt_exec = CANON_FIX_MADDS * 11 + 2, EXEC_FIX_MADDS * EXEC_MADD + 2
             sg = 2 / 8 + 3 + 2
             top = kernel_entry("k_fd_coefpoint", rows * t, "one coefficient: G * p_k by the fixed-base table, x_C * Z == X against the "
                                "compressed commitment", pt_canon, pt_exec, sp[1], step_mean)
@@ -684,9 +687,9 @@ def run_b200(args):
             ph = [statistics.mean(p[i] for p in phase_ms) for i in range(4)]
             ref = statistics.mean(serial_ms)
             # 128 shared doublings (GLV), per point: table 3P/5P/7P (44) + 2 x 128/5 additions + 128/5 products by beta; + part 0; + G*s, compare
-            comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + 33 * 11 + 4
+            comb_canon = (128 * 8 + (m_parts - 1) * (44 + 52 * 12 + 26) + 12 if m_parts > 1 else 0) + CANON_FIX_MADDS * 11 + 4
             comb_exec = ((128 * EXEC_DBL + (m_parts - 1) * (EXEC_DBL + 3 * EXEC_ADD + 52 * EXEC_ADD + 26) + EXEC_ADD if m_parts > 1 else 0)
-                         + 33 * EXEC_MADD + 4)
+                         + EXEC_FIX_MADDS * EXEC_MADD + 4)
             kernels = [
                 kernel_entry("k_fd_seed", rows * m_parts * h_part, "one Horner evaluation of a part (dealer, part, seed point)",
                              sum(canonical_horner_modmul(h_part, x) for x in seeds) / h_part,

@@ -178,9 +178,11 @@ k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict_
 // Montgomery products before.
 __global__ void __launch_bounds__(1024)
 k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact, uint32_t* __restrict__ coef, uint8_t* __restrict__ poly_ok,
-             uint8_t* __restrict__ state, uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t) {
+             uint8_t* __restrict__ state, uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t, const uint32_t* __restrict__ map,
+             const uint32_t* __restrict__ n_map) {
   extern __shared__ uint32_t fr_sm[];  // pub[2][blockDim.x], E[t]
-  const uint32_t dl = blockIdx.x, i = threadIdx.x, nt = blockDim.x;
+  if (map && blockIdx.x >= *n_map) return;  // second pass of the repair route: one block per candidate
+  const uint32_t dl = map ? map[blockIdx.x] : blockIdx.x, i = threadIdx.x, nt = blockDim.x;
   if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a share >= r already failed condition (1)
   Fr* pub = (Fr*)fr_sm;
   Fr* E = pub + 2 * (size_t)nt;
@@ -243,11 +245,21 @@ k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact
 // (warp = 32 dealers x one k, the layout of the seeds); writes Z (limbs 0..11) and Y (12..23) of G * p_k to the chunk-local planes yz[(k*24 + w) * n_cols + dl].
 __global__ void __launch_bounds__(FD_NT)
 k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab,
-               uint8_t* __restrict__ poly_ok, uint32_t* __restrict__ yz, uint32_t d0, uint32_t n_d, uint32_t n_cols, uint32_t t) {
+               uint8_t* __restrict__ poly_ok, uint32_t* __restrict__ yz, uint32_t d0, uint32_t n_d, uint32_t n_cols, uint32_t t,
+               const uint32_t* __restrict__ map, const uint32_t* __restrict__ n_map) {
   extern __shared__ U4 opfile[];
-  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
-  bool active = d0 + dl < n_d;
-  uint32_t dc = active ? dl : n_d - 1 - d0;
+  // column c of the Y / Z planes; without a map column c is dealer d0 + c, with one (second pass of the repair route: the
+  // candidates compacted into dense groups) it is dealer d0 + map[c], c < *n_map
+  const uint32_t c = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y;
+  uint32_t dl = c;
+  bool active = d0 + c < n_d;
+  if (map) {
+    const uint32_t nm = *n_map;
+    if (blockIdx.x * 32 >= nm) return;
+    active = c < nm;
+    dl = map[active ? c : 0];
+  }
+  uint32_t dc = active ? dl : (map ? dl : n_d - 1 - d0);
 #if defined(__CUDA_ARCH__)
   if (__ballot_sync(0xffffffffu, active && poly_ok[d0 + dl]) == 0) return;  // nobody in this group can still pass
 #endif
@@ -257,7 +269,7 @@ k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef
   for (int l = 0; l < 8; l++) sc[l] = coef[((size_t)dc * t + k) * 8 + l];
   Fp y, z;
   bool same = fd_coef_point(f, gtab, sc, vv + ((size_t)(d0 + dc) * t + k) * 48, &y, &z);
-  uint32_t* o = yz + (size_t)k * 24 * n_cols + dl;
+  uint32_t* o = yz + (size_t)k * 24 * n_cols + c;
 #pragma unroll
   for (int w = 0; w < 12; w++) {
     o[(size_t)w * n_cols] = z.l[w];
@@ -270,15 +282,20 @@ k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef
 // A dealer still marked ok here had every one of its points written by k_fd_coefpoint (poly_ok only ever drops).
 __global__ void __launch_bounds__(128)
 k_fd_coefsign(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ yz, uint8_t* __restrict__ poly_ok, uint32_t d0, uint32_t n_d,
-              uint32_t n_cols, uint32_t t) {
-  uint32_t dl = blockIdx.x * 32 + threadIdx.x, k0 = (blockIdx.y * blockDim.y + threadIdx.y) * FD_SIGN_K;
+              uint32_t n_cols, uint32_t t, const uint32_t* __restrict__ map, const uint32_t* __restrict__ n_map) {
+  const uint32_t c = blockIdx.x * 32 + threadIdx.x, k0 = (blockIdx.y * blockDim.y + threadIdx.y) * FD_SIGN_K;
+  uint32_t dl = c;
+  if (map) {
+    if (c >= *n_map) return;
+    dl = map[c];
+  }
   if (d0 + dl >= n_d || k0 >= t || !poly_ok[d0 + dl]) return;
   int cnt = (int)(t - k0 < (uint32_t)FD_SIGN_K ? t - k0 : (uint32_t)FD_SIGN_K);
   Fp z[FD_SIGN_K], y[FD_SIGN_K];
   uint8_t fs[FD_SIGN_K];
 #pragma unroll 1
   for (int i = 0; i < cnt; i++) {
-    const uint32_t* e = yz + (size_t)(k0 + i) * 24 * n_cols + dl;
+    const uint32_t* e = yz + (size_t)(k0 + i) * 24 * n_cols + c;
 #pragma unroll
     for (int w = 0; w < 12; w++) {
       z[i].l[w] = e[(size_t)w * n_cols];
@@ -411,7 +428,7 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
                    uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s) {
   const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
   CK(ctx->fd_cols.reserve((size_t)n_r * 4));
-  CK(ctx->fd_flags.reserve((size_t)n_pad * 3 + groups + (size_t)n_pad * 8 + 64));
+  CK(ctx->fd_flags.reserve((size_t)n_pad * 3 + groups + (size_t)n_pad * 12 + 64));
   uint32_t* cols = (uint32_t*)ctx->fd_cols.p;
   uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
   uint8_t* need_group = poly_ok + n_pad;
@@ -445,12 +462,13 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
       k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, nullptr, d0, n_cols, n_d,
                                                                        n_r);
       k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
-                                                               n_r, t);
+                                                               n_r, t, nullptr, nullptr);
       if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
       k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
-                                                             n_d, n_cols, t);
+                                                             n_d, n_cols, t, nullptr, nullptr);
       if (first) CK(cudaEventRecord(ctx->ev_sc[2], s));
-      k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d, n_cols, t);
+      k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d, n_cols, t, nullptr,
+                                                                         nullptr);
       if (last) CK(cudaEventRecord(ctx->ev_sc[3], s));
       ctx->launches += 4;
     }
@@ -488,6 +506,8 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   uint32_t* deg = (uint32_t*)(((uintptr_t)(ok2 + n_pad) + 15) & ~(uintptr_t)15);
   uint32_t* cnt = deg + n_pad;
   uint32_t* repaired = cnt + n_pad;
+  uint32_t* n_cand = repaired + 1;
+  uint32_t* cand = n_cand + 3;  // [n_pad] dealers (chunk-local) of the second pass, compacted
   if (ctx->rs_n != n_r || ctx->rs_t != t) {  // tables of the shape: dual weights, 1 / d, powers (11 MB at (1024, 683))
     CK(ctx->rs_tab.reserve(((size_t)2 * n_r + (size_t)n_r * nsyn) * 32));
     k_rs_tables<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, nsyn, (uint32_t*)ctx->rs_tab.p, (uint32_t*)ctx->rs_tab.p + (size_t)n_r * 8,
@@ -519,7 +539,8 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   if (!attr) {
     CK(cudaFuncSetAttribute(k_rs_syndromes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
     CK(cudaFuncSetAttribute(k_rs_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (2048 + 1024 + 40) * 32));
-    CK(cudaFuncSetAttribute(k_rs_divdiff, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 68));
+    CK(cudaFuncSetAttribute(k_rs_divdiff, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 68 + 2048 * 32 + 256));
+    CK(cudaFuncSetAttribute(k_rs_correct, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 + 2048 * 4));
     attr = true;
   }
   const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32, batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
@@ -532,13 +553,17 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)n_r * 32, s>>>((const uint32_t*)ctx->fd_sl.p, state, tab_u, tab_pw, syn, d0, n_r, nsyn);
     k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, d0, nsyn, tau);
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
-    k_rs_divdiff<<<n_here, dd_threads, (size_t)t * 68, s>>>((const uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, tab_inv, nodes, newt, d0, n_r, t);
-    k_rs_correct<<<dim3(n_here, gy), 128, 0, s>>>((uint32_t*)ctx->fd_sl.p, err, state, nodes, newt, d0, n_r, t);
-    k_rs_stage<<<(n_here + 127) / 128, 128, 0, s>>>(state, ok2, d0, n_here);
+    k_rs_divdiff<<<n_here, dd_threads, (size_t)t * 68 + (size_t)n_r * 32 + 256, s>>>((const uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, tab_inv, nodes, newt, d0, n_r, t);
+    k_rs_correct<<<n_here, 256, (size_t)t * 32 + (size_t)n_r * 4, s>>>((uint32_t*)ctx->fd_sl.p, err, state, nodes, newt, d0, n_r, t);
+    CK(cudaMemsetAsync(n_cand, 0, 4, s));
+    k_rs_stage<<<(n_here + 127) / 128, 128, 0, s>>>(state, ok2, cand, n_cand, d0, n_here);
     // second pass of the exact conditions on the corrected table: t-th differences + coefficients, compress(G * p_k) == C_k
-    k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, ok2, nullptr, d0, n_d, n_r, t);
-    k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, ok2, (uint32_t*)ctx->fd_yz.p, d0, n_d, n_cols, t);
-    k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, ok2, d0, n_d, n_cols, t);
+    // (the candidates are compacted into dense groups: a handful of wrong dealers costs a handful of warps, not every group)
+    k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, ok2, nullptr, d0, n_d, n_r, t,
+                                                             cand, n_cand);
+    k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, ok2, (uint32_t*)ctx->fd_yz.p, d0, n_d, n_cols, t,
+                                                           cand, n_cand);
+    k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, ok2, d0, n_d, n_cols, t, cand, n_cand);
     k_rs_verdicts<<<dim3(n_here, gy), 128, 0, s>>>(d_status, err, oor, ok2, poly_ok, state, cols, repaired, d0, n_r);
     ctx->launches += 11;
   }

@@ -188,12 +188,13 @@ k_rs_chien(const uint32_t* __restrict__ lam, const uint32_t* __restrict__ deg, c
 
 // Newton's divided differences through the first t positions that are not located as wrong: one block per dealer, thread k owns
 // entry k.  out: nodes[dl][k] = x_k, newt[dl][k] = f[x_0 .. x_k] (Montgomery).  The located count must equal the locator's degree.
+// The table 1 / d of the shape is staged in shared memory (every round needs one entry per thread, picked by a node distance).
 __global__ void __launch_bounds__(1024)
 k_rs_divdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ err, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ deg,
              uint8_t* __restrict__ state, const uint32_t* __restrict__ inv, uint32_t* __restrict__ nodes, uint32_t* __restrict__ newt, uint32_t d0,
              uint32_t n_r, uint32_t t) {
-  extern __shared__ uint32_t rs_sm[];  // A[2][t][8], node[t], scan scratch
-  const uint32_t dl = blockIdx.x, k = threadIdx.x;
+  extern __shared__ uint32_t rs_sm[];  // A[2][t][8], INV[n_r][8], node[t], wsum[33]
+  const uint32_t dl = blockIdx.x, k = threadIdx.x, nthr = blockDim.x;
   if (state[d0 + dl] != RS_REPAIR) return;
   if (cnt[d0 + dl] != deg[d0 + dl]) {  // the locator does not split over 1..n: not a correctable error pattern
     if (k == 0) state[d0 + dl] = RS_FAILED;
@@ -201,16 +202,32 @@ k_rs_divdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ err, c
   }
   Fr* A0 = (Fr*)rs_sm;
   Fr* A1 = A0 + t;
-  uint32_t* node = (uint32_t*)(A1 + t);
-  __shared__ uint32_t run;
-  if (k == 0) {  // positions are few thousand at most: a serial compaction by one thread costs less than the barriers of a scan
-    uint32_t c = 0;
-    for (uint32_t x = 0; x < n_r && c < t; x++)
-      if (!err[(size_t)dl * n_r + x]) node[c++] = x + 1;
-    run = c;
+  Fr* INV = A1 + t;
+  uint32_t* node = (uint32_t*)(INV + n_r);
+  uint32_t* wsum = node + t;
+  for (uint32_t i = k; i < n_r; i += nthr) INV[i] = fr_load(inv + (size_t)i * 8);
+  // compaction of the positions not located as wrong (ascending), a block-wide scan over chunks of blockDim positions
+  uint32_t base_cnt = 0;
+#pragma unroll 1
+  for (uint32_t base = 0; base < n_r; base += nthr) {
+    const uint32_t x = base + k;
+    const bool good = x < n_r && !err[(size_t)dl * n_r + x];
+    const uint32_t bal = __ballot_sync(0xffffffffu, good), lane = k & 31, warp = k >> 5;
+    const uint32_t before = __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = base_cnt, total = 0;
+    for (uint32_t w = 0; w < (nthr >> 5); w++) {
+      const uint32_t c = wsum[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (good && off + before < t) node[off + before] = x + 1;
+    base_cnt += total;
   }
   __syncthreads();
-  if (run < t) {
+  if (base_cnt < t) {
     if (k == 0) state[d0 + dl] = RS_FAILED;
     return;
   }
@@ -223,7 +240,7 @@ k_rs_divdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ err, c
   for (uint32_t j = 1; j < t; j++) {
     if (k < t) {
       Fr v = cur[k];
-      if (k >= j) v = mul(sub(v, cur[k - 1]), fr_load(inv + (size_t)(xk - node[k - j]) * 8));
+      if (k >= j) v = mul(sub(v, cur[k - 1]), INV[xk - node[k - j]]);
       nxt[k] = v;
     }
     __syncthreads();
@@ -237,38 +254,82 @@ k_rs_divdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ err, c
   }
 }
 
-// the located positions: p(x) by Horner in the Newton basis; p(x) != share: the table gets the corrected value (err stays 1);
-// p(x) == share: the locator was wrong about this position (err <- 0; the second pass will then fail the dealer or not, exactly)
-__global__ void __launch_bounds__(128)
+// The located positions: p(x) in the Newton basis, one WARP per position.  Lane l owns the l-th run of ceil(t / 32) basis terms:
+// its partial sum S_l = sum_k a_k prod_{m in run, m < k} (x - x_m) and the run's product P_l; p(x) = sum_l (P_0 ... P_{l-1}) S_l by a
+// warp scan.  p(x) != share: the table gets the corrected value (err stays 1); p(x) == share: the locator was wrong about this
+// position (err <- 0; the second pass then decides about the dealer, exactly).  block = one dealer, 8 warps.
+__global__ void __launch_bounds__(256)
 k_rs_correct(uint32_t* __restrict__ sl, uint8_t* __restrict__ err, const uint8_t* __restrict__ state, const uint32_t* __restrict__ nodes,
              const uint32_t* __restrict__ newt, uint32_t d0, uint32_t n_r, uint32_t t) {
-  const uint32_t dl = blockIdx.x, xi = blockIdx.y * blockDim.x + threadIdx.x;
-  if (state[d0 + dl] != RS_REPAIR || xi >= n_r || !err[(size_t)dl * n_r + xi]) return;
-  const uint32_t x = xi + 1;
-  const uint32_t* np = nodes + (size_t)dl * t;
+  extern __shared__ uint32_t rs_sm[];  // NM[t][8] (nodes in Montgomery form), list[n_r]
+  __shared__ uint32_t n_err;
+  const uint32_t dl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (state[d0 + dl] != RS_REPAIR) return;
+  Fr* NM = (Fr*)rs_sm;
+  uint32_t* list = (uint32_t*)(NM + t);
+  if (tid == 0) n_err = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < t; i += blockDim.x) NM[i] = fr_from_small(nodes[(size_t)dl * t + i]);
+  for (uint32_t x = tid; x < n_r; x += blockDim.x)
+    if (err[(size_t)dl * n_r + x]) list[atomicAdd(&n_err, 1u)] = x;
+  __syncthreads();
+  const uint32_t run = (t + 31) / 32, k0 = lane * run, k1 = k0 + run < t ? k0 + run : t;
   const uint32_t* ap = newt + (size_t)dl * t * 8;
-  Fr v = fr_load(ap + (size_t)(t - 1) * 8);
 #pragma unroll 1
-  for (int k = (int)t - 2; k >= 0; k--) {
-    uint32_t xk = np[k];
-    Fr diff = x >= xk ? fr_from_small(x - xk) : neg(fr_from_small(xk - x));
-    v = add(mul(v, diff), fr_load(ap + (size_t)k * 8));
+  for (uint32_t e = warp; e < n_err; e += blockDim.x >> 5) {
+    const uint32_t xi = list[e];
+    const Fr xm = fr_from_small(xi + 1);
+    Fr S = zero<FrParams>(), P = one<FrParams>();
+#pragma unroll 1
+    for (uint32_t k = k0; k < k1; k++) {
+      S = add(S, mul(fr_load(ap + (size_t)k * 8), P));
+      P = mul(P, sub(xm, NM[k]));
+    }
+    // inclusive scan of the run products, then the exclusive prefix times the run's sum
+    Fr pre = P;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+      Fr o;
+#pragma unroll
+      for (int l = 0; l < 8; l++) o.l[l] = __shfl_up_sync(0xffffffffu, pre.l[l], off);
+      if ((int)lane >= off) pre = mul(pre, o);
+    }
+    Fr excl;
+#pragma unroll
+    for (int l = 0; l < 8; l++) excl.l[l] = __shfl_up_sync(0xffffffffu, pre.l[l], 1);
+    if (lane == 0) excl = one<FrParams>();
+    Fr v = mul(excl, S);
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+      Fr o;
+#pragma unroll
+      for (int l = 0; l < 8; l++) o.l[l] = __shfl_down_sync(0xffffffffu, v.l[l], off);
+      v = add(v, o);
+    }
+    if (lane == 0) {
+      Fr c = from_mont(v);
+      uint32_t* s = sl + ((size_t)dl * n_r + xi) * 8;
+      if (eq(c, fr_load(s)))
+        err[(size_t)dl * n_r + xi] = 0;
+      else
+        fr_store(s, c);
+    }
   }
-  Fr c = from_mont(v);
-  uint32_t* s = sl + ((size_t)dl * n_r + xi) * 8;
-  if (eq(c, fr_load(s)))
-    err[(size_t)dl * n_r + xi] = 0;
-  else
-    fr_store(s, c);
 }
 
-// after the correction: the dealers under repair become candidates of the second pass (ok2 = 1), everyone else 0
-__global__ void __launch_bounds__(128) k_rs_stage(uint8_t* __restrict__ state, uint8_t* __restrict__ ok2, uint32_t d0, uint32_t n_here) {
+// after the correction: the dealers under repair become candidates of the second pass (ok2 = 1, listed in cand[0 .. *n_cand)),
+// everyone else 0
+__global__ void __launch_bounds__(128)
+k_rs_stage(uint8_t* __restrict__ state, uint8_t* __restrict__ ok2, uint32_t* __restrict__ cand, uint32_t* __restrict__ n_cand, uint32_t d0,
+           uint32_t n_here) {
   uint32_t dl = blockIdx.x * blockDim.x + threadIdx.x;
   if (dl >= n_here) return;
-  const bool cand = state[d0 + dl] == RS_REPAIR;
-  ok2[d0 + dl] = cand ? 1 : 0;
-  if (cand) state[d0 + dl] = RS_CANDIDATE;
+  const bool c = state[d0 + dl] == RS_REPAIR;
+  ok2[d0 + dl] = c ? 1 : 0;
+  if (c) {
+    state[d0 + dl] = RS_CANDIDATE;
+    cand[atomicAdd(n_cand, 1u)] = dl;
+  }
 }
 
 // verdicts of the dealers the second pass confirmed (ok2 still 1): located -> SHARE_MISMATCH, out of range keeps SECRET_RANGE, else OK;
