@@ -107,7 +107,7 @@ k_pairing_vm(const G1Aff* __restrict__ pk, const uint8_t* __restrict__ pk_st, co
   const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const uint32_t i = blockIdx.x * PVM_LANES + lane, ii = i < m ? i : m - 1;
   const uint32_t hi = hm_idx ? hm_idx[ii] : 0;
-  const PvmCtx c{pvm_file + lane, (const uint32_t*)(hm_lines + (size_t)hi * G2_PREP_LINES), (const uint32_t*)&pk[ii], (const uint32_t*)&sig[ii]};
+  const PvmCtx c{pvm_file + lane, (const uint32_t*)(hm_lines + (size_t)hi * G2_PREP_LINES), (const uint32_t*)&pk[ii], (const uint32_t*)&sig[ii], nullptr};
   if (role == 0) pvm_init_point(c);
   __syncthreads();
 #pragma unroll 1
@@ -148,6 +148,32 @@ k_pairing_vm(const G1Aff* __restrict__ pk, const uint8_t* __restrict__ pk_st, co
       st = pvm_status(pk[i].inf != 0, sig[i].inf != 0, hm[hi].inf != 0, pvm_result_is_one(c));
     }
     status[i] = st;
+  }
+}
+
+// The Miller-loop lines of the hashed messages by the same VM (segments P_D / P_A): PVM_R warps per 32 messages instead of one
+// thread per message - with ONE message (a finalization) the one-thread kernel was a 68-step serial chain of ~2 ms.
+__global__ void __launch_bounds__(PVM_LANES * PVM_R, 2)
+k_g2_prepare_vm(const G2Aff* __restrict__ hm, const uint8_t* __restrict__ st, G2Line* __restrict__ lines, uint32_t n_hm) {
+  extern __shared__ U4 pvm_file[];
+  const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * PVM_LANES + lane, ii = i < n_hm ? i : n_hm - 1;
+  // lanes beyond n_hm run message n_hm - 1 again and store the same values to the same places; a message that did not decode or is
+  // the identity gets lines nobody reads (the check is decided without them)
+  (void)st;
+  const PvmCtx c{pvm_file + lane, nullptr, nullptr, (const uint32_t*)&hm[ii], (uint32_t*)(lines + (size_t)ii * G2_PREP_LINES)};
+  if (role == 0) pvm_init_point(c);
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t ci = 0; ci < PVM_N_PREP_CALLS; ci++) {
+    const PvmCall k = pvm_prep_call(ci);
+    uint32_t pc = pvm_seg_start[k.a][role];
+#pragma unroll 1
+    for (;;) {
+      pc = pvm_exec(c, pc, k.b);
+      if (pc & PVM_END_FLAG) break;
+      __syncthreads();
+    }
   }
 }
 
@@ -254,38 +280,53 @@ extern "C" int dkgv_bls_verify_batch_dev(dkgv_ctx* ctx, uint32_t m, const uint8_
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   CK(ctx->scratch_a.reserve((size_t)n_hm * sizeof(G2Aff)));
   CK(ctx->scratch_b.reserve(n_hm));
-  k_g2_decode<<<(n_hm + 31) / 32, 32, 0, s>>>(d_hm, (G2Aff*)ctx->scratch_a.p, (uint8_t*)ctx->scratch_b.p, n_hm);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  // messages shared by several checks: their lines are computed once (19.6 KB per message)
-  const G2Line* lines = nullptr;
-  const bool want_vm = ctx->bls_path != DKGV_BLS_PATH_THREAD;
-  if (((size_t)n_hm * 4 <= m || want_vm) && (size_t)n_hm * G2_PREP_LINES * sizeof(G2Line) <= ((size_t)1 << 30)) {
-    CK(ctx->scratch_c.reserve((size_t)n_hm * G2_PREP_LINES * sizeof(G2Line)));
-    k_g2_prepare<<<(n_hm + 31) / 32, 32, 0, s>>>((const G2Aff*)ctx->scratch_a.p, (const uint8_t*)ctx->scratch_b.p, (G2Line*)ctx->scratch_c.p,
-                                                 n_hm);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    lines = (const G2Line*)ctx->scratch_c.p;
-  }
-  // decode keys and signatures in their own kernels
   CK(ctx->bls_pk.reserve((size_t)m * sizeof(G1Aff)));
   CK(ctx->bls_sig.reserve((size_t)m * sizeof(G2Aff)));
   CK(ctx->bls_st.reserve((size_t)m * 2));
   uint8_t* pk_st = (uint8_t*)ctx->bls_st.p;
   uint8_t* sig_st = pk_st + m;
-  k_g2_decode<<<(m + 31) / 32, 32, 0, s>>>(d_sig, (G2Aff*)ctx->bls_sig.p, sig_st, m);
-  k_g1_decode<<<(m + 63) / 64, 64, 0, s>>>(d_pk, (G1Aff*)ctx->bls_pk.p, pk_st, m);
+  const bool want_vm = ctx->bls_path != DKGV_BLS_PATH_THREAD;
+  const bool prep = ((size_t)n_hm * 4 <= m || want_vm) && (size_t)n_hm * G2_PREP_LINES * sizeof(G2Line) <= ((size_t)1 << 30);
+  if (prep) CK(ctx->scratch_c.reserve((size_t)n_hm * G2_PREP_LINES * sizeof(G2Line)));
+  if (!ctx->pvm_attr_set) {
+    CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PVM_SMEM));
+    CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_g2_prepare_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PVM_SMEM));
+    ctx->pvm_attr_set = true;
+  }
+  // Three independent chains before the pairing kernel - hashed messages: decode -> lines; signatures: decode; keys: decode - each a
+  // long serial computation per item.  They run on three streams of the ctx and join before the pairing kernel: for a small batch
+  // (a finalization: 1 024 checks) their latencies overlap instead of adding up.
+  cudaStream_t sa = ctx->fd_streams[0], sb = ctx->fd_streams[1], sc = ctx->fd_streams[2];
+  CK(cudaEventRecord(ctx->fd_fork, s));
+  CK(cudaStreamWaitEvent(sa, ctx->fd_fork, 0));
+  CK(cudaStreamWaitEvent(sb, ctx->fd_fork, 0));
+  CK(cudaStreamWaitEvent(sc, ctx->fd_fork, 0));
+  k_g2_decode<<<(n_hm + 31) / 32, 32, 0, sa>>>(d_hm, (G2Aff*)ctx->scratch_a.p, (uint8_t*)ctx->scratch_b.p, n_hm);
+  ctx->launches++;
+  // messages shared by several checks: their lines are computed once (19.6 KB per message)
+  const G2Line* lines = nullptr;
+  if (prep) {
+    if (want_vm)
+      k_g2_prepare_vm<<<(n_hm + PVM_LANES - 1) / PVM_LANES, PVM_LANES * PVM_R, PVM_SMEM, sa>>>((const G2Aff*)ctx->scratch_a.p, (const uint8_t*)ctx->scratch_b.p,
+                                                                                             (G2Line*)ctx->scratch_c.p, n_hm);
+    else
+      k_g2_prepare<<<(n_hm + 31) / 32, 32, 0, sa>>>((const G2Aff*)ctx->scratch_a.p, (const uint8_t*)ctx->scratch_b.p, (G2Line*)ctx->scratch_c.p, n_hm);
+    ctx->launches++;
+    lines = (const G2Line*)ctx->scratch_c.p;
+  }
+  // decode keys and signatures in their own kernels
+  k_g2_decode<<<(m + 31) / 32, 32, 0, sb>>>(d_sig, (G2Aff*)ctx->bls_sig.p, sig_st, m);
+  k_g1_decode<<<(m + 63) / 64, 64, 0, sc>>>(d_pk, (G1Aff*)ctx->bls_pk.p, pk_st, m);
   ctx->launches += 2;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->fd_join[0], sa));
+  CK(cudaEventRecord(ctx->fd_join[1], sb));
+  CK(cudaEventRecord(ctx->fd_join[2], sc));
+  for (int i = 0; i < 3; i++) CK(cudaStreamWaitEvent(s, ctx->fd_join[i], 0));
   if (lines && ctx->bls_path != DKGV_BLS_PATH_THREAD) {
     // the VM needs the prepared lines of every hashed message (19.6 KB each); batches with more distinct messages than
     // that budget allows take the one-thread-per-check kernel below
-    if (!ctx->pvm_attr_set) {
-      CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PVM_SMEM));
-      CK(cudaFuncSetAttribute(k_pairing_vm, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      ctx->pvm_attr_set = true;
-    }
     const uint32_t blocks = (m + PVM_LANES - 1) / PVM_LANES, m_pad = blocks * PVM_LANES;
     CK(ctx->bls_scratch.reserve((size_t)2 * 6 * 6 * m_pad * sizeof(U4)));
     CK(cudaEventRecord(ctx->ev_bls0, s));

@@ -41,6 +41,7 @@ struct PvmCtx {
   const uint32_t* line;  // this check's prepared lines of H(m): G2Line[G2_PREP_LINES] as words (72 per line)
   const uint32_t* pk;    // G1Aff words: x[12] y[12]
   const uint32_t* sig;   // G2Aff words: x.c0[12] x.c1[12] y.c0[12] y.c1[12]
+  uint32_t* line_out;    // line preparation only: where STXL writes (same layout as `line`)
 };
 
 DKGV_HD void pvm_ld_slot(const PvmCtx& c, uint32_t s, Fp& a, Fp& b) {
@@ -112,6 +113,15 @@ DKGV_HD uint32_t pvm_exec(const PvmCtx& c, uint32_t pc, uint32_t line_idx) {
         y1 = zero<FpParams>();
         break;
       }
+      case PVM_STXL: {  // coefficient arg of the line being prepared
+        U4* q = (U4*)(c.line_out + ((size_t)line_idx * 3 + arg) * 24);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          q[k] = U4{x0.l[4 * k], x0.l[4 * k + 1], x0.l[4 * k + 2], x0.l[4 * k + 3]};
+          q[3 + k] = U4{x1.l[4 * k], x1.l[4 * k + 1], x1.l[4 * k + 2], x1.l[4 * k + 3]};
+        }
+        break;
+      }
       case PVM_MUL: {  // (x0 y0 - x1 y1, x0 y1 + x1 y0): two fused sum-of-two-products routines
         t0 = neg(y1);
         mul2add_pair(t0, t1, x0, y0, x1, t0, x0, y1, x1, y0);  // the two sums interleaved: four carry chains in flight
@@ -153,6 +163,10 @@ struct PvmCall {
 };
 DKGV_HD PvmCall pvm_call(uint32_t i) {
   uint32_t w = pvm_calls[i];
+  return PvmCall{w & 15u, (w >> 4) & 0xffu, w >> 12};
+}
+DKGV_HD PvmCall pvm_prep_call(uint32_t i) {  // call list of the line preparation (one point step per Miller step)
+  uint32_t w = pvm_prep_calls[i];
   return PvmCall{w & 15u, (w >> 4) & 0xffu, w >> 12};
 }
 

@@ -248,27 +248,39 @@ int he_pairing_vm(const uint8_t* pk48, const uint8_t* sig96, const uint8_t* hm96
   G2Aff sig, hm;
   if (g2_decompress(hm96, &hm, true) != G1_DEC_OK) return -1;
   uint32_t sst = g2_decompress(sig96, &sig, true), pst = g1_decompress(pk48, &pk, true);
-  std::vector<G2Line> lines(G2_PREP_LINES);
-  if (!hm.inf) g2_prepare(lines.data(), &hm);
+  std::vector<G2Line> lines(G2_PREP_LINES), ref_lines(G2_PREP_LINES);
   const int lane = 5;  // any lane of the 32-wide file
   std::vector<U4> file((size_t)PVM_SLOTS * 6 * PVM_LANES);
   std::vector<U4> scratch((size_t)2 * 6 * 6);
-  PvmCtx c{file.data() + lane, (const uint32_t*)lines.data(), (const uint32_t*)&pk, (const uint32_t*)&sig};
+  auto run_segment = [&](const PvmCtx& cc, const PvmCall& k) -> bool {
+    uint32_t pc[PVM_R];
+    for (uint32_t r = 0; r < PVM_R; r++) pc[r] = pvm_seg_start[k.a][r];
+    for (;;) {  // one level: every role up to its barrier
+      uint32_t ended = 0;
+      for (uint32_t r = 0; r < PVM_R; r++) {
+        pc[r] = pvm_exec(cc, pc[r], k.b);
+        ended += (pc[r] & PVM_END_FLAG) ? 1 : 0;
+      }
+      if (ended == PVM_R) return true;
+      if (ended != 0) return false;  // the roles of a segment must agree on the number of levels
+    }
+  };
+  if (!hm.inf) {
+    // the lines of the hashed message by the VM's own preparation program (k_g2_prepare_vm), which must reproduce tower.cuh's
+    // g2_prepare bit for bit (same formulas, same projective representatives)
+    g2_prepare(ref_lines.data(), &hm);
+    PvmCtx pc{file.data() + lane, nullptr, nullptr, (const uint32_t*)&hm, (uint32_t*)lines.data()};
+    pvm_init_point(pc);
+    for (uint32_t ci = 0; ci < PVM_N_PREP_CALLS; ci++)
+      if (!run_segment(pc, pvm_prep_call(ci))) return -2;
+    if (memcmp(lines.data(), ref_lines.data(), sizeof(G2Line) * G2_PREP_LINES) != 0) return -3;
+  }
+  PvmCtx c{file.data() + lane, (const uint32_t*)lines.data(), (const uint32_t*)&pk, (const uint32_t*)&sig, nullptr};
   pvm_init_point(c);
   for (uint32_t ci = 0; ci < PVM_N_CALLS; ci++) {
     PvmCall k = pvm_call(ci);
     if (k.kind == 0) {
-      uint32_t pc[PVM_R];
-      for (uint32_t r = 0; r < PVM_R; r++) pc[r] = pvm_seg_start[k.a][r];
-      for (;;) {  // one level: every role up to its barrier
-        uint32_t ended = 0;
-        for (uint32_t r = 0; r < PVM_R; r++) {
-          pc[r] = pvm_exec(c, pc[r], k.b);
-          ended += (pc[r] & PVM_END_FLAG) ? 1 : 0;
-        }
-        if (ended == PVM_R) break;
-        if (ended != 0) return -2;  // the roles of a segment must agree on the number of levels
-      }
+      if (!run_segment(c, k)) return -2;
     } else {
       for (uint32_t s2 = 0; s2 < 6; s2++)
         for (uint32_t ch = 0; ch < 6; ch++) {

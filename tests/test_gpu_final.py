@@ -287,3 +287,35 @@ def test_pairing_vm_against_thread_kernel_and_oracle(verifier, m):
         if kind[i] == 3 and r == -48:
             want = 49
         assert st_vm[i] == want, (i, int(kind[i]), int(st_vm[i]), r)
+
+
+def test_bad_partial_key_batch_at_scale(verifier):
+    """BASELINE config 5, second half, at a size the oracle can follow: 8 192 items over a (64, 43) session, half of them corrupted.
+    Every status equals the one the construction predicts; every item that is NOT valid and a 1/64 sample of the valid ones is
+    re-decided by the C++ oracle (decoding, pairing equality on all host threads, expected key of quirk Q1)."""
+    from dvt_circuits_b200 import synthetic
+    fin = synthetic.make_finalization(verifier, 64, 43)
+    m = 8192
+    it = synthetic.make_bad_partial_items(verifier, fin, m, p_bad=0.5)
+    st, exp, sst = verifier.bad_partial_key_verify_batch(fin["vv"], it["perp"], it["pk"], it["sig"], [fin["message"]])
+    assert sst == 0 and (st == it["expected"]).all(), np.argwhere(st != it["expected"])[:10]
+    hist = {int(k): int(c) for k, c in zip(*np.unique(st, return_counts=True))}
+    assert set(hist) == {0, 5, 6, 7, 8} and 0.4 * m < hist[0] < 0.6 * m
+    ast, co, keys = O.agg_coefficients(fin["vv"], fin["ids"])
+    q1 = np.array([list(O.evaluate_polynomial(keys.tobytes(), 64, p + 1)[1]) for p in range(64)], dtype=np.uint8)
+    assert (q1 == exp).all()
+    check = np.nonzero((st != 0) | (np.arange(m) % 64 == 0))[0]
+    want = np.zeros(len(check), dtype=np.uint8)
+    need_pairing = []
+    for n_, i in enumerate(check):
+        if O.g1_decompress(bytes(it["pk"][i]))[0]:
+            want[n_] = 5
+        elif O.g2_decompress(bytes(it["sig"][i]))[0]:
+            want[n_] = 6
+        else:
+            need_pairing.append(n_)
+    idx = check[need_pairing]
+    out = O.bls_verify_batch(it["pk"][idx], it["sig"][idx], bytes(fin["hm"]), threads=os.cpu_count() or 1)
+    for n_, i, ok in zip(need_pairing, idx, out):
+        want[n_] = (0 if bytes(it["pk"][i]) == bytes(exp[it["perp"][i]]) else 8) if ok == 1 else 7
+    assert (st[check] == want).all(), np.argwhere(st[check] != want)[:10]

@@ -39,9 +39,10 @@ OPS = ["END", "BAR",
        "LDXL", "ADDXL",                                                 # arg = coefficient 0..2 of the current prepared line of H(m)
        "LDXIN", "ADDXIN", "SUBXIN", "LDYIN", "ADDYIN",                  # arg = input 0: (xp, yp) of pk, 1: sig.x, 2: sig.y
        "LDYS",                                                          # arg = component 0 / 1 of input 0: Y = (xp or yp, 0)
+       "STXL",                                                          # arg = coefficient 0..2: X -> the prepared-line buffer (line preparation)
        "MUL", "SQR", "XI", "NEGX", "DBLX", "TPLX", "CONJX", "INVX"]   # X <- X*Y, X^2, X*(1+u), -X, 2X, 3X, conj X, 1/X
 OP = {n: i for i, n in enumerate(OPS)}
-COST = {"mul": 888, "sqr": 600, "lin": 0, "inv": 607 * 300 + 1500}  # wide multiply-accumulates (scheduling weights)
+COST = {"mul": 888, "sqr": 600, "lin": 0, "inv": 21 * 888}  # scheduling weights in wide-MAC issue slots (inversion: binary extended Euclid, ~38 k ALU instructions)
 ADD_COST = 45
 
 
@@ -237,6 +238,12 @@ class Prog:
     def inv(self, a, dst=None):
         return self._node("inv", Lin.of(a), None, dst, (0, 1))
 
+    def line_out(self, k, a):
+        """coefficient k of the line being prepared <- a (global memory, written once, never read back by the segment)"""
+        r = self._node("lin", Lin.of(a), None, None, (0, 1))
+        self.nodes[-1].line_out = k
+        return r
+
     # ---- scheduling
     def schedule(self, R, balance=True):
         nodes = self.nodes
@@ -342,6 +349,9 @@ class Prog:
             v = n.out
             if v.loc is not None:
                 v.slot = fixed_index[v.loc[1]]
+                continue
+            if getattr(n, "line_out", None) is not None:
+                v.slot = 0  # never stored to a slot
                 continue
             end = last.get(v, n.level)
             pick = None
@@ -476,7 +486,10 @@ class Prog:
                     s.append(("XI", 0))
                 if n.post[1] != 1:
                     s += [(o, 0) for o in factor_chain(n.post[1])]
-                s.append(("STX", n.out.slot))
+                if getattr(n, "line_out", None) is not None:
+                    s.append(("STXL", n.line_out))
+                else:
+                    s.append(("STX", n.out.slot))
             for s in streams:
                 s.append(("BAR", 0))
         for s in streams:
@@ -593,6 +606,49 @@ def t_part_add(p):
     Lc = merged_line(p, h, [Pg - Ph, l01, l11])
     for nm, e in zip(["L00", "L01", "L02", "L11", "L12"], Lc):
         p.lin(e, dst=nm)
+
+
+def prep_dbl(p):
+    """line preparation, doubling step of the running multiple of H(m) (tower.cuh g2_line_dbl): the P-independent coefficients
+    c00 = Y^2 - b3 Z^2, c01 = -3 X^2, c11 = 2 Y Z go to the line buffer, T <- 2T"""
+    X, Y, Z = p.state("TX"), p.state("TY"), p.state("TZ")
+    A, C = p.sqr(Y), p.sqr(X)
+    t2 = p.sqr(Z, post=(1, 12))
+    D, E = p.mul(Y, Z), p.mul(X, Y)
+    p.line_out(0, A - t2)
+    p.line_out(1, -(3 * C))
+    p.line_out(2, 2 * D)
+    P1 = p.mul(t2, A, post=(0, 8))
+    P2 = p.mul(A - 3 * t2, A + t2)
+    p.mul(D, A, dst="TZ", post=(0, 8))
+    p.mul(A - 3 * t2, E, dst="TX", post=(0, 2))
+    p.lin(P1 + P2, dst="TY")
+
+
+def prep_add(p):
+    """line preparation, addition step (tower.cuh g2_line_add): c00 = n xQ - d yQ, c01 = -n, c11 = d with n = yQ Z - Y, d = xQ Z - X; T <- T + Q"""
+    X, Y, Z = p.state("TX"), p.state("TY"), p.state("TZ")
+    xq, yq = p.inp(IN_QX), p.inp(IN_QY)
+    t0, t1 = p.mul(X, xq), p.mul(Y, yq)
+    t3p = p.mul(X + Y, xq + yq)
+    n_, d_ = p.mul(Z, yq), p.mul(Z, xq)
+    t2 = p.lin(12 * Z.xi())
+    t3 = t3p - t0 - t1
+    t4, y3 = n_ + Y, d_ + X
+    x3 = 3 * t0
+    z3, t1m = t1 + t2, t1 - t2
+    y3b = 12 * y3.xi()
+    Pa, Pb = p.mul(t3, t1m), p.mul(y3b, t4)
+    Pc, Pd = p.mul(t1m, z3), p.mul(y3b, x3)
+    Pe, Pf = p.mul(z3, t4), p.mul(x3, t3)
+    n, d = n_ - Y, d_ - X
+    Pg, Ph = p.mul(n, xq), p.mul(d, yq)
+    p.line_out(0, Pg - Ph)
+    p.line_out(1, Y - n_)
+    p.line_out(2, d)
+    p.lin(Pa - Pb, dst="TX")
+    p.lin(Pc + Pd, dst="TY")
+    p.lin(Pe + Pf, dst="TZ")
 
 
 def f_state(p, pre="A"):
@@ -714,6 +770,8 @@ def build_segments(R):
     seg("S_0", STATE_MILLER, t_part_dbl, f_part_copy)           # first step: f <- L_0
     seg("S_D", STATE_MILLER, f_part_sqr, t_part_dbl, f_part_mul)
     seg("S_A", STATE_MILLER, t_part_add, f_part_mul)
+    seg("P_D", STATE_MILLER, prep_dbl)   # preparation of the lines of a hashed message (its own small kernel)
+    seg("P_A", STATE_MILLER, prep_add)
     seg("FE_MUL", STATE_FE, seg_fe_mul)
     seg("FE_CYC", STATE_FE, seg_fe_cyc)
     seg("FE_INV", STATE_FE, seg_fe_inv)
@@ -726,7 +784,7 @@ def build_segments(R):
     return segs, n_slots
 
 
-SEG_ORDER = ["S_0", "S_D", "S_A", "FE_MUL", "FE_CYC", "FE_INV", "FE_CONJA", "FE_CONJB", "FE_FROBB"]
+SEG_ORDER = ["S_0", "S_D", "S_A", "P_D", "P_A", "FE_MUL", "FE_CYC", "FE_INV", "FE_CONJA", "FE_CONJB", "FE_FROBB"]
 
 
 def miller_steps():
@@ -811,6 +869,7 @@ def simulate_segment(p, streams, slots, line, inputs, consts):
                 elif op == "LDYIN": Y = inputs[arg]
                 elif op == "ADDYIN": Y = f2add(Y, inputs[arg])
                 elif op == "LDYS": Y = (inputs[0][arg], 0)
+                elif op == "STXL": line[arg] = X
                 elif op == "MUL": X = f2mul(X, Y)
                 elif op == "SQR": X = f2mul(X, X)
                 elif op == "XI": X = f2xi(X)
@@ -830,8 +889,9 @@ def check_hazards(p):
         for n in p.nodes:
             if n.level != lv:
                 continue
-            assert n.out.slot not in w or w[n.out.slot] == n.role, (p.name, lv, "write/write")
-            w[n.out.slot] = n.role
+            if getattr(n, "line_out", None) is None:
+                assert n.out.slot not in w or w[n.out.slot] == n.role, (p.name, lv, "write/write")
+                w[n.out.slot] = n.role
             for v in n.inputs():
                 if v.slot is not None and (v.loc is None or v.loc[0] == "S"):
                     r[v.slot].add(n.role)
@@ -845,48 +905,18 @@ def simulate_check(segs, streams, pk, sig, hm, n_slots):
     """whole check on integers -> RA (six Fp2).  pk: G1 affine ints, sig / hm: G2 affine ((x0,x1),(y0,y1))."""
     from oracle.pyref import bls12_381 as B
     consts = constants()
-    # prepared lines of hm exactly as tower.cuh g2_prepare (projective tangent / chord coefficients before scaling by P)
+    # the prepared lines of hm: by the VM's own preparation segments (P_D / P_A, what k_g2_prepare_vm runs)
+    fi = FIXED_INDEX
     lines = []
-    T = (hm[0], hm[1], (1, 0))
-    b3 = lambda a: f2xi(tuple(12 * c % P for c in a))
-
-    def dbl(T):
-        X, Y, Z = T
-        A, Bq, C = f2mul(Y, Y), f2mul(Z, Z), f2mul(X, X)
-        t2 = b3(Bq)
-        c00 = f2sub(A, t2)
-        c01 = f2neg(tuple(3 * c % P for c in C))
-        D = f2mul(Y, Z)
-        c11 = f2add(D, D)
-        z8 = tuple(8 * c % P for c in A)
-        x3 = f2mul(t2, z8)
-        y3 = f2add(A, t2)
-        Z3 = f2mul(D, z8)
-        t0 = f2sub(A, tuple(3 * c % P for c in t2))
-        Y3 = f2add(x3, f2mul(t0, y3))
-        X3 = tuple(2 * c % P for c in f2mul(t0, f2mul(X, Y)))
-        return (c00, c01, c11), (X3, Y3, Z3)
-
-    def add(T, Q):
-        X, Y, Z = T
-        xq, yq = Q
-        n = f2sub(f2mul(yq, Z), Y)
-        d = f2sub(f2mul(xq, Z), X)
-        c00 = f2sub(f2mul(n, xq), f2mul(d, yq))
-        line = (c00, f2neg(n), d)
-        # T + Q in affine arithmetic then back to projective (any representative is fine for the following steps)
-        aff = lambda T: (f2mul(T[0], f2inv(T[2])), f2mul(T[1], f2inv(T[2])))
-        S = B.E2.add(aff(T), Q)
-        return line, (S[0], S[1], (1, 0))
+    pslots = {i: (0, 0) for i in range(n_slots)}
+    pslots[fi["TX"]], pslots[fi["TY"]], pslots[fi["TZ"]] = hm[0], hm[1], (1, 0)
     for k in miller_steps():
-        if k == "D":
-            l, T = dbl(T)
-        else:
-            l, T = add(T, hm)
-        lines.append(l)
+        line = [None, None, None]
+        simulate_segment(segs["P_" + k], streams["P_" + k], pslots, line, [None, hm[0], hm[1]], consts)
+        assert None not in line
+        lines.append(tuple(line))
     slots = {i: (0, 0) for i in range(n_slots)}
     G = {0: None, 1: None}
-    fi = FIXED_INDEX
     slots[fi["TX"]], slots[fi["TY"]], slots[fi["TZ"]] = sig[0], sig[1], (1, 0)
     inputs = [(pk[0], pk[1]), sig[0], sig[1]]
     for item in driver_sequence():
@@ -997,6 +1027,9 @@ def write_inc(path, R):
             seq.append((3, reg[item[1]], item[2]))
         else:
             seq.append((0, SEG_ORDER.index(item[0]), 0xFFFF if item[1] is None else item[1]))
+    prep = [(0, SEG_ORDER.index("P_" + k), j) for j, k in enumerate(miller_steps())]
+    out.append(f"#define PVM_N_PREP_CALLS {len(prep)}")
+    out.append("PVM_CONST uint32_t pvm_prep_calls[PVM_N_PREP_CALLS] = {" + ", ".join("0x%07xu" % (k | (a << 4) | (b << 12)) for k, a, b in prep) + "};")
     out.append(f"#define PVM_N_CALLS {len(seq)}")
     out.append("PVM_CONST uint32_t pvm_calls[PVM_N_CALLS] = {")
     enc = [k | (a << 4) | (b << 12) for k, a, b in seq]
