@@ -692,11 +692,11 @@ def run_b200(args):
                 {"kernel": "pack + all-gather + flag read-back (the rest of the step)", "kernel_ms": step_mean - sum(sp),
                  "kernel_share_of_step": (step_mean - sum(sp)) / step_mean}]
             roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
-            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r1_default_path_v3.md): dram read 57 367 296 B +
-            # write 32 190 208 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
-            roof["traffic"] = int(round((57367296 + 32190208) / 699392 * rows * t))
-            roof["traffic_ref"] = ("profiles/r1_default_path_v3.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
-                                   "(128.1 B per coefficient, scaled to this launch's coefficients)")
+            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r2_default_path.md): dram read 71 463 936 B +
+            # write 44 385 280 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
+            roof["traffic"] = int(round((71463936 + 44385280) / 699392 * rows * t))
+            roof["traffic_ref"] = ("profiles/r2_default_path.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
+                                   "(165.6 B per coefficient, scaled to this launch's coefficients)")
         if "full_evaluation" in legs:
             plan = dk.share_fd_plan(t, n, args.parts)
             m_parts, h_part = plan["parts"], plan["h"]
