@@ -213,17 +213,18 @@ def cpu_same_algorithm(n, t, threads):
     import numpy as np
     import oracle_lib as O
     ids = np.arange(1, n + 1, dtype=np.uint32)
-    vv, shares = cpu_share_session(n, t, threads, ids)
+    rows = threads * 8
+    vv, shares = cpu_share_session(n, t, rows, ids)
     O.share_matrix_shortcut(vv[:1], shares[:1], threads=1)  # builds the fixed-base table (untimed, as the GPU's)
     t0 = time.perf_counter()
     st, fb = O.share_matrix_shortcut(vv, shares, threads=threads)
     dt = time.perf_counter() - t0
     assert fb == 0 and not st.any()
-    return {"value": threads * n / dt, "unit": "shares/s", "cores": threads, "kind": "port",
-            "sample": f"{threads} dealers x {n} shares, the consistency shortcut of the GPU path run by the CPU oracle, {dt:.2f}s wall"}
+    return {"value": rows * n / dt, "unit": "shares/s", "cores": threads, "kind": "port",
+            "sample": f"{rows} dealers x {n} shares, the consistency shortcut of the GPU path run by the CPU oracle, {dt:.2f}s wall"}
 
 
-def cpu_pairing(threads, per_thread=12):
+def cpu_pairing(threads, per_thread=96):
     """oracle bls_verify_precomputed_hash exactly as the reference computes it (two full pairings + Gt equality, decoding included)"""
     import numpy as np
     import oracle_lib as O
