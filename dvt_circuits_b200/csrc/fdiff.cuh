@@ -415,27 +415,226 @@ DKGV_HD Fr fr_submul_small(const Fr& prev, const Fr& a, uint32_t j) {
   return w;
 }
 
+// ---- lazy residues for the difference table ---------------------------------------------------------------------
+// The table only ever subtracts neighbours (phase 1) and adds a small multiple (phase 2), so the entries need not be canonical
+// after every step: a 9-limb (288-bit) value v with v == e (mod r) is carried instead, two's complement in phase 1 (|v| doubles
+// per round at most), non-negative in phase 2 (v grows by a factor <= t per round), and brought back to [0, r) only every
+// DT1_PERIOD rounds / every dt2_period(t) rounds - 9 subtract-with-borrow (or 9 multiply-adds) per entry and round instead of
+// a modular subtraction (~30 instructions) / fr_submul_small (~80).
+struct Lz {
+  uint32_t l[9];
+};
+constexpr uint32_t DT1_PERIOD = 30;  // |v| < 2^255 * 2^30 = 2^285 before a reduction
+// rounds between reductions in phase 2: v < 2^255 * t^period <= 2^285 (the round with factor j multiplies the bound by j + 1 <= t)
+DKGV_HD uint32_t dt2_period(uint32_t t) {
+  uint32_t lg = 1;
+  while ((1u << lg) < t) lg++;
+  uint32_t p = 30 / lg;
+  return p ? p : 1;
+}
+DKGV_HD Lz lz_from(const Fr& a) {
+  Lz r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = a.l[i];
+  r.l[8] = 0;
+  return r;
+}
+DKGV_HD Fr lz_low(const Lz& a) {  // a canonical (after lz_reduce)
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = a.l[i];
+  return r;
+}
+DKGV_HD Lz lz_zero() {
+  Lz r;
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.l[i] = 0;
+  return r;
+}
+DKGV_HD bool lz_is_zero(const Lz& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) o |= a.l[i];
+  return o == 0;
+}
+// a - b mod 2^288
+DKGV_HD Lz lz_sub(const Lz& a, const Lz& b) {
+  Lz r;
+#if defined(__CUDA_ARCH__)
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.l[0]) : "r"(a.l[0]), "r"(b.l[0]));
+#pragma unroll
+  for (int i = 1; i < 8; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.l[i]) : "r"(a.l[i]), "r"(b.l[i]));
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r.l[8]) : "r"(a.l[8]), "r"(b.l[8]));
+#else
+  uint64_t br = 0;
+  for (int i = 0; i < 9; i++) {
+    uint64_t d = (uint64_t)a.l[i] - b.l[i] - br;
+    r.l[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+#endif
+  return r;
+}
+// prev + j * a mod 2^288 (j < 2^11).  Device: the products of the even limbs on one carry chain over prev, the products of the
+// odd limbs on a second chain over that (the pattern of field.cuh's rows: lo / hi pairs become one wide multiply-add each).
+DKGV_HD Lz lz_muladd_small(const Lz& prev, const Lz& a, uint32_t j) {
+  Lz r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.l[i] = prev.l[i];
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(r.l[0]), "+r"(r.l[1]) : "r"(a.l[0]), "r"(j));
+#pragma unroll
+  for (int i = 2; i < 8; i += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(r.l[i]), "+r"(r.l[i + 1]) : "r"(a.l[i]), "r"(j));
+  asm volatile("madc.lo.u32 %0, %1, %2, %0;" : "+r"(r.l[8]) : "r"(a.l[8]), "r"(j));
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(r.l[1]), "+r"(r.l[2]) : "r"(a.l[1]), "r"(j));
+#pragma unroll
+  for (int i = 3; i < 8; i += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(r.l[i]), "+r"(r.l[i + 1]) : "r"(a.l[i]), "r"(j));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 9; i++) {
+    c += (uint64_t)a.l[i] * j + prev.l[i];
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+  return r;
+}
+// v -> the canonical residue of v mod r.  is_signed: v is two's complement with |v| <= 2^285; else 0 <= v <= 2^286.
+// w = v + 2^31 r >= 0 (signed case), q = floor(floor(w / 2^224) * floor(2^286 / r) / 2^62) in [floor(w / r) - 2, floor(w / r)]
+// (the two truncations lose < w / 2^286 + 2^-30 < 1.4), w - q r < 3r, two conditional subtractions.
+DKGV_HD void lz_reduce(Lz& v, bool is_signed) {
+  constexpr uint32_t R31[9] = {0x80000000u, 0x80000000u, 0x7fffffffu, 0x7fff2dffu, 0xa9ded201u, 0x04d0ec02u, 0x199cec04u, 0x94cebea4u, 0x39f6d3a9u};  // r << 31
+  constexpr uint32_t M = 0x8d54253bu;  // floor(2^286 / r)
+  if (is_signed) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      c += (uint64_t)v.l[i] + R31[i];
+      v.l[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  uint64_t lo = (uint64_t)v.l[7] * M, hi = (uint64_t)v.l[8] * M;
+  uint32_t q = (uint32_t)((hi + (lo >> 32)) >> 30);
+  uint32_t qr[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)FrParams::mod(i) * q;
+    qr[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  qr[8] = (uint32_t)c;
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    uint64_t d = (uint64_t)v.l[i] - qr[i] - br;
+    v.l[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    uint32_t t[9];
+    br = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+      uint64_t d = (uint64_t)v.l[i] - (i < 8 ? FrParams::mod(i) : 0u) - br;
+      t[i] = (uint32_t)d;
+      br = (d >> 32) & 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) v.l[i] = br ? v.l[i] : t[i];
+  }
+}
+// r - a for canonical a (0 stays 0)
+DKGV_HD Fr fr_neg_canonical(const Fr& a) {
+  Fr r;
+  uint64_t br = 0;
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)FrParams::mod(i) - a.l[i] - br;
+    r.l[i] = (uint32_t)d;
+    br = (d >> 32) & 1;
+    nz |= a.l[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = nz ? r.l[i] : 0u;
+  return r;
+}
+// the published copy of an entry: 9 words of thread i in three planes of a block-wide array (two 16-byte chunks + one word,
+// conflict-free vector accesses); `pub` has 9 * nt words
+DKGV_HD void lz_publish(uint32_t* pub, uint32_t nt, uint32_t i, const Lz& v) {
+#if defined(__CUDA_ARCH__)
+  ((uint4*)pub)[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  ((uint4*)(pub + 4 * (size_t)nt))[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+#else
+  for (int k = 0; k < 4; k++) pub[4 * (size_t)i + k] = v.l[k];
+  for (int k = 0; k < 4; k++) pub[4 * (size_t)nt + 4 * (size_t)i + k] = v.l[4 + k];
+#endif
+  pub[8 * (size_t)nt + i] = v.l[8];
+}
+DKGV_HD Lz lz_published(const uint32_t* pub, uint32_t nt, uint32_t i) {
+  Lz v;
+#if defined(__CUDA_ARCH__)
+  uint4 x = ((const uint4*)pub)[i], y = ((const uint4*)(pub + 4 * (size_t)nt))[i];
+  v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
+  v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+#else
+  for (int k = 0; k < 4; k++) v.l[k] = pub[4 * (size_t)i + k];
+  for (int k = 0; k < 4; k++) v.l[4 + k] = pub[4 * (size_t)nt + 4 * (size_t)i + k];
+#endif
+  v.l[8] = pub[8 * (size_t)nt + i];
+  return v;
+}
+
 // One thread of the table owns the adjacent entries a = e[2i], b = e[2i+1]; per round it publishes b, waits for the block,
 // and reads its left neighbour's b.
 struct DtPair {
-  Fr a, b;
+  Lz a, b;
 };
-// phase 1, round r = 1..t: e[k] <- e[k] - e[k-1] for k >= r.  After t rounds e[k] = Delta^k s(1) for k < t and
-// Delta^t s(k - t + 1) for k >= t (zero for every such k <=> the n shares lie on a polynomial of degree < t).
+// phase 1, round r = 1..t: e[k] <- e[k] - e[k-1] for k >= r (lazy, two's complement; canonical again after every DT1_PERIOD-th
+// round and after dt1_finish).  After t rounds e[k] = Delta^k s(1) for k < t and Delta^t s(k - t + 1) for k >= t (zero for every
+// such k <=> the n shares lie on a polynomial of degree < t).
 DKGV_HD bool dt1_active(uint32_t i, uint32_t r) { return 2 * i + 1 >= r; }
 DKGV_HD bool dt1_publishes(uint32_t i, uint32_t r) { return 2 * i + 2 >= r; }  // the right neighbour still updates its a
-DKGV_HD void dt1_step(DtPair& p, uint32_t i, uint32_t r, const Fr* pub) {
-  Fr nb = sub(p.b, p.a);
-  if (2 * i >= r) p.a = i ? sub(p.a, pub[i - 1]) : p.a;  // (i = 0: e[0] never changes; 2i >= r >= 1 excludes it anyway)
+// `reduce`: r is a multiple of DT1_PERIOD (the caller counts)
+DKGV_HD void dt1_step(DtPair& p, uint32_t i, uint32_t r, bool reduce, const uint32_t* pub, uint32_t nt) {
+  Lz nb = lz_sub(p.b, p.a);
+  if (2 * i >= r && i) p.a = lz_sub(p.a, lz_published(pub, nt, i - 1));  // (i = 0: e[0] never changes; 2i >= r >= 1 excludes it anyway)
   p.b = nb;  // dt1_active(i, r) holds
+  if (reduce) {
+    lz_reduce(p.a, true);
+    lz_reduce(p.b, true);
+  }
+}
+DKGV_HD void dt1_finish(DtPair& p) {  // entries that dropped out between two reductions are still lazy
+  lz_reduce(p.a, true);
+  lz_reduce(p.b, true);
 }
 // phase 2, round j = t-1 .. 1 on the coefficient vector of P <- P (x - j) + E_{j-1} (E_k = Delta^k s(1) / k!, deg P = t-1-j
-// before the round): c[k] <- c[k-1] - j c[k], c[-1] := E_{j-1}.  Entries k > t - j are still zero.
+// before the round): c[k] <- c[k-1] - j c[k], c[-1] := E_{j-1}.  Entries k > t - j are still zero.  Carried with alternating
+// signs, d[k] = (-1)^(k + rounds done) c[k], the step is d[k] <- d[k-1] + j d[k] - additions only, so the lazy values stay
+// non-negative; the injected value is dt2_injected(E, t, j - 1) and dt2_finish undoes the sign.
 DKGV_HD bool dt2_active(uint32_t i, uint32_t j, uint32_t t) { return 2 * i <= t - j; }
-DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, const Fr* pub, const Fr* E) {
-  Fr nb = fr_submul_small(p.a, p.b, j);
-  p.a = fr_submul_small(i ? pub[i - 1] : E[j - 1], p.a, j);
+DKGV_HD Fr dt2_signed_e(const Fr& e, uint32_t t, uint32_t k) { return ((t - 1 - k) & 1) ? fr_neg_canonical(e) : e; }  // what to store as E'[k]
+// `reduce`: this is the dt2_period(t)-th round since the last reduction (the caller counts; the same for every thread)
+DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, bool reduce, const uint32_t* pub, uint32_t nt, const Fr* Es) {
+  Lz nb = lz_muladd_small(p.a, p.b, j);
+  p.a = lz_muladd_small(i ? lz_published(pub, nt, i - 1) : lz_from(Es[j - 1]), p.a, j);
   p.b = nb;
+  if (reduce) {
+    lz_reduce(p.a, false);
+    lz_reduce(p.b, false);
+  }
+}
+DKGV_HD void dt2_finish(DtPair& p, uint32_t i, uint32_t t) {  // after the t - 1 rounds: c[k] = (-1)^(k + t - 1) d[k]
+  lz_reduce(p.a, false);
+  lz_reduce(p.b, false);
+  if ((2 * i + t - 1) & 1) p.a = lz_from(fr_neg_canonical(lz_low(p.a)));
+  if ((2 * i + 1 + t - 1) & 1) p.b = lz_from(fr_neg_canonical(lz_low(p.b)));
 }
 
 // ---- condition (3) against the COMPRESSED commitment (share_fd.cu k_fd_coefpoint / k_fd_coefsign) -----------------

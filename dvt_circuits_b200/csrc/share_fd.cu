@@ -108,7 +108,7 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // the exact per-share verdicts.  Exact and deterministic - no random linear combination.
 // Default formulation: (2) and the interpolation in one difference table per dealer (k_fd_difftab), (3) against the
 // compressed commitments (k_fd_coefpoint + k_fd_coefsign) with the decode deferred until a group needs the evaluation.
-constexpr uint32_t FD_SHORTCUT_MAX_T = 1024;  // fr_submul_small: factors j < 2^10
+constexpr uint32_t FD_SHORTCUT_MAX_T = 2047;  // lz_muladd_small: factors j < 2^11; t < n_r <= FD_SHORTCUT_MAX_N
 constexpr uint32_t FD_SHORTCUT_MAX_N = 2048;  // k_fd_difftab: one block per dealer, two entries per thread
 
 // c[j] = (-1)^j C(t, j) mod r (j = 0..t), inv[j] = 1/j mod r (j = 1..t) and ifact[j] = 1/j! mod r, Montgomery form; one thread per j
@@ -168,42 +168,46 @@ k_fd_share_limbs(const uint8_t* __restrict__ shares, const uint32_t* __restrict_
   for (int i = 0; i < 8; i++) o[i] = ok ? l[i] : 0u;
 }
 
-// Condition (2) and the interpolation in ONE difference table per dealer (n_r <= 2048), canonical residues, no products except by small integers (fdiff.cuh, "difference table"):
+// Condition (2) and the interpolation in ONE difference table per dealer (n_r <= 2048), lazy residues (fdiff.cuh, "lazy residues for the
+// difference table": 9-limb values reduced every 30 / every dt2_period(t) rounds), no products except by small integers:
 //   phase 1  t rounds e[k] <- e[k] - e[k-1] (k >= r) over all n_r shares: e[k] = Delta^k s(1) for k < t, and the entries
 //            k >= t are the t-th differences Delta^t s(k-t+1) - all zero <=> condition (2);
 //   phase 2  E_k = e[k] / k!, then P <- P (x - j) + E_{j-1} for j = t-1 .. 1 on monomial coefficients: c[k] <- c[k-1] - j c[k].
 // One block per dealer, thread i owns entries 2i and 2i+1 in registers and publishes only e[2i+1] per round (double-buffered,
 // one barrier per round); entries that are already final (phase 1: k < r) or still zero (phase 2: k > t - j) are skipped, so
-// whole warps drop out.  Work per dealer: t n - t^2/2 subtractions + t^2/2 small products, against (n - t)(t + 1) + t^2/2 full
-// Montgomery products before.
+// whole warps drop out.  Work per dealer: t n - t^2/2 nine-limb subtractions + t^2/2 nine-limb multiply-adds by a small integer.
 __global__ void __launch_bounds__(1024)
 k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact, uint32_t* __restrict__ coef, uint8_t* __restrict__ poly_ok,
              uint8_t* __restrict__ state, uint32_t d0, uint32_t n_d, uint32_t n_r, uint32_t t, const uint32_t* __restrict__ map,
              const uint32_t* __restrict__ n_map) {
-  extern __shared__ uint32_t fr_sm[];  // pub[2][blockDim.x], E[t]
+  extern __shared__ uint32_t fr_sm[];  // pub[2][9 * blockDim.x] (lz_publish planes), E'[t]
   if (map && blockIdx.x >= *n_map) return;  // second pass of the repair route: one block per candidate
   const uint32_t dl = map ? map[blockIdx.x] : blockIdx.x, i = threadIdx.x, nt = blockDim.x;
   if (d0 + dl >= n_d || !poly_ok[d0 + dl]) return;  // whole block; a share >= r already failed condition (1)
-  Fr* pub = (Fr*)fr_sm;
-  Fr* E = pub + 2 * (size_t)nt;
+  uint32_t* pub = fr_sm;
+  Fr* E = (Fr*)(fr_sm + 18 * (size_t)nt);
   const uint32_t k0 = 2 * i, k1 = 2 * i + 1;
   DtPair p;
-  p.a = zero<FrParams>();
-  p.b = zero<FrParams>();
+  p.a = lz_zero();
+  p.b = lz_zero();
   const uint32_t* row = sl + (size_t)dl * n_r * 8;
 #pragma unroll
   for (int l = 0; l < 8; l++) {
     if (k0 < n_r) p.a.l[l] = row[(size_t)k0 * 8 + l];
     if (k1 < n_r) p.b.l[l] = row[(size_t)k1 * 8 + l];
   }
+  uint32_t left = DT1_PERIOD;
 #pragma unroll 1
   for (uint32_t r = 1; r <= t; r++) {
-    Fr* pr = pub + (size_t)(r & 1) * nt;
-    if (dt1_publishes(i, r)) pr[i] = p.b;
+    uint32_t* pr = pub + (size_t)(r & 1) * 9 * nt;
+    if (dt1_publishes(i, r)) lz_publish(pr, nt, i, p.b);
     __syncthreads();
-    if (dt1_active(i, r)) dt1_step(p, i, r, pr);
+    const bool red = --left == 0;
+    if (red) left = DT1_PERIOD;
+    if (dt1_active(i, r)) dt1_step(p, i, r, red, pr, nt);
   }
-  bool bad = (k0 >= t && k0 < n_r && !is_zero(p.a)) || (k1 >= t && k1 < n_r && !is_zero(p.b));
+  dt1_finish(p);
+  bool bad = (k0 >= t && k0 < n_r && !lz_is_zero(p.a)) || (k1 >= t && k1 < n_r && !lz_is_zero(p.b));
   if (__syncthreads_or(bad)) {  // some t-th difference is not zero: the shares are not on a polynomial of degree < t
     if (i == 0) {
       poly_ok[d0 + dl] = 0;
@@ -215,24 +219,29 @@ k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact
   if (k0 < t) {
 #pragma unroll
     for (int l = 0; l < 8; l++) f.l[l] = ifact[(size_t)k0 * 8 + l];
-    E[k0] = mul(p.a, f);  // canonical x Montgomery = canonical
+    E[k0] = dt2_signed_e(mul(lz_low(p.a), f), t, k0);  // canonical x Montgomery = canonical
   }
   if (k1 < t) {
 #pragma unroll
     for (int l = 0; l < 8; l++) f.l[l] = ifact[(size_t)k1 * 8 + l];
-    E[k1] = mul(p.b, f);
+    E[k1] = dt2_signed_e(mul(lz_low(p.b), f), t, k1);
   }
   __syncthreads();
-  p.a = i == 0 ? E[t - 1] : zero<FrParams>();
-  p.b = zero<FrParams>();
+  p.a = i == 0 ? lz_from(E[t - 1]) : lz_zero();
+  p.b = lz_zero();
+  const uint32_t period = dt2_period(t);
+  left = period;
 #pragma unroll 1
   for (uint32_t j = t - 1; j >= 1; j--) {
-    Fr* pr = pub + (size_t)(j & 1) * nt;
+    uint32_t* pr = pub + (size_t)(j & 1) * 9 * nt;
     const bool act = dt2_active(i, j, t);
-    if (act) pr[i] = p.b;
+    if (act) lz_publish(pr, nt, i, p.b);
     __syncthreads();
-    if (act) dt2_step(p, i, j, pr, E);
+    const bool red = --left == 0;
+    if (red) left = period;
+    if (act) dt2_step(p, i, j, red, pr, nt, E);
   }
+  dt2_finish(p, i, t);
   uint32_t* o = coef + (size_t)dl * t * 8;
 #pragma unroll
   for (int l = 0; l < 8; l++) {
@@ -388,7 +397,7 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   if (const char* e = getenv("DKGV_FD_IPB")) ctx->fd_ipb_force = (uint32_t)atoi(e);  // experiments; read once per ctx
-  CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 1024 + FD_SHORTCUT_MAX_T) * 32)));
+  CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 9 * 1024 * 4 + FD_SHORTCUT_MAX_T * 32)));
   CK(cudaFuncSetAttribute(k_fd_difftab, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   size_t stack = 0;  // k_fd_coefsign keeps 3 x FD_SIGN_K field elements in local memory (1.2 KB frame); only ever raise the limit
   CK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
@@ -461,7 +470,7 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
       const bool first = d0 == 0, last = d0 + chunk >= n_d;
       k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, nullptr, d0, n_cols, n_d,
                                                                        n_r);
-      k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
+      k_fd_difftab<<<n_here, nt, (size_t)nt * 72 + (size_t)t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
                                                                n_r, t, nullptr, nullptr);
       if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
       k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
@@ -559,7 +568,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     k_rs_stage<<<(n_here + 127) / 128, 128, 0, s>>>(state, ok2, cand, n_cand, d0, n_here);
     // second pass of the exact conditions on the corrected table: t-th differences + coefficients, compress(G * p_k) == C_k
     // (the candidates are compacted into dense groups: a handful of wrong dealers costs a handful of warps, not every group)
-    k_fd_difftab<<<n_here, nt, ((size_t)2 * nt + t) * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, ok2, nullptr, d0, n_d, n_r, t,
+    k_fd_difftab<<<n_here, nt, (size_t)nt * 72 + (size_t)t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, ok2, nullptr, d0, n_d, n_r, t,
                                                              cand, n_cand);
     k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, ok2, (uint32_t*)ctx->fd_yz.p, d0, n_d, n_cols, t,
                                                            cand, n_cand);

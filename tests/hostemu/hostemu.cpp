@@ -330,53 +330,74 @@ void he_fr_submul_small(const uint8_t* prev32, const uint8_t* a32, uint32_t j, u
 int he_difftab(const uint8_t* shares, uint32_t n_r, uint32_t t, const uint8_t* ifact, uint8_t* coef) {
   const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
   std::vector<DtPair> th(nt);
-  std::vector<Fr> pub(2 * (size_t)nt), E(t);
+  std::vector<uint32_t> pub(18 * (size_t)nt);
+  std::vector<Fr> E(t);
   for (uint32_t i = 0; i < nt; i++) {
-    th[i].a = zero<FrParams>();
-    th[i].b = zero<FrParams>();
-    if (2 * i < n_r) be32_to_fr(th[i].a, shares + (size_t)(2 * i) * 32);
-    if (2 * i + 1 < n_r) be32_to_fr(th[i].b, shares + (size_t)(2 * i + 1) * 32);
+    Fr a = zero<FrParams>(), b = zero<FrParams>();
+    if (2 * i < n_r) be32_to_fr(a, shares + (size_t)(2 * i) * 32);
+    if (2 * i + 1 < n_r) be32_to_fr(b, shares + (size_t)(2 * i + 1) * 32);
+    th[i].a = lz_from(a);
+    th[i].b = lz_from(b);
   }
+  uint32_t left = DT1_PERIOD;
   for (uint32_t r = 1; r <= t; r++) {
-    Fr* pr = pub.data() + (size_t)(r & 1) * nt;
+    uint32_t* pr = pub.data() + (size_t)(r & 1) * 9 * nt;
     for (uint32_t i = 0; i < nt; i++)
-      if (dt1_publishes(i, r)) pr[i] = th[i].b;
+      if (dt1_publishes(i, r)) lz_publish(pr, nt, i, th[i].b);
+    const bool red = --left == 0;
+    if (red) left = DT1_PERIOD;
     for (uint32_t i = 0; i < nt; i++)
-      if (dt1_active(i, r)) dt1_step(th[i], i, r, pr);
+      if (dt1_active(i, r)) dt1_step(th[i], i, r, red, pr, nt);
   }
   bool bad = false;
   for (uint32_t i = 0; i < nt; i++) {
+    dt1_finish(th[i]);
     uint32_t k0 = 2 * i, k1 = 2 * i + 1;
-    bad |= (k0 >= t && k0 < n_r && !is_zero(th[i].a)) || (k1 >= t && k1 < n_r && !is_zero(th[i].b));
+    bad |= (k0 >= t && k0 < n_r && !lz_is_zero(th[i].a)) || (k1 >= t && k1 < n_r && !lz_is_zero(th[i].b));
   }
   if (bad) return 1;
   for (uint32_t i = 0; i < nt; i++) {
     Fr f;
     if (2 * i < t) {
       be32_to_fr(f, ifact + (size_t)(2 * i) * 32);
-      E[2 * i] = mul(th[i].a, to_mont(f));
+      E[2 * i] = dt2_signed_e(mul(lz_low(th[i].a), to_mont(f)), t, 2 * i);
     }
     if (2 * i + 1 < t) {
       be32_to_fr(f, ifact + (size_t)(2 * i + 1) * 32);
-      E[2 * i + 1] = mul(th[i].b, to_mont(f));
+      E[2 * i + 1] = dt2_signed_e(mul(lz_low(th[i].b), to_mont(f)), t, 2 * i + 1);
     }
   }
   for (uint32_t i = 0; i < nt; i++) {
-    th[i].a = i == 0 ? E[t - 1] : zero<FrParams>();
-    th[i].b = zero<FrParams>();
+    th[i].a = i == 0 ? lz_from(E[t - 1]) : lz_zero();
+    th[i].b = lz_zero();
   }
+  const uint32_t period = dt2_period(t);
+  left = period;
   for (uint32_t j = t - 1; j >= 1; j--) {
-    Fr* pr = pub.data() + (size_t)(j & 1) * nt;
+    uint32_t* pr = pub.data() + (size_t)(j & 1) * 9 * nt;
     for (uint32_t i = 0; i < nt; i++)
-      if (dt2_active(i, j, t)) pr[i] = th[i].b;
+      if (dt2_active(i, j, t)) lz_publish(pr, nt, i, th[i].b);
+    const bool red = --left == 0;
+    if (red) left = period;
     for (uint32_t i = 0; i < nt; i++)
-      if (dt2_active(i, j, t)) dt2_step(th[i], i, j, pr, E.data());
+      if (dt2_active(i, j, t)) dt2_step(th[i], i, j, red, pr, nt, E.data());
   }
   for (uint32_t i = 0; i < nt; i++) {
-    if (2 * i < t) fr_to_be32(coef + (size_t)(2 * i) * 32, th[i].a);
-    if (2 * i + 1 < t) fr_to_be32(coef + (size_t)(2 * i + 1) * 32, th[i].b);
+    dt2_finish(th[i], i, t);
+    if (2 * i < t) fr_to_be32(coef + (size_t)(2 * i) * 32, lz_low(th[i].a));
+    if (2 * i + 1 < t) fr_to_be32(coef + (size_t)(2 * i + 1) * 32, lz_low(th[i].b));
   }
   return 0;
+}
+// lz_reduce on a 36-byte little-endian-limb value (9 x u32, host order): out = the canonical residue, 32 bytes big-endian
+void he_lz_reduce(const uint32_t* limbs9, int is_signed, uint8_t* out32) {
+  Lz v;
+  for (int i = 0; i < 9; i++) v.l[i] = limbs9[i];
+  lz_reduce(v, is_signed != 0);
+  out32[0] = v.l[8] ? 0xff : 0;  // poisons the answer if the top limb is not clear
+  uint8_t tmp[32];
+  fr_to_be32(tmp, lz_low(v));
+  for (int i = 0; i < 32; i++) out32[i] = (i == 0 ? out32[0] : 0) | tmp[i];
 }
 
 // Condition (3) of the consistency shortcut against COMPRESSED commitments (fdiff.cuh fd_coef_point + fd_coef_signs, the

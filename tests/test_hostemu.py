@@ -198,6 +198,23 @@ def test_difference_table_shortcut(L):
         L.he_fr_submul_small(p_.to_bytes(32, "big"), a_.to_bytes(32, "big"), j_, o)
         assert int.from_bytes(o.raw, "big") == (p_ - j_ * a_) % R, (hex(p_), hex(a_), j_)
 
+    # lz_reduce (fdiff.cuh): the lazy 9-limb values of the table back to canonical residues, on the extremes of both ranges
+    import struct
+
+    def reduce(v, signed):
+        w = v % (1 << 288)
+        L.he_lz_reduce(struct.pack("<9I", *[(w >> (32 * i)) & 0xffffffff for i in range(9)]), int(signed), o)
+        return int.from_bytes(o.raw, "big")
+
+    sig_edge = [0, 1, -1, R, -R, R - 1, 1 - R, (1 << 285), -(1 << 285), (1 << 285) - 1, 1 - (1 << 285), (1 << 256), -(1 << 256),
+                3 * R, -3 * R, (R << 30), -(R << 30), (R << 30) - 1, (R << 30) + 1, ((1 << 285) // R) * R, -(((1 << 285) // R) * R)]
+    for v in sig_edge + [rnd.randrange(-(1 << 285), (1 << 285) + 1) for _ in range(3000)] + [rnd.randrange(-R, R) for _ in range(500)]:
+        assert reduce(v, True) == v % R, hex(v)
+    uns_edge = [0, 1, R - 1, R, R + 1, 2 * R, 3 * R - 1, 1 << 256, (1 << 286), (1 << 286) - 1, ((1 << 286) // R) * R, ((1 << 286) // R) * R - 1,
+                (1 << 224) - 1, 1 << 224, (1 << 255) - 1]
+    for v in uns_edge + [rnd.randrange((1 << 286) + 1) for _ in range(3000)] + [rnd.randrange(1 << rnd.randrange(1, 287)) for _ in range(1000)]:
+        assert reduce(v, False) == v % R, hex(v)
+
     def run(s, t):
         n = len(s)
         ifact = b"".join(pow(factorial(k), -1, R).to_bytes(32, "big") for k in range(t))
@@ -212,7 +229,7 @@ def test_difference_table_shortcut(L):
         return v
 
     for t, n in [(1, 2), (1, 5), (2, 3), (2, 5), (3, 9), (7, 12), (8, 9), (20, 33), (33, 64), (43, 64), (64, 65), (97, 200), (130, 131),
-                 (683, 1024), (1024, 1025), (1023, 2048)]:
+                 (683, 1024), (1024, 1025), (1023, 2048), (1500, 2048), (2047, 2048)]:
         a = [rnd.randrange(R) for _ in range(t)]
         if t > 2:
             a[t - 1] = 0 if n % 2 else a[t - 1]  # a polynomial of lower degree is fine too
