@@ -63,8 +63,8 @@ def canonical_horner_modmul(t, x):
 # (mul2add, 444 MACs) replaces three pairs in the additions and one in the doubling
 EXEC_ADD, EXEC_DBL, EXEC_MADD = 6 + 3 * 444 / 300, 6 + 444 / 300, 5 + 3 * 444 / 300
 # fixed-base multiplication G * s: the canonical algorithm of SURVEY 8(d) is 8-bit windows (32 + 1 mixed additions); the library's table
-# has 13-bit windows (csrc/feldman.cuh GTAB_BITS): 20 + 1 mixed additions
-CANON_FIX_MADDS, EXEC_FIX_MADDS = 33, 21
+# has signed odd 16-bit windows (csrc/feldman.cuh GTAB_BITS): the first entry initialises the sum, 15 mixed additions
+CANON_FIX_MADDS, EXEC_FIX_MADDS = 33, 15
 
 
 def executed_horner_modmul(t, x):
@@ -672,8 +672,8 @@ def run_b200(args):
         roof = {"bound": "int_pipe", "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9, "mac_per_modmul": MAC_PER_MODMUL, "traffic": None, "algorithmic_bytes": None}
         if settled_by_shortcut and len(short_ms) == args.steps:
-            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (21 mixed
-            # additions over the 13-bit-window table; canonical: 33 over byte windows) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
+            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (15 mixed
+            # additions over the signed 16-bit-window table; canonical: 33 over byte windows) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
             # ALU work + 2 products) - per point 3 products of the simultaneous inversion + Y / Z + the canonical form for the sign
             sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
             pt_canon, pt_exec = CANON_FIX_MADDS * 11 + 2, EXEC_FIX_MADDS * EXEC_MADD + 2

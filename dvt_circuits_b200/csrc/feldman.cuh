@@ -71,56 +71,81 @@ DKGV_HD G1Proj feldman_eval(const VVView& v, uint32_t t, uint32_t d, uint32_t id
   return acc;
 }
 
-// Offset fixed-base table for the generator (no zero digits, so the mixed addition never meets the
-// identity and needs no select), GTAB_BITS-bit windows:
-//   gtab[(w * 2^B + b) * 24 ..] = ((b + 1) * 2^(B w)) * G      b < 2^B, w < GTAB_WINDOWS   (affine Montgomery)
-//   gtab[GTAB_WINDOWS * 2^B * 24 ..] = -(sum_w 2^(B w)) * G    (correction point)
-// G*s = sum_w gtab[w][digit_w(s)] + correction.  B = 13: 20 windows, 21 mixed additions per multiplication instead of the 33 of byte
-// windows; 163 841 entries = 15.7 MB, resident in the 126 MB L2 (the default share path does t fixed-base multiplications per
-// dealer - 699 392 per (1024, 683) ceremony - and its x-half kernel is 2/3 of the step).
-constexpr int GTAB_BITS = 13;
+// Fixed-base table for the generator with SIGNED ODD digits, GTAB_BITS-bit windows.  The scalar is made odd first (u = s or
+// s + r: G has order r and 2r < 2^256), and an odd u < 2^256 has exactly one representation u = sum_w d_w 2^(B w) with every
+// d_w odd, |d_w| < 2^B (d_w = [bits B w .. B w + B of u, bit B w forced to 1] - 2^B for w < W - 1, the last digit is what remains):
+// no digit is zero - the mixed addition never meets the identity and needs no select, no correction point either - and only the
+// odd positive multiples are stored, a negative digit negates y:
+//   gtab[(w * 2^(B-1) + m) * 24 ..] = ((2m + 1) * 2^(B w)) * G      m < 2^(B-1), w < GTAB_WINDOWS   (affine Montgomery)
+// G*s = sum_w +-gtab[w][(|d_w| - 1) / 2].  B = 16: 16 windows, the first entry initialises the sum, 15 mixed additions per
+// multiplication (21 with the unsigned 13-bit offset windows of the same idea before, 33 with byte windows); 524 288 entries = 50 MB,
+// in the 126 MB L2 (the default share path does t fixed-base multiplications per dealer - 699 392 per (1024, 683) ceremony - and
+// its x-half kernel is more than half of the step).
+constexpr int GTAB_BITS = 16;
 constexpr int GTAB_WINDOWS = (256 + GTAB_BITS - 1) / GTAB_BITS;
-constexpr uint32_t GTAB_ENTRIES = GTAB_WINDOWS * (1u << GTAB_BITS) + 1;
+constexpr uint32_t GTAB_ENTRIES = GTAB_WINDOWS * (1u << (GTAB_BITS - 1));
 constexpr size_t GTAB_WORDS = (size_t)GTAB_ENTRIES * 24;
 
 DKGV_HD G1Aff gtab_entry(uint32_t idx) {
-  if (idx < GTAB_WINDOWS * (1u << GTAB_BITS)) {
-    uint32_t w = idx >> GTAB_BITS, b = idx & ((1u << GTAB_BITS) - 1u);
-    G1Proj p = g1_from_affine(g1_generator());
+  uint32_t w = idx >> (GTAB_BITS - 1), m = idx & ((1u << (GTAB_BITS - 1)) - 1u);
+  G1Proj p = g1_from_affine(g1_generator());
 #pragma unroll 1
-    for (uint32_t i = 0; i < GTAB_BITS * w; i++) p = g1_dbl(p);
-    return g1_to_affine(g1_mul_small(p, b + 1));
-  }
-  G1Proj g = g1_from_affine(g1_generator()), acc = g1_identity();
-#pragma unroll 1
-  for (uint32_t w = 0; w < GTAB_WINDOWS; w++) {
-    acc = g1_add(acc, g);
-#pragma unroll 1
-    for (int i = 0; i < GTAB_BITS; i++) g = g1_dbl(g);
-  }
-  return g1_to_affine(g1_neg(acc));
+  for (uint32_t i = 0; i < GTAB_BITS * w; i++) p = g1_dbl(p);
+  return g1_to_affine(g1_mul_small(p, 2 * m + 1));
 }
 
-// index of the table entry for window w of the 256-bit scalar s_raw (8 little-endian limbs); w == GTAB_WINDOWS: the correction point
-DKGV_HD uint32_t gtab_index(const uint32_t* s_raw, int w) {
-  if (w >= GTAB_WINDOWS) return (uint32_t)GTAB_WINDOWS << GTAB_BITS;
+// u = the odd representative of s mod r (s < r: the callers range-check; for other 256-bit values the sum may wrap and the point is
+// unspecified - still a memory-safe walk through the table)
+DKGV_HD void gtab_scalar(uint32_t* u, const uint32_t* s_raw /*8 limbs*/) {
+  const uint32_t m = (s_raw[0] & 1u) ? 0u : 0xffffffffu;
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)s_raw[i] + (FrParams::mod(i) & m);
+    u[i] = (uint32_t)c;
+    c >>= 32;
+  }
+}
+// index of the table entry for window w of the odd scalar u (gtab_scalar), *neg: the digit is negative
+DKGV_HD uint32_t gtab_index(const uint32_t* u, int w, bool* neg) {
   const uint32_t bit = (uint32_t)w * GTAB_BITS, limb = bit >> 5, sh = bit & 31;
-  uint32_t v = s_raw[limb] >> sh;
-  if (sh + GTAB_BITS > 32 && limb + 1 < 8) v |= s_raw[limb + 1] << (32 - sh);
-  return ((uint32_t)w << GTAB_BITS) + (v & ((1u << GTAB_BITS) - 1u));
+  uint32_t v = u[limb] >> sh;
+  if (sh + GTAB_BITS + 1 > 32 && limb + 1 < 8) v |= sh ? u[limb + 1] << (32 - sh) : 0u;
+  uint32_t mag;
+  if (w == GTAB_WINDOWS - 1) {  // the last digit is what remains: positive (fewer than GTAB_BITS + 1 bits are left of u < 2^256)
+    mag = (v & ((1u << GTAB_BITS) - 1u)) | 1u;
+    *neg = false;
+  } else {
+    const uint32_t x = (v & ((2u << GTAB_BITS) - 1u)) | 1u, low = x & ((1u << GTAB_BITS) - 1u);
+    const bool pos = (x >> GTAB_BITS) & 1u;
+    mag = pos ? low : (1u << GTAB_BITS) - low;
+    *neg = !pos;
+  }
+  return ((uint32_t)w << (GTAB_BITS - 1)) + (mag >> 1);
+}
+// the entry of window w for u: x, and y with the digit's sign
+DKGV_HD void gtab_lookup(const uint32_t* gtab, const uint32_t* u, int w, Fp* x, Fp* y) {
+  bool ng;
+  const uint32_t* e = gtab + (size_t)gtab_index(u, w, &ng) * 24;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x->l[i] = e[i];
+    y->l[i] = e[12 + i];
+  }
+  if (ng) *y = neg(*y);
 }
 
 DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 limbs*/) {
-  G1Proj acc = g1_identity();
+  uint32_t u[8];
+  gtab_scalar(u, s_raw);
+  G1Aff first;
+  first.inf = 0;
+  gtab_lookup(gtab, u, 0, &first.x, &first.y);
+  G1Proj acc = g1_from_affine(first);
 #pragma unroll 1
-  for (int w = 0; w <= GTAB_WINDOWS; w++) {
-    const uint32_t* e = gtab + (size_t)gtab_index(s_raw, w) * 24;
+  for (int w = 1; w < GTAB_WINDOWS; w++) {
     Fp x, y;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      x.l[i] = e[i];
-      y.l[i] = e[12 + i];
-    }
+    gtab_lookup(gtab, u, w, &x, &y);
     acc = g1_add_mixed_nz(acc, x, y);
   }
   return acc;

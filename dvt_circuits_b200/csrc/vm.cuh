@@ -252,23 +252,20 @@ DKGV_HD void vm_feldman_eval(const OpFile& f, const VVView& v, uint32_t t, uint3
   }
 }
 
-DKGV_HD void vm_load_affine_q(const OpFile& f, const uint32_t* e) {
-  Fp x, y;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    x.l[i] = e[i];
-    y.l[i] = e[12 + i];
-  }
-  of_store(f, T5, x);
-  of_store(f, T6, y);
-}
-
-// B <- G * s  (s raw little-endian limbs, any 256-bit value; the caller range-checks it)
+// B <- G * s  (s raw little-endian limbs; the caller range-checks it: feldman.cuh gtab_scalar)
 DKGV_HD void vm_fixed_base_mul(const OpFile& f, const uint32_t* gtab, const uint32_t* s_raw) {
-  vm_set_point(f, BX, g1_identity());
+  uint32_t u[8];
+  gtab_scalar(u, s_raw);
+  G1Aff first;
+  first.inf = 0;
+  gtab_lookup(gtab, u, 0, &first.x, &first.y);
+  vm_set_point(f, BX, g1_from_affine(first));
 #pragma unroll 1
-  for (int w = 0; w <= GTAB_WINDOWS; w++) {
-    vm_load_affine_q(f, gtab + (size_t)gtab_index(s_raw, w) * 24);
+  for (int w = 1; w < GTAB_WINDOWS; w++) {
+    Fp x, y;
+    gtab_lookup(gtab, u, w, &x, &y);
+    of_store(f, T5, x);
+    of_store(f, T6, y);
     vm_g1_madd(f, BX);
   }
 }

@@ -13,6 +13,25 @@
 
 using namespace dkgv;
 
+// the fixed-base table is 50 MB: one lazily allocated copy, only the entries a scalar touches are computed (gtab_entry, as k_build_gtab does)
+static std::vector<uint32_t>& he_gtab_for(const uint32_t* s_raw) {
+  static std::vector<uint32_t> gtab;
+  if (gtab.empty()) gtab.assign(GTAB_WORDS, 0);
+  uint32_t u[8];
+  gtab_scalar(u, s_raw);
+  for (int w = 0; w < GTAB_WINDOWS; w++) {
+    bool ng;
+    uint32_t idx = gtab_index(u, w, &ng);
+    if (gtab[(size_t)idx * 24] | gtab[(size_t)idx * 24 + 1]) continue;
+    G1Aff e = gtab_entry(idx);
+    for (int i = 0; i < 12; i++) {
+      gtab[(size_t)idx * 24 + i] = e.x.l[i];
+      gtab[(size_t)idx * 24 + 12 + i] = e.y.l[i];
+    }
+  }
+  return gtab;
+}
+
 extern "C" {
 
 // canonical 48-byte big-endian a, b -> canonical a*b mod p, a+b, a-b
@@ -78,18 +97,10 @@ uint32_t he_share_check(const uint8_t* vv, uint32_t t, uint32_t id, const uint8_
     vv_store(limbs.data(), inf.data(), n_pad, k, 0, a);
   }
   VVView view{limbs.data(), inf.data(), n_pad};
-  // the 33 table entries this scalar touches, computed by the same routine as k_build_gtab
-  std::vector<uint32_t> gtab(GTAB_WORDS, 0);
+  // the table entries this scalar touches, computed by the same routine as k_build_gtab
   uint32_t s[8];
   fr_raw_from_be32(s, secret32);
-  for (int w = 0; w <= GTAB_WINDOWS; w++) {
-    uint32_t idx = gtab_index(s, w);
-    G1Aff e = gtab_entry(idx);
-    for (int i = 0; i < 12; i++) {
-      gtab[(size_t)idx * 24 + i] = e.x.l[i];
-      gtab[(size_t)idx * 24 + 12 + i] = e.y.l[i];
-    }
-  }
+  std::vector<uint32_t>& gtab = he_gtab_for(s);
   g1_compress(g1_to_affine(feldman_eval(view, t, 0, id)), eval48);
   g1_compress(g1_to_affine(fixed_base_mul(gtab.data(), s)), pk48);
   uint32_t st = share_check(view, t, 0, id, secret32, gtab.data(), bad);
@@ -412,15 +423,7 @@ void he_coef_bytes_check(const uint8_t* scalars32, const uint8_t* enc48, uint32_
   for (uint32_t i = 0; i < n; i++) {
     uint32_t sc[8];
     fr_raw_from_be32(sc, scalars32 + (size_t)i * 32);
-    std::vector<uint32_t> gtab(GTAB_WORDS, 0);
-    for (int w = 0; w <= GTAB_WINDOWS; w++) {
-      uint32_t idx = gtab_index(sc, w);
-      G1Aff e = gtab_entry(idx);
-      for (int l = 0; l < 12; l++) {
-        gtab[(size_t)idx * 24 + l] = e.x.l[l];
-        gtab[(size_t)idx * 24 + 12 + l] = e.y.l[l];
-      }
-    }
+    std::vector<uint32_t>& gtab = he_gtab_for(sc);
     same[i] = fd_coef_point(f, gtab.data(), sc, enc48 + (size_t)i * 48, &ys[i], &zs[i]);
   }
   for (uint32_t k0 = 0; k0 < n; k0 += FD_SIGN_K) {

@@ -104,6 +104,13 @@ def test_share_check_all_formulations(L):
             assert L.he_share_check(vv, t, i, s.to_bytes(32, "big"), ev, pk) == 0, (t, i)
             assert L.he_share_check(vv, t, i, ((s + 1) % B.R).to_bytes(32, "big"), ev, pk) == 4
         assert L.he_share_check(vv, t, 3, B.R.to_bytes(32, "big"), ev, pk) == 1
+    # the signed-odd fixed-base table (feldman.cuh gtab_*): G * s on the digit extremes - even / odd scalars, all-zero and all-one
+    # windows, carries into the next window, s = 0 (the sum meets P + (-P))
+    edge = [0, 1, 2, 3, B.R - 1, B.R - 2, 0xFFFF, 0x10000, 0x10001, 0xFFFF0000FFFF, (1 << 240) + 1, (1 << 240), (1 << 254) - 1,
+            0x8000800080008000800080008000800080008000800080008000800080008000 % B.R, int("55" * 32, 16) % B.R, int("aa" * 32, 16) % B.R]
+    for s in edge + [rnd.randrange(B.R) for _ in range(24)]:
+        L.he_share_check(b"", 0, 1, s.to_bytes(32, "big"), ev, pk)
+        assert pk.raw == B.g1_compress(B.g1_mul(B.G1, s)), hex(s)
 
 
 def test_tower_pairing_h2c(L):
