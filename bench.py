@@ -63,8 +63,8 @@ def canonical_horner_modmul(t, x):
 # (mul2add, 444 MACs) replaces three pairs in the additions and one in the doubling
 EXEC_ADD, EXEC_DBL, EXEC_MADD = 6 + 3 * 444 / 300, 6 + 444 / 300, 5 + 3 * 444 / 300
 # fixed-base multiplication G * s: the canonical algorithm of SURVEY 8(d) is 8-bit windows (32 + 1 mixed additions); the library's table
-# has signed odd 16-bit windows (csrc/feldman.cuh GTAB_BITS): the first entry initialises the sum, 15 mixed additions
-CANON_FIX_MADDS, EXEC_FIX_MADDS = 33, 15
+# has signed odd B-bit windows (csrc/feldman.cuh; B per ctx, default 22): the first entry initialises the sum, ceil(256 / B) - 1 mixed additions
+CANON_FIX_MADDS = 33
 
 
 def executed_horner_modmul(t, x):
@@ -341,6 +341,8 @@ def run_b200(args):
     rows = n // split
 
     v = dk.Verifier(local)
+    gtab_bits = v.gtab_bits()
+    EXEC_FIX_MADDS = (256 + gtab_bits - 1) // gtab_bits - 1
     if world > 1:  # the library owns the collectives; torch.distributed only carries the 128-byte id to the other ranks
         box = [dk.Verifier.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -672,8 +674,8 @@ def run_b200(args):
         roof = {"bound": "int_pipe", "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9, "mac_per_modmul": MAC_PER_MODMUL, "traffic": None, "algorithmic_bytes": None}
         if settled_by_shortcut and len(short_ms) == args.steps:
-            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (15 mixed
-            # additions over the signed 16-bit-window table; canonical: 33 over byte windows) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
+            # no decode at all - compress(G * p_k) == C_k per coefficient.  x halves (k_fd_coefpoint): fixed-base multiplication (ceil(256 / B) - 1 mixed
+            # additions over the signed B-bit-window table; canonical: 33 over byte windows) + to-Montgomery + x_C * Z; sign halves (k_fd_coefsign): batches of 8 with one inversion (binary extended Euclid:
             # ALU work + 2 products) - per point 3 products of the simultaneous inversion + Y / Z + the canonical form for the sign
             sp = [statistics.mean(p_[i] for p_ in short_ms) for i in range(4)]
             pt_canon, pt_exec = CANON_FIX_MADDS * 11 + 2, EXEC_FIX_MADDS * EXEC_MADD + 2
@@ -742,6 +744,8 @@ def run_b200(args):
                        "n": n, "t": t, "shares_per_step": shares_total, "l2": "flushed (256 MB fill) between timed iterations",
                        "share_path": ("consistency shortcut (range, t-th differences of the shares, compress(G*p_k) == C_k per coefficient) settled every "
                                       "dealer: no evaluation in the exponent, no commitment decoded" if settled_by_shortcut else "evaluation"),
+                       "fixed_base_table": (f"{gtab_bits}-bit signed odd windows: {EXEC_FIX_MADDS} mixed additions per G * s, "
+                                            f"{(EXEC_FIX_MADDS + 1) * (1 << (gtab_bits - 1)) * 96 / 1e6:.0f} MB per ctx"),
                        "parallelism": (f"row-block x{world}; inside dkgv_share_matrix_verify_sharded_dev: one NCCL all-gather of the verdict bitmask + job flags "
                                        f"({chunk * 4} B per rank), one host synchronisation") if world > 1 else "single GPU"},
             "clocks": clocks,

@@ -58,6 +58,9 @@ _u32 = ctypes.c_uint32
 # symbol -> (restype, argtypes); must list every function include/dkgv.h declares
 DECLARED_SYMBOLS = {
     "dkgv_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "dkgv_ctx_create_ex": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(_vp)]),
+    "dkgv_gtab_bits": (ctypes.c_uint32, [_vp]),
+    "dkgv_gtab_selfcheck": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]),
     "dkgv_ctx_destroy": (None, [_vp]),
     "dkgv_last_error": (ctypes.c_char_p, [_vp]),
     "dkgv_launch_count": (ctypes.c_uint64, [_vp]),
@@ -160,14 +163,23 @@ def _p(a):
 class Verifier:
     """One dkgv_ctx bound to one GPU."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, gtab_bits=0):
+        """gtab_bits: window width of the fixed-base table (dkgv_ctx_create_ex; 0 = DKGV_GTAB_BITS or the library's default)"""
         self._lib = load_library()
         h = _vp()
-        rc = self._lib.dkgv_ctx_create(int(device), ctypes.byref(h))
+        rc = self._lib.dkgv_ctx_create_ex(int(device), int(gtab_bits), ctypes.byref(h))
         if rc != 0:
             raise DkgvError(f"dkgv_ctx_create failed ({rc}): {self._lib.dkgv_last_error(None).decode()}")
         self._h = h
         self.device = device
+
+    def gtab_bits(self):
+        return int(self._lib.dkgv_gtab_bits(self._h))
+
+    def gtab_selfcheck(self, first, stride, count):
+        bad = ctypes.c_uint32(0)
+        self._ck(self._lib.dkgv_gtab_selfcheck(self._h, int(first), int(stride), int(count), ctypes.byref(bad)))
+        return int(bad.value)
 
     def close(self):
         if getattr(self, "_h", None):

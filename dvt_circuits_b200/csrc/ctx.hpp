@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/dkgv.h"
+#include "gtab.hpp"
 
 struct ncclUniqueIdBytes {
   char internal[128];
@@ -38,7 +39,8 @@ struct DevBuf {
 struct dkgv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  uint32_t* gtab = nullptr;
+  uint32_t* gtab_mem = nullptr;  // fixed-base table of the generator (feldman.cuh), built once per ctx
+  dkgv::GTab gtab{nullptr, 0, 0};
   uint64_t launches = 0;
   std::string err;
   dkgv_host::DevBuf vv_limbs, vv_inf, dealer_bad;      // session scratch (decoded verification vectors)

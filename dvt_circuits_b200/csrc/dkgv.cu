@@ -30,17 +30,28 @@ int dkgv_feldman_eval_fd(dkgv_ctx* ctx, const VVView& view, uint32_t n_d, uint32
                          const uint32_t* d_ids, const uint32_t* h_ids, uint8_t* d_out48, cudaStream_t s);
 
 // ============================================================================ kernels
-// Offset fixed-base table of the generator (layout in feldman.cuh).
-__global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= GTAB_ENTRIES) return;
-  G1Aff a = gtab_entry(tid);
-  uint32_t* e = gtab + (size_t)tid * 24;
+// Fixed-base table of the generator (layout and the per-thread routines in feldman.cuh): the W window bases first, then one thread
+// per run of GTAB_RUN entries.
+__global__ void __launch_bounds__(32) k_gtab_bases(uint32_t bits, uint32_t windows, uint32_t* __restrict__ base) {
+  if (threadIdx.x < windows) gtab_base(bits, threadIdx.x, base);
+}
+__global__ void __launch_bounds__(128) k_gtab_fill(uint32_t bits, uint32_t windows, const uint32_t* __restrict__ base, uint32_t* __restrict__ gtab) {
+  const uint32_t run = blockIdx.x * blockDim.x + threadIdx.x, per_window = (1u << (bits - 1)) / GTAB_RUN;
+  if (run >= windows * per_window) return;
+  gtab_fill_run(bits, base, run / per_window, (run % per_window) * GTAB_RUN, gtab);
+}
+// debug: entries idx = first, first + stride, ... against the slow definition (gtab_entry); *bad counts the differences
+__global__ void __launch_bounds__(128) k_gtab_check(GTab g, uint32_t first, uint32_t stride, uint32_t count, uint32_t* __restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t idx = first + i * stride;
+  if (idx >= gtab_entries(g.bits)) return;
+  G1Aff a = gtab_entry(g.bits, idx);
+  const uint32_t* e = g.p + (size_t)idx * 24;
+  bool same = true;
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    e[i] = a.x.l[i];
-    e[12 + i] = a.y.l[i];
-  }
+  for (int k = 0; k < 12; k++) same = same && e[k] == a.x.l[k] && e[12 + k] == a.y.l[k];
+  if (!same) atomicAdd(bad, 1u);
 }
 
 // Decode + subgroup-check the verification vectors into the limb-planar layout of feldman.cuh.
@@ -77,7 +88,7 @@ constexpr size_t SVM_SMEM = (size_t)VM_SLOTS * 3 * SVM_NT * sizeof(U4);
 typedef VVView HotView;
 __global__ void __launch_bounds__(SVM_NT)
 k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids,
-               const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status,
+               const uint8_t* __restrict__ shares, GTab gtab, uint8_t* __restrict__ status,
                uint32_t n_d, uint32_t n_r, uint32_t t) {
   extern __shared__ U4 opfile[];
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -100,7 +111,7 @@ k_share_verify(HotView vv, const uint8_t* __restrict__ dealer_bad, const uint32_
 __global__ void __launch_bounds__(32)
 k_share_items(VVView vv, const uint8_t* __restrict__ dealer_bad, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ s_dealer,
               const uint32_t* __restrict__ s_col, const uint32_t* __restrict__ s_orig, const uint32_t* __restrict__ warp_first,
-              const uint8_t* __restrict__ secrets, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ status, uint32_t t) {
+              const uint8_t* __restrict__ secrets, GTab gtab, uint8_t* __restrict__ status, uint32_t t) {
   extern __shared__ U4 opfile[];
   uint32_t first = warp_first[blockIdx.x], cnt = warp_first[blockIdx.x + 1] - first;
   bool active = threadIdx.x < cnt;
@@ -145,7 +156,7 @@ k_feldman_eval(VVView vv, const uint32_t* __restrict__ ids, uint8_t* __restrict_
 }
 
 __global__ void __launch_bounds__(128)
-k_fixed_base_mul(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ gtab, uint8_t* __restrict__ out,
+k_fixed_base_mul(const uint8_t* __restrict__ scalars, GTab gtab, uint8_t* __restrict__ out,
                  uint8_t* __restrict__ status, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -206,7 +217,9 @@ thread_local std::string g_create_error;
 
 static int fail(dkgv_ctx* ctx, const char* msg) { return dkgv_fail(ctx, msg); }
 
-extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
+extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) { return dkgv_ctx_create_ex(device, 0, out); }
+
+extern "C" int dkgv_ctx_create_ex(int device, uint32_t gtab_bits, dkgv_ctx** out) {
   if (!out) return -1;
   *out = nullptr;
   int ndev = 0;
@@ -233,8 +246,25 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
       (e = cudaEventCreate(&ctx->ev_dec0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_dec1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_bls0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_bls1)) != cudaSuccess)
     return bail("cudaEventCreate", e);
-  if ((e = cudaMalloc(&ctx->gtab, GTAB_WORDS * 4)) != cudaSuccess) return bail("cudaMalloc gtab", e);
-  if ((e = cudaMemsetAsync(ctx->gtab, 0, GTAB_WORDS * 4, ctx->stream)) != cudaSuccess) return bail("memset", e);
+  // fixed-base table: the window width asked for (0 = DKGV_GTAB_BITS from the environment, else the default), stepping down while the
+  // device cannot hold it
+  if (gtab_bits == 0) {
+    const char* env = getenv("DKGV_GTAB_BITS");
+    gtab_bits = env ? (uint32_t)atoi(env) : GTAB_BITS_DEFAULT;
+  }
+  if (gtab_bits < GTAB_BITS_MIN || gtab_bits > GTAB_BITS_MAX) {
+    g_create_error = "gtab_bits out of range";
+    dkgv_ctx_destroy(ctx);
+    return -1;
+  }
+  for (;; gtab_bits -= 2) {
+    e = cudaMalloc(&ctx->gtab_mem, gtab_words(gtab_bits) * 4);
+    if (e == cudaSuccess) break;
+    ctx->gtab_mem = nullptr;
+    cudaGetLastError();
+    if (gtab_bits < 16 + 2) return bail("cudaMalloc gtab", e);
+  }
+  ctx->gtab = GTab{ctx->gtab_mem, gtab_bits, gtab_windows(gtab_bits)};
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVM_SMEM)) != cudaSuccess)
     return bail("cudaFuncSetAttribute smem", e);
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess)
@@ -248,9 +278,17 @@ extern "C" int dkgv_ctx_create(int device, dkgv_ctx** out) {
     dkgv_ctx_destroy(ctx);
     return -2;
   }
-  k_build_gtab<<<(GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
-  ctx->launches++;
-  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("k_build_gtab", e);
+  {
+    uint32_t* base = nullptr;
+    if ((e = cudaMalloc(&base, 32 * 48 * 4)) != cudaSuccess) return bail("cudaMalloc gtab bases", e);
+    const uint32_t runs = ctx->gtab.windows * ((1u << (gtab_bits - 1)) / GTAB_RUN);
+    k_gtab_bases<<<1, 32, 0, ctx->stream>>>(gtab_bits, ctx->gtab.windows, base);
+    k_gtab_fill<<<(runs + 127) / 128, 128, 0, ctx->stream>>>(gtab_bits, ctx->gtab.windows, base, ctx->gtab_mem);
+    ctx->launches += 2;
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(base);
+    if (e != cudaSuccess) return bail("k_gtab_fill", e);
+  }
   *out = ctx;
   return 0;
 }
@@ -272,7 +310,7 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
-  if (ctx->gtab) cudaFree(ctx->gtab);
+  if (ctx->gtab_mem) cudaFree(ctx->gtab_mem);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->ev_dec0) cudaEventDestroy(ctx->ev_dec0);
@@ -285,6 +323,21 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
 
 extern "C" const char* dkgv_last_error(const dkgv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 extern "C" uint64_t dkgv_launch_count(const dkgv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint32_t dkgv_gtab_bits(const dkgv_ctx* ctx) { return ctx ? ctx->gtab.bits : 0; }
+extern "C" int dkgv_gtab_selfcheck(dkgv_ctx* ctx, uint32_t first, uint32_t stride, uint32_t count, uint32_t* n_bad) {
+  if (!ctx || !n_bad) return -1;
+  CK(cudaSetDevice(ctx->device));
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 4);
+  if (e != cudaSuccess) return fail(ctx, "cudaMalloc");
+  cudaMemsetAsync(d, 0, 4, ctx->stream);
+  if (count) k_gtab_check<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->gtab, first, stride, count, d);
+  ctx->launches++;
+  e = cudaMemcpyAsync(n_bad, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : fail(ctx, cudaGetErrorString(e));
+}
 extern "C" int dkgv_last_hot_kernel_ms(dkgv_ctx* ctx, float* ms) {
   if (!ctx || !ms) return -1;
   if (!ctx->hot_recorded) return fail(ctx, "no hot kernel launched yet");

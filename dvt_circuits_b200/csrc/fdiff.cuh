@@ -293,7 +293,7 @@ DKGV_HD void fd_combine_eval(const OpFile& f, const uint32_t* evals, uint32_t n_
 // (crates/dkg/src/verification.rs:92-99,138-146), same status contract as vm_share_check
 DKGV_HD uint8_t fd_combine_compare_item(const OpFile& f, const uint32_t* evals, uint32_t n_padv, uint32_t n_pad, uint32_t m, size_t e,
                                         uint32_t d, const int8_t* dig, int top, uint32_t* tab, const uint8_t* secret_be,
-                                        const uint32_t* gtab, bool dealer_bad) {
+                                        GTab gtab, bool dealer_bad) {
   fd_combine_eval(f, evals, n_padv, n_pad, m, e, d, dig, top, tab);
   uint32_t s[8];
   bool in_range = fr_raw_from_be32(s, secret_be);
@@ -646,7 +646,7 @@ DKGV_HD void dt2_finish(DtPair& p, uint32_t i, uint32_t t) {  // after the t - 1
 //
 // B <- G * sc; true when flags and x of c48 agree with B.  y_out / z_out: what the sign half consumes - (0, 1) for an agreeing
 // identity (its sign flag must be 0 = lex_largest(0)) and whenever the answer is already false (keeps the batch invertible).
-DKGV_HD bool fd_coef_point(const OpFile& f, const uint32_t* gtab, const uint32_t* sc, const uint8_t* c48, Fp* y_out, Fp* z_out) {
+DKGV_HD bool fd_coef_point(const OpFile& f, GTab gtab, const uint32_t* sc, const uint8_t* c48, Fp* y_out, Fp* z_out) {
   vm_fixed_base_mul(f, gtab, sc);
   uint8_t b[48];
 #pragma unroll

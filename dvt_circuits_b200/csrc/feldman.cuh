@@ -13,6 +13,7 @@
 #pragma once
 #include "../../include/dkgv.h"
 #include "g1.cuh"
+#include "gtab.hpp"
 
 namespace dkgv {
 
@@ -71,27 +72,99 @@ DKGV_HD G1Proj feldman_eval(const VVView& v, uint32_t t, uint32_t d, uint32_t id
   return acc;
 }
 
-// Fixed-base table for the generator with SIGNED ODD digits, GTAB_BITS-bit windows.  The scalar is made odd first (u = s or
+// Fixed-base table for the generator with SIGNED ODD digits, B-bit windows.  The scalar is made odd first (u = s or
 // s + r: G has order r and 2r < 2^256), and an odd u < 2^256 has exactly one representation u = sum_w d_w 2^(B w) with every
 // d_w odd, |d_w| < 2^B (d_w = [bits B w .. B w + B of u, bit B w forced to 1] - 2^B for w < W - 1, the last digit is what remains):
 // no digit is zero - the mixed addition never meets the identity and needs no select, no correction point either - and only the
 // odd positive multiples are stored, a negative digit negates y:
-//   gtab[(w * 2^(B-1) + m) * 24 ..] = ((2m + 1) * 2^(B w)) * G      m < 2^(B-1), w < GTAB_WINDOWS   (affine Montgomery)
+//   gtab[(w * 2^(B-1) + m) * 24 ..] = ((2m + 1) * 2^(B w)) * G      m < 2^(B-1), w < W = ceil(256 / B)   (affine Montgomery)
 // G*s = sum_w +-gtab[w][(|d_w| - 1) / 2].  B = 16: 16 windows, the first entry initialises the sum, 15 mixed additions per
 // multiplication (21 with the unsigned 13-bit offset windows of the same idea before, 33 with byte windows); 524 288 entries = 50 MB,
 // in the 126 MB L2 (the default share path does t fixed-base multiplications per dealer - 699 392 per (1024, 683) ceremony - and
 // its x-half kernel is more than half of the step).
-constexpr int GTAB_BITS = 16;
-constexpr int GTAB_WINDOWS = (256 + GTAB_BITS - 1) / GTAB_BITS;
-constexpr uint32_t GTAB_ENTRIES = GTAB_WINDOWS * (1u << (GTAB_BITS - 1));
-constexpr size_t GTAB_WORDS = (size_t)GTAB_ENTRIES * 24;
+// The window width B is chosen per ctx (GTAB_BITS_MIN..GTAB_BITS_MAX): the table walk is one random 96-byte read per window, which the
+// HBM serves as well as the L2 does, so a wider window trades memory for mixed additions - B = 16: 50 MB / 15 additions, B = 22
+// (default): 2.4 GB / 11, B = 26: 32 GB / 9.
+constexpr uint32_t GTAB_BITS_MIN = 8, GTAB_BITS_MAX = 26, GTAB_BITS_DEFAULT = 22;
+DKGV_HD uint32_t gtab_windows(uint32_t bits) { return (256 + bits - 1) / bits; }
+DKGV_HD uint32_t gtab_entries(uint32_t bits) { return gtab_windows(bits) << (bits - 1); }
+DKGV_HD size_t gtab_words(uint32_t bits) { return (size_t)gtab_entries(bits) * 24; }
 
-DKGV_HD G1Aff gtab_entry(uint32_t idx) {
-  uint32_t w = idx >> (GTAB_BITS - 1), m = idx & ((1u << (GTAB_BITS - 1)) - 1u);
+// entry idx of the table with `bits`-bit windows, the slow way (doublings + a small multiplication + one inversion): the reference the
+// table builder (dkgv.cu k_gtab_*) is tested against, and what the host emulation fills its sparse table with
+DKGV_HD G1Aff gtab_entry(uint32_t bits, uint32_t idx) {
+  uint32_t w = idx >> (bits - 1), m = idx & ((1u << (bits - 1)) - 1u);
   G1Proj p = g1_from_affine(g1_generator());
 #pragma unroll 1
-  for (uint32_t i = 0; i < GTAB_BITS * w; i++) p = g1_dbl(p);
+  for (uint32_t i = 0; i < bits * w; i++) p = g1_dbl(p);
   return g1_to_affine(g1_mul_small(p, 2 * m + 1));
+}
+
+// ---- building the table (dkgv.cu k_gtab_bases / k_gtab_fill; the same routines run on the host in tests/hostemu) --------------
+// base[w * 48 ..]: affine x, y of 2^(B w) G (24 words), then of 2 * 2^(B w) G (24 words)
+DKGV_HD void gtab_base(uint32_t bits, uint32_t w, uint32_t* base) {
+  G1Proj p = g1_from_affine(g1_generator());
+#pragma unroll 1
+  for (uint32_t i = 0; i < bits * w; i++) p = g1_dbl(p);
+  G1Aff a = g1_to_affine(p), d = g1_to_affine(g1_dbl(p));
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    base[(size_t)w * 48 + i] = a.x.l[i];
+    base[(size_t)w * 48 + 12 + i] = a.y.l[i];
+    base[(size_t)w * 48 + 24 + i] = d.x.l[i];
+    base[(size_t)w * 48 + 36 + i] = d.y.l[i];
+  }
+}
+// GTAB_RUN consecutive entries m0 .. m0 + GTAB_RUN - 1 of window w: one small multiplication for the first, then a walk by
+// 2 * 2^(B w) G with one mixed addition per entry, and ONE inversion for the whole run (Montgomery's trick over the Z's; the
+// projective X, Y wait in their own table slots).  ~28 products per entry instead of the ~3 000 of gtab_entry.
+constexpr uint32_t GTAB_RUN = 32;
+DKGV_HD void gtab_fill_run(uint32_t bits, const uint32_t* base, uint32_t w, uint32_t m0, uint32_t* gtab) {
+  G1Aff g;
+  Fp dx, dy;
+  g.inf = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    g.x.l[i] = base[(size_t)w * 48 + i];
+    g.y.l[i] = base[(size_t)w * 48 + 12 + i];
+    dx.l[i] = base[(size_t)w * 48 + 24 + i];
+    dy.l[i] = base[(size_t)w * 48 + 36 + i];
+  }
+  G1Proj p = g1_mul_small(g1_from_affine(g), 2 * m0 + 1);
+  uint32_t* e0 = gtab + ((size_t)(w << (bits - 1)) + m0) * 24;
+  Fp zs[GTAB_RUN], pre[GTAB_RUN];  // Z_i and Z_0 ... Z_i (no multiple of the generator in the table is the identity: Z_i != 0)
+#pragma unroll 1
+  for (uint32_t i = 0; i < GTAB_RUN; i++) {
+    uint32_t* e = e0 + (size_t)i * 24;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      e[k] = p.x.l[k];
+      e[12 + k] = p.y.l[k];
+    }
+    zs[i] = p.z;
+    pre[i] = i ? mul(pre[i - 1], p.z) : p.z;
+    if (i + 1 < GTAB_RUN) p = g1_add_mixed_nz(p, dx, dy);
+  }
+  Fp inv = fp_inv_bgcd(pre[GTAB_RUN - 1]);
+#pragma unroll 1
+  for (int i = (int)GTAB_RUN - 1; i >= 0; i--) {
+    Fp zi = i ? mul(inv, pre[i - 1]) : inv;
+    inv = mul(inv, zs[i]);
+    uint32_t* e = e0 + (size_t)i * 24;
+    Fp x, y;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      x.l[k] = e[k];
+      y.l[k] = e[12 + k];
+    }
+    x = mul(x, zi);
+    y = mul(y, zi);
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      e[k] = x.l[k];
+      e[12 + k] = y.l[k];
+    }
+  }
 }
 
 // u = the odd representative of s mod r (s < r: the callers range-check; for other 256-bit values the sum may wrap and the point is
@@ -107,26 +180,26 @@ DKGV_HD void gtab_scalar(uint32_t* u, const uint32_t* s_raw /*8 limbs*/) {
   }
 }
 // index of the table entry for window w of the odd scalar u (gtab_scalar), *neg: the digit is negative
-DKGV_HD uint32_t gtab_index(const uint32_t* u, int w, bool* neg) {
-  const uint32_t bit = (uint32_t)w * GTAB_BITS, limb = bit >> 5, sh = bit & 31;
+DKGV_HD uint32_t gtab_index(uint32_t bits, uint32_t windows, const uint32_t* u, uint32_t w, bool* neg) {
+  const uint32_t bit = w * bits, limb = bit >> 5, sh = bit & 31;
   uint32_t v = u[limb] >> sh;
-  if (sh + GTAB_BITS + 1 > 32 && limb + 1 < 8) v |= sh ? u[limb + 1] << (32 - sh) : 0u;
+  if (sh + bits + 1 > 32 && limb + 1 < 8) v |= sh ? u[limb + 1] << (32 - sh) : 0u;
   uint32_t mag;
-  if (w == GTAB_WINDOWS - 1) {  // the last digit is what remains: positive (fewer than GTAB_BITS + 1 bits are left of u < 2^256)
-    mag = (v & ((1u << GTAB_BITS) - 1u)) | 1u;
+  if (w == windows - 1) {  // the last digit is what remains: positive (fewer than bits + 1 bits are left of u < 2^256)
+    mag = (v & ((1u << bits) - 1u)) | 1u;
     *neg = false;
   } else {
-    const uint32_t x = (v & ((2u << GTAB_BITS) - 1u)) | 1u, low = x & ((1u << GTAB_BITS) - 1u);
-    const bool pos = (x >> GTAB_BITS) & 1u;
-    mag = pos ? low : (1u << GTAB_BITS) - low;
+    const uint32_t x = (v & ((2u << bits) - 1u)) | 1u, low = x & ((1u << bits) - 1u);
+    const bool pos = (x >> bits) & 1u;
+    mag = pos ? low : (1u << bits) - low;
     *neg = !pos;
   }
-  return ((uint32_t)w << (GTAB_BITS - 1)) + (mag >> 1);
+  return (w << (bits - 1)) + (mag >> 1);
 }
 // the entry of window w for u: x, and y with the digit's sign
-DKGV_HD void gtab_lookup(const uint32_t* gtab, const uint32_t* u, int w, Fp* x, Fp* y) {
+DKGV_HD void gtab_lookup(const GTab& g, const uint32_t* u, uint32_t w, Fp* x, Fp* y) {
   bool ng;
-  const uint32_t* e = gtab + (size_t)gtab_index(u, w, &ng) * 24;
+  const uint32_t* e = g.p + (size_t)gtab_index(g.bits, g.windows, u, w, &ng) * 24;
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     x->l[i] = e[i];
@@ -135,7 +208,7 @@ DKGV_HD void gtab_lookup(const uint32_t* gtab, const uint32_t* u, int w, Fp* x, 
   if (ng) *y = neg(*y);
 }
 
-DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 limbs*/) {
+DKGV_HD G1Proj fixed_base_mul(const GTab& gtab, const uint32_t* s_raw /*8 limbs*/) {
   uint32_t u[8];
   gtab_scalar(u, s_raw);
   G1Aff first;
@@ -143,7 +216,7 @@ DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 li
   gtab_lookup(gtab, u, 0, &first.x, &first.y);
   G1Proj acc = g1_from_affine(first);
 #pragma unroll 1
-  for (int w = 1; w < GTAB_WINDOWS; w++) {
+  for (uint32_t w = 1; w < gtab.windows; w++) {
     Fp x, y;
     gtab_lookup(gtab, u, w, &x, &y);
     acc = g1_add_mixed_nz(acc, x, y);
@@ -154,7 +227,7 @@ DKGV_HD G1Proj fixed_base_mul(const uint32_t* gtab, const uint32_t* s_raw /*8 li
 // One share: status of (dealer d, recipient id) - the body of verify_seed_exchange_commitment
 // after the hash / lookup checks (crates/dkg/src/verification.rs:92-99,129-146).
 DKGV_HD uint8_t share_check(const VVView& vv, uint32_t t, uint32_t d, uint32_t id, const uint8_t* secret_be,
-                            const uint32_t* gtab, bool dealer_bad) {
+                            GTab gtab, bool dealer_bad) {
   G1Proj ev = feldman_eval(vv, t, d, id);
   uint32_t s[8];
   bool in_range = fr_raw_from_be32(s, secret_be);

@@ -76,7 +76,7 @@ k_fd_digits(uint32_t n_r, uint32_t h, uint32_t m, int8_t* __restrict__ dig, int3
 // tab holds one table plane per (tab_r0 + blockIdx.y, point, slot)
 __global__ void __launch_bounds__(FD_NT)
 k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
-             const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, const uint32_t* __restrict__ gtab,
+             const uint32_t* __restrict__ ids, const uint8_t* __restrict__ shares, GTab gtab,
              const uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ status, uint32_t* __restrict__ tab, uint32_t n_pad,
              uint32_t n_d, uint32_t n_r, uint32_t j0, const uint32_t* __restrict__ cols, uint32_t tab_r0, uint32_t d0,
              const uint8_t* __restrict__ need_group) {
@@ -253,7 +253,7 @@ k_fd_difftab(const uint32_t* __restrict__ sl, const uint32_t* __restrict__ ifact
 // condition (3) WITHOUT decoding the commitments (fdiff.cuh, "against the COMPRESSED commitment"): x half.  Same launch shape
 // (warp = 32 dealers x one k, the layout of the seeds); writes Z (limbs 0..11) and Y (12..23) of G * p_k to the chunk-local planes yz[(k*24 + w) * n_cols + dl].
 __global__ void __launch_bounds__(FD_NT)
-k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef, const uint32_t* __restrict__ gtab,
+k_fd_coefpoint(const uint8_t* __restrict__ vv, const uint32_t* __restrict__ coef, GTab gtab,
                uint8_t* __restrict__ poly_ok, uint32_t* __restrict__ yz, uint32_t d0, uint32_t n_d, uint32_t n_cols, uint32_t t,
                const uint32_t* __restrict__ map, const uint32_t* __restrict__ n_map) {
   extern __shared__ U4 opfile[];

@@ -253,7 +253,7 @@ DKGV_HD void vm_feldman_eval(const OpFile& f, const VVView& v, uint32_t t, uint3
 }
 
 // B <- G * s  (s raw little-endian limbs; the caller range-checks it: feldman.cuh gtab_scalar)
-DKGV_HD void vm_fixed_base_mul(const OpFile& f, const uint32_t* gtab, const uint32_t* s_raw) {
+DKGV_HD void vm_fixed_base_mul(const OpFile& f, GTab gtab, const uint32_t* s_raw) {
   uint32_t u[8];
   gtab_scalar(u, s_raw);
   G1Aff first;
@@ -261,7 +261,7 @@ DKGV_HD void vm_fixed_base_mul(const OpFile& f, const uint32_t* gtab, const uint
   gtab_lookup(gtab, u, 0, &first.x, &first.y);
   vm_set_point(f, BX, g1_from_affine(first));
 #pragma unroll 1
-  for (int w = 1; w < GTAB_WINDOWS; w++) {
+  for (uint32_t w = 1; w < gtab.windows; w++) {
     Fp x, y;
     gtab_lookup(gtab, u, w, &x, &y);
     of_store(f, T5, x);
@@ -283,7 +283,7 @@ DKGV_HD bool vm_g1_eq_ab(const OpFile& f) {
 
 // one share (same contract as share_check in feldman.cuh)
 DKGV_HD uint8_t vm_share_check(const OpFile& f, const VVView& vv, uint32_t t, uint32_t d, uint32_t id, const uint8_t* secret_be,
-                               const uint32_t* gtab, bool dealer_bad) {
+                               GTab gtab, bool dealer_bad) {
   vm_feldman_eval(f, vv, t, d, id);
   uint32_t s[8];
   bool in_range = fr_raw_from_be32(s, secret_be);

@@ -69,6 +69,16 @@ enum dkgv_decode { DKGV_DEC_OK = 0, DKGV_DEC_BAD_FLAGS = 1, DKGV_DEC_X_RANGE = 2
 /* ---- context ------------------------------------------------------------------------------ */
 /* Binds to CUDA device `device`, builds the fixed-base table for G1 generator multiplication.   */
 int dkgv_ctx_create(int device, dkgv_ctx** out);
+/* Same with the window width of the fixed-base table chosen by the caller: G * s (bls_keys.rs:98-114; t times per dealer on the default
+ * share path) costs ceil(256 / gtab_bits) - 1 mixed additions against a table of ceil(256 / gtab_bits) * 2^(gtab_bits - 1) affine
+ * points (96 B each) in device memory - 16: 50 MB / 15 additions, 22: 2.4 GB / 11, 26: 32 GB / 9.  gtab_bits = 0: the environment
+ * variable DKGV_GTAB_BITS if set, else 22.  8 <= gtab_bits <= 26; when the device cannot hold the table the width steps down by 2
+ * (not below 16) - dkgv_gtab_bits tells what the ctx ended up with. */
+int dkgv_ctx_create_ex(int device, uint32_t gtab_bits, dkgv_ctx** out);
+uint32_t dkgv_gtab_bits(const dkgv_ctx* ctx);
+/* debug: compares `count` entries of the fixed-base table (index first, first + stride, ...) with their definition computed the slow
+ * way on the device; *n_bad = how many differ.  Synchronous. */
+int dkgv_gtab_selfcheck(dkgv_ctx* ctx, uint32_t first, uint32_t stride, uint32_t count, uint32_t* n_bad);
 void dkgv_ctx_destroy(dkgv_ctx* ctx);
 const char* dkgv_last_error(const dkgv_ctx* ctx); /* ctx may be NULL: last create error */
 /* number of kernel launches issued through this ctx so far (bench accounting) */

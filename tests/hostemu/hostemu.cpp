@@ -13,23 +13,26 @@
 
 using namespace dkgv;
 
-// the fixed-base table is 50 MB: one lazily allocated copy, only the entries a scalar touches are computed (gtab_entry, as k_build_gtab does)
-static std::vector<uint32_t>& he_gtab_for(const uint32_t* s_raw) {
+// host emulation of the fixed-base table: 16-bit windows (50 MB), one lazily allocated copy, only the entries a scalar touches are
+// computed (gtab_entry, the slow definition the builder of dkgv.cu is checked against)
+static const uint32_t HE_GTAB_BITS = 16;
+static GTab he_gtab_for(const uint32_t* s_raw) {
   static std::vector<uint32_t> gtab;
-  if (gtab.empty()) gtab.assign(GTAB_WORDS, 0);
+  if (gtab.empty()) gtab.assign(gtab_words(HE_GTAB_BITS), 0);
+  GTab g{gtab.data(), HE_GTAB_BITS, gtab_windows(HE_GTAB_BITS)};
   uint32_t u[8];
   gtab_scalar(u, s_raw);
-  for (int w = 0; w < GTAB_WINDOWS; w++) {
+  for (uint32_t w = 0; w < g.windows; w++) {
     bool ng;
-    uint32_t idx = gtab_index(u, w, &ng);
+    uint32_t idx = gtab_index(g.bits, g.windows, u, w, &ng);
     if (gtab[(size_t)idx * 24] | gtab[(size_t)idx * 24 + 1]) continue;
-    G1Aff e = gtab_entry(idx);
+    G1Aff e = gtab_entry(g.bits, idx);
     for (int i = 0; i < 12; i++) {
       gtab[(size_t)idx * 24 + i] = e.x.l[i];
       gtab[(size_t)idx * 24 + 12 + i] = e.y.l[i];
     }
   }
-  return gtab;
+  return g;
 }
 
 extern "C" {
@@ -100,21 +103,21 @@ uint32_t he_share_check(const uint8_t* vv, uint32_t t, uint32_t id, const uint8_
   // the table entries this scalar touches, computed by the same routine as k_build_gtab
   uint32_t s[8];
   fr_raw_from_be32(s, secret32);
-  std::vector<uint32_t>& gtab = he_gtab_for(s);
+  GTab gtab = he_gtab_for(s);
   g1_compress(g1_to_affine(feldman_eval(view, t, 0, id)), eval48);
-  g1_compress(g1_to_affine(fixed_base_mul(gtab.data(), s)), pk48);
-  uint32_t st = share_check(view, t, 0, id, secret32, gtab.data(), bad);
+  g1_compress(g1_to_affine(fixed_base_mul(gtab, s)), pk48);
+  uint32_t st = share_check(view, t, 0, id, secret32, gtab, bad);
   // the operand-file (vm.cuh) formulation used by the hot kernel must agree
   const uint32_t NT = 4, me = 2;  // pretend to be thread 2 of a 4-thread block
   std::vector<U4> file((size_t)VM_SLOTS * 3 * NT);
   OpFile f{file.data() + me, NT};
-  uint32_t st_vm = vm_share_check(f, view, t, 0, id, secret32, gtab.data(), bad);
+  uint32_t st_vm = vm_share_check(f, view, t, 0, id, secret32, gtab, bad);
   if (st_vm != st) return 0x100 | st_vm;
   vm_feldman_eval(f, view, t, 0, id);
   uint8_t ev2[48];
   g1_compress(g1_to_affine(vm_get_point(f, AX)), ev2);
   if (memcmp(ev2, eval48, 48)) return 0x200;
-  vm_fixed_base_mul(f, gtab.data(), s);
+  vm_fixed_base_mul(f, gtab, s);
   g1_compress(g1_to_affine(vm_get_point(f, BX)), ev2);
   if (memcmp(ev2, pk48, 48)) return 0x300;
   return st;
@@ -319,6 +322,40 @@ void he_sha256(const uint8_t* msg, size_t len, uint8_t* out32) {
   sha_finish(&s, out32);
 }
 
+// G * s through a table of `bits`-bit windows holding just the entries s touches (digit logic for every width the ctx accepts)
+void he_fixed_base_bits(uint32_t bits, const uint8_t* scalar32, uint8_t* out48) {
+  uint32_t s[8], u[8];
+  fr_raw_from_be32(s, scalar32);
+  gtab_scalar(u, s);
+  // a compact table: window w keeps only its one touched entry, the lookup is redirected through a private GTab per window
+  G1Proj acc = g1_identity();
+  const uint32_t W = gtab_windows(bits);
+  for (uint32_t w = 0; w < W; w++) {
+    bool ng;
+    uint32_t idx = gtab_index(bits, W, u, w, &ng);
+    G1Aff e = gtab_entry(bits, idx);
+    if (ng) e.y = neg(e.y);
+    acc = w ? g1_add_mixed_nz(acc, e.x, e.y) : g1_from_affine(e);
+  }
+  g1_compress(g1_to_affine(acc), out48);
+}
+// the table builder's per-thread routines (gtab_base, gtab_fill_run) for the run holding entry (w, m) against gtab_entry: 0 = all
+// GTAB_RUN entries of the run agree
+int he_gtab_builder(uint32_t bits, uint32_t w, uint32_t m) {
+  std::vector<uint32_t> base(48 * (size_t)gtab_windows(bits), 0), tab(24 * (size_t)GTAB_RUN, 0);
+  gtab_base(bits, w, base.data());
+  const uint32_t m0 = m - m % GTAB_RUN;
+  // gtab_fill_run addresses the full table: hand it a pointer offset so that its run lands in `tab`
+  uint32_t* fake = tab.data() - ((size_t)(w << (bits - 1)) + m0) * 24;
+  gtab_fill_run(bits, base.data(), w, m0, fake);
+  int bad = 0;
+  for (uint32_t i = 0; i < GTAB_RUN; i++) {
+    G1Aff e = gtab_entry(bits, (w << (bits - 1)) + m0 + i);
+    for (int k = 0; k < 12; k++) bad += tab[(size_t)i * 24 + k] != e.x.l[k] || tab[(size_t)i * 24 + 12 + k] != e.y.l[k];
+  }
+  return bad;
+}
+
 // prev - j * a mod r through fr_submul_small (canonical 32-byte big-endian in / out)
 static void be32_to_fr(Fr& f, const uint8_t* b) { fr_raw_from_be32(f.l, b); }
 static void fr_to_be32(uint8_t* out32, const Fr& r) {
@@ -423,8 +460,8 @@ void he_coef_bytes_check(const uint8_t* scalars32, const uint8_t* enc48, uint32_
   for (uint32_t i = 0; i < n; i++) {
     uint32_t sc[8];
     fr_raw_from_be32(sc, scalars32 + (size_t)i * 32);
-    std::vector<uint32_t>& gtab = he_gtab_for(sc);
-    same[i] = fd_coef_point(f, gtab.data(), sc, enc48 + (size_t)i * 48, &ys[i], &zs[i]);
+    GTab gtab = he_gtab_for(sc);
+    same[i] = fd_coef_point(f, gtab, sc, enc48 + (size_t)i * 48, &ys[i], &zs[i]);
   }
   for (uint32_t k0 = 0; k0 < n; k0 += FD_SIGN_K) {
     int cnt = (int)std::min<uint32_t>(FD_SIGN_K, n - k0);

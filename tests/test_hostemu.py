@@ -21,7 +21,9 @@ H = bytes.fromhex
 def L():
     path = os.path.join(O.ROOT, "tests", "hostemu", "libhostemu.so")
     src = os.path.join(O.ROOT, "tests", "hostemu", "hostemu.cpp")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    csrc = os.path.join(O.ROOT, "dvt_circuits_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp", ".inc"))]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", path, src])
     return ctypes.CDLL(path)
 
@@ -111,6 +113,14 @@ def test_share_check_all_formulations(L):
     for s in edge + [rnd.randrange(B.R) for _ in range(24)]:
         L.he_share_check(b"", 0, 1, s.to_bytes(32, "big"), ev, pk)
         assert pk.raw == B.g1_compress(B.g1_mul(B.G1, s)), hex(s)
+    # every window width a ctx accepts (dkgv_ctx_create_ex): the digit extraction crosses limb boundaries differently for each
+    for bits in range(8, 27):
+        for s in [0, 1, 2, B.R - 1, B.R - 2, (1 << 254) - 1, int("55" * 32, 16) % B.R, rnd.randrange(B.R), rnd.randrange(B.R)]:
+            L.he_fixed_base_bits(bits, s.to_bytes(32, "big"), pk)
+            assert pk.raw == B.g1_compress(B.g1_mul(B.G1, s)), (bits, hex(s))
+    # the table builder (one small multiplication, a walk of mixed additions, one inversion per run) against the definition
+    for bits, w, m in [(8, 0, 0), (8, 31, 127), (13, 5, 4000), (16, 15, 32767), (22, 11, (1 << 21) - 1), (22, 0, 0), (26, 9, (1 << 25) - 5)]:
+        assert L.he_gtab_builder(bits, w, m) == 0, (bits, w, m)
 
 
 def test_tower_pairing_h2c(L):
