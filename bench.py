@@ -92,6 +92,9 @@ def parse():
     ap.add_argument("--t", type=int, default=THRESH)
     ap.add_argument("--cpu-sample", type=int, default=0, help="recipient ids per host thread in the CPU-baseline sample (0 = 24)")
     ap.add_argument("--no-cpu", action="store_true", help="skip every CPU-baseline leg")
+    ap.add_argument("--gtab-bits", type=int, default=26,
+                    help="window width of the fixed-base table of the ctx (dkgv_ctx_create_ex): 26 = 32 GB of the 180 GB, 9 mixed additions per G * s; "
+                         "the library's own default is 22 (2.4 GB, 11)")
     ap.add_argument("--quick", action="store_true", help="main leg only (value, e2e, roofline of the default path): for profiling runs")
     ap.add_argument("--no-peak", action="store_true", help="do not run bench/imad_peak (use the paper peak); for runs under ncu")
     ap.add_argument("--emulate-world", type=int, default=0,
@@ -340,7 +343,7 @@ def run_b200(args):
         raise SystemExit("participants must divide by the number of ranks")
     rows = n // split
 
-    v = dk.Verifier(local)
+    v = dk.Verifier(local, gtab_bits=int(os.environ.get("DKGV_GTAB_BITS", args.gtab_bits)))
     gtab_bits = v.gtab_bits()
     EXEC_FIX_MADDS = (256 + gtab_bits - 1) // gtab_bits - 1
     if world > 1:  # the library owns the collectives; torch.distributed only carries the 128-byte id to the other ranks

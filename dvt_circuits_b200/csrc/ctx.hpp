@@ -49,6 +49,9 @@ struct dkgv_ctx {
   dkgv_host::DevBuf bls_pk, bls_sig, bls_st;           // decoded keys / signatures of a pairing batch
   dkgv_host::DevBuf bls_scratch;                       // Fp12 values the pairing VM parks in global memory
   cudaEvent_t ev_bls0 = nullptr, ev_bls1 = nullptr;    // bracket the pairing kernel
+  // host-buffer share path: the verification vectors are copied on a second stream WHILE the difference tables run; the first kernel
+  // that reads them waits for this event (dkgv_take_vv_wait), nullptr = nothing to wait for
+  cudaEvent_t vv_wait = nullptr, ev_vv = nullptr, ev_sh = nullptr;
   bool bls_recorded = false, pvm_attr_set = false;
   int bls_path = 0, last_bls_path = 0;                 // enum dkgv_bls_path
   // communicator (comm.cu): NCCL, one process per GPU

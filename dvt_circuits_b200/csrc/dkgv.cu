@@ -244,7 +244,9 @@ extern "C" int dkgv_ctx_create_ex(int device, uint32_t gtab_bits, dkgv_ctx** out
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_hot0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_hot1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_dec0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_dec1)) != cudaSuccess ||
-      (e = cudaEventCreate(&ctx->ev_bls0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_bls1)) != cudaSuccess)
+      (e = cudaEventCreate(&ctx->ev_bls0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_bls1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_vv, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_sh, cudaEventDisableTiming)) != cudaSuccess)
     return bail("cudaEventCreate", e);
   // fixed-base table: the window width asked for (0 = DKGV_GTAB_BITS from the environment, else the default), stepping down while the
   // device cannot hold it
@@ -317,6 +319,8 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
   if (ctx->ev_dec1) cudaEventDestroy(ctx->ev_dec1);
   if (ctx->ev_bls0) cudaEventDestroy(ctx->ev_bls0);
   if (ctx->ev_bls1) cudaEventDestroy(ctx->ev_bls1);
+  if (ctx->ev_vv) cudaEventDestroy(ctx->ev_vv);
+  if (ctx->ev_sh) cudaEventDestroy(ctx->ev_sh);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;  // every DevBuf member frees its allocation (ctx.hpp)
 }
@@ -464,6 +468,16 @@ static int share_matrix_horner(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32
 // ceremony, verification.rs:50-66,129) allow the consistency shortcut and, behind it, t Horner evaluations + finite differences
 // per dealer.  Whether the ids are such a permutation is decided ON THE DEVICE (flags[0]) while the shortcut already runs
 // speculatively; whether any dealer group still needs the evaluation is flags[1].  share_finish acts on the two words.
+// the stream's next kernel reads the verification vectors: wait for their copy if one is in flight (dkgv_share_matrix_verify)
+int dkgv_take_vv_wait(dkgv_ctx* ctx, cudaStream_t s) {
+  if (ctx->vv_wait) {
+    cudaEvent_t ev = ctx->vv_wait;
+    ctx->vv_wait = nullptr;
+    CK(cudaStreamWaitEvent(s, ev, 0));
+  }
+  return 0;
+}
+
 static int share_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,
                         const uint8_t* d_shares, uint8_t* d_status, uint32_t* d_flags, cudaStream_t s) {
   dkgv_ctx::ShareJob& job = ctx->job;
@@ -482,6 +496,7 @@ static int share_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, c
     job.fd = plan.cost_fd != ~0ull && (plan.use || ctx->share_path == DKGV_SHARE_PATH_FDIFF);
   }
   if (!job.fd) {  // nothing to speculate on: the whole Horner route is queued now
+    if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;
     CK(cudaMemsetAsync(job.d_flags, 0, 8, s));
     return share_matrix_horner(ctx, n_d, n_r, t, d_vv, d_ids, d_shares, d_status, s);
   }
@@ -567,12 +582,22 @@ extern "C" int dkgv_share_matrix_verify(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_
   CK(ctx->in_b.reserve(idb));
   CK(ctx->in_c.reserve(shb));
   CK(ctx->out_a.reserve(stb));
-  if (vvb) CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+  // ids and shares first; the verification vectors follow on a second stream, so the share half of the default path (limbs, difference
+  // tables) runs under their copy - the first kernel that reads them waits for ev_vv (dkgv_take_vv_wait)
   CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ctx->in_c.p, shares, shb, cudaMemcpyHostToDevice, s));
+  if (vvb) {
+    cudaStream_t s2 = ctx->fd_streams[0];
+    CK(cudaEventRecord(ctx->ev_sh, s));
+    CK(cudaStreamWaitEvent(s2, ctx->ev_sh, 0));
+    CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s2));
+    CK(cudaEventRecord(ctx->ev_vv, s2));
+    ctx->vv_wait = ctx->ev_vv;
+  }
   if (int rc = share_submit(ctx, n_d, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, (const uint8_t*)ctx->in_c.p,
                             (uint8_t*)ctx->out_a.p, nullptr, s))
     return rc;
+  if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;  // (a path that never read them: the copy still ends before the call returns)
   // the verdicts and the two flag words come back together: ONE synchronisation when the shortcut settled the ceremony
   CK(cudaMemcpyAsync(status, ctx->out_a.p, stb, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ctx->h_job_flags, ctx->job.d_flags, 8, cudaMemcpyDeviceToHost, s));

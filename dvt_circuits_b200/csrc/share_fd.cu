@@ -433,6 +433,8 @@ bool dkgv_fd_shortcut_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t) {
 // Queues, WITHOUT synchronising: cols from the device ids (flags[0] = ids are not a permutation of 1..n_r) and, when `shortcut`,
 // the consistency shortcut over all dealers - verdict OK written for every dealer group that met the three conditions,
 // need_group / flags[1] = the dealers that did not.  Without the shortcut flags[1] = 1: everything is still pending.
+int dkgv_take_vv_wait(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
+
 int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
                    uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s) {
   const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
@@ -442,6 +444,8 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   uint8_t* poly_ok = (uint8_t*)ctx->fd_flags.p;
   uint8_t* need_group = poly_ok + n_pad;
   uint8_t* state = need_group + groups;  // [n_pad] dealer states of the repair route; behind it ok2 [n_pad], deg / cnt [n_pad] u32, counter
+  if (!shortcut)
+    if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;
   CK(cudaEventRecord(ctx->ev_sc[0], s));
   CK(cudaEventRecord(ctx->ev_hot0, s));
   const uint32_t prep_n = std::max(n_r, n_pad);
@@ -473,6 +477,7 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
       k_fd_difftab<<<n_here, nt, (size_t)nt * 72 + (size_t)t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
                                                                n_r, t, nullptr, nullptr);
       if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
+      if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;
       k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
                                                              n_d, n_cols, t, nullptr, nullptr);
       if (first) CK(cudaEventRecord(ctx->ev_sc[2], s));
@@ -526,21 +531,18 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     ctx->launches++;
   }
   const uint32_t* tab_u = (const uint32_t*)ctx->rs_tab.p;
-  const uint32_t* tab_inv = tab_u + (size_t)n_r * 8;
   const uint32_t* tab_pw = tab_u + (size_t)2 * n_r * 8;
   const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
-  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 164 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32;
+  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 128 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32;
   const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
   CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
   CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
   CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
-  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)t * 36 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32) + 256));
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32) + 256));
   uint8_t* w = (uint8_t*)ctx->rs_work.p;
   uint32_t* syn = (uint32_t*)w;
   uint32_t* lam = syn + (size_t)chunk * nsyn * 8;
-  uint32_t* newt = lam + (size_t)chunk * (tau + 1) * 8;
-  uint32_t* nodes = newt + (size_t)chunk * t * 8;
-  uint8_t* err = (uint8_t*)(nodes + (size_t)chunk * t);
+  uint8_t* err = (uint8_t*)(lam + (size_t)chunk * (tau + 1) * 8);
   uint8_t* oor = err + (size_t)chunk * n_r;
   CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
   CK(cudaMemsetAsync(ok2, 0, n_pad, s));
@@ -548,12 +550,11 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   if (!attr) {
     CK(cudaFuncSetAttribute(k_rs_syndromes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
     CK(cudaFuncSetAttribute(k_rs_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (2048 + 1024 + 40) * 32));
-    CK(cudaFuncSetAttribute(k_rs_divdiff, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 68 + 2048 * 32 + 256));
-    CK(cudaFuncSetAttribute(k_rs_correct, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 + 2048 * 4));
+    CK(cudaFuncSetAttribute(k_rs_forney, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 1024 + 2) * 32 + 2048 * 4));
     attr = true;
   }
   const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32, batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
-  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u), dd_threads = (t + 31) & ~31u;
+  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u);
   const unsigned gy = (n_r + 127) / 128;
   for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
     const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
@@ -562,8 +563,8 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)n_r * 32, s>>>((const uint32_t*)ctx->fd_sl.p, state, tab_u, tab_pw, syn, d0, n_r, nsyn);
     k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, d0, nsyn, tau);
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
-    k_rs_divdiff<<<n_here, dd_threads, (size_t)t * 68 + (size_t)n_r * 32 + 256, s>>>((const uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, tab_inv, nodes, newt, d0, n_r, t);
-    k_rs_correct<<<n_here, 256, (size_t)t * 32 + (size_t)n_r * 4, s>>>((uint32_t*)ctx->fd_sl.p, err, state, nodes, newt, d0, n_r, t);
+    k_rs_forney<<<n_here, 256, ((size_t)4 * tau + 2) * 32 + (size_t)n_r * 4, s>>>((uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, syn, lam, tab_u, d0, n_r,
+                                                                                  nsyn, tau);
     CK(cudaMemsetAsync(n_cand, 0, 4, s));
     k_rs_stage<<<(n_here + 127) / 128, 128, 0, s>>>(state, ok2, cand, n_cand, d0, n_here);
     // second pass of the exact conditions on the corrected table: t-th differences + coefficients, compress(G * p_k) == C_k
@@ -574,7 +575,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
                                                            cand, n_cand);
     k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, ok2, d0, n_d, n_cols, t, cand, n_cand);
     k_rs_verdicts<<<dim3(n_here, gy), 128, 0, s>>>(d_status, err, oor, ok2, poly_ok, state, cols, repaired, d0, n_r);
-    ctx->launches += 11;
+    ctx->launches += 10;
   }
   CK(cudaMemsetAsync(need_group, 0, groups, s));
   CK(cudaMemsetAsync(d_flags + 1, 0, 4, s));

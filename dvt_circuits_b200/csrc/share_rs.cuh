@@ -5,12 +5,11 @@
 //   k_rs_syndromes   S_j = sum_i u_i r_i i^j, j < n - t          (u_i = 1 / prod_{k != i} (i - k): the dual code's weights)
 //   k_rs_bm          inversion-free Berlekamp-Massey on S -> error locator Lambda, degree L = number of wrong shares
 //   k_rs_chien       the positions x with Lambda*(x) = sum_k Lambda_k x^(L-k) = 0
-//   k_rs_divdiff     Newton's divided differences through the first t shares that are NOT located as wrong
-//   k_rs_correct     p(x) at the located positions (Horner in the Newton basis) replaces the wrong values in the share table
+//   k_rs_forney      the error values at the located positions by Forney's formula; share - error replaces the wrong values in the table
 // after which the SAME exact conditions as for an honest dealer are checked on the corrected table - the t-th differences of all n
 // values vanish (k_fd_difftab, which also yields the monomial coefficients) and compress(G * p_k) == C_k for every k
 // (k_fd_coefpoint / k_fd_coefsign).  Only then the verdicts are written: located position with p(x) != share -> SHARE_MISMATCH, every
-// other share OK.  The decoder merely PROPOSES p; exactness rests on the two conditions, as for the honest path: p equals the
+// other share OK.  The decoder merely PROPOSES the corrected table; exactness rests on the two conditions, as for the honest path: p equals the
 // committed polynomial, so a share is valid iff it equals p(x).  A dealer the decoder cannot repair (more than tau wrong shares,
 // or a proposal that fails a condition) goes to the evaluation as before.  verify_seed_exchange_commitment
 // (crates/dkg/src/verification.rs:68-149) per share, unchanged verdicts; no randomness anywhere.
@@ -186,135 +185,75 @@ k_rs_chien(const uint32_t* __restrict__ lam, const uint32_t* __restrict__ deg, c
   if (root) atomicAdd(&cnt[d0 + dl], 1u);
 }
 
-// Newton's divided differences through the first t positions that are not located as wrong: one block per dealer, thread k owns
-// entry k.  out: nodes[dl][k] = x_k, newt[dl][k] = f[x_0 .. x_k] (Montgomery).  The located count must equal the locator's degree.
-// The table 1 / d of the shape is staged in shared memory (every round needs one entry per thread, picked by a node distance).
-__global__ void __launch_bounds__(1024)
-k_rs_divdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ err, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ deg,
-             uint8_t* __restrict__ state, const uint32_t* __restrict__ inv, uint32_t* __restrict__ nodes, uint32_t* __restrict__ newt, uint32_t d0,
-             uint32_t n_r, uint32_t t) {
-  extern __shared__ uint32_t rs_sm[];  // A[2][t][8], INV[n_r][8], node[t], wsum[33]
-  const uint32_t dl = blockIdx.x, k = threadIdx.x, nthr = blockDim.x;
-  if (state[d0 + dl] != RS_REPAIR) return;
-  if (cnt[d0 + dl] != deg[d0 + dl]) {  // the locator does not split over 1..n: not a correctable error pattern
-    if (k == 0) state[d0 + dl] = RS_FAILED;
-    return;
-  }
-  Fr* A0 = (Fr*)rs_sm;
-  Fr* A1 = A0 + t;
-  Fr* INV = A1 + t;
-  uint32_t* node = (uint32_t*)(INV + n_r);
-  uint32_t* wsum = node + t;
-  for (uint32_t i = k; i < n_r; i += nthr) INV[i] = fr_load(inv + (size_t)i * 8);
-  // compaction of the positions not located as wrong (ascending), a block-wide scan over chunks of blockDim positions
-  uint32_t base_cnt = 0;
-#pragma unroll 1
-  for (uint32_t base = 0; base < n_r; base += nthr) {
-    const uint32_t x = base + k;
-    const bool good = x < n_r && !err[(size_t)dl * n_r + x];
-    const uint32_t bal = __ballot_sync(0xffffffffu, good), lane = k & 31, warp = k >> 5;
-    const uint32_t before = __popc(bal & ((1u << lane) - 1u));
-    __syncthreads();
-    if (lane == 0) wsum[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t off = base_cnt, total = 0;
-    for (uint32_t w = 0; w < (nthr >> 5); w++) {
-      const uint32_t c = wsum[w];
-      if (w < warp) off += c;
-      total += c;
-    }
-    if (good && off + before < t) node[off + before] = x + 1;
-    base_cnt += total;
-  }
-  __syncthreads();
-  if (base_cnt < t) {
-    if (k == 0) state[d0 + dl] = RS_FAILED;
-    return;
-  }
-  uint32_t xk = k < t ? node[k] : 0;
-  if (k < t) A0[k] = to_mont(fr_load(sl + ((size_t)dl * n_r + xk - 1) * 8));
-  __syncthreads();
-  Fr* cur = A0;
-  Fr* nxt = A1;
-#pragma unroll 1
-  for (uint32_t j = 1; j < t; j++) {
-    if (k < t) {
-      Fr v = cur[k];
-      if (k >= j) v = mul(sub(v, cur[k - 1]), INV[xk - node[k - j]]);
-      nxt[k] = v;
-    }
-    __syncthreads();
-    Fr* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
-  }
-  if (k < t) {
-    fr_store(newt + ((size_t)dl * t + k) * 8, cur[k]);
-    nodes[(size_t)dl * t + k] = xk;
-  }
-}
-
-// The located positions: p(x) in the Newton basis, one WARP per position.  Lane l owns the l-th run of ceil(t / 32) basis terms:
-// its partial sum S_l = sum_k a_k prod_{m in run, m < k} (x - x_m) and the run's product P_l; p(x) = sum_l (P_0 ... P_{l-1}) S_l by a
-// warp scan.  p(x) != share: the table gets the corrected value (err stays 1); p(x) == share: the locator was wrong about this
-// position (err <- 0; the second pass then decides about the dealer, exactly).  block = one dealer, 8 warps.
+// Forney's formula: the VALUES of the located errors straight from the syndromes and the locator, no interpolation.  With
+// S(z) = sum_j S_j z^j = sum_i Y_i / (1 - X_i z) (Y_i = u_i eps_i, X_i the wrong positions, eps_i = share - p(X_i)) and
+// Lambda(z) = lambda_0 prod_i (1 - X_i z):  Omega(z) = S(z) Lambda(z) mod z^L,  Y_i = -X_i Omega(1 / X_i) / Lambda'(1 / X_i).  Both sides are
+// evaluated through their reversed polynomials (the common factor X_i^-(L-1) cancels - no inverse of a position is needed):
+//   Om*(x) = sum_{k < L} Omega_k x^(L-1-k),  Omega_k = sum_{m <= k} Lambda_m S_{k-m};      D*(x) = sum_{1 <= k <= L} k Lambda_k x^(L-k)
+//   eps_i = -X_i Om*(X_i) / (D*(X_i) u_i),   corrected share = share - eps_i.
+// One block per dealer under repair, one thread per coefficient / per error: O(L^2) products + one inversion per error, against the
+// O(t^2) of an interpolation through t good shares.  The located count must equal the locator's degree.  eps_i == 0: the locator was
+// wrong about this position (err <- 0; the second pass then decides about the dealer, exactly).  A vanishing D*(X_i) (a repeated
+// root) -> RS_FAILED.
 __global__ void __launch_bounds__(256)
-k_rs_correct(uint32_t* __restrict__ sl, uint8_t* __restrict__ err, const uint8_t* __restrict__ state, const uint32_t* __restrict__ nodes,
-             const uint32_t* __restrict__ newt, uint32_t d0, uint32_t n_r, uint32_t t) {
-  extern __shared__ uint32_t rs_sm[];  // NM[t][8] (nodes in Montgomery form), list[n_r]
-  __shared__ uint32_t n_err;
-  const uint32_t dl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+k_rs_forney(uint32_t* __restrict__ sl, uint8_t* __restrict__ err, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ deg,
+            uint8_t* __restrict__ state, const uint32_t* __restrict__ syn, const uint32_t* __restrict__ lam, const uint32_t* __restrict__ u,
+            uint32_t d0, uint32_t n_r, uint32_t nsyn, uint32_t tau) {
+  extern __shared__ uint32_t rs_sm[];  // LAM[tau + 1], SY[tau], OM[tau], DL[tau + 1], list[n_r]
+  __shared__ uint32_t n_err, failed;
+  const uint32_t dl = blockIdx.x, tid = threadIdx.x;
   if (state[d0 + dl] != RS_REPAIR) return;
-  Fr* NM = (Fr*)rs_sm;
-  uint32_t* list = (uint32_t*)(NM + t);
-  if (tid == 0) n_err = 0;
+  const uint32_t L = deg[d0 + dl];
+  if (cnt[d0 + dl] != L || L == 0 || L > tau) {  // the locator does not split over 1..n: not a correctable error pattern
+    if (tid == 0) state[d0 + dl] = RS_FAILED;
+    return;
+  }
+  Fr* LAM = (Fr*)rs_sm;
+  Fr* SY = LAM + (tau + 1);
+  Fr* OM = SY + tau;
+  Fr* DL = OM + tau;
+  uint32_t* list = (uint32_t*)(DL + (tau + 1));
+  if (tid == 0) n_err = 0, failed = 0;
+  for (uint32_t k = tid; k <= L; k += blockDim.x) {
+    Fr l = fr_load(lam + ((size_t)dl * (tau + 1) + k) * 8);
+    LAM[k] = l;
+    DL[k] = mul(l, fr_from_small(k));
+  }
+  for (uint32_t k = tid; k < L; k += blockDim.x) SY[k] = fr_load(syn + ((size_t)dl * nsyn + k) * 8);
   __syncthreads();
-  for (uint32_t i = tid; i < t; i += blockDim.x) NM[i] = fr_from_small(nodes[(size_t)dl * t + i]);
   for (uint32_t x = tid; x < n_r; x += blockDim.x)
     if (err[(size_t)dl * n_r + x]) list[atomicAdd(&n_err, 1u)] = x;
-  __syncthreads();
-  const uint32_t run = (t + 31) / 32, k0 = lane * run, k1 = k0 + run < t ? k0 + run : t;
-  const uint32_t* ap = newt + (size_t)dl * t * 8;
+  for (uint32_t k = tid; k < L; k += blockDim.x) {
+    Fr a = zero<FrParams>();
 #pragma unroll 1
-  for (uint32_t e = warp; e < n_err; e += blockDim.x >> 5) {
-    const uint32_t xi = list[e];
-    const Fr xm = fr_from_small(xi + 1);
-    Fr S = zero<FrParams>(), P = one<FrParams>();
-#pragma unroll 1
-    for (uint32_t k = k0; k < k1; k++) {
-      S = add(S, mul(fr_load(ap + (size_t)k * 8), P));
-      P = mul(P, sub(xm, NM[k]));
-    }
-    // inclusive scan of the run products, then the exclusive prefix times the run's sum
-    Fr pre = P;
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-      Fr o;
-#pragma unroll
-      for (int l = 0; l < 8; l++) o.l[l] = __shfl_up_sync(0xffffffffu, pre.l[l], off);
-      if ((int)lane >= off) pre = mul(pre, o);
-    }
-    Fr excl;
-#pragma unroll
-    for (int l = 0; l < 8; l++) excl.l[l] = __shfl_up_sync(0xffffffffu, pre.l[l], 1);
-    if (lane == 0) excl = one<FrParams>();
-    Fr v = mul(excl, S);
-#pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-      Fr o;
-#pragma unroll
-      for (int l = 0; l < 8; l++) o.l[l] = __shfl_down_sync(0xffffffffu, v.l[l], off);
-      v = add(v, o);
-    }
-    if (lane == 0) {
-      Fr c = from_mont(v);
-      uint32_t* s = sl + ((size_t)dl * n_r + xi) * 8;
-      if (eq(c, fr_load(s)))
-        err[(size_t)dl * n_r + xi] = 0;
-      else
-        fr_store(s, c);
-    }
+    for (uint32_t m = 0; m <= k; m++) a = add(a, mul(LAM[m], SY[k - m]));
+    OM[k] = a;
   }
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t e = tid; e < n_err; e += blockDim.x) {
+    const uint32_t xi = list[e];
+    const Fr x = fr_from_small(xi + 1);
+    Fr om = zero<FrParams>(), dd = zero<FrParams>();
+#pragma unroll 1
+    for (uint32_t k = 0; k < L; k++) {
+      om = add(mul(om, x), OM[k]);
+      dd = add(mul(dd, x), DL[k + 1]);
+    }
+    const Fr den = mul(dd, fr_load(u + (size_t)xi * 8));
+    if (is_zero(den)) {
+      failed = 1;
+      continue;
+    }
+    const Fr eps = from_mont(neg(mul(mul(x, om), fr_inverse(den))));
+    uint32_t* sp = sl + ((size_t)dl * n_r + xi) * 8;
+    if (is_zero(eps))
+      err[(size_t)dl * n_r + xi] = 0;
+    else
+      fr_store(sp, sub(fr_load(sp), eps));  // canonical residues: the modular subtraction does not care about the form
+  }
+  __syncthreads();
+  if (failed && tid == 0) state[d0 + dl] = RS_FAILED;
 }
 
 // after the correction: the dealers under repair become candidates of the second pass (ok2 = 1, listed in cand[0 .. *n_cand)),
