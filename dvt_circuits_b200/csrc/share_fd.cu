@@ -522,26 +522,28 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   uint32_t* repaired = cnt + n_pad;
   uint32_t* n_cand = repaired + 1;
   uint32_t* cand = n_cand + 3;  // [n_pad] dealers (chunk-local) of the second pass, compacted
-  if (ctx->rs_n != n_r || ctx->rs_t != t) {  // tables of the shape: dual weights, 1 / d, powers (11 MB at (1024, 683))
-    CK(ctx->rs_tab.reserve(((size_t)2 * n_r + (size_t)n_r * nsyn) * 32));
-    k_rs_tables<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, nsyn, (uint32_t*)ctx->rs_tab.p, (uint32_t*)ctx->rs_tab.p + (size_t)n_r * 8,
-                                                 (uint32_t*)ctx->rs_tab.p + (size_t)2 * n_r * 8);
+  if (ctx->rs_n != n_r || ctx->rs_t != t) {  // tables of the shape: dual weights u[n], syndrome matrix mt[nsyn][nsyn] (3.7 MB at (1024, 683)), scratch
+    CK(ctx->rs_tab.reserve(((size_t)n_r + (size_t)nsyn * nsyn + (size_t)3 * nsyn) * 32));
+    uint32_t* tab = (uint32_t*)ctx->rs_tab.p;
+    k_rs_tables<<<(n_r + 127) / 128, 128, 0, s>>>(n_r, tab);
+    k_rs_mtab<<<1, 1024, 0, s>>>(n_r, nsyn, tab + (size_t)n_r * 8, tab + ((size_t)n_r + (size_t)nsyn * nsyn) * 8);
     ctx->rs_n = n_r;
     ctx->rs_t = t;
-    ctx->launches++;
+    ctx->launches += 2;
   }
   const uint32_t* tab_u = (const uint32_t*)ctx->rs_tab.p;
-  const uint32_t* tab_pw = tab_u + (size_t)2 * n_r * 8;
+  const uint32_t* tab_mt = tab_u + (size_t)n_r * 8;
   const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
-  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 128 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32;
+  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 128 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32;
   const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
   CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
   CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
   CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
-  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)nsyn * 32 + (size_t)(tau + 1) * 32) + 256));
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32) + 256));
   uint8_t* w = (uint8_t*)ctx->rs_work.p;
   uint32_t* syn = (uint32_t*)w;
-  uint32_t* lam = syn + (size_t)chunk * nsyn * 8;
+  uint32_t* gdf = syn + (size_t)chunk * nsyn * 8;
+  uint32_t* lam = gdf + (size_t)chunk * nsyn * 8;
   uint8_t* err = (uint8_t*)(lam + (size_t)chunk * (tau + 1) * 8);
   uint8_t* oor = err + (size_t)chunk * n_r;
   CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
@@ -549,6 +551,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(k_rs_syndromes, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 32));
+    CK(cudaFuncSetAttribute(k_rs_gdiff, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 9 * 1024 * 4));
     CK(cudaFuncSetAttribute(k_rs_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (2048 + 1024 + 40) * 32));
     CK(cudaFuncSetAttribute(k_rs_forney, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 1024 + 2) * 32 + 2048 * 4));
     attr = true;
@@ -560,7 +563,8 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
     // the share table of this chunk again (chunks of a large session share the buffers), now with the out-of-range marks
     k_fd_share_limbs<<<dim3(gy, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, oor, d0, n_cols, n_d, n_r);
-    k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)n_r * 32, s>>>((const uint32_t*)ctx->fd_sl.p, state, tab_u, tab_pw, syn, d0, n_r, nsyn);
+    k_rs_gdiff<<<n_here, nt, (size_t)nt * 72, s>>>((const uint32_t*)ctx->fd_sl.p, state, gdf, d0, n_r, t, nsyn);
+    k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, tab_mt, syn, d0, nsyn);
     k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, d0, nsyn, tau);
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
     k_rs_forney<<<n_here, 256, ((size_t)4 * tau + 2) * 32 + (size_t)n_r * 4, s>>>((uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, syn, lam, tab_u, d0, n_r,
@@ -575,7 +579,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
                                                            cand, n_cand);
     k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, ok2, d0, n_d, n_cols, t, cand, n_cand);
     k_rs_verdicts<<<dim3(n_here, gy), 128, 0, s>>>(d_status, err, oor, ok2, poly_ok, state, cols, repaired, d0, n_r);
-    ctx->launches += 10;
+    ctx->launches += 11;
   }
   CK(cudaMemsetAsync(need_group, 0, groups, s));
   CK(cudaMemsetAsync(d_flags + 1, 0, 4, s));

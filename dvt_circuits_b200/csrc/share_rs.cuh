@@ -2,7 +2,8 @@
 // evaluation in the exponent right away.  The shares of a dealer are a Reed-Solomon codeword over Fr (evaluations of a polynomial
 // of degree < t at the n points 1..n) with errors; as long as at most tau = floor((n - t) / 2) of them are wrong the committed
 // polynomial is recovered by scalar arithmetic alone:
-//   k_rs_syndromes   S_j = sum_i u_i r_i i^j, j < n - t          (u_i = 1 / prod_{k != i} (i - k): the dual code's weights)
+//   k_rs_gdiff / k_rs_syndromes   S_j = sum_i u_i r_i i^j, j < n - t (u_i = 1 / prod_{k != i} (i - k): the dual code's weights), out of the
+//                    difference table of the shares carried on to order n - 1 and a fixed triangular matrix of the shape
 //   k_rs_bm          inversion-free Berlekamp-Massey on S -> error locator Lambda, degree L = number of wrong shares
 //   k_rs_chien       the positions x with Lambda*(x) = sum_k Lambda_k x^(L-k) = 0
 //   k_rs_forney      the error values at the located positions by Forney's formula; share - error replaces the wrong values in the table
@@ -52,10 +53,8 @@ DKGV_HD void fr_store(uint32_t* p, const Fr& v) {
 #if defined(__CUDACC__)
 using namespace dkgv;
 
-// tables of a shape (n, t), Montgomery form: u[i] (i = 0..n-1 for the point x = i + 1), inv[d] = 1 / d (d = 1..n-1; inv[0] unused),
-// pw[i][j] = (i + 1)^j for j < n - t
-__global__ void __launch_bounds__(128)
-k_rs_tables(uint32_t n, uint32_t nsyn, uint32_t* __restrict__ u, uint32_t* __restrict__ inv, uint32_t* __restrict__ pw) {
+// table of a shape (n, t), Montgomery form: u[i] = 1 / prod_{k != i} (x_i - x_k) for the point x_i = i + 1 (the dual code's weights)
+__global__ void __launch_bounds__(128) k_rs_tables(uint32_t n, uint32_t* __restrict__ u) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // prod_{k != x} (x - k) = (x-1)! * (-1)^(n-x) (n-x)!,  x = i + 1
@@ -64,31 +63,100 @@ k_rs_tables(uint32_t n, uint32_t nsyn, uint32_t* __restrict__ u, uint32_t* __res
   for (uint32_t k = 2; k <= n - 1 - i; k++) a = mul(a, fr_from_small(k));
   if ((n - 1 - i) & 1) a = neg(a);
   fr_store(u + (size_t)i * 8, fr_inverse(a));
-  fr_store(inv + (size_t)i * 8, i ? fr_inverse(fr_from_small(i)) : zero<FrParams>());
-  Fr x = fr_from_small(i + 1), p = one<FrParams>();
+}
+
+// The syndromes come out of the DIFFERENCE TABLE of the shares, not out of n (n - t) products per dealer.  With the weights above
+//   S_j = sum_i u_i r_i x_i^j = Delta^(n-1)[x^j r(x)](1) / (n-1)!
+// (u_i = (-1)^(n-i) C(n-1, i-1) / (n-1)!), and by the Leibniz rule for differences, x^j having degree j < n - t,
+//   S_j = sum_{k <= j} M[j][k] G_k,   G_k = Delta^(n-1-k) r(1 + k),   M[j][k] = C(n-1, k) Delta^k[x^j](1) / (n-1)!.
+// G_k is the LAST entry of the table after n - 1 - k rounds - orders t .. n-1, i.e. the table of condition (2) simply carried on
+// (k_rs_gdiff: (n - t)^2 / 2 more subtractions) - and M is a fixed triangular matrix of the shape: (n - t)^2 / 2 products per
+// dealer instead of n (n - t).
+// k_rs_mtab: A(j, k) = Delta^k[x^j](1) by A(j+1, k) = (1 + k) A(j, k) + k A(j, k-1), A(0, 0) = 1, one block, thread(s) per k, a
+// round per j; out mt[k][j] (k-major: a thread per j reads consecutive words), Montgomery form, entries k > j are never read.
+__global__ void __launch_bounds__(1024) k_rs_mtab(uint32_t n, uint32_t nsyn, uint32_t* __restrict__ mt, uint32_t* __restrict__ scratch) {
+  // scratch: A[2][nsyn] (global, double-buffered), cf[nsyn]
+  Fr* A0 = (Fr*)scratch;
+  Fr* A1 = A0 + nsyn;
+  Fr* cf = A1 + nsyn;
+  for (uint32_t k = threadIdx.x; k < nsyn; k += blockDim.x) {
+    // C(n-1, k) / (n-1)! = 1 / (k! (n-1-k)!)
+    Fr a = one<FrParams>();
+    for (uint32_t m = 2; m <= k; m++) a = mul(a, fr_from_small(m));
+    for (uint32_t m = 2; m <= n - 1 - k; m++) a = mul(a, fr_from_small(m));
+    cf[k] = fr_inverse(a);
+    A0[k] = k == 0 ? one<FrParams>() : zero<FrParams>();
+  }
+  __syncthreads();
+  Fr* cur = A0;
+  Fr* nxt = A1;
+#pragma unroll 1
   for (uint32_t j = 0; j < nsyn; j++) {
-    fr_store(pw + ((size_t)i * nsyn + j) * 8, p);
-    p = mul(p, x);
+    for (uint32_t k = threadIdx.x; k < nsyn; k += blockDim.x) {
+      const Fr a = cur[k];
+      fr_store(mt + ((size_t)k * nsyn + j) * 8, mul(a, cf[k]));
+      Fr v = mul(a, fr_from_small(k + 1));
+      if (k) v = add(v, mul(cur[k - 1], fr_from_small(k)));
+      nxt[k] = v;
+    }
+    __syncthreads();
+    Fr* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
   }
 }
 
-// S_j for the dealers under repair: block = (dealer, 128 syndromes), the weighted shares w_i = u_i r_i staged in shared memory
+// G_k for the dealers under repair: the difference table of k_fd_difftab (same lazy per-thread routines) carried on to order n - 1;
+// the thread that owns the last entry stores it (canonical) after every round r >= t: g[dl][n - 1 - r].  One block per dealer.
+__global__ void __launch_bounds__(1024)
+k_rs_gdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ state, uint32_t* __restrict__ g, uint32_t d0, uint32_t n_r, uint32_t t,
+           uint32_t nsyn) {
+  extern __shared__ uint32_t rs_sm[];  // pub[2][9 * blockDim.x]
+  const uint32_t dl = blockIdx.x, i = threadIdx.x, nt = blockDim.x;
+  if (state[d0 + dl] != RS_REPAIR) return;
+  const uint32_t k0 = 2 * i, k1 = 2 * i + 1, last = n_r - 1;
+  DtPair p;
+  p.a = lz_zero();
+  p.b = lz_zero();
+  const uint32_t* row = sl + (size_t)dl * n_r * 8;
+#pragma unroll
+  for (int l = 0; l < 8; l++) {
+    if (k0 < n_r) p.a.l[l] = row[(size_t)k0 * 8 + l];
+    if (k1 < n_r) p.b.l[l] = row[(size_t)k1 * 8 + l];
+  }
+  uint32_t left = DT1_PERIOD;
+#pragma unroll 1
+  for (uint32_t r = 1; r < n_r; r++) {
+    uint32_t* pr = rs_sm + (size_t)(r & 1) * 9 * nt;
+    if (dt1_publishes(i, r)) lz_publish(pr, nt, i, p.b);
+    __syncthreads();
+    const bool red = --left == 0;
+    if (red) left = DT1_PERIOD;
+    if (dt1_active(i, r)) dt1_step(p, i, r, red, pr, nt);
+    if (r >= t && (k0 == last || k1 == last)) {
+      Lz v = k0 == last ? p.a : p.b;
+      lz_reduce(v, true);
+      fr_store(g + ((size_t)dl * nsyn + (last - r)) * 8, lz_low(v));
+    }
+  }
+}
+
+// S_j = sum_{k <= j} M[j][k] G_k for the dealers under repair: block = (dealer, 128 syndromes), G (to Montgomery form) staged in shared
+// memory; the longest rows first (blockIdx.y counts down)
 __global__ void __launch_bounds__(128)
-k_rs_syndromes(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ state, const uint32_t* __restrict__ u, const uint32_t* __restrict__ pw,
-               uint32_t* __restrict__ syn, uint32_t d0, uint32_t n_r, uint32_t nsyn) {
-  extern __shared__ uint32_t rs_sm[];  // w[n_r][8]
+k_rs_syndromes(const uint32_t* __restrict__ g, const uint8_t* __restrict__ state, const uint32_t* __restrict__ mt, uint32_t* __restrict__ syn,
+               uint32_t d0, uint32_t nsyn) {
+  extern __shared__ uint32_t rs_sm[];  // G[nsyn][8]
   const uint32_t dl = blockIdx.x;
   if (state[d0 + dl] != RS_REPAIR) return;
-  for (uint32_t i = threadIdx.x; i < n_r; i += blockDim.x) {
-    Fr r = to_mont(fr_load(sl + ((size_t)dl * n_r + i) * 8));
-    fr_store(rs_sm + (size_t)i * 8, mul(r, fr_load(u + (size_t)i * 8)));
-  }
+  const uint32_t yb = gridDim.y - 1 - blockIdx.y, jmax = min(nsyn, (yb + 1) * blockDim.x);
+  for (uint32_t k = threadIdx.x; k < jmax; k += blockDim.x) fr_store(rs_sm + (size_t)k * 8, to_mont(fr_load(g + ((size_t)dl * nsyn + k) * 8)));
   __syncthreads();
-  const uint32_t j = blockIdx.y * blockDim.x + threadIdx.x;
+  const uint32_t j = yb * blockDim.x + threadIdx.x;
   if (j >= nsyn) return;
   Fr acc = zero<FrParams>();
 #pragma unroll 1
-  for (uint32_t i = 0; i < n_r; i++) acc = add(acc, mul(fr_load(rs_sm + (size_t)i * 8), fr_load(pw + ((size_t)i * nsyn + j) * 8)));
+  for (uint32_t k = 0; k <= j; k++) acc = add(acc, mul(fr_load(rs_sm + (size_t)k * 8), fr_load(mt + ((size_t)k * nsyn + j) * 8)));
   fr_store(syn + ((size_t)dl * nsyn + j) * 8, acc);
 }
 
