@@ -600,15 +600,19 @@ struct DtPair {
 // such k <=> the n shares lie on a polynomial of degree < t).
 DKGV_HD bool dt1_active(uint32_t i, uint32_t r) { return 2 * i + 1 >= r; }
 DKGV_HD bool dt1_publishes(uint32_t i, uint32_t r) { return 2 * i + 2 >= r; }  // the right neighbour still updates its a
-// `reduce`: r is a multiple of DT1_PERIOD (the caller counts)
-DKGV_HD void dt1_step(DtPair& p, uint32_t i, uint32_t r, bool reduce, const uint32_t* pub, uint32_t nt) {
+// `reduce`: r is a multiple of DT1_PERIOD (the caller counts); left = the left neighbour's published b (read only when 2i >= r, i > 0)
+DKGV_HD void dt1_step_with(DtPair& p, uint32_t i, uint32_t r, bool reduce, const Lz& left) {
   Lz nb = lz_sub(p.b, p.a);
-  if (2 * i >= r && i) p.a = lz_sub(p.a, lz_published(pub, nt, i - 1));  // (i = 0: e[0] never changes; 2i >= r >= 1 excludes it anyway)
+  if (2 * i >= r && i) p.a = lz_sub(p.a, left);  // (i = 0: e[0] never changes; 2i >= r >= 1 excludes it anyway)
   p.b = nb;  // dt1_active(i, r) holds
   if (reduce) {
     lz_reduce(p.a, true);
     lz_reduce(p.b, true);
   }
+}
+DKGV_HD bool dt1_needs_left(uint32_t i, uint32_t r) { return 2 * i >= r && i; }
+DKGV_HD void dt1_step(DtPair& p, uint32_t i, uint32_t r, bool reduce, const uint32_t* pub, uint32_t nt) {
+  dt1_step_with(p, i, r, reduce, dt1_needs_left(i, r) ? lz_published(pub, nt, i - 1) : lz_zero());
 }
 DKGV_HD void dt1_finish(DtPair& p) {  // entries that dropped out between two reductions are still lazy
   lz_reduce(p.a, true);
@@ -620,15 +624,19 @@ DKGV_HD void dt1_finish(DtPair& p) {  // entries that dropped out between two re
 // non-negative; the injected value is dt2_injected(E, t, j - 1) and dt2_finish undoes the sign.
 DKGV_HD bool dt2_active(uint32_t i, uint32_t j, uint32_t t) { return 2 * i <= t - j; }
 DKGV_HD Fr dt2_signed_e(const Fr& e, uint32_t t, uint32_t k) { return ((t - 1 - k) & 1) ? fr_neg_canonical(e) : e; }  // what to store as E'[k]
-// `reduce`: this is the dt2_period(t)-th round since the last reduction (the caller counts; the same for every thread)
-DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, bool reduce, const uint32_t* pub, uint32_t nt, const Fr* Es) {
+// `reduce`: this is the dt2_period(t)-th round since the last reduction (the caller counts; the same for every thread);
+// left = d[2i - 1] before the round: the left neighbour's published b, E'[j - 1] for thread 0
+DKGV_HD void dt2_step_with(DtPair& p, uint32_t j, bool reduce, const Lz& left) {
   Lz nb = lz_muladd_small(p.a, p.b, j);
-  p.a = lz_muladd_small(i ? lz_published(pub, nt, i - 1) : lz_from(Es[j - 1]), p.a, j);
+  p.a = lz_muladd_small(left, p.a, j);
   p.b = nb;
   if (reduce) {
     lz_reduce(p.a, false);
     lz_reduce(p.b, false);
   }
+}
+DKGV_HD void dt2_step(DtPair& p, uint32_t i, uint32_t j, bool reduce, const uint32_t* pub, uint32_t nt, const Fr* Es) {
+  dt2_step_with(p, j, reduce, i ? lz_published(pub, nt, i - 1) : lz_from(Es[j - 1]));
 }
 DKGV_HD void dt2_finish(DtPair& p, uint32_t i, uint32_t t) {  // after the t - 1 rounds: c[k] = (-1)^(k + t - 1) d[k]
   lz_reduce(p.a, false);

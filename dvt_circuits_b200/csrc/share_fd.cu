@@ -539,13 +539,14 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
   CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
   CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
-  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32) + 256));
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + 1 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32) + 256));
   uint8_t* w = (uint8_t*)ctx->rs_work.p;
   uint32_t* syn = (uint32_t*)w;
   uint32_t* gdf = syn + (size_t)chunk * nsyn * 8;
   uint32_t* lam = gdf + (size_t)chunk * nsyn * 8;
   uint8_t* err = (uint8_t*)(lam + (size_t)chunk * (tau + 1) * 8);
   uint8_t* oor = err + (size_t)chunk * n_r;
+  uint8_t* bmdone = oor + (size_t)chunk * n_r;
   CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
   CK(cudaMemsetAsync(ok2, 0, n_pad, s));
   static bool attr = false;
@@ -564,8 +565,16 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     // the share table of this chunk again (chunks of a large session share the buffers), now with the out-of-range marks
     k_fd_share_limbs<<<dim3(gy, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, oor, d0, n_cols, n_d, n_r);
     k_rs_gdiff<<<n_here, nt, (size_t)nt * 72, s>>>((const uint32_t*)ctx->fd_sl.p, state, gdf, d0, n_r, t, nsyn);
-    k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, tab_mt, syn, d0, nsyn);
-    k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, d0, nsyn, tau);
+    // two stages (share_rs.cuh k_rs_bm): few wrong shares per dealer finish on the first RS_STAGE1 syndromes
+    CK(cudaMemsetAsync(bmdone, 0, n_here, s));
+    const uint32_t stage1 = std::min<uint32_t>(RS_STAGE1, nsyn);
+    k_rs_syndromes<<<dim3(n_here, (stage1 + 127) / 128), 128, (size_t)stage1 * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, stage1);
+    k_rs_bm<<<n_here, bm_threads, ((size_t)stage1 + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, stage1, tau);
+    if (stage1 < nsyn) {
+      k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, nsyn);
+      k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, nsyn, tau);
+      ctx->launches += 2;
+    }
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
     k_rs_forney<<<n_here, 256, ((size_t)4 * tau + 2) * 32 + (size_t)n_r * 4, s>>>((uint32_t*)ctx->fd_sl.p, err, cnt, deg, state, syn, lam, tab_u, d0, n_r,
                                                                                   nsyn, tau);

@@ -141,19 +141,19 @@ k_rs_gdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ state, u
   }
 }
 
-// S_j = sum_{k <= j} M[j][k] G_k for the dealers under repair: block = (dealer, 128 syndromes), G (to Montgomery form) staged in shared
-// memory; the longest rows first (blockIdx.y counts down)
+// S_j = sum_{k <= j} M[j][k] G_k, j < rows, for the dealers under repair the first stage of k_rs_bm has not finished: block = (dealer,
+// 128 syndromes), G (to Montgomery form) staged in shared memory; the longest rows first (blockIdx.y counts down)
 __global__ void __launch_bounds__(128)
-k_rs_syndromes(const uint32_t* __restrict__ g, const uint8_t* __restrict__ state, const uint32_t* __restrict__ mt, uint32_t* __restrict__ syn,
-               uint32_t d0, uint32_t nsyn) {
-  extern __shared__ uint32_t rs_sm[];  // G[nsyn][8]
+k_rs_syndromes(const uint32_t* __restrict__ g, const uint8_t* __restrict__ state, const uint8_t* __restrict__ done, const uint32_t* __restrict__ mt,
+               uint32_t* __restrict__ syn, uint32_t d0, uint32_t nsyn, uint32_t rows) {
+  extern __shared__ uint32_t rs_sm[];  // G[rows][8]
   const uint32_t dl = blockIdx.x;
-  if (state[d0 + dl] != RS_REPAIR) return;
-  const uint32_t yb = gridDim.y - 1 - blockIdx.y, jmax = min(nsyn, (yb + 1) * blockDim.x);
+  if (state[d0 + dl] != RS_REPAIR || done[dl]) return;
+  const uint32_t yb = gridDim.y - 1 - blockIdx.y, jmax = min(rows, (yb + 1) * blockDim.x);
   for (uint32_t k = threadIdx.x; k < jmax; k += blockDim.x) fr_store(rs_sm + (size_t)k * 8, to_mont(fr_load(g + ((size_t)dl * nsyn + k) * 8)));
   __syncthreads();
   const uint32_t j = yb * blockDim.x + threadIdx.x;
-  if (j >= nsyn) return;
+  if (j >= rows) return;
   Fr acc = zero<FrParams>();
 #pragma unroll 1
   for (uint32_t k = 0; k <= j; k++) acc = add(acc, mul(fr_load(rs_sm + (size_t)k * 8), fr_load(mt + ((size_t)k * nsyn + j) * 8)));
@@ -188,32 +188,47 @@ __device__ __forceinline__ Fr rs_block_sum(Fr v, Fr* red) {
   return red[nw];
 }
 
+constexpr uint32_t RS_BM_QUIET = 16;
+constexpr uint32_t RS_STAGE1 = 96;  // syndromes of the first stage: finishes dealers with up to (96 - 16) / 2 = 40 wrong shares
 // Inversion-free Berlekamp-Massey, one block per dealer under repair, thread k owns Lambda_k (k <= tau + 1).
 //   d = sum_{k <= L} Lambda_k S_{r-k};  d != 0:  Lambda <- b Lambda - d z^m B  (and, when 2 L <= r: B <- old Lambda, L <- r + 1 - L, b <- d, m <- 1)
 // out: lam[dl][0..tau] (Montgomery), deg[d] = L, or state -> RS_FAILED when L > tau (more wrong shares than the code corrects)
+// Two stages: the first sees only the first `avail` < nsyn syndromes - a dealer with few wrong shares is finished there (done[dl] = 1)
+// and costs neither the long rows of the syndrome product nor the long recurrence; the second (avail == nsyn) takes the rest from the start.
 __global__ void __launch_bounds__(1024)
-k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t* __restrict__ lam, uint32_t* __restrict__ deg, uint32_t d0,
-        uint32_t nsyn, uint32_t tau) {
-  extern __shared__ uint32_t rs_sm[];  // S[nsyn], B[blockDim.x], red[blockDim.x / 32 + 1]
+k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t* __restrict__ lam, uint32_t* __restrict__ deg, uint8_t* __restrict__ done,
+        uint32_t d0, uint32_t nsyn, uint32_t avail, uint32_t tau) {
+  extern __shared__ uint32_t rs_sm[];  // S[avail], B[blockDim.x], red[blockDim.x / 32 + 1]
   const uint32_t dl = blockIdx.x, k = threadIdx.x;
-  if (state[d0 + dl] != RS_REPAIR) return;
+  if (state[d0 + dl] != RS_REPAIR || done[dl]) return;
   Fr* S = (Fr*)rs_sm;
-  Fr* B = S + nsyn;
+  Fr* B = S + avail;
   Fr* red = B + blockDim.x;
-  for (uint32_t j = k; j < nsyn; j += blockDim.x) S[j] = fr_load(syn + ((size_t)dl * nsyn + j) * 8);
+  for (uint32_t j = k; j < avail; j += blockDim.x) S[j] = fr_load(syn + ((size_t)dl * nsyn + j) * 8);
   Fr c = k == 0 ? one<FrParams>() : zero<FrParams>();
   B[k] = c;
   Fr b = one<FrParams>();
   uint32_t L = 0, m = 1;
   __syncthreads();
+  uint32_t quiet = 0;  // consecutive rounds without a discrepancy
+  bool settled = false;
 #pragma unroll 1
-  for (uint32_t r = 0; r < nsyn; r++) {
+  for (uint32_t r = 0; r < avail; r++) {
+    // The locator is final once 2 L syndromes have gone in and the recurrence keeps predicting the next ones; RS_BM_QUIET predicted
+    // syndromes are taken as enough.  Stopping early cannot cost exactness - the decoder only proposes, the second pass decides -
+    // only, against shares crafted to fool the stop, the repair of that dealer (it goes to the evaluation).
+    if (quiet >= RS_BM_QUIET && 2 * L <= r) {
+      settled = true;
+      break;
+    }
     Fr term = (k <= L && k <= r) ? mul(c, S[r - k]) : zero<FrParams>();
     Fr d = rs_block_sum(term, red);
     if (is_zero(d)) {
       m++;
+      quiet++;
       continue;
     }
+    quiet = 0;
     Fr shifted = k >= m ? B[k - m] : zero<FrParams>();
     Fr nc = sub(mul(b, c), mul(d, shifted));
     const bool grow = 2 * L <= r;
@@ -229,6 +244,8 @@ k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t*
     c = nc;
     __syncthreads();
   }
+  if (!settled && avail < nsyn) return;  // first stage, not finished: the second stage decodes this dealer from all the syndromes
+  if (k == 0) done[dl] = 1;
   if (L > tau) {
     if (k == 0) state[d0 + dl] = RS_FAILED;
     return;
