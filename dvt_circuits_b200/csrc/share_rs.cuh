@@ -141,18 +141,18 @@ k_rs_gdiff(const uint32_t* __restrict__ sl, const uint8_t* __restrict__ state, u
   }
 }
 
-// S_j = sum_{k <= j} M[j][k] G_k, j < rows, for the dealers under repair the first stage of k_rs_bm has not finished: block = (dealer,
+// S_j = sum_{k <= j} M[j][k] G_k, row0 <= j < rows, for the dealers under repair the first stage of k_rs_bm has not finished: block = (dealer,
 // 128 syndromes), G (to Montgomery form) staged in shared memory; the longest rows first (blockIdx.y counts down)
 __global__ void __launch_bounds__(128)
 k_rs_syndromes(const uint32_t* __restrict__ g, const uint8_t* __restrict__ state, const uint8_t* __restrict__ done, const uint32_t* __restrict__ mt,
-               uint32_t* __restrict__ syn, uint32_t d0, uint32_t nsyn, uint32_t rows) {
+               uint32_t* __restrict__ syn, uint32_t d0, uint32_t nsyn, uint32_t row0, uint32_t rows) {
   extern __shared__ uint32_t rs_sm[];  // G[rows][8]
   const uint32_t dl = blockIdx.x;
   if (state[d0 + dl] != RS_REPAIR || done[dl]) return;
-  const uint32_t yb = gridDim.y - 1 - blockIdx.y, jmax = min(rows, (yb + 1) * blockDim.x);
+  const uint32_t yb = gridDim.y - 1 - blockIdx.y, jmax = min(rows, row0 + (yb + 1) * blockDim.x);
   for (uint32_t k = threadIdx.x; k < jmax; k += blockDim.x) fr_store(rs_sm + (size_t)k * 8, to_mont(fr_load(g + ((size_t)dl * nsyn + k) * 8)));
   __syncthreads();
-  const uint32_t j = yb * blockDim.x + threadIdx.x;
+  const uint32_t j = row0 + yb * blockDim.x + threadIdx.x;
   if (j >= rows) return;
   Fr acc = zero<FrParams>();
 #pragma unroll 1
@@ -194,26 +194,35 @@ constexpr uint32_t RS_STAGE1 = 96;  // syndromes of the first stage: finishes de
 //   d = sum_{k <= L} Lambda_k S_{r-k};  d != 0:  Lambda <- b Lambda - d z^m B  (and, when 2 L <= r: B <- old Lambda, L <- r + 1 - L, b <- d, m <- 1)
 // out: lam[dl][0..tau] (Montgomery), deg[d] = L, or state -> RS_FAILED when L > tau (more wrong shares than the code corrects)
 // Two stages: the first sees only the first `avail` < nsyn syndromes - a dealer with few wrong shares is finished there (done[dl] = 1)
-// and costs neither the long rows of the syndrome product nor the long recurrence; the second (avail == nsyn) takes the rest from the start.
+// and costs neither the long rows of the syndrome product nor the long recurrence; an unfinished dealer parks its state in `park`
+// (per dealer: blockDim.x x {c, B} then b, then L, m, quiet) and the second stage (first = avail of the first stage, avail == nsyn)
+// resumes from it.
 __global__ void __launch_bounds__(1024)
 k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t* __restrict__ lam, uint32_t* __restrict__ deg, uint8_t* __restrict__ done,
-        uint32_t d0, uint32_t nsyn, uint32_t avail, uint32_t tau) {
+        uint32_t* __restrict__ park, uint32_t d0, uint32_t nsyn, uint32_t first, uint32_t avail, uint32_t tau) {
   extern __shared__ uint32_t rs_sm[];  // S[avail], B[blockDim.x], red[blockDim.x / 32 + 1]
   const uint32_t dl = blockIdx.x, k = threadIdx.x;
   if (state[d0 + dl] != RS_REPAIR || done[dl]) return;
   Fr* S = (Fr*)rs_sm;
   Fr* B = S + avail;
   Fr* red = B + blockDim.x;
+  uint32_t* pk = park + (size_t)dl * ((size_t)blockDim.x * 16 + 16);
   for (uint32_t j = k; j < avail; j += blockDim.x) S[j] = fr_load(syn + ((size_t)dl * nsyn + j) * 8);
   Fr c = k == 0 ? one<FrParams>() : zero<FrParams>();
-  B[k] = c;
   Fr b = one<FrParams>();
-  uint32_t L = 0, m = 1;
+  uint32_t L = 0, m = 1, quiet = 0;  // quiet: consecutive rounds without a discrepancy
+  if (first) {
+    c = fr_load(pk + (size_t)k * 16);
+    B[k] = fr_load(pk + (size_t)k * 16 + 8);
+    b = fr_load(pk + (size_t)blockDim.x * 16);
+    L = pk[(size_t)blockDim.x * 16 + 8], m = pk[(size_t)blockDim.x * 16 + 9], quiet = pk[(size_t)blockDim.x * 16 + 10];
+  } else {
+    B[k] = c;
+  }
   __syncthreads();
-  uint32_t quiet = 0;  // consecutive rounds without a discrepancy
   bool settled = false;
 #pragma unroll 1
-  for (uint32_t r = 0; r < avail; r++) {
+  for (uint32_t r = first; r < avail; r++) {
     // The locator is final once 2 L syndromes have gone in and the recurrence keeps predicting the next ones; RS_BM_QUIET predicted
     // syndromes are taken as enough.  Stopping early cannot cost exactness - the decoder only proposes, the second pass decides -
     // only, against shares crafted to fool the stop, the repair of that dealer (it goes to the evaluation).
@@ -244,7 +253,15 @@ k_rs_bm(const uint32_t* __restrict__ syn, uint8_t* __restrict__ state, uint32_t*
     c = nc;
     __syncthreads();
   }
-  if (!settled && avail < nsyn) return;  // first stage, not finished: the second stage decodes this dealer from all the syndromes
+  if (!settled && avail < nsyn) {  // first stage, not finished: the second stage resumes here with all the syndromes
+    fr_store(pk + (size_t)k * 16, c);
+    fr_store(pk + (size_t)k * 16 + 8, B[k]);
+    if (k == 0) {
+      fr_store(pk + (size_t)blockDim.x * 16, b);
+      pk[(size_t)blockDim.x * 16 + 8] = L, pk[(size_t)blockDim.x * 16 + 9] = m, pk[(size_t)blockDim.x * 16 + 10] = quiet;
+    }
+    return;
+  }
   if (k == 0) done[dl] = 1;
   if (L > tau) {
     if (k == 0) state[d0 + dl] = RS_FAILED;
