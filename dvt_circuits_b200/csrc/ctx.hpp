@@ -97,11 +97,6 @@ struct dkgv_ctx {
   bool fd_last_need = false; // the last finite-difference run had to continue beyond t for some dealer group
   cudaStream_t fd_streams[16] = {};
   cudaEvent_t fd_fork = nullptr, fd_join[16] = {};
-  // default share path, overlapped: the difference tables of dealer sub-chunk c + 1 (ALU pipe) run on a high-priority stream UNDER the
-  // x / sign halves of sub-chunk c (multiplier pipe) on a second one; fd_overlap_sub = dealers per sub-chunk, 0 = one kernel after the other
-  cudaStream_t fd_hi = nullptr;
-  cudaEvent_t fd_tab_ev = nullptr;
-  uint32_t fd_overlap_sub = 0;
   std::vector<uint32_t> fd_cols_host;
   int share_path = 0;       // DKGV_SHARE_PATH_* requested
   uint32_t share_parts = 0; // 0: planner's choice of parts per dealer; else forced

@@ -312,8 +312,6 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
-  if (ctx->fd_hi) cudaStreamSynchronize(ctx->fd_hi), cudaStreamDestroy(ctx->fd_hi);
-  if (ctx->fd_tab_ev) cudaEventDestroy(ctx->fd_tab_ev);
   if (ctx->gtab_mem) cudaFree(ctx->gtab_mem);
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);

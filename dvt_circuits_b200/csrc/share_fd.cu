@@ -109,7 +109,6 @@ k_fd_combine(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const i
 // Default formulation: (2) and the interpolation in one difference table per dealer (k_fd_difftab), (3) against the
 // compressed commitments (k_fd_coefpoint + k_fd_coefsign) with the decode deferred until a group needs the evaluation.
 constexpr uint32_t FD_SHORTCUT_MAX_T = 2047;  // lz_muladd_small: factors j < 2^11; t < n_r <= FD_SHORTCUT_MAX_N
-constexpr uint32_t FD_OVERLAP_SUB_DEFAULT = 0;   // dealers per sub-chunk of the overlapped default path (0 = off); DKGV_FD_SUB overrides
 constexpr uint32_t FD_SHORTCUT_MAX_N = 2048;  // k_fd_difftab: one block per dealer, two entries per thread
 
 // c[j] = (-1)^j C(t, j) mod r (j = 0..t), inv[j] = 1/j mod r (j = 1..t) and ifact[j] = 1/j! mod r, Montgomery form; one thread per j
@@ -408,14 +407,6 @@ int dkgv_fd_setup(dkgv_ctx* ctx) {
     CK(cudaEventCreate(&ctx->ev_sc[i]));
   }
   CK(cudaEventCreateWithFlags(&ctx->fd_fork, cudaEventDisableTiming));
-  {
-    int lo = 0, hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CK(cudaStreamCreateWithPriority(&ctx->fd_hi, cudaStreamNonBlocking, hi));
-    CK(cudaEventCreateWithFlags(&ctx->fd_tab_ev, cudaEventDisableTiming));
-    const char* env = getenv("DKGV_FD_SUB");
-    ctx->fd_overlap_sub = env ? (uint32_t)atoi(env) & ~31u : FD_OVERLAP_SUB_DEFAULT;
-  }
   for (uint32_t i = 0; i < FD_MAX_PARTS; i++) {
     CK(cudaStreamCreateWithFlags(&ctx->fd_streams[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->fd_join[i], cudaEventDisableTiming));
@@ -478,46 +469,23 @@ int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
     const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32;
     const uint32_t batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
-    // Overlapped (fd_overlap_sub != 0 and more than one sub-chunk): tables on the high-priority stream, halves of the sub-chunk before on
-    // a second stream - the tables keep the ALU pipe busy, the halves the multiplier pipe, and a sub-chunk of at most one table per SM
-    // leaves the registers and shared memory the halves need.  Phase events then bracket overlapping intervals (tables | x | sign).
-    const uint32_t sub = ctx->fd_overlap_sub && n_d > ctx->fd_overlap_sub ? ctx->fd_overlap_sub : chunk;
-    const bool overlap = sub < chunk;
-    cudaStream_t sa = overlap ? ctx->fd_hi : s, sb = overlap ? ctx->fd_streams[1] : s;
-    if (overlap) {
-      CK(cudaEventRecord(ctx->fd_fork, s));
-      CK(cudaStreamWaitEvent(sa, ctx->fd_fork, 0));
-      CK(cudaStreamWaitEvent(sb, ctx->fd_fork, 0));
+    for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
+      const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
+      const bool first = d0 == 0, last = d0 + chunk >= n_d;
+      k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, s>>>(d_shares, cols, (uint32_t*)ctx->fd_sl.p, poly_ok, state, nullptr, d0, n_cols, n_d,
+                                                                       n_r);
+      k_fd_difftab<<<n_here, nt, (size_t)nt * 72 + (size_t)t * 32, s>>>((const uint32_t*)ctx->fd_sl.p, ifact, (uint32_t*)ctx->fd_coef.p, poly_ok, state, d0, n_d,
+                                                               n_r, t, nullptr, nullptr);
+      if (first) CK(cudaEventRecord(ctx->ev_sc[1], s));  // phases (of the first chunk): [limbs + difference table | x halves | sign halves | flags]
+      if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;
+      k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, s>>>(d_vv, (const uint32_t*)ctx->fd_coef.p, ctx->gtab, poly_ok, (uint32_t*)ctx->fd_yz.p, d0,
+                                                             n_d, n_cols, t, nullptr, nullptr);
+      if (first) CK(cudaEventRecord(ctx->ev_sc[2], s));
+      k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, s>>>(d_vv, (const uint32_t*)ctx->fd_yz.p, poly_ok, d0, n_d, n_cols, t, nullptr,
+                                                                         nullptr);
+      if (last) CK(cudaEventRecord(ctx->ev_sc[3], s));
+      ctx->launches += 4;
     }
-    for (uint32_t c0 = 0; c0 < n_d; c0 += chunk) {
-      const uint32_t c_cols = std::min(chunk, n_pad - c0);
-      for (uint32_t o = 0; o < c_cols && c0 + o < n_d; o += sub) {
-        const uint32_t d0 = c0 + o;
-        const uint32_t n_cols = std::min(sub, c_cols - o), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
-        const bool first = d0 == 0, last = d0 + sub >= n_d;
-        uint32_t* sl = (uint32_t*)ctx->fd_sl.p + (size_t)o * n_r * 8;
-        uint32_t* coef = (uint32_t*)ctx->fd_coef.p + (size_t)o * t * 8;
-        uint32_t* yz = (uint32_t*)ctx->fd_yz.p + (size_t)t * 24 * o;
-        k_fd_share_limbs<<<dim3((n_r + 127) / 128, n_here), 128, 0, sa>>>(d_shares, cols, sl, poly_ok, state, nullptr, d0, n_cols, n_d, n_r);
-        k_fd_difftab<<<n_here, nt, (size_t)nt * 72 + (size_t)t * 32, sa>>>(sl, ifact, coef, poly_ok, state, d0, n_d, n_r, t, nullptr, nullptr);
-        if (overlap ? last : first) CK(cudaEventRecord(ctx->ev_sc[1], sa));  // phases: [limbs + difference table | x halves | sign halves | flags]
-        if (overlap) {
-          CK(cudaEventRecord(ctx->fd_tab_ev, sa));
-          CK(cudaStreamWaitEvent(sb, ctx->fd_tab_ev, 0));
-        }
-        if (int rc = dkgv_take_vv_wait(ctx, sb)) return rc;
-        k_fd_coefpoint<<<dim3(g_here, t), FD_NT, FD_SMEM, sb>>>(d_vv, coef, ctx->gtab, poly_ok, yz, d0, n_d, n_cols, t, nullptr, nullptr);
-        if (overlap ? last : first) CK(cudaEventRecord(ctx->ev_sc[2], sb));
-        k_fd_coefsign<<<dim3(g_here, (batches + 3) / 4), dim3(32, 4), 0, sb>>>(d_vv, yz, poly_ok, d0, n_d, n_cols, t, nullptr, nullptr);
-        if (last) CK(cudaEventRecord(ctx->ev_sc[3], sb));
-        ctx->launches += 4;
-      }
-      if (overlap) {  // the next chunk reuses the buffers: its tables wait for this chunk's halves
-        CK(cudaEventRecord(ctx->fd_join[1], sb));
-        CK(cudaStreamWaitEvent(sa, ctx->fd_join[1], 0));
-      }
-    }
-    if (overlap) CK(cudaStreamWaitEvent(s, ctx->fd_join[1], 0));
     k_fd_need<<<(n_d + 127) / 128, 128, 0, s>>>(poly_ok, n_d, need_group, d_flags);
     k_fd_fill_ok<<<dim3(n_d, (n_r + 127) / 128), 128, 0, s>>>(d_status, need_group, state, n_d, n_r);
     ctx->launches += 2;
@@ -566,13 +534,12 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   const uint32_t* tab_u = (const uint32_t*)ctx->rs_tab.p;
   const uint32_t* tab_mt = tab_u + (size_t)n_r * 8;
   const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
-  const size_t per_dealer = (size_t)n_r * 35 + (size_t)t * 128 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 96 + 256;
+  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 128 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32;
   const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
   CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
   CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
   CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
-  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u);
-  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + 1 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32 + (size_t)bm_threads * 64 + 64) + 512));
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + 1 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32) + 256));
   uint8_t* w = (uint8_t*)ctx->rs_work.p;
   uint32_t* syn = (uint32_t*)w;
   uint32_t* gdf = syn + (size_t)chunk * nsyn * 8;
@@ -580,7 +547,6 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   uint8_t* err = (uint8_t*)(lam + (size_t)chunk * (tau + 1) * 8);
   uint8_t* oor = err + (size_t)chunk * n_r;
   uint8_t* bmdone = oor + (size_t)chunk * n_r;
-  uint32_t* park = (uint32_t*)(((uintptr_t)(bmdone + chunk) + 63) & ~(uintptr_t)63);  // [chunk][bm_threads * 16 + 16] words
   CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
   CK(cudaMemsetAsync(ok2, 0, n_pad, s));
   static bool attr = false;
@@ -592,6 +558,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     attr = true;
   }
   const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32, batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
+  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u);
   const unsigned gy = (n_r + 127) / 128;
   for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
     const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
@@ -601,12 +568,11 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     // two stages (share_rs.cuh k_rs_bm): few wrong shares per dealer finish on the first RS_STAGE1 syndromes
     CK(cudaMemsetAsync(bmdone, 0, n_here, s));
     const uint32_t stage1 = std::min<uint32_t>(RS_STAGE1, nsyn);
-    k_rs_syndromes<<<dim3(n_here, (stage1 + 127) / 128), 128, (size_t)stage1 * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, 0, stage1);
-    k_rs_bm<<<n_here, bm_threads, ((size_t)stage1 + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, park, d0, nsyn, 0, stage1, tau);
+    k_rs_syndromes<<<dim3(n_here, (stage1 + 127) / 128), 128, (size_t)stage1 * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, stage1);
+    k_rs_bm<<<n_here, bm_threads, ((size_t)stage1 + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, stage1, tau);
     if (stage1 < nsyn) {
-      k_rs_syndromes<<<dim3(n_here, (nsyn - stage1 + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, stage1, nsyn);
-      k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, park, d0, nsyn, stage1, nsyn,
-                                                                                                 tau);
+      k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, nsyn);
+      k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, nsyn, tau);
       ctx->launches += 2;
     }
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
