@@ -534,12 +534,13 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   const uint32_t* tab_u = (const uint32_t*)ctx->rs_tab.p;
   const uint32_t* tab_mt = tab_u + (size_t)n_r * 8;
   const uint32_t* ifact = (const uint32_t*)ctx->fd_binom.p + (size_t)(t + 1) * 16;
-  const size_t per_dealer = (size_t)n_r * 34 + (size_t)t * 128 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32;
+  const size_t per_dealer = (size_t)n_r * 35 + (size_t)t * 128 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 96 + 256;
   const uint32_t chunk = (uint32_t)std::min<size_t>(std::min<size_t>(n_pad, 32768), std::max<size_t>(32, (((size_t)4 << 30) / per_dealer) & ~(size_t)31));
   CK(ctx->fd_sl.reserve((size_t)chunk * n_r * 32));
   CK(ctx->fd_coef.reserve((size_t)chunk * t * 32));
   CK(ctx->fd_yz.reserve((size_t)t * 24 * chunk * 4));
-  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + 1 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32) + 256));
+  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u);
+  CK(ctx->rs_work.reserve((size_t)chunk * ((size_t)n_r * 2 + 1 + (size_t)nsyn * 64 + (size_t)(tau + 1) * 32 + (size_t)bm_threads * 64 + 64) + 512));
   uint8_t* w = (uint8_t*)ctx->rs_work.p;
   uint32_t* syn = (uint32_t*)w;
   uint32_t* gdf = syn + (size_t)chunk * nsyn * 8;
@@ -547,6 +548,7 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
   uint8_t* err = (uint8_t*)(lam + (size_t)chunk * (tau + 1) * 8);
   uint8_t* oor = err + (size_t)chunk * n_r;
   uint8_t* bmdone = oor + (size_t)chunk * n_r;
+  uint32_t* park = (uint32_t*)(((uintptr_t)(bmdone + chunk) + 63) & ~(uintptr_t)63);  // [chunk][bm_threads * 16 + 16] words
   CK(cudaMemsetAsync(deg, 0, (size_t)n_pad * 8 + 16, s));  // deg, cnt, repaired
   CK(cudaMemsetAsync(ok2, 0, n_pad, s));
   static bool attr = false;
@@ -558,7 +560,6 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     attr = true;
   }
   const uint32_t nt = (((n_r + 1) / 2 + 31) / 32) * 32, batches = (t + FD_SIGN_K - 1) / FD_SIGN_K;
-  const uint32_t bm_threads = std::max<uint32_t>(64, (tau + 2 + 31) & ~31u);
   const unsigned gy = (n_r + 127) / 128;
   for (uint32_t d0 = 0; d0 < n_d; d0 += chunk) {
     const uint32_t n_cols = std::min(chunk, n_pad - d0), n_here = std::min(n_cols, n_d - d0), g_here = n_cols / 32;
@@ -568,11 +569,12 @@ int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const 
     // two stages (share_rs.cuh k_rs_bm): few wrong shares per dealer finish on the first RS_STAGE1 syndromes
     CK(cudaMemsetAsync(bmdone, 0, n_here, s));
     const uint32_t stage1 = std::min<uint32_t>(RS_STAGE1, nsyn);
-    k_rs_syndromes<<<dim3(n_here, (stage1 + 127) / 128), 128, (size_t)stage1 * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, stage1);
-    k_rs_bm<<<n_here, bm_threads, ((size_t)stage1 + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, stage1, tau);
+    k_rs_syndromes<<<dim3(n_here, (stage1 + 127) / 128), 128, (size_t)stage1 * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, 0, stage1);
+    k_rs_bm<<<n_here, bm_threads, ((size_t)stage1 + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, park, d0, nsyn, 0, stage1, tau);
     if (stage1 < nsyn) {
-      k_rs_syndromes<<<dim3(n_here, (nsyn + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, nsyn);
-      k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, d0, nsyn, nsyn, tau);
+      k_rs_syndromes<<<dim3(n_here, (nsyn - stage1 + 127) / 128), 128, (size_t)nsyn * 32, s>>>(gdf, state, bmdone, tab_mt, syn, d0, nsyn, stage1, nsyn);
+      k_rs_bm<<<n_here, bm_threads, ((size_t)nsyn + bm_threads + bm_threads / 32 + 1) * 32, s>>>(syn, state, lam, deg, bmdone, park, d0, nsyn, stage1, nsyn,
+                                                                                                 tau);
       ctx->launches += 2;
     }
     k_rs_chien<<<dim3(n_here, gy), 128, 0, s>>>(lam, deg, state, err, cnt, d0, n_r, tau);
