@@ -51,6 +51,30 @@ impl Gpu {
         Ok(Gpu { ctx })
     }
 
+    /// Same with the window width of the fixed-base table chosen by the caller (`dkgv_ctx_create_ex`): 16 = 50 MB of device memory and
+    /// 15 mixed additions per `G * s`, 22 (the default of [`Gpu::new`]) = 2.4 GB / 11, 26 = 32 GB / 9.
+    pub fn with_table(device: i32, gtab_bits: u32) -> Result<Gpu, GpuError> {
+        let mut ctx: *mut sys::dkgv_ctx = std::ptr::null_mut();
+        let rc = unsafe { sys::dkgv_ctx_create_ex(device as c_int, gtab_bits, &mut ctx) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sys::dkgv_last_error(std::ptr::null())) }.to_string_lossy().into_owned();
+            return Err(GpuError(format!("dkgv_ctx_create_ex({device}, {gtab_bits}) failed ({rc}): {msg}")));
+        }
+        Ok(Gpu { ctx })
+    }
+
+    /// This rank's row block of dealers through the default share path, then ONE all-gather inside the library: `d_gather` receives the
+    /// verdict bitmask of the whole ceremony (world x ceil(n_local * n_recipients / 32) words + the job flags).
+    ///
+    /// # Safety
+    /// All pointers are DEVICE pointers of this `Gpu`'s device, sized as `include/dkgv.h` states; `stream` is a CUDA stream handle or null.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn share_matrix_verify_sharded_dev(&mut self, n_local: u32, n_recipients: u32, t: u32, d_vv_local: *const u8, d_ids: *const u32,
+        d_shares_local: *const u8, d_status_local: *mut u8, d_gather: *mut u32, stream: *mut std::os::raw::c_void) -> Result<(), GpuError> {
+        self.check(sys::dkgv_share_matrix_verify_sharded_dev(self.ctx, n_local, n_recipients, t, d_vv_local, d_ids, d_shares_local,
+            d_status_local, d_gather, stream))
+    }
+
     fn check(&self, rc: c_int) -> Result<(), GpuError> {
         if rc == 0 {
             return Ok(());
