@@ -405,6 +405,8 @@ def run_b200(args):
         for _ in range(count):
             if do_flush:
                 flush.fill_(1)  # L2 flush between timed iterations (not timed)
+            if world > 1:
+                barrier()  # every step starts on all ranks together: its collective is not charged with host-side skew between the ranks
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
             fn()
