@@ -100,6 +100,10 @@ def parse():
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="single GPU: process only the row block one rank of a W-rank job would hold (no collective) - the per-kernel view "
                          "of the N = W step for ncu; the printed value is NOT a whole-ceremony number")
+    ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1],
+                    help="1 (default): value = K ceremonies queued back to back through dkgv_share_matrix_enqueue_sharded_dev, one synchronisation at the "
+                         "end; 0: value = K synchronous calls (one host synchronisation per ceremony), reported as `sync_call` otherwise")
+    ap.add_argument("--lanes", type=int, default=0, help="ctxs (and streams) per GPU the pipelined ceremonies alternate between (0 = by row-block size)")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1], help="dkgv_set_share_overlap mode of the evaluation steps")
     ap.add_argument("--parts", type=int, default=0, help="parts per dealer polynomial on the finite-difference path (0 = planner)")
     return ap.parse_args()
@@ -107,21 +111,62 @@ def parse():
 
 # ------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe: the fields of its nvidia-smi line).
+    Default: NVML inside this process (the library nvidia-smi itself reads), one device handle, a thread polling every 20 ms - a
+    separate `nvidia-smi -lms` process attaches to every GPU of the box and was seen to perturb the 1.2 ms steps of an 8-rank job
+    (profiles/r2_n8_rest_of_step.md).  DKGV_BENCH_SAMPLER=smi: the nvidia-smi process; =off: no samples (diagnosis only)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.stamps, self.proc = gpu_index, [], [], None
+        self.gpu, self.rows, self.stamps, self.proc, self.thr = gpu_index, [], [], None, None
+        self.mode = os.environ.get("DKGV_BENCH_SAMPLER", "nvml")
+        self.stop_flag = threading.Event()
+        self.source = None
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+                self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+                self.source = "NVML in-process, 20 ms period"
+                self.thr = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.thr.start()
+                return
+            except Exception:  # noqa: BLE001 - no NVML binding: the nvidia-smi process below
+                pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 50"
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except OSError:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown, nv.nvmlClocksEventReasonSwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwPowerCap]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            mx = ""
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append([str(self.gpu), str(sm), str(mx), "", hex(rs)] + ["Active" if rs & b else "Not Active" for b in bits])
+                self.stamps.append(time.perf_counter())
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -130,27 +175,32 @@ class ClockSampler:
 
     def stop(self, since=None):
         """summary of the samples taken after perf_counter() time `since` (None: all of them)"""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        if self.mode == "off":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler switched off (DKGV_BENCH_SAMPLER=off)"]}
+        if self.proc is None and self.thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        elif self.thr:
+            self.thr.join(timeout=2)
         if since is not None:
             n_rows = min(len(self.rows), len(self.stamps))
             self.rows = [self.rows[i] for i in range(n_rows) if self.stamps[i] >= since]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
+                for nm, v in zip(self.NAMES, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_int_peak():
@@ -358,6 +408,13 @@ def run_b200(args):
     chunk = v.share_gather_words(rows, n)
     words = (rows * n + 31) // 32
 
+    def lanes_for(rows_):
+        # Ceremonies in flight per GPU (one ctx + stream each; the ctxs of a device share the fixed-base table).  The difference tables
+        # (ALU pipe, barrier latency) of one ceremony run under the fixed-base multiplications (multiplier pipe) of another.  Measured
+        # (profiles/r2_pipeline_lanes.md), ms per ceremony with 1 / 2 / 4 lanes: 1024 dealers 5.71 / 5.35 / 5.36, 512: 3.15 / 2.69 / 2.69,
+        # 256: 1.73 / 1.39 / 1.37, 128 (one wave of tables, latency-bound alone): 1.10 / 0.81 / 0.73.
+        return 2 if rows_ >= 512 else 4
+
     def dmax(x):
         tt = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
@@ -403,17 +460,29 @@ def run_b200(args):
     def timed_steps(fn, count, do_flush=True):
         out = []
         for _ in range(count):
-            if do_flush:
+            if do_flush and os.environ.get("DKGV_BENCH_FLUSH", "1") != "0":  # (=0: diagnosis only, the number is then not a bench value)
                 flush.fill_(1)  # L2 flush between timed iterations (not timed)
             if world > 1:
                 barrier()  # every step starts on all ranks together: its collective is not charged with host-side skew between the ranks
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
+            h0 = time.perf_counter()
             fn()
+            host_ms.append((time.perf_counter() - h0) * 1e3)
             e1.record(ts)
             e1.synchronize()
             out.append(e0.elapsed_time(e1))
         return out
+
+    host_ms = []  # host wall clock inside every timed call (launches + the call's own synchronisation), same order as the device times
+
+    def all_ranks(x):  # per-step list of this rank -> [rank][step] on every rank
+        a = torch.tensor(x, dtype=torch.float64, device=dev)
+        if world == 1:
+            return [a.tolist()]
+        box = [torch.empty_like(a) for _ in range(world)]
+        dist.all_gather(box, a)
+        return [b.tolist() for b in box]
 
     def bad_bits():
         g = d_gather[:, :words]
@@ -435,6 +504,7 @@ def run_b200(args):
         barrier()
         wall0 = time.perf_counter()
         step_ms, short_ms = [], []
+        del host_ms[:]
         for _ in range(args.steps):
             step_ms += timed_steps(step_device, 1)
             if v.last_share_path == v.PATH_FDIFF and not v.last_share_continued:
@@ -446,6 +516,87 @@ def run_b200(args):
         # sampling period: keep the same steps running, untimed, until the GPU has been under this load for ~0.6 s, so that the
         # clocks line rests on several samples.  The count comes from the max-over-ranks step time: identical on every rank.
         ms_per_step = dmax(sum(step_ms)) / args.steps
+        per_rank = all_ranks(step_ms)
+        per_rank_host = all_ranks(host_ms[:args.steps])
+        step_spread = {"per_step_max_over_ranks_ms": [round(max(r[i] for r in per_rank), 4) for i in range(args.steps)],
+                       "per_rank_mean_ms": [round(sum(r) / args.steps, 4) for r in per_rank],
+                       "median_of_per_step_max_ms": round(statistics.median(max(r[i] for r in per_rank) for i in range(args.steps)), 4),
+                       "per_rank_host_ms_in_call_mean": [round(sum(r) / args.steps, 4) for r in per_rank_host],
+                       "note": "ms_per_step (the contract's number) = max over ranks of the mean; the per-step maxima show how much of it is single slow steps"}
+        sync_call = {"ms_per_step": ms_per_step, "value": rows * n * world / (ms_per_step * 1e-3), "unit": "shares/s", "step_spread": step_spread,
+                     "what": "K synchronous dkgv_share_matrix_verify_sharded_dev calls: every ceremony ends with its own host synchronisation "
+                             "(flag read-back); L2 flushed (256 MB fill) before every call; per-call CUDA events, max over ranks of the mean"}
+        pipe = None
+        if args.pipeline:
+            # ---- the headline: K ceremonies in flight.  A host with many ceremonies queues them back to back (enqueue), synchronises once and
+            # settles them; nothing on the honest path waits for the host between two ceremonies.  Inputs: a ring of distinct device copies
+            # larger than twice the L2, so no ceremony finds its verification vectors or shares in the cache; one flush before the region.
+            n_lanes = args.lanes or lanes_for(rows)
+            lane_v, lane_s = [v], [ts]
+            for _ in range(n_lanes - 1):
+                lv = dk.Verifier(local, gtab_bits=gtab_bits)
+                if world > 1:
+                    box = [dk.Verifier.comm_unique_id() if rank == 0 else None]
+                    dist.broadcast_object_list(box, src=0)
+                    lv.comm_init(box[0], rank, world)
+                lv.set_share_parts(args.parts)
+                lv.set_share_overlap(args.overlap)
+                lane_v.append(lv)
+                lane_s.append(torch.cuda.Stream(device=dev))
+            bytes_step = d_vv.numel() + d_sh.numel()
+            ring = int(min(64, max(2, -(-2 * 126 * (1 << 20) // bytes_step) + 1)))
+            slots = [{"vv": d_vv.clone() if i else d_vv, "sh": d_sh.clone() if i else d_sh} for i in range(ring)]
+            depth = min(args.steps, 256)
+            outs = [{"st": torch.empty_like(d_st), "g": torch.zeros_like(d_gather), "hf": torch.zeros(2 * world, dtype=torch.int32).pin_memory()}
+                    for _ in range(max(depth, args.warmup, n_lanes))]
+
+            def job_args(k, lane):
+                sl, o = slots[k % ring], outs[k % len(outs)]
+                return (rows, n, t, sl["vv"].data_ptr(), d_ids.data_ptr(), sl["sh"].data_ptr(), o["st"].data_ptr(), o["g"].data_ptr(), o["hf"].data_ptr(),
+                        lane_s[lane].cuda_stream)
+
+            def pipe_pass(count):
+                """count ceremonies, device time from before the first enqueue to after the last settle (ms) and the ceremonies settle ran again"""
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reran, first = 0, 0
+                e0.record(ts)
+                for s_ in lane_s[1:]:
+                    s_.wait_event(e0)
+                for k in range(count):
+                    lane_v[k % n_lanes].share_matrix_enqueue_sharded_dev(*job_args(k, k % n_lanes))
+                    if (k + 1 - first) == len(outs) or k == count - 1:  # a wave is in flight: join the lanes, ONE synchronisation, settle
+                        for s_ in lane_s[1:]:
+                            ev = torch.cuda.Event()
+                            ev.record(s_)
+                            ts.wait_event(ev)
+                        ts.synchronize()
+                        for kk in range(first, k + 1):
+                            reran += lane_v[kk % n_lanes].share_matrix_settle_sharded_dev(*job_args(kk, kk % n_lanes))
+                        first = k + 1
+                e1.record(ts)
+                e1.synchronize()
+                return e0.elapsed_time(e1), reran
+
+            pipe_pass(max(args.warmup, n_lanes))  # warm-up of every lane (its scratch is allocated on first use)
+            flush.fill_(1)
+            barrier()
+            launches0 = sum(lv.launch_count for lv in lane_v)
+            wall0p = time.perf_counter()
+            pipe_ms, pipe_reran = pipe_pass(args.steps)
+            wall_pipe = time.perf_counter() - wall0p
+            launches_pipe = sum(lv.launch_count for lv in lane_v) - launches0
+            barrier()
+            pipe_bad = sum(int(torch.count_nonzero(o["g"][:, :words]).item()) for o in outs[:min(depth, args.steps)]) + pipe_reran
+            repeats = []
+            for _ in range(2):  # spread only: the number is the first pass
+                flush.fill_(1)
+                barrier()
+                repeats.append(dmax(pipe_pass(args.steps)[0]) / args.steps)
+            ms_per_step = dmax(pipe_ms) / args.steps
+            pipe = {"lanes": n_lanes, "ring": ring, "ring_bytes": int(ring * bytes_step), "bad": pipe_bad, "repeat_ms_per_step": repeats,
+                    "wall_s": wall_pipe, "launches": launches_pipe}
+            for lv in lane_v[1:]:
+                lv.close()
         extra_steps = max(0, min(2000, int(0.6 / max(ms_per_step * 1e-3, 1e-4)) - args.steps))
         for _ in range(extra_steps):
             step_device()
@@ -669,12 +820,11 @@ def run_b200(args):
 
         def kernel_entry(name, units, unit_is, canon_unit, exec_unit, ms, ref_ms):
             a, e = units * canon_unit * MAC_PER_MODMUL / (ms * 1e-3), units * exec_unit * MAC_PER_MODMUL / (ms * 1e-3)
-            return {"kernel": name, "achieved": a / 1e9, "frac": a / peak["imad_wide"],
-                    "frac_of_carry_chain_peak": (a / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
-                    "executed_gmac_per_s": e / 1e9, "executed_frac": e / peak["imad_wide"],
-                    "executed_frac_of_carry_chain_peak": (e / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+            return {"kernel": name, "achieved": e / 1e9, "frac": e / peak["imad_wide"],
+                    "frac_of_carry_chain_peak": (e / peak["imad_wide_x"]) if peak["imad_wide_x"] else None,
+                    "canonical_gmac_per_s": a / 1e9, "canonical_frac": a / peak["imad_wide"],
                     "kernel_ms": ms, "kernel_share_of_step": ms / ref_ms, "units_per_launch_total": units, "unit_is": unit_is,
-                    "modmul_per_unit": canon_unit, "executed_modmul_per_unit": exec_unit}
+                    "modmul_per_unit": exec_unit, "canonical_modmul_per_unit": canon_unit}
 
         roof = {"bound": "int_pipe", "peak": peak["imad_wide"] / 1e9, "unit": "G wide-MAC/s (32x32->64)", "peak_source": peak["source"],
                 "peak_carry_chain": (peak["imad_wide_x"] or 0) / 1e9, "mac_per_modmul": MAC_PER_MODMUL, "traffic": None, "algorithmic_bytes": None}
@@ -687,8 +837,8 @@ def run_b200(args):
             sg = 2 / 8 + 3 + 2
             top = kernel_entry("k_fd_coefpoint", rows * t, "one coefficient: G * p_k by the fixed-base table, x_C * Z == X against the "
                                "compressed commitment", pt_canon, pt_exec, sp[1], step_mean)
-            roof.update({k_: top[k_] for k_ in ("kernel", "achieved", "frac", "frac_of_carry_chain_peak", "executed_gmac_per_s", "executed_frac",
-                                                "executed_frac_of_carry_chain_peak", "kernel_ms", "kernel_share_of_step", "unit_is", "modmul_per_unit")})
+            roof.update({k_: top[k_] for k_ in ("kernel", "achieved", "frac", "frac_of_carry_chain_peak", "canonical_gmac_per_s", "canonical_frac",
+                                                "kernel_ms", "kernel_share_of_step", "unit_is", "modmul_per_unit", "canonical_modmul_per_unit")})
             roof["units_per_launch"] = top["units_per_launch_total"]
             roof["shortcut_kernels"] = [
                 top,
@@ -740,7 +890,13 @@ def run_b200(args):
                              "modmul_per_dealer_fdiff": plan["modmul_fd"], "modmul_per_dealer_horner": plan["modmul_horner"]}
         roof["note"] = ("`kernel` ... `modmul_per_unit`: the dominant kernel of the timed (default-path) steps, timed live inside them, all of them under "
                         "`shortcut_kernels`; `kernels` / `evaluation_top_kernel`: the evaluation kernels (the steps behind `full_evaluation`, run "
-                        "phase after phase).  `frac` = canonical wide MACs / measured IMAD.WIDE.U32 peak; `executed_frac` counts the fused products as executed")
+                        "phase after phase).  `achieved` / `frac` = the wide MACs the kernel EXECUTES per launch (`modmul_per_unit` Montgomery products of 300 MACs, "
+                        "fused sums of two products counted as 444) / its launch time, against the measured carry-free IMAD.WIDE.U32 peak; "
+                        "`frac_of_carry_chain_peak`: against the measured rate of the carry-chained IMAD.WIDE.U32.X the product is built from; "
+                        "`canonical_*`: SURVEY 8(d)'s textbook count for the same result (33 additions of 11 products per fixed-base multiplication, "
+                        "12 per projective addition) - above 1 where the table / formulas do less work than the textbook, so not a utilisation.  "
+                        "Kernel times: CUDA events of the library inside the synchronous calls of `sync_call` (same kernels, same inputs as the "
+                        "pipelined headline steps, where two lanes may overlap them)")
         line = {
             "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -761,8 +917,18 @@ def run_b200(args):
             "gpu_launches": int(launches), "collectives_in_library": world > 1,
             "roofline": roof,
             "parity": {"bad_verdict_bits_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},
-            "wall_s_timed_region": wall,
+            "wall_s_timed_region": wall_pipe if pipe else wall,
+            "sync_call": sync_call,
         }
+        if pipe:
+            line["config"]["l2"] = (f"inputs larger than L2: the K ceremonies read their verification vectors and shares from a ring of {pipe['ring']} distinct "
+                                    f"device copies ({pipe['ring_bytes'] / 1e6:.0f} MB > 2 x 126 MB L2), L2 flushed (256 MB fill) once before the timed region")
+            line["config"]["pipeline"] = (f"K = {args.steps} ceremonies queued back to back through dkgv_share_matrix_enqueue_sharded_dev over {pipe['lanes']} "
+                                          f"ctx / stream lane(s) per GPU, ONE host synchronisation, then dkgv_share_matrix_settle_sharded_dev for each; CUDA events "
+                                          f"from before the first enqueue to after the last settle, max over ranks")
+            line["gpu_launches"] = int(pipe["launches"])
+            line["parity"]["bad_verdict_bits_pipelined"] = pipe["bad"]
+            line["pipeline_repeats_ms_per_step"] = pipe["repeat_ms_per_step"]
         if args.emulate_world and world == 1:
             line["emulated"] = (f"ONE rank's row block of a {split}-rank job ({rows} dealers) on one GPU, no collective: value is NOT a whole-ceremony "
                                 f"number; ms_per_step is the per-rank step time to expect at N = {split}")

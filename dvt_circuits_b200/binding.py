@@ -106,6 +106,8 @@ DECLARED_SYMBOLS = {
     "dkgv_all_gather_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "dkgv_share_gather_words": (_u32, [_u32, _u32]),
     "dkgv_share_matrix_verify_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_enqueue_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_settle_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "dkgv_bls_verify_batch_sharded_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "dkgv_agg_final_keys_sharded": (ctypes.c_int, [_vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     "dkgv_set_bls_path": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -458,6 +460,17 @@ class Verifier:
     def share_matrix_verify_sharded_dev(self, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, stream=None):
         """this rank's dealer row block; d_gather [world, share_gather_words(n_local, n_r)] u32 on the device"""
         self._ck(self._lib.dkgv_share_matrix_verify_sharded_dev(self._h, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, stream))
+
+    def share_matrix_enqueue_sharded_dev(self, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, h_flags, stream=None):
+        """pipelined form: queued without synchronising; h_flags = pinned host memory, 2 * world u32 (settle reads it after a sync)"""
+        self._ck(self._lib.dkgv_share_matrix_enqueue_sharded_dev(self._h, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, h_flags, stream))
+
+    def share_matrix_settle_sharded_dev(self, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, h_flags, stream=None):
+        """after the stream has been synchronised: True when the ceremony had to be run again (corrupted shares / foreign ids)"""
+        reran = ctypes.c_int(0)
+        self._ck(self._lib.dkgv_share_matrix_settle_sharded_dev(self._h, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, h_flags, stream,
+                                                               ctypes.byref(reran)))
+        return bool(reran.value)
 
     def bls_verify_batch_sharded_dev(self, m_local, d_pk, d_sig, n_hm, d_hm, d_hm_idx, d_status_all, stream=None):
         self._ck(self._lib.dkgv_bls_verify_batch_sharded_dev(self._h, m_local, d_pk, d_sig, n_hm, d_hm, d_hm_idx, d_status_all, stream))

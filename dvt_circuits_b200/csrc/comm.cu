@@ -191,6 +191,48 @@ extern "C" int dkgv_share_matrix_verify_sharded_dev(dkgv_ctx* ctx, uint32_t n_lo
   return 0;
 }
 
+// Pipelined form of the same call for a host that verifies many ceremonies: `enqueue` queues the shortcut, the pack, the ONE all-gather
+// and the copy of every rank's two flag words to h_flags (pinned host memory of the caller, 2 * world words) and returns WITHOUT
+// synchronising - any number of ceremonies can be in flight on a stream (the ctx's scratch is reused in stream order), and the call is
+// CUDA-graph capturable.  After the caller has synchronised (stream, event) it calls `settle` with the same arguments: flags all zero
+// (the honest ceremony, every rank settled by the shortcut) - nothing to do, the verdicts are final; otherwise the ceremony is run again
+// through the synchronous entry point (repair route / evaluation, second gather).  Every rank sees every flag, so all ranks take the
+// same branch.  *reran (optional) tells which.
+extern "C" int dkgv_share_matrix_enqueue_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint32_t t, const uint8_t* d_vv_local,
+                                                     const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local,
+                                                     uint32_t* d_gather, uint32_t* h_flags, void* stream) {
+  if (!ctx) return -1;
+  if (n_local == 0 || n_r == 0) return dkgv_fail(ctx, "empty row block");
+  if (!d_ids || !d_shares_local || !d_status_local || !d_gather || !h_flags || (t && !d_vv_local)) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  const int world = ctx->comm_world, rank = ctx->comm_rank;
+  const size_t n = (size_t)n_local * n_r, words = (n + 31) / 32;
+  const uint32_t chunk = dkgv_share_gather_words(n_local, n_r);
+  if (int rc = dkgv_share_submit_internal(ctx, n_local, n_r, t, d_vv_local, d_ids, d_shares_local, d_status_local, nullptr, s)) return rc;
+  uint32_t* mine = d_gather + (size_t)rank * chunk;
+  k_pack_verdicts_flags<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_status_local, mine, n, words, ctx->job.d_flags);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (int rc = all_gather(ctx, mine, d_gather, (size_t)chunk * 4, s)) return rc;
+  CK(cudaMemcpy2DAsync(h_flags, 8, d_gather + words, (size_t)chunk * 4, 8, world, cudaMemcpyDeviceToHost, s));
+  ctx->job.open = false;  // nothing is pending on the ctx: `settle` starts over from the caller's arguments if it has to
+  return 0;
+}
+
+extern "C" int dkgv_share_matrix_settle_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint32_t t, const uint8_t* d_vv_local,
+                                                    const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local,
+                                                    uint32_t* d_gather, const uint32_t* h_flags, void* stream, int* reran) {
+  if (!ctx) return -1;
+  if (!h_flags) return dkgv_fail(ctx, "null pointer argument");
+  if (reran) *reran = 0;
+  bool any = false;
+  for (int r = 0; r < ctx->comm_world; r++) any |= h_flags[2 * r] != 0 || h_flags[2 * r + 1] != 0;
+  if (!any) return 0;
+  if (reran) *reran = 1;
+  return dkgv_share_matrix_verify_sharded_dev(ctx, n_local, n_r, t, d_vv_local, d_ids, d_shares_local, d_status_local, d_gather, stream);
+}
+
 // ---- pairing checks, items sharded --------------------------------------------------------------------------------------
 // every rank: its m_local (pk, sig) pairs -> d_status_all [world][m_local]
 extern "C" int dkgv_bls_verify_batch_sharded_dev(dkgv_ctx* ctx, uint32_t m_local, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,

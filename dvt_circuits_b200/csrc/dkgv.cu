@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <algorithm>
 #include <string>
@@ -213,6 +214,23 @@ k_fr_poly_eval(const uint8_t* __restrict__ coeffs, const uint32_t* __restrict__ 
 using dkgv_host::DevBuf;
 namespace {
 thread_local std::string g_create_error;
+// The fixed-base table is read-only once built: every ctx of a process on the same device with the same window width shares ONE copy
+// (reference-counted), so a host that keeps several ctxs per GPU - one per ceremony in flight, see dkgv_share_matrix_enqueue_sharded_dev -
+// pays for the table (2.4 GB at 22 bits, 32 GB at 26) once.
+struct SharedTab {
+  int device;
+  uint32_t bits;
+  uint32_t* mem;
+  int refs;
+};
+std::mutex g_tab_mu;
+std::vector<SharedTab> g_tabs;
+thread_local bool g_tab_locked = false;  // this thread is inside dkgv_ctx_create_ex and holds g_tab_mu (its failure paths call dkgv_ctx_destroy)
+struct TabLock {
+  std::unique_lock<std::mutex> l;
+  TabLock() : l(g_tab_mu) { g_tab_locked = true; }
+  ~TabLock() { g_tab_locked = false; }
+};
 }
 
 static int fail(dkgv_ctx* ctx, const char* msg) { return dkgv_fail(ctx, msg); }
@@ -259,13 +277,24 @@ extern "C" int dkgv_ctx_create_ex(int device, uint32_t gtab_bits, dkgv_ctx** out
     dkgv_ctx_destroy(ctx);
     return -1;
   }
+  TabLock tab_lock;  // held until the table is built: a second ctx created meanwhile waits and shares it
+  bool tab_shared = false;
   for (;; gtab_bits -= 2) {
+    for (SharedTab& st : g_tabs)
+      if (st.device == device && st.bits == gtab_bits) {
+        st.refs++;
+        ctx->gtab_mem = st.mem;
+        tab_shared = true;
+        break;
+      }
+    if (tab_shared) break;
     e = cudaMalloc(&ctx->gtab_mem, gtab_words(gtab_bits) * 4);
     if (e == cudaSuccess) break;
     ctx->gtab_mem = nullptr;
     cudaGetLastError();
     if (gtab_bits < 16 + 2) return bail("cudaMalloc gtab", e);
   }
+  if (!tab_shared) g_tabs.push_back(SharedTab{device, gtab_bits, ctx->gtab_mem, 1});
   ctx->gtab = GTab{ctx->gtab_mem, gtab_bits, gtab_windows(gtab_bits)};
   if ((e = cudaFuncSetAttribute(k_share_verify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVM_SMEM)) != cudaSuccess)
     return bail("cudaFuncSetAttribute smem", e);
@@ -280,7 +309,7 @@ extern "C" int dkgv_ctx_create_ex(int device, uint32_t gtab_bits, dkgv_ctx** out
     dkgv_ctx_destroy(ctx);
     return -2;
   }
-  {
+  if (!tab_shared) {
     uint32_t* base = nullptr;
     if ((e = cudaMalloc(&base, 32 * 48 * 4)) != cudaSuccess) return bail("cudaMalloc gtab bases", e);
     const uint32_t runs = ctx->gtab.windows * ((1u << (gtab_bits - 1)) / GTAB_RUN);
@@ -312,7 +341,18 @@ extern "C" void dkgv_ctx_destroy(dkgv_ctx* ctx) {
     if (ctx->fd_join[i]) cudaEventDestroy(ctx->fd_join[i]);
   }
   if (ctx->fd_fork) cudaEventDestroy(ctx->fd_fork);
-  if (ctx->gtab_mem) cudaFree(ctx->gtab_mem);
+  if (ctx->gtab_mem) {  // the last ctx that uses the shared table frees it
+    std::unique_lock<std::mutex> tab_lock(g_tab_mu, std::defer_lock);
+    if (!g_tab_locked) tab_lock.lock();
+    for (size_t i = 0; i < g_tabs.size(); i++)
+      if (g_tabs[i].mem == ctx->gtab_mem) {
+        if (--g_tabs[i].refs == 0) {
+          cudaFree(ctx->gtab_mem);
+          g_tabs.erase(g_tabs.begin() + (long)i);
+        }
+        break;
+      }
+  }
   if (ctx->ev_hot0) cudaEventDestroy(ctx->ev_hot0);
   if (ctx->ev_hot1) cudaEventDestroy(ctx->ev_hot1);
   if (ctx->ev_dec0) cudaEventDestroy(ctx->ev_dec0);

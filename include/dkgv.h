@@ -278,6 +278,17 @@ uint32_t dkgv_share_gather_words(uint32_t n_local, uint32_t n_recipients);
 int dkgv_share_matrix_verify_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv_local,
                                          const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local, uint32_t* d_gather,
                                          void* stream);
+/* Pipelined form for a host with many ceremonies in flight.  enqueue: the shortcut, the pack, the ONE all-gather and the copy of every
+ * rank's two flag words to h_flags (PINNED host memory, 2 * world words) are queued on `stream`; no synchronisation, CUDA-graph
+ * capturable; the ctx's scratch is reused in stream order, so ceremonies may be queued back to back.  settle (after the caller has
+ * synchronised): flags all zero - an honest ceremony, verdicts final, nothing is launched; otherwise the ceremony goes through
+ * dkgv_share_matrix_verify_sharded_dev with the same arguments (all ranks see all flags and take the same branch); *reran = 0 / 1. */
+int dkgv_share_matrix_enqueue_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv_local,
+                                          const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local, uint32_t* d_gather,
+                                          uint32_t* h_flags, void* stream);
+int dkgv_share_matrix_settle_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv_local,
+                                         const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local, uint32_t* d_gather,
+                                         const uint32_t* h_flags, void* stream, int* reran);
 /* Pairing checks sharded by items: every rank its m_local pairs; d_status_all [world][m_local] on every rank.  Asynchronous. */
 int dkgv_bls_verify_batch_sharded_dev(dkgv_ctx* ctx, uint32_t m_local, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
                                       const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status_all, void* stream);

@@ -75,6 +75,32 @@ impl Gpu {
             d_status_local, d_gather, stream))
     }
 
+    /// Pipelined form: queues the ceremony (shortcut, pack, all-gather, flag copy to `h_flags` = pinned host memory of 2 x world words)
+    /// without synchronising; any number may be in flight on one stream.
+    ///
+    /// # Safety
+    /// As `share_matrix_verify_sharded_dev`; `h_flags` must stay valid (and pinned) until the stream has been synchronised.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn share_matrix_enqueue_sharded_dev(&mut self, n_local: u32, n_recipients: u32, t: u32, d_vv_local: *const u8, d_ids: *const u32,
+        d_shares_local: *const u8, d_status_local: *mut u8, d_gather: *mut u32, h_flags: *mut u32, stream: *mut std::os::raw::c_void) -> Result<(), GpuError> {
+        self.check(sys::dkgv_share_matrix_enqueue_sharded_dev(self.ctx, n_local, n_recipients, t, d_vv_local, d_ids, d_shares_local,
+            d_status_local, d_gather, h_flags, stream))
+    }
+
+    /// After the stream has been synchronised: `Ok(false)` - the flags of every rank were zero, the verdicts are final; `Ok(true)` - the
+    /// ceremony had corrupted shares or foreign ids and was run again through the synchronous entry point (same on every rank).
+    ///
+    /// # Safety
+    /// As `share_matrix_enqueue_sharded_dev`, same arguments.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn share_matrix_settle_sharded_dev(&mut self, n_local: u32, n_recipients: u32, t: u32, d_vv_local: *const u8, d_ids: *const u32,
+        d_shares_local: *const u8, d_status_local: *mut u8, d_gather: *mut u32, h_flags: *const u32, stream: *mut std::os::raw::c_void) -> Result<bool, GpuError> {
+        let mut reran: c_int = 0;
+        self.check(sys::dkgv_share_matrix_settle_sharded_dev(self.ctx, n_local, n_recipients, t, d_vv_local, d_ids, d_shares_local,
+            d_status_local, d_gather, h_flags, stream, &mut reran))?;
+        Ok(reran != 0)
+    }
+
     fn check(&self, rc: c_int) -> Result<(), GpuError> {
         if rc == 0 {
             return Ok(());

@@ -50,6 +50,34 @@ def main():
             got = np.concatenate([dk.verdict_bits_to_matrix(g[r, :words], rows, n) for r in range(world)])
             assert (got == (want != 0)).all(), f"rank {rank}: gathered bitmask differs from the single-GPU verdicts"
             assert (d_st.cpu().numpy() == want[sl]).all()
+        # pipelined pair on TWO ctxs per rank (own communicator each, shared table): honest / corrupted / honest queued back to back on two
+        # streams, one synchronisation, settle - only the corrupted ceremony runs again, on every rank
+        v2 = dk.Verifier(local)
+        box = [dk.Verifier.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        v2.comm_init(box[0], rank, world)
+        ts2 = torch.cuda.Stream(device=dev)
+        lanes = [(v, ts), (v2, ts2), (v, ts)]
+        jobs = []
+        for shares, want in ((full["shares"], np.zeros((n, n), dtype=np.uint8)), (bad, exp), (full["shares"], np.zeros((n, n), dtype=np.uint8))):
+            jobs.append({"sh": torch.from_numpy(shares[sl].copy()).to(dev), "st": torch.empty((rows, n), dtype=torch.uint8, device=dev),
+                         "g": torch.zeros((world, chunk), dtype=torch.int32, device=dev),
+                         "hf": torch.full((2 * world,), 0x7FFFFFFF, dtype=torch.int32).pin_memory(), "want": want})
+        torch.cuda.synchronize()
+        for (lv, ls), j in zip(lanes, jobs):
+            lv.share_matrix_enqueue_sharded_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), j["sh"].data_ptr(), j["st"].data_ptr(), j["g"].data_ptr(),
+                                                j["hf"].data_ptr(), ls.cuda_stream)
+        torch.cuda.synchronize()
+        reran = [lv.share_matrix_settle_sharded_dev(rows, n, t, d_vv.data_ptr(), d_ids.data_ptr(), j["sh"].data_ptr(), j["st"].data_ptr(), j["g"].data_ptr(),
+                                                    j["hf"].data_ptr(), ls.cuda_stream) for (lv, ls), j in zip(lanes, jobs)]
+        torch.cuda.synchronize()
+        assert reran == [False, True, False], f"rank {rank}: settle reran {reran}"
+        for j in jobs:
+            g = j["g"].cpu().numpy().view(np.uint32)
+            got = np.concatenate([dk.verdict_bits_to_matrix(g[r, :words], rows, n) for r in range(world)])
+            assert (got == (j["want"] != 0)).all(), f"rank {rank}: pipelined bitmask differs from the single-GPU verdicts"
+            assert (j["st"].cpu().numpy() == j["want"][sl]).all()
+        v2.close()
         fin = synthetic.make_finalization(v, n, t)
         a0 = v.agg_final_keys(fin["vv"], fin["ids"])
         a1 = v.agg_final_keys_sharded(fin["vv"][sl], fin["ids"])
@@ -68,7 +96,7 @@ def main():
     v.close()
     dist.destroy_process_group()
     if rank == 0:
-        print(f"multi-GPU parity OK on {world} ranks (share matrix, aggregation, pairing checks)")
+        print(f"multi-GPU parity OK on {world} ranks (share matrix: synchronous and pipelined over two ctxs; aggregation; pairing checks)")
 
 
 if __name__ == "__main__":
