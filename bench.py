@@ -850,11 +850,17 @@ def run_b200(args):
                 {"kernel": "pack + all-gather + flag read-back (the rest of the step)", "kernel_ms": step_mean - sum(sp),
                  "kernel_share_of_step": (step_mean - sum(sp)) / step_mean}]
             roof["algorithmic_bytes"] = rows * t * (48 + 32 + 96)  # commitment + coefficient in, Y and Z planes out
-            # ncu --set full of k_fd_coefpoint at 699 392 coefficients (profiles/r2_default_path.md): dram read 71 463 936 B +
-            # write 44 385 280 B per launch; part of the Y / Z planes stays in L2 for k_fd_coefsign
-            roof["traffic"] = int(round((71463936 + 44385280) / 699392 * rows * t))
-            roof["traffic_ref"] = ("profiles/r2_default_path.md: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
-                                   "(165.6 B per coefficient, scaled to this launch's coefficients)")
+            # ncu --set full of k_fd_coefpoint at 699 392 coefficients, dram__bytes_read.sum + dram__bytes_write.sum per launch:
+            #   26-bit windows (profiles/r2_default_path_26bit.md): 1 270.76 MB + 79.03 MB - the 32 GB table does not fit any cache, every one of
+            #     the 9 table entries of a coefficient (96 B, random) comes from DRAM in 64-byte pieces: the price of 9 instead of 21 additions;
+            #   13-bit windows (profiles/r2_default_path.md): 71.46 MB + 44.39 MB (the 15.7 MB table stays in L2)
+            if gtab_bits >= 24:
+                per_coef, ref_file = (1270.76e6 + 79.032832e6) / 699392, "profiles/r2_default_path_26bit.md"
+            else:
+                per_coef, ref_file = (71463936 + 44385280) / 699392, "profiles/r2_default_path.md (13-bit table, L2-resident)"
+            roof["traffic"] = int(round(per_coef * rows * t))
+            roof["traffic_ref"] = (f"{ref_file}: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
+                                   f"({per_coef:.0f} B per coefficient, scaled to this launch's coefficients)")
         if "full_evaluation" in legs:
             plan = dk.share_fd_plan(t, n, args.parts)
             m_parts, h_part = plan["parts"], plan["h"]
