@@ -373,7 +373,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import dvt_circuits_b200 as dk
-    from dvt_circuits_b200 import synthetic
+    from dvt_circuits_b200 import pipeline, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -407,13 +407,6 @@ def run_b200(args):
     stream = ts.cuda_stream
     chunk = v.share_gather_words(rows, n)
     words = (rows * n + 31) // 32
-
-    def lanes_for(rows_):
-        # Ceremonies in flight per GPU (one ctx + stream each; the ctxs of a device share the fixed-base table).  The difference tables
-        # (ALU pipe, barrier latency) of one ceremony run under the fixed-base multiplications (multiplier pipe) of another.  Measured
-        # (profiles/r2_pipeline_lanes.md), ms per ceremony with 1 / 2 / 4 lanes: 1024 dealers 5.71 / 5.35 / 5.36, 512: 3.15 / 2.69 / 2.69,
-        # 256: 1.73 / 1.39 / 1.37, 128 (one wave of tables, latency-bound alone): 1.10 / 0.81 / 0.73.
-        return 2 if rows_ >= 512 else 4
 
     def dmax(x):
         tt = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -531,7 +524,7 @@ def run_b200(args):
             # ---- the headline: K ceremonies in flight.  A host with many ceremonies queues them back to back (enqueue), synchronises once and
             # settles them; nothing on the honest path waits for the host between two ceremonies.  Inputs: a ring of distinct device copies
             # larger than twice the L2, so no ceremony finds its verification vectors or shares in the cache; one flush before the region.
-            n_lanes = args.lanes or lanes_for(rows)
+            n_lanes = args.lanes or pipeline.lanes_for(rows)
             lane_v, lane_s = [v], [ts]
             for _ in range(n_lanes - 1):
                 lv = dk.Verifier(local, gtab_bits=gtab_bits)
@@ -544,7 +537,7 @@ def run_b200(args):
                 lane_v.append(lv)
                 lane_s.append(torch.cuda.Stream(device=dev))
             bytes_step = d_vv.numel() + d_sh.numel()
-            ring = int(min(64, max(2, -(-2 * 126 * (1 << 20) // bytes_step) + 1)))
+            ring = pipeline.ring_size(bytes_step)
             slots = [{"vv": d_vv.clone() if i else d_vv, "sh": d_sh.clone() if i else d_sh} for i in range(ring)]
             depth = min(args.steps, 256)
             outs = [{"st": torch.empty_like(d_st), "g": torch.zeros_like(d_gather), "hf": torch.zeros(2 * world, dtype=torch.int32).pin_memory()}
@@ -595,8 +588,6 @@ def run_b200(args):
             ms_per_step = dmax(pipe_ms) / args.steps
             pipe = {"lanes": n_lanes, "ring": ring, "ring_bytes": int(ring * bytes_step), "bad": pipe_bad, "repeat_ms_per_step": repeats,
                     "wall_s": wall_pipe, "launches": launches_pipe}
-            for lv in lane_v[1:]:
-                lv.close()
         extra_steps = max(0, min(2000, int(0.6 / max(ms_per_step * 1e-3, 1e-4)) - args.steps))
         for _ in range(extra_steps):
             step_device()
@@ -608,7 +599,7 @@ def run_b200(args):
         settled_by_shortcut = v.last_share_path == v.PATH_FDIFF and not v.last_share_continued
         shares_total = rows * n * world
 
-        # end-to-end with host buffers
+        # end-to-end with host buffers: synchronous calls (one ceremony per call) ...
         step_e2e()
         barrier()
         e2e_t = []
@@ -618,8 +609,43 @@ def run_b200(args):
             step_e2e()
             torch.cuda.synchronize()
             e2e_t.append(time.perf_counter() - t0)
-        e2e_s_per_step = dmax(sum(e2e_t)) / args.steps
+        e2e_sync_s_per_step = dmax(sum(e2e_t)) / args.steps
+        e2e_s_per_step = e2e_sync_s_per_step
         bad_e2e = int(h_st.count_nonzero().item())
+        e2e_pipe = None
+        if pipe:
+            # ... and the same K ceremonies in flight: dkgv_share_matrix_enqueue_sharded (pinned host rows in; status bytes, gathered bitmask and
+            # flags back on the host) alternating over the lanes, dkgv_sync per lane, settle for each - host wall clock around all of it
+            h_outs = [{"st": torch.empty((rows, n), dtype=torch.uint8).pin_memory(), "g": torch.empty((world, chunk), dtype=torch.int32).pin_memory(),
+                       "hf": torch.zeros(2 * world, dtype=torch.int32).pin_memory()} for _ in range(len(outs))]
+
+            def e2e_args(k):
+                o = h_outs[k % len(h_outs)]
+                return (rows, n, t, h_vv.data_ptr(), h_ids.data_ptr(), h_sh.data_ptr(), o["st"].data_ptr(), o["g"].data_ptr(), o["hf"].data_ptr())
+
+            def e2e_pass(count):
+                reran, first = 0, 0
+                t0 = time.perf_counter()
+                for k in range(count):
+                    lane_v[k % n_lanes].share_matrix_enqueue_sharded(*e2e_args(k))
+                    if (k + 1 - first) == len(h_outs) or k == count - 1:
+                        for lv in lane_v:
+                            lv.sync()
+                        for kk in range(first, k + 1):
+                            reran += lane_v[kk % n_lanes].share_matrix_settle_sharded(*e2e_args(kk))
+                        first = k + 1
+                return time.perf_counter() - t0, reran
+
+            e2e_pass(max(args.warmup, n_lanes))
+            barrier()
+            e2e_wall, e2e_reran = e2e_pass(args.steps)
+            barrier()
+            e2e_s_per_step = dmax(e2e_wall) / args.steps
+            bad_e2e += e2e_reran + sum(int(o["st"].count_nonzero().item()) + int(torch.count_nonzero(o["g"][:, :words]).item())
+                                       for o in h_outs[:min(len(h_outs), args.steps)])
+            e2e_pipe = True
+            for lv in lane_v[1:]:
+                lv.close()
 
         legs = {}
         if not args.quick:
@@ -854,13 +880,18 @@ def run_b200(args):
             #   26-bit windows (profiles/r2_default_path_26bit.md): 1 270.76 MB + 79.03 MB - the 32 GB table does not fit any cache, every one of
             #     the 9 table entries of a coefficient (96 B, random) comes from DRAM in 64-byte pieces: the price of 9 instead of 21 additions;
             #   13-bit windows (profiles/r2_default_path.md): 71.46 MB + 44.39 MB (the 15.7 MB table stays in L2)
-            if gtab_bits >= 24:
+            if gtab_bits == 26:
                 per_coef, ref_file = (1270.76e6 + 79.032832e6) / 699392, "profiles/r2_default_path_26bit.md"
-            else:
+            elif gtab_bits <= 16:
                 per_coef, ref_file = (71463936 + 44385280) / 699392, "profiles/r2_default_path.md (13-bit table, L2-resident)"
-            roof["traffic"] = int(round(per_coef * rows * t))
-            roof["traffic_ref"] = (f"{ref_file}: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
-                                   f"({per_coef:.0f} B per coefficient, scaled to this launch's coefficients)")
+            else:
+                per_coef, ref_file = None, None
+            if per_coef:
+                roof["traffic"] = int(round(per_coef * rows * t))
+                roof["traffic_ref"] = (f"{ref_file}: dram__bytes_read.sum + dram__bytes_write.sum of one k_fd_coefpoint launch "
+                                       f"({per_coef:.0f} B per coefficient, scaled to this launch's coefficients)")
+            else:
+                roof["traffic_ref"] = f"no ncu capture of k_fd_coefpoint with a {gtab_bits}-bit table (captured: 13 and 26 bits)"
         if "full_evaluation" in legs:
             plan = dk.share_fd_plan(t, n, args.parts)
             m_parts, h_part = plan["parts"], plan["h"]
@@ -918,8 +949,12 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": shares_total / e2e_s_per_step, "unit": "shares/s",
                     "h2d_bytes_per_step": int(h_vv.numel() + h_sh.numel() + h_ids.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(h_st.numel() + (h_gather.numel() * 4 if world > 1 else 0)) * world,
-                    "timing": "host wall clock, max over ranks: pinned host buffers in, verdicts (and the gathered bitmask) back on the host"},
+                    "d2h_bytes_per_step": int(h_st.numel() + (h_gather.numel() * 4 + 8 * world if (world > 1 or e2e_pipe) else 0)) * world,
+                    "timing": ("host wall clock around K ceremonies through dkgv_share_matrix_enqueue_sharded (pinned host rows in; status bytes, the gathered "
+                               "bitmask and the flags back on the host), alternating over the lanes, dkgv_sync, settle; max over ranks" if e2e_pipe else
+                               "host wall clock, max over ranks: pinned host buffers in, verdicts (and the gathered bitmask) back on the host"),
+                    "sync_call_value": shares_total / e2e_sync_s_per_step,
+                    "sync_call": "one synchronous call per ceremony (N = 1: dkgv_share_matrix_verify), host wall clock per call"},
             "gpu_launches": int(launches), "collectives_in_library": world > 1,
             "roofline": roof,
             "parity": {"bad_verdict_bits_device": bad, "bad_verdicts_e2e": bad_e2e, "expected": 0},

@@ -106,6 +106,8 @@ DECLARED_SYMBOLS = {
     "dkgv_all_gather_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "dkgv_share_gather_words": (_u32, [_u32, _u32]),
     "dkgv_share_matrix_verify_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_enqueue_sharded": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dkgv_share_matrix_settle_sharded": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "dkgv_share_matrix_enqueue_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dkgv_share_matrix_settle_sharded_dev": (ctypes.c_int, [_vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "dkgv_bls_verify_batch_sharded_dev": (ctypes.c_int, [_vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
@@ -470,6 +472,16 @@ class Verifier:
         reran = ctypes.c_int(0)
         self._ck(self._lib.dkgv_share_matrix_settle_sharded_dev(self._h, n_local, n_r, t, d_vv, d_ids, d_shares, d_status, d_gather, h_flags, stream,
                                                                ctypes.byref(reran)))
+        return bool(reran.value)
+
+    def share_matrix_enqueue_sharded(self, n_local, n_r, t, h_vv, h_ids, h_shares, h_status, h_gather, h_flags):
+        """host-buffer form (addresses of PINNED host memory; h_gather may be None): queued on the ctx's own stream, no synchronisation"""
+        self._ck(self._lib.dkgv_share_matrix_enqueue_sharded(self._h, n_local, n_r, t, h_vv, h_ids, h_shares, h_status, h_gather, h_flags))
+
+    def share_matrix_settle_sharded(self, n_local, n_r, t, h_vv, h_ids, h_shares, h_status, h_gather, h_flags):
+        """after sync(): True when the ceremony had to be run again"""
+        reran = ctypes.c_int(0)
+        self._ck(self._lib.dkgv_share_matrix_settle_sharded(self._h, n_local, n_r, t, h_vv, h_ids, h_shares, h_status, h_gather, h_flags, ctypes.byref(reran)))
         return bool(reran.value)
 
     def bls_verify_batch_sharded_dev(self, m_local, d_pk, d_sig, n_hm, d_hm, d_hm_idx, d_status_all, stream=None):

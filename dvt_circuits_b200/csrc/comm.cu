@@ -233,6 +233,93 @@ extern "C" int dkgv_share_matrix_settle_sharded_dev(dkgv_ctx* ctx, uint32_t n_lo
   return dkgv_share_matrix_verify_sharded_dev(ctx, n_local, n_r, t, d_vv_local, d_ids, d_shares_local, d_status_local, d_gather, stream);
 }
 
+// The same pair with HOST buffers (pinned memory for the copies to be asynchronous): the rows, ids and shares go to the ctx's staging
+// buffers, the status bytes of the own rows, the gathered chunks (gather may be NULL) and every rank's flag words come back - all queued
+// on the ctx's own stream, nothing synchronised.  A host keeps one ctx per ceremony in flight on a GPU (the ctxs of a device share the
+// fixed-base table): the copies of one ceremony then run under the kernels of another.  dkgv_sync, then settle.
+int dkgv_take_vv_wait(dkgv_ctx* ctx, cudaStream_t s);  // dkgv.cu
+static int stage_rows(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint32_t t, const uint8_t* vv, const uint32_t* ids, const uint8_t* shares,
+                      bool vv_on_second_stream, cudaStream_t s) {
+  const size_t vvb = (size_t)n_local * t * 48, idb = (size_t)n_r * 4, shb = (size_t)n_local * n_r * 32;
+  CK(ctx->in_a.reserve(vvb ? vvb : 1));
+  CK(ctx->in_b.reserve(idb));
+  CK(ctx->in_c.reserve(shb));
+  CK(ctx->out_a.reserve((size_t)n_local * n_r));
+  CK(ctx->share_gather.reserve((size_t)ctx->comm_world * dkgv_share_gather_words(n_local, n_r) * 4));
+  CK(cudaMemcpyAsync(ctx->in_b.p, ids, idb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->in_c.p, shares, shb, cudaMemcpyHostToDevice, s));
+  if (!vvb) return 0;
+  if (!vv_on_second_stream) {
+    CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  // as dkgv_share_matrix_verify: the verification vectors follow on a second stream, under the difference tables; the first kernel
+  // that reads them waits for ev_vv.  ev_sh orders the copy behind everything already queued on s (the previous ceremony of this ctx).
+  cudaStream_t s2 = ctx->fd_streams[0];
+  CK(cudaEventRecord(ctx->ev_sh, s));
+  CK(cudaStreamWaitEvent(s2, ctx->ev_sh, 0));
+  CK(cudaMemcpyAsync(ctx->in_a.p, vv, vvb, cudaMemcpyHostToDevice, s2));
+  CK(cudaEventRecord(ctx->ev_vv, s2));
+  ctx->vv_wait = ctx->ev_vv;
+  return 0;
+}
+static int unstage_results(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint8_t* status, uint32_t* gather, cudaStream_t s) {
+  CK(cudaMemcpyAsync(status, ctx->out_a.p, (size_t)n_local * n_r, cudaMemcpyDeviceToHost, s));
+  if (gather)
+    CK(cudaMemcpyAsync(gather, ctx->share_gather.p, (size_t)ctx->comm_world * dkgv_share_gather_words(n_local, n_r) * 4, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+extern "C" int dkgv_share_matrix_enqueue_sharded(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint32_t t, const uint8_t* vv_local,
+                                                 const uint32_t* ids, const uint8_t* shares_local, uint8_t* status_local, uint32_t* gather,
+                                                 uint32_t* h_flags) {
+  if (!ctx) return -1;
+  if (n_local == 0 || n_r == 0) return dkgv_fail(ctx, "empty row block");
+  if (!ids || !shares_local || !status_local || !h_flags || (t && !vv_local)) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (int rc = stage_rows(ctx, n_local, n_r, t, vv_local, ids, shares_local, true, s)) return rc;
+  const size_t n = (size_t)n_local * n_r, words = (n + 31) / 32;
+  const uint32_t chunk = dkgv_share_gather_words(n_local, n_r);
+  if (int rc = dkgv_share_submit_internal(ctx, n_local, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p,
+                                          (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, nullptr, s))
+    return rc;
+  if (int rc = dkgv_take_vv_wait(ctx, s)) return rc;  // a path that never read them: the copy still ends before the next ceremony's
+  uint32_t* all = (uint32_t*)ctx->share_gather.p;
+  uint32_t* mine = all + (size_t)ctx->comm_rank * chunk;
+  k_pack_verdicts_flags<<<(unsigned)((words + 255) / 256), 256, 0, s>>>((const uint8_t*)ctx->out_a.p, mine, n, words, ctx->job.d_flags);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (int rc = all_gather(ctx, mine, all, (size_t)chunk * 4, s)) return rc;
+  if (int rc = unstage_results(ctx, n_local, n_r, status_local, gather, s)) return rc;
+  CK(cudaMemcpy2DAsync(h_flags, 8, all + words, (size_t)chunk * 4, 8, ctx->comm_world, cudaMemcpyDeviceToHost, s));
+  ctx->job.open = false;
+  return 0;
+}
+
+extern "C" int dkgv_share_matrix_settle_sharded(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_r, uint32_t t, const uint8_t* vv_local,
+                                                const uint32_t* ids, const uint8_t* shares_local, uint8_t* status_local, uint32_t* gather,
+                                                const uint32_t* h_flags, int* reran) {
+  if (!ctx) return -1;
+  if (!h_flags) return dkgv_fail(ctx, "null pointer argument");
+  if (reran) *reran = 0;
+  bool any = false;
+  for (int r = 0; r < ctx->comm_world; r++) any |= h_flags[2 * r] != 0 || h_flags[2 * r + 1] != 0;
+  if (!any) return 0;
+  if (reran) *reran = 1;
+  if (n_local == 0 || n_r == 0) return dkgv_fail(ctx, "empty row block");
+  if (!ids || !shares_local || !status_local || (t && !vv_local)) return dkgv_fail(ctx, "null pointer argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (int rc = stage_rows(ctx, n_local, n_r, t, vv_local, ids, shares_local, false, s)) return rc;
+  if (int rc = dkgv_share_matrix_verify_sharded_dev(ctx, n_local, n_r, t, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p,
+                                                    (const uint8_t*)ctx->in_c.p, (uint8_t*)ctx->out_a.p, (uint32_t*)ctx->share_gather.p, s))
+    return rc;
+  if (int rc = unstage_results(ctx, n_local, n_r, status_local, gather, s)) return rc;
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
 // ---- pairing checks, items sharded --------------------------------------------------------------------------------------
 // every rank: its m_local (pk, sig) pairs -> d_status_all [world][m_local]
 extern "C" int dkgv_bls_verify_batch_sharded_dev(dkgv_ctx* ctx, uint32_t m_local, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,

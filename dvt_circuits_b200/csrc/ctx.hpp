@@ -58,7 +58,7 @@ struct dkgv_ctx {
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
   uint64_t collectives = 0;
-  dkgv_host::DevBuf comm_flags, comm_buf;
+  dkgv_host::DevBuf comm_flags, comm_buf, share_gather;
   uint32_t* h_comm_flags = nullptr;
   size_t h_comm_flags_cap = 0;
   cudaEvent_t ev_hot0 = nullptr, ev_hot1 = nullptr;    // bracket the hot kernel (roofline timing)

@@ -289,6 +289,17 @@ int dkgv_share_matrix_enqueue_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint3
 int dkgv_share_matrix_settle_sharded_dev(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* d_vv_local,
                                          const uint32_t* d_ids, const uint8_t* d_shares_local, uint8_t* d_status_local, uint32_t* d_gather,
                                          const uint32_t* h_flags, void* stream, int* reran);
+/* The same pair with HOST buffers - the reference-facing form for a host with many ceremonies (verification.rs:68-149 per ceremony):
+ * rows, ids and shares in (PINNED memory, or the copies are not asynchronous), status_local [n_local][n_recipients], gather
+ * [world][chunk] (may be NULL) and h_flags (2 * world words) out; everything queued on the ctx's own stream, nothing synchronised.
+ * One ctx per ceremony in flight on a GPU (ctxs of a device share the fixed-base table): the copies of one ceremony run under the
+ * kernels of another.  dkgv_sync(ctx), then settle with the same arguments (synchronous when it has to run the ceremony again). */
+int dkgv_share_matrix_enqueue_sharded(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* vv_local,
+                                      const uint32_t* ids, const uint8_t* shares_local, uint8_t* status_local, uint32_t* gather,
+                                      uint32_t* h_flags);
+int dkgv_share_matrix_settle_sharded(dkgv_ctx* ctx, uint32_t n_local, uint32_t n_recipients, uint32_t t, const uint8_t* vv_local,
+                                     const uint32_t* ids, const uint8_t* shares_local, uint8_t* status_local, uint32_t* gather,
+                                     const uint32_t* h_flags, int* reran);
 /* Pairing checks sharded by items: every rank its m_local pairs; d_status_all [world][m_local] on every rank.  Asynchronous. */
 int dkgv_bls_verify_batch_sharded_dev(dkgv_ctx* ctx, uint32_t m_local, const uint8_t* d_pk, const uint8_t* d_sig, uint32_t n_hm,
                                       const uint8_t* d_hm, const uint32_t* d_hm_idx, uint8_t* d_status_all, void* stream);

@@ -43,6 +43,19 @@ def _worker(rank, world, port, n, t, q):
     got = np.concatenate([dk.verdict_bits_to_matrix(allw.numpy()[r * per:(r + 1) * per], rows, n) for r in range(world)])
     ok = ok and bool((got == (exp != 0)).all())
     ok = ok and sorted(np.nonzero(got.any(axis=1))[0].tolist()) == sorted(np.nonzero((exp != 0).any(axis=1))[0].tolist())
+    # ceremonies in flight: every rank's chunk ends with its two flag words; after the all-gather every rank takes the SAME settle decision
+    from dvt_circuits_b200 import pipeline
+    for case, flag1 in enumerate(([0] * world, [0] * (world - 1) + [3])):  # honest / the last rank has 3 unsettled dealers
+        chunk = torch.tensor([rank, 0, flag1[rank]], dtype=torch.int32)  # [payload word, flag 0, flag 1]
+        allc = torch.empty((world * 3,), dtype=torch.int32)
+        dist.all_gather_into_tensor(allc, chunk)
+        h_flags = allc.reshape(world, 3)[:, 1:].reshape(-1).numpy()
+        decision = pipeline.settle_needed(h_flags, world)
+        votes = torch.tensor([int(decision)], dtype=torch.int32)
+        lo, hi = votes.clone(), votes.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and int(lo.item()) == int(hi.item()) == case
     # max-over-ranks timing reduction used by bench.py
     tms = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -65,3 +78,14 @@ def test_row_block_sharding_and_gather():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_pipeline_planning():
+    from dvt_circuits_b200 import pipeline
+    assert [pipeline.lanes_for(r) for r in (1024, 512, 256, 128, 1)] == [2, 2, 4, 4, 4]
+    # (1024, 683) on one GPU: 33.5 MB of commitments + 33.5 MB of shares; one rank of eight: an eighth of that
+    for b in (67_000_000, 8_400_000, 1):
+        r = pipeline.ring_size(b)
+        assert 2 <= r <= 64 and (r * b > 2 * pipeline.L2_BYTES or r == 64)
+    assert pipeline.ring_size(10 ** 12) == 2
+    assert not pipeline.settle_needed([0, 0, 0, 0], 2) and pipeline.settle_needed([0, 0, 0, 5], 2) and pipeline.settle_needed([1, 0, 0, 0], 2)

@@ -21,6 +21,10 @@ def main():
     s = synthetic.make_session(v, n, n, t)
     rng = np.random.Generator(np.random.PCG64(7))
     mask = rng.random((n, n)) < p_bad
+    if p_bad < 0:  # one dealer entirely wrong (-k: k dealers spread over the session): beyond the repair route, its group is evaluated
+        mask[:] = False
+        k = int(-p_bad)
+        mask[[(n // 2 + 37 * i * 32) % n for i in range(k)], :] = True
     bad = s["shares"].copy()
     bad[mask, 31] ^= 1
     dev = torch.device("cuda:0")
