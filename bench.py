@@ -669,7 +669,8 @@ def run_b200(args):
             # ---- corrupted shares: the reference exists to PROVE misbehaviour; how the default path degrades with the corruption rate
             rng = np.random.Generator(np.random.PCG64([0xBAD, rank]))
             corr = {}
-            for name, kind in (("one_share", 1), ("one_dealer", 2), ("p_1pct", 0.01), ("p_10pct", 0.10), ("p_50pct_config5", 0.50)):
+            for name, kind in (("one_share", 1), ("one_dealer", 2), ("one_dealer_in_every_group", 3), ("p_1pct", 0.01), ("p_10pct", 0.10),
+                               ("p_50pct_config5", 0.50)):
                 mask = np.zeros((rows, n), dtype=bool)
                 if kind == 1:
                     if rank == 0:
@@ -677,6 +678,8 @@ def run_b200(args):
                 elif kind == 2:
                     if rank == 0:
                         mask[rows // 2, :] = True
+                elif kind == 3:  # every 32-dealer group holds one dealer that is wrong throughout: the per-dealer fallback evaluates rows / 32 dealers
+                    mask[5::32, :] = True
                 else:
                     mask = rng.random((rows, n)) < kind
                 sh_bad = sess["shares"].copy()

@@ -68,7 +68,7 @@ struct dkgv_ctx {
   bool hot_recorded = false;
   bool stack_set = false;
   // finite-difference share path (share_fd.cu)
-  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef, fd_yz;
+  dkgv_host::DevBuf fd_evals, fd_p0, fd_p1, fd_da, fd_db, fd_seedx, fd_dig, fd_top, fd_tab, fd_cols, fd_sl, fd_flags, fd_binom, fd_coef, fd_yz, fd_cmp_list, fd_cmp_sh, fd_cmp_st;
   std::vector<int32_t> fd_seed_host;
   cudaEvent_t ev_fd[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the evaluation
   cudaEvent_t ev_sc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // ... of the consistency shortcut

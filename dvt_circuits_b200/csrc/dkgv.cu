@@ -22,6 +22,9 @@ bool dkgv_fd_shortcut_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t);
 int dkgv_fd_submit(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids, const uint8_t* d_shares,
                    uint8_t* d_status, bool shortcut, uint32_t* d_flags, cudaStream_t s);
 const uint8_t* dkgv_fd_need_groups(const dkgv_ctx* ctx, uint32_t n_d);
+int dkgv_fd_compact_unsettled(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t count, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s,
+                              const uint32_t** list, const uint8_t** shares_c, uint8_t** status_c);
+int dkgv_fd_scatter_status(dkgv_ctx* ctx, uint32_t n_r, uint32_t count, uint8_t* d_status, cudaStream_t s);
 bool dkgv_fd_repair_applies(const dkgv_ctx* ctx, uint32_t n_r, uint32_t t);
 int dkgv_fd_repair(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint8_t* d_shares, uint8_t* d_status,
                    uint32_t* d_flags, cudaStream_t s);
@@ -60,16 +63,20 @@ __global__ void __launch_bounds__(128) k_gtab_check(GTab g, uint32_t first, uint
 //   (the reference panics on `.expect("Invalid pubkey")`, verification.rs:132-137).
 __global__ void __launch_bounds__(128)
 k_decompress_vv(const uint8_t* __restrict__ vv, uint32_t n_d, uint32_t t, uint32_t n_pad, uint32_t* __restrict__ limbs,
-                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status) {
+                uint8_t* __restrict__ inf, uint8_t* __restrict__ dealer_bad, uint8_t* __restrict__ point_status,
+                const uint8_t* __restrict__ group_filter, const uint32_t* __restrict__ map) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= (size_t)n_pad * t) return;
   uint32_t d = (uint32_t)(p % n_pad), k = (uint32_t)(p / n_pad);
+  // a warp = one 32-dealer group and one coefficient: only the groups the evaluation will read (nullptr: all of them)
+  if (group_filter && !group_filter[d / 32]) return;
   G1Aff a;
   a.x = zero<FpParams>();
   a.y = zero<FpParams>();
   a.inf = 1;
   if (d < n_d) {
-    uint32_t st = g1_decompress(vv + ((size_t)d * t + k) * 48, &a, true);
+    const uint32_t src = map ? map[d] : d;  // dense session of listed dealers (per-dealer fallback): column d holds dealer map[d]
+    uint32_t st = g1_decompress(vv + ((size_t)src * t + k) * 48, &a, true);
     if (st != G1_DEC_OK) dealer_bad[d] = 1;
     if (point_status) point_status[(size_t)d * t + k] = (uint8_t)st;
   }
@@ -407,7 +414,8 @@ extern "C" int dkgv_sync(dkgv_ctx* ctx) {
 }
 
 // decode + subgroup-check vv into the ctx session buffers (asynchronous on s)
-static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, cudaStream_t s, VVView* view, uint32_t* n_pad_out) {
+static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t* d_vv, cudaStream_t s, VVView* view, uint32_t* n_pad_out,
+                          const uint8_t* group_filter = nullptr, const uint32_t* map = nullptr) {
   uint32_t n_pad = (n_d + 31) & ~31u;
   uint32_t tt = t ? t : 1;
   CK(ctx->vv_limbs.reserve((size_t)tt * 24 * n_pad * 4));
@@ -418,7 +426,7 @@ static int session_decode(dkgv_ctx* ctx, uint32_t n_d, uint32_t t, const uint8_t
     size_t total = (size_t)n_pad * t;
     if (ctx->ev_dec0) CK(cudaEventRecord(ctx->ev_dec0, s));
     k_decompress_vv<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_vv, n_d, t, n_pad, (uint32_t*)ctx->vv_limbs.p, (uint8_t*)ctx->vv_inf.p,
-                                                                  (uint8_t*)ctx->dealer_bad.p, nullptr);
+                                                                  (uint8_t*)ctx->dealer_bad.p, nullptr, group_filter, map);
     if (ctx->ev_dec1) CK(cudaEventRecord(ctx->ev_dec1, s));
     ctx->dec_recorded = true;
     ctx->launches++;
@@ -561,6 +569,7 @@ static int share_finish(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) 
   }
   if (h_flags[0]) return share_matrix_horner(ctx, job.n_d, job.n_r, job.t, job.d_vv, job.d_ids, job.d_shares, job.d_status, s);
   if (!h_flags[1]) return 0;  // every verdict is OK and already written
+  uint32_t unsettled = h_flags[1];  // with the shortcut: the dealers that failed a condition
   if (job.shortcut && dkgv_fd_repair_applies(ctx, job.n_r, job.t)) {
     // some dealers' shares are not on one polynomial: decode them as Reed-Solomon words with errors before anything is evaluated
     // in the exponent; what the decoder settles (exactly - share_rs.cuh) needs no evaluation.  One more read-back of the flags.
@@ -569,14 +578,27 @@ static int share_finish(dkgv_ctx* ctx, const uint32_t* h_flags, cudaStream_t s) 
     CK(cudaStreamSynchronize(s));
     ctx->last_repaired = ctx->h_job_flags[2];
     if (!ctx->h_job_flags[1]) return 0;
+    unsettled = ctx->h_job_flags[1];
   }
   ctx->fd_last_need = true;
   VVView view;
   uint32_t n_pad;
-  if (int rc = session_decode(ctx, job.n_d, job.t, job.d_vv, s, &view, &n_pad)) return rc;
   FdPlan plan = fd_make_plan(job.t, job.n_r, job.parts, 0);
-  return dkgv_share_matrix_fd(ctx, view, job.n_d, job.n_r, job.t, plan, job.d_ids, job.d_shares, job.d_status,
-                              job.shortcut ? dkgv_fd_need_groups(ctx, job.n_d) : nullptr, s);
+  if (job.shortcut && unsettled && (size_t)unsettled * 2 <= job.n_d && ((uintptr_t)job.d_shares & 15) == 0) {
+    // per-dealer fallback: the few dealers left are evaluated as a dense session of their own (8 wrong dealers spread over 8 groups cost
+    // one group, not eight); the settled dealers of their groups get their verdicts without evaluation
+    const uint32_t* list;
+    const uint8_t* sh_c;
+    uint8_t* st_c;
+    if (int rc = dkgv_fd_compact_unsettled(ctx, job.n_d, job.n_r, unsettled, job.d_shares, job.d_status, s, &list, &sh_c, &st_c)) return rc;
+    if (int rc = session_decode(ctx, unsettled, job.t, job.d_vv, s, &view, &n_pad, nullptr, list)) return rc;
+    if (int rc = dkgv_share_matrix_fd(ctx, view, unsettled, job.n_r, job.t, plan, job.d_ids, sh_c, st_c, nullptr, s)) return rc;
+    return dkgv_fd_scatter_status(ctx, job.n_r, unsettled, job.d_status, s);
+  }
+  // only the commitments of the dealer groups that go on to the evaluation are decoded
+  const uint8_t* need = job.shortcut ? dkgv_fd_need_groups(ctx, job.n_d) : nullptr;
+  if (int rc = session_decode(ctx, job.n_d, job.t, job.d_vv, s, &view, &n_pad, need)) return rc;
+  return dkgv_share_matrix_fd(ctx, view, job.n_d, job.n_r, job.t, plan, job.d_ids, job.d_shares, job.d_status, need, s);
 }
 
 int dkgv_share_submit_internal(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t t, const uint8_t* d_vv, const uint32_t* d_ids,

@@ -364,6 +364,69 @@ k_fd_fill_ok(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_grou
   status[(size_t)d * n_r + j] = DKGV_OK;
 }
 
+// ---- per-dealer fallback: the dealers still unsettled after the shortcut and the repair route, compacted into dense groups ------------
+// ordered list of the dealers with poly_ok == 0 (one warp; n_d <= 65535)
+__global__ void __launch_bounds__(32) k_fd_need_list(const uint8_t* __restrict__ poly_ok, uint32_t n_d, uint32_t* __restrict__ list, uint32_t cap) {
+  uint32_t count = 0;
+  for (uint32_t base = 0; base < n_d; base += 32) {
+    const uint32_t d = base + threadIdx.x;
+    const bool f = d < n_d && poly_ok[d] == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, f);
+    const uint32_t pos = count + __popc(m & ((1u << threadIdx.x) - 1));
+    if (f && pos < cap) list[pos] = d;
+    count += __popc(m);
+  }
+}
+// verdict OK for the settled dealers inside the groups k_fd_fill_ok left alone (a repaired dealer keeps its own verdicts)
+__global__ void __launch_bounds__(128)
+k_fd_fill_ok_dealers(uint8_t* __restrict__ status, const uint8_t* __restrict__ need_group, const uint8_t* __restrict__ poly_ok,
+                     const uint8_t* __restrict__ state, uint32_t n_d, uint32_t n_r) {
+  uint32_t j = blockIdx.y * blockDim.x + threadIdx.x, d = blockIdx.x;
+  if (j >= n_r || d >= n_d || !need_group[d / 32] || !poly_ok[d] || state[d] == RS_CANDIDATE) return;
+  status[(size_t)d * n_r + j] = DKGV_OK;
+}
+// share rows (n_r x 32 B, 16-byte pieces) of the listed dealers into a dense table; status rows of the dense table back
+__global__ void __launch_bounds__(128)
+k_fd_gather_rows(const uint4* __restrict__ src, uint4* __restrict__ dst, const uint32_t* __restrict__ list, uint32_t row16) {
+  const uint32_t c = blockIdx.x, i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i < row16) dst[(size_t)c * row16 + i] = src[(size_t)list[c] * row16 + i];
+}
+__global__ void __launch_bounds__(128)
+k_fd_scatter_status(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const uint32_t* __restrict__ list, uint32_t n_r) {
+  const uint32_t c = blockIdx.x, j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j < n_r) dst[(size_t)list[c] * n_r + j] = src[(size_t)c * n_r + j];
+}
+
+// The `count` dealers still unsettled (flags[1], read back by the caller) as a dense session: *list (device) their indices in ascending
+// order, *shares_c / *status_c dense share and status tables; the settled dealers of their groups get their OK verdicts here.
+int dkgv_fd_compact_unsettled(dkgv_ctx* ctx, uint32_t n_d, uint32_t n_r, uint32_t count, const uint8_t* d_shares, uint8_t* d_status, cudaStream_t s,
+                              const uint32_t** list, const uint8_t** shares_c, uint8_t** status_c) {
+  const uint32_t n_pad = (n_d + 31) & ~31u, groups = n_pad / 32;
+  const uint8_t* poly_ok = (const uint8_t*)ctx->fd_flags.p;
+  const uint8_t* need_group = poly_ok + n_pad;
+  const uint8_t* state = need_group + groups;
+  CK(ctx->fd_cmp_list.reserve((size_t)count * 4));
+  CK(ctx->fd_cmp_sh.reserve((size_t)count * n_r * 32));
+  CK(ctx->fd_cmp_st.reserve((size_t)count * n_r));
+  const unsigned gy = (n_r + 127) / 128;
+  k_fd_need_list<<<1, 32, 0, s>>>(poly_ok, n_d, (uint32_t*)ctx->fd_cmp_list.p, count);
+  k_fd_fill_ok_dealers<<<dim3(n_d, gy), 128, 0, s>>>(d_status, need_group, poly_ok, state, n_d, n_r);
+  k_fd_gather_rows<<<dim3(count, (n_r * 2 + 127) / 128), 128, 0, s>>>((const uint4*)d_shares, (uint4*)ctx->fd_cmp_sh.p, (const uint32_t*)ctx->fd_cmp_list.p,
+                                                                   n_r * 2);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  *list = (const uint32_t*)ctx->fd_cmp_list.p;
+  *shares_c = (const uint8_t*)ctx->fd_cmp_sh.p;
+  *status_c = (uint8_t*)ctx->fd_cmp_st.p;
+  return 0;
+}
+int dkgv_fd_scatter_status(dkgv_ctx* ctx, uint32_t n_r, uint32_t count, uint8_t* d_status, cudaStream_t s) {
+  k_fd_scatter_status<<<dim3(count, (n_r + 127) / 128), 128, 0, s>>>((const uint8_t*)ctx->fd_cmp_st.p, d_status, (const uint32_t*)ctx->fd_cmp_list.p, n_r);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // evaluate_polynomial output instead of the share comparison: out[dealer][column j] = compress(f_d(ids[j]))
 __global__ void __launch_bounds__(FD_NT)
 k_fd_combine_out(const uint32_t* __restrict__ evals, int32_t lo, uint32_t m, const int8_t* __restrict__ dig, const int32_t* __restrict__ top,
