@@ -724,9 +724,16 @@ def run_b200(args):
             want = torch.from_numpy(np.where(wrong, 7, 0).astype(np.uint8)).to(dev)
             pair_ok = bool((d_pall == want.unsqueeze(0)).all().item())
             # e2e: host buffers through dkgv_bls_verify_batch (H2D of keys + signatures, D2H of the statuses inside)
-            t0 = time.perf_counter()
-            st_h = v.bls_verify_batch(pk_np, sg_np, fin["hm"])
-            pair_e2e_s = dmax(time.perf_counter() - t0)
+            h_pk, h_sg = torch.from_numpy(pk_np).pin_memory(), torch.from_numpy(sg_np).pin_memory()
+            h_hm, h_pst = torch.from_numpy(fin["hm"].copy()).pin_memory(), torch.empty(m_loc, dtype=torch.uint8).pin_memory()
+            pair_e2e_t = []
+            for _ in range(3):  # the first call is the warm-up of the staging buffers
+                barrier()
+                t0 = time.perf_counter()
+                v._ck(v._lib.dkgv_bls_verify_batch(v._h, m_loc, h_pk.data_ptr(), h_sg.data_ptr(), 1, h_hm.data_ptr(), None, h_pst.data_ptr()))
+                pair_e2e_t.append(time.perf_counter() - t0)
+            pair_e2e_s = dmax(sum(pair_e2e_t[1:])) / 2
+            st_h = h_pst.numpy()
             prog = json.load(open(os.path.join(ROOT, "dvt_circuits_b200", "csrc", "pairing_prog.json")))
             kms = statistics.mean(pair_kernel_ms)
             legs["pairing"] = {
@@ -735,7 +742,7 @@ def run_b200(args):
                 "verdicts_flag_exactly_the_wrong_signatures": pair_ok and bool((st_h == np.where(wrong, 7, 0)).all()),
                 "path": {1: "pairing VM (6 warps per 32 checks, operands in shared memory)", 2: "one thread per check"}[v.last_bls_path],
                 "e2e": {"value": m_total / pair_e2e_s, "unit": "checks/s", "h2d_bytes_per_step": int(m_total * 144 + 96), "d2h_bytes_per_step": m_total,
-                        "timing": "host wall clock around dkgv_bls_verify_batch (host buffers), max over ranks"},
+                        "timing": "host wall clock around dkgv_bls_verify_batch (pinned host buffers), mean of 2 calls after one warm-up, max over ranks"},
                 "note": "e(pk,H(m)) == e(G1,sig) as ONE product of two Miller loops + one final exponentiation per check, incl. G1/G2 decoding "
                         "with subgroup checks and the preparation of the hashed message's lines",
             }
