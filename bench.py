@@ -450,12 +450,14 @@ def run_b200(args):
             h_st.copy_(d_st, non_blocking=True)
             ts.synchronize()
 
-    def timed_steps(fn, count, do_flush=True):
+    def timed_steps(fn, count, do_flush=True, ranks_together=True):
+        """per-step CUDA events around fn(); ranks_together: every rank calls this the same number of times (a barrier precedes each step) -
+        False inside a leg only ONE rank runs (a barrier there would wait for ranks that never come)"""
         out = []
         for _ in range(count):
             if do_flush and os.environ.get("DKGV_BENCH_FLUSH", "1") != "0":  # (=0: diagnosis only, the number is then not a bench value)
                 flush.fill_(1)  # L2 flush between timed iterations (not timed)
-            if world > 1:
+            if world > 1 and ranks_together:
                 barrier()  # every step starts on all ranks together: its collective is not charged with host-side skew between the ranks
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(ts)
@@ -839,10 +841,10 @@ def run_b200(args):
                 def step_a():
                     v.share_matrix_verify_dev(64, 64, 43, da_vv.data_ptr(), da_ids.data_ptr(), da_sh.data_ptr(), da_st.data_ptr(), stream)
                 step_a()
-                a_ms = statistics.mean(timed_steps(step_a, 5, do_flush=False))
+                a_ms = statistics.mean(timed_steps(step_a, 5, do_flush=False, ranks_together=False))
                 v.set_share_shortcut(False)
                 step_a()
-                a_full_ms = statistics.mean(timed_steps(step_a, 3, do_flush=False))
+                a_full_ms = statistics.mean(timed_steps(step_a, 3, do_flush=False, ranks_together=False))
                 v.set_share_shortcut(True)
                 legs["config_a"] = {"metric": "verified shares/sec (n=64,t=43), full 64x64 matrix on one GPU", "value": 4096 / (a_ms * 1e-3),
                                     "unit": "shares/s", "ms_per_step": a_ms, "bad_verdicts": int(da_st.count_nonzero().item()),

@@ -108,3 +108,42 @@ def test_bench_clock_sampler_window():
     assert out["samples"] == 0 and out["sm_mhz"] is None and out["reasons"] == []
     out = sampler(rows, [1.0, 2.0]).stop(since=1.5)  # a row whose stamp has not been appended yet is ignored
     assert out["samples"] == 1
+
+
+def test_bench_has_no_collective_inside_a_single_rank_leg():
+    """bench.py at N > 1: a barrier / max-over-ranks / gather inside an `if rank == 0:` block waits for ranks that never come (the full
+    run at N = 2 once hung on the per-step barrier of timed_steps inside the rank-0 config-A leg).  Static check over the source."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    collective = {"barrier", "dmax", "all_ranks", "gather_stats"}
+    dist_calls = {"barrier", "all_reduce", "all_gather", "all_gather_into_tensor", "broadcast_object_list", "broadcast", "all_gather_object"}
+
+    def is_rank0_test(t):
+        return (isinstance(t, ast.Compare) and isinstance(t.left, ast.Name) and t.left.id == "rank" and len(t.ops) == 1
+                and isinstance(t.ops[0], ast.Eq) and isinstance(t.comparators[0], ast.Constant) and t.comparators[0].value == 0)
+
+    bad, seen = [], 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and is_rank0_test(node.test):
+            seen += 1
+            for stmt in node.body:
+                for c in ast.walk(stmt):
+                    if not isinstance(c, ast.Call):
+                        continue
+                    f = c.func
+                    if isinstance(f, ast.Name) and f.id in collective:
+                        bad.append((f.id, c.lineno))
+                    if isinstance(f, ast.Name) and f.id == "timed_steps":
+                        kw = {k.arg: k.value for k in c.keywords}
+                        if not (isinstance(kw.get("ranks_together"), ast.Constant) and kw["ranks_together"].value is False):
+                            bad.append(("timed_steps without ranks_together=False", c.lineno))
+                    if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "dist" and f.attr in dist_calls:
+                        bad.append(("dist." + f.attr, c.lineno))
+                    if isinstance(f, ast.Attribute) and f.attr in ("comm_init", "all_gather_dev", "share_matrix_verify_sharded_dev",
+                                                                   "share_matrix_enqueue_sharded_dev", "share_matrix_enqueue_sharded",
+                                                                   "bls_verify_batch_sharded_dev", "agg_final_keys_sharded"):
+                        bad.append((f.attr, c.lineno))
+    assert seen >= 5
+    assert not bad, bad
