@@ -10,11 +10,21 @@ DEFAULT_SEED = 0xD1C62026
 
 
 def make_coefficients(n_dealers, t, seed=DEFAULT_SEED, dealer_offset=0):
-    """[n_dealers, t, 32] big-endian scalars < 2^248 < r; dealer d's row depends only on (seed, d)."""
+    """[n_dealers, t, 32] big-endian scalars a_{i,k} = SHA-256(seed || "coef" || i || k) mod r (seeded PRNG = SHA-256 in
+    counter mode over seed || label || index; the whole range of Fr).  Dealer i's row depends only on (seed, i), so every rank of a
+    multi-GPU job generates exactly its own rows."""
+    import hashlib
     out = np.zeros((n_dealers, t, 32), dtype=np.uint8)
+    base = hashlib.sha256(int(seed).to_bytes(8, "little") + b"coef")
     for d in range(n_dealers):
-        rng = np.random.Generator(np.random.PCG64([seed, dealer_offset + d]))
-        out[d, :, 1:] = rng.integers(0, 256, size=(t, 31), dtype=np.uint8)
+        hd = base.copy()
+        hd.update(int(dealer_offset + d).to_bytes(4, "little"))
+        row = bytearray(t * 32)
+        for k in range(t):
+            h = hd.copy()
+            h.update(k.to_bytes(4, "little"))
+            row[k * 32:(k + 1) * 32] = (int.from_bytes(h.digest(), "big") % R_INT).to_bytes(32, "big")
+        out[d] = np.frombuffer(bytes(row), dtype=np.uint8).reshape(t, 32)
     return out
 
 
