@@ -147,3 +147,43 @@ def test_bench_has_no_collective_inside_a_single_rank_leg():
                         bad.append((f.attr, c.lineno))
     assert seen >= 5
     assert not bad, bad
+
+
+def test_python_sources_have_no_undefined_names():
+    """coarse static check (no linter in this image): every name a function of bench.py / the package loads is bound somewhere in that
+    function, at module level or in builtins - a typo in a branch only an N > 1 run takes would otherwise wait for the GPU box"""
+    import ast
+    import builtins
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = ["bench.py", "__graft_entry__.py", "dvt_circuits_b200/binding.py", "dvt_circuits_b200/synthetic.py", "dvt_circuits_b200/pipeline.py",
+             "tools/multi_gpu_check.py", "tools/diag_gather.py", "tools/pairing_lanes.py", "tools/profile_repair.py"]
+    for rel in files:
+        tree = ast.parse(open(os.path.join(root, rel)).read())
+        mod = set(dir(builtins)) | {"__file__", "__name__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                mod.add(n.name)
+        for n in tree.body:
+            if isinstance(n, (ast.Import, ast.ImportFrom)):
+                mod |= {(a.asname or a.name).split(".")[0] for a in n.names}
+            elif isinstance(n, (ast.Assign, ast.AugAssign, ast.AnnAssign, ast.For, ast.With, ast.If, ast.Try)):
+                mod |= {x.id for x in ast.walk(n) if isinstance(x, ast.Name) and isinstance(x.ctx, ast.Store)}
+                for x in ast.walk(n):
+                    if isinstance(x, (ast.Import, ast.ImportFrom)):
+                        mod |= {(a.asname or a.name).split(".")[0] for a in x.names}
+        for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+            bound = set(mod)
+            # names of the enclosing functions are visible too: collect over the outermost function that contains fn
+            for outer in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and any(x is fn for x in ast.walk(n))]:
+                for x in ast.walk(outer):
+                    if isinstance(x, ast.Name) and isinstance(x.ctx, (ast.Store, ast.Del)):
+                        bound.add(x.id)
+                    elif isinstance(x, ast.arg):
+                        bound.add(x.arg)
+                    elif isinstance(x, (ast.Import, ast.ImportFrom)):
+                        bound |= {(a.asname or a.name).split(".")[0] for a in x.names}
+                    elif isinstance(x, ast.ExceptHandler) and x.name:
+                        bound.add(x.name)
+            missing = sorted({(x.id, x.lineno) for x in ast.walk(fn) if isinstance(x, ast.Name) and isinstance(x.ctx, ast.Load) and x.id not in bound})
+            assert not missing, (rel, fn.name, missing)
