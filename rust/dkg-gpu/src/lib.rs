@@ -101,6 +101,37 @@ impl Gpu {
         Ok(reran != 0)
     }
 
+    /// Host-buffer form of the pipelined pair: this rank's rows, the ids and the shares are copied in, the status bytes of the own rows,
+    /// the gathered chunks (`gather` may be null) and every rank's flag words come back - all queued on the ctx's own stream, nothing
+    /// synchronised.  Call `sync`, then `share_matrix_settle_sharded` with the same arguments.
+    ///
+    /// # Safety
+    /// Every pointer is HOST memory sized as `include/dkgv.h` states, pinned (page-locked) for the copies to be asynchronous, and must
+    /// stay valid until `sync` has returned.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn share_matrix_enqueue_sharded(&mut self, n_local: u32, n_recipients: u32, t: u32, vv_local: *const u8, ids: *const u32,
+        shares_local: *const u8, status_local: *mut u8, gather: *mut u32, h_flags: *mut u32) -> Result<(), GpuError> {
+        self.check(sys::dkgv_share_matrix_enqueue_sharded(self.ctx, n_local, n_recipients, t, vv_local, ids, shares_local, status_local, gather, h_flags))
+    }
+
+    /// `Ok(false)`: honest ceremony, the verdicts `enqueue` delivered are final; `Ok(true)`: it was run again (synchronously).
+    ///
+    /// # Safety
+    /// As `share_matrix_enqueue_sharded`, same arguments, after `sync`.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn share_matrix_settle_sharded(&mut self, n_local: u32, n_recipients: u32, t: u32, vv_local: *const u8, ids: *const u32,
+        shares_local: *const u8, status_local: *mut u8, gather: *mut u32, h_flags: *const u32) -> Result<bool, GpuError> {
+        let mut reran: c_int = 0;
+        self.check(sys::dkgv_share_matrix_settle_sharded(self.ctx, n_local, n_recipients, t, vv_local, ids, shares_local, status_local, gather,
+            h_flags, &mut reran))?;
+        Ok(reran != 0)
+    }
+
+    /// Waits for everything queued on the ctx's own stream.
+    pub fn sync(&mut self) -> Result<(), GpuError> {
+        self.check(unsafe { sys::dkgv_sync(self.ctx) })
+    }
+
     fn check(&self, rc: c_int) -> Result<(), GpuError> {
         if rc == 0 {
             return Ok(());
