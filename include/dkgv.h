@@ -15,10 +15,12 @@
  *    and do not synchronise it, with ONE documented exception: dkgv_share_matrix_verify_dev reads a
  *    two-word flag back (one stream synchronisation) to decide whether anything is left to evaluate;
  *    its split form dkgv_share_matrix_submit_dev / dkgv_share_matrix_finish_dev leaves that read-back
- *    to the caller and is fully asynchronous (CUDA-graph capturable once its buffers exist).
- *  - A ctx is single-owner (Send, not Sync), bound to one GPU.  Multi-GPU: one ctx per process/GPU with
- *    a dkgv_comm (NCCL inside the library: dkgv_comm_*, *_sharded entry points), or one dkgv_multi
- *    driving several GPUs from one host thread (dkgv_multi_*).
+ *    to the caller and is fully asynchronous (CUDA-graph capturable once its buffers exist); the sharded
+ *    synchronous calls (dkgv_share_matrix_verify_sharded_dev, dkgv_agg_final_keys_sharded) synchronise once
+ *    after their all-gather, their pipelined forms (dkgv_share_matrix_enqueue_sharded[_dev] + _settle_) do not.
+ *  - A ctx is single-owner (Send, not Sync), bound to one GPU.  Multi-GPU: one process per GPU, a
+ *    dkgv_comm per ctx (NCCL inside the library: dkgv_comm_*, *_sharded entry points).  Several ctxs of one
+ *    process may share a GPU (one per ceremony in flight); they share ONE fixed-base table per window width.
  *  - There is no CPU fallback: without a CUDA device dkgv_ctx_create fails.
  */
 #ifndef DKGV_H
