@@ -259,3 +259,11 @@ def test_full_bench_control_flow(world):
 def test_quick_bench_control_flow_two_ranks():
     line = _run(2, ["--gpus", "2", "--n", "8", "--t", "3", "--steps", "3", "--warmup", "1", "--quick", "--no-cpu", "--no-peak"], timeout=120)
     assert line["n_gpus"] == 2 and "sync_call" in line and "pairing" not in line
+
+
+def test_more_steps_than_output_slots_and_a_single_step():
+    """K = 300 ceremonies go through the pipelined legs in waves of 256 (the output slots); K = 1, W = 0 uses one lane only"""
+    line = _run(2, ["--gpus", "2", "--n", "8", "--t", "3", "--steps", "300", "--warmup", "1", "--quick", "--no-cpu", "--no-peak"], timeout=200)
+    assert line["steps"] == 300 and line["gpu_launches"] == 300 * 9
+    line = _run(1, ["--n", "8", "--t", "3", "--steps", "1", "--warmup", "0", "--quick", "--no-cpu", "--no-peak"], timeout=100)
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["gpu_launches"] == 9
