@@ -267,3 +267,11 @@ def test_more_steps_than_output_slots_and_a_single_step():
     assert line["steps"] == 300 and line["gpu_launches"] == 300 * 9
     line = _run(1, ["--n", "8", "--t", "3", "--steps", "1", "--warmup", "0", "--quick", "--no-cpu", "--no-peak"], timeout=100)
     assert line["steps"] == 1 and line["warmup"] == 0 and line["gpu_launches"] == 9
+
+
+def test_reference_arm_under_two_ranks():
+    """--impl reference launched like the B200 arm (torchrun, N = 2): rank 0 alone runs the oracle and prints the one line, rank 1
+    exits 0 without work and without touching a process group"""
+    line = _run(2, ["--impl", "reference", "--gpus", "2", "--n", "8", "--t", "3", "--steps", "1", "--warmup", "0", "--cpu-sample", "2"], timeout=200)
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["gpu_launches"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
